@@ -1,0 +1,386 @@
+// cb_math.h -- integer / decimal / hash arithmetic shared by every comet_b200 kernel.
+//
+// Plain C++ with no includes so that the same text compiles three ways:
+//   * under NVRTC as part of a JIT-specialised pipeline kernel (sm_100a),
+//   * under nvcc for the ahead-of-time kernels (parquet decode, partition, hash table),
+//   * under g++ (CB_HOST_TEST) so tests/ can check every function against the oracle on CPU.
+//
+// Semantics follow the reference (apache/datafusion-comet); each block cites the file:line of the
+// Rust it replaces (paths relative to native/).
+#ifndef CB_MATH_H
+#define CB_MATH_H
+
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#define CB_HD __host__ __device__ __forceinline__
+#define CB_D __device__ __forceinline__
+#else
+#define CB_HD inline
+#define CB_D inline
+#endif
+
+namespace cb {
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+typedef int i32;
+typedef unsigned char u8;
+typedef unsigned short u16;
+
+// ------------------------------------------------------------------------------------------------
+// 64x64 -> 128 primitives
+// ------------------------------------------------------------------------------------------------
+CB_HD u64 umulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// 128-bit two's-complement integer, Arrow Decimal128 layout (little-endian lo, hi).
+struct
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+    __align__(16)
+#endif
+        i128 {
+    u64 lo;
+    i64 hi;
+};
+
+struct u128 {
+    u64 lo, hi;
+};
+struct u256 {
+    u64 w[4];
+};
+
+CB_HD i128 mk128(u64 lo, i64 hi) { i128 r; r.lo = lo; r.hi = hi; return r; }
+CB_HD i128 i128_from_i64(i64 v) { return mk128((u64)v, v >> 63); }
+CB_HD bool i128_is_neg(i128 a) { return a.hi < 0; }
+CB_HD bool i128_eq(i128 a, i128 b) { return a.lo == b.lo && a.hi == b.hi; }
+CB_HD bool i128_lt(i128 a, i128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+CB_HD bool i128_le(i128 a, i128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo <= b.lo); }
+CB_HD i128 i128_add(i128 a, i128 b) { // wrapping
+    i128 r; r.lo = a.lo + b.lo; r.hi = (i64)((u64)a.hi + (u64)b.hi + (r.lo < a.lo ? 1ull : 0ull)); return r;
+}
+CB_HD i128 i128_sub(i128 a, i128 b) { // wrapping
+    i128 r; r.lo = a.lo - b.lo; r.hi = (i64)((u64)a.hi - (u64)b.hi - (a.lo < b.lo ? 1ull : 0ull)); return r;
+}
+CB_HD i128 i128_neg(i128 a) { return i128_sub(mk128(0, 0), a); }
+// overflowing_add: returns true when the signed addition overflowed
+CB_HD bool i128_add_overflow(i128 a, i128 b, i128& r) {
+    r = i128_add(a, b);
+    return ((a.hi ^ r.hi) & (b.hi ^ r.hi)) < 0;
+}
+CB_HD bool i128_sub_overflow(i128 a, i128 b, i128& r) {
+    r = i128_sub(a, b);
+    return ((a.hi ^ b.hi) & (a.hi ^ r.hi)) < 0;
+}
+CB_HD u128 i128_abs_u(i128 a) { // |a| as unsigned (|i128::MIN| = 2^127 is representable)
+    if (a.hi < 0) a = i128_neg(a);
+    u128 r; r.lo = a.lo; r.hi = (u64)a.hi; return r;
+}
+CB_HD bool i128_fits_i64(i128 a) { return a.hi == ((i64)a.lo >> 63); }
+
+// full signed 64x64 -> 128 product
+CB_HD i128 mul_i64_i64(i64 a, i64 b) {
+    u64 lo = (u64)a * (u64)b;
+    u64 hi = umulhi64((u64)a, (u64)b);
+    if (a < 0) hi -= (u64)b;
+    if (b < 0) hi -= (u64)a;
+    return mk128(lo, (i64)hi);
+}
+
+CB_HD u256 umul_128x128(u128 a, u128 b) {
+    u256 r;
+    u64 p0l = a.lo * b.lo, p0h = umulhi64(a.lo, b.lo);
+    u64 p1l = a.lo * b.hi, p1h = umulhi64(a.lo, b.hi);
+    u64 p2l = a.hi * b.lo, p2h = umulhi64(a.hi, b.lo);
+    u64 p3l = a.hi * b.hi, p3h = umulhi64(a.hi, b.hi);
+    r.w[0] = p0l;
+    u64 s = p0h + p1l; u64 c = s < p0h;
+    u64 s2 = s + p2l; c += s2 < s;
+    r.w[1] = s2;
+    u64 t = p1h + p2h; u64 c2 = t < p1h;
+    u64 t2 = t + p3l; c2 += t2 < t;
+    u64 t3 = t2 + c; c2 += t3 < t2;
+    r.w[2] = t3;
+    r.w[3] = p3h + c2;
+    return r;
+}
+CB_HD int u256_cmp(const u256& a, const u256& b) {
+    for (int i = 3; i >= 0; i--) {
+        if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1;
+    }
+    return 0;
+}
+CB_HD bool u256_add(u256& a, const u256& b) { // returns carry out
+    u64 c = 0;
+    for (int i = 0; i < 4; i++) {
+        u64 s = a.w[i] + b.w[i]; u64 c1 = s < a.w[i];
+        u64 s2 = s + c; c1 += s2 < s;
+        a.w[i] = s2; c = c1;
+    }
+    return c != 0;
+}
+CB_HD void u256_sub(u256& a, const u256& b) { // a >= b assumed
+    u64 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u64 d = a.w[i] - b.w[i]; u64 b1 = a.w[i] < b.w[i];
+        u64 d2 = d - br; b1 += d < br;
+        a.w[i] = d2; br = b1;
+    }
+}
+// a *= m (m < 2^64); returns true on overflow past 256 bits
+CB_HD bool u256_mul_small(u256& a, u64 m) {
+    u64 carry = 0;
+    for (int i = 0; i < 4; i++) {
+        u64 lo = a.w[i] * m, hi = umulhi64(a.w[i], m);
+        u64 s = lo + carry; hi += s < lo;
+        a.w[i] = s; carry = hi;
+    }
+    return carry != 0;
+}
+// a /= d (d < 2^32), schoolbook over 32-bit digits; returns remainder
+CB_HD u32 u256_div_small(u256& a, u32 d) {
+    u64 rem = 0;
+    for (int i = 3; i >= 0; i--) {
+        u64 hi32 = a.w[i] >> 32, lo32 = a.w[i] & 0xffffffffull;
+        u64 cur = (rem << 32) | hi32; u64 qh = cur / d; rem = cur % d;
+        cur = (rem << 32) | lo32; u64 ql = cur / d; rem = cur % d;
+        a.w[i] = (qh << 32) | ql;
+    }
+    return (u32)rem;
+}
+CB_HD u64 pow10_u64(int e) { u64 r = 1; for (int i = 0; i < e; i++) r *= 10; return r; }
+CB_HD bool u256_mul_pow10(u256& a, int e) { // returns overflow
+    bool o = false;
+    while (e >= 19) { o |= u256_mul_small(a, 10000000000000000000ull); e -= 19; }
+    if (e > 0) o |= u256_mul_small(a, pow10_u64(e));
+    return o;
+}
+CB_HD void u256_div_pow10(u256& a, int e) { // truncating
+    while (e >= 9) { u256_div_small(a, 1000000000u); e -= 9; }
+    if (e > 0) u256_div_small(a, (u32)pow10_u64(e));
+}
+CB_HD u256 u256_pow10(int e) { u256 r; r.w[0] = 1; r.w[1] = r.w[2] = r.w[3] = 0; u256_mul_pow10(r, e); return r; }
+CB_HD u256 u256_from_u128(u128 a) { u256 r; r.w[0] = a.lo; r.w[1] = a.hi; r.w[2] = r.w[3] = 0; return r; }
+
+// ------------------------------------------------------------------------------------------------
+// decimal precision bound:  |v| <= 10^p - 1      (spark-expr/src/utils.rs:332-336)
+// ------------------------------------------------------------------------------------------------
+CB_HD u128 pow10_u128(int p) { // p in [0,38]
+    u128 r; r.lo = 1; r.hi = 0;
+    for (int i = 0; i < p; i++) {
+        u64 lo = r.lo * 10ull, hi = umulhi64(r.lo, 10ull) + r.hi * 10ull;
+        r.lo = lo; r.hi = hi;
+    }
+    return r;
+}
+// bound = 10^p as (lo,hi); valid iff |v| < 10^p
+CB_HD bool dec_fits(i128 v, u64 bound_lo, u64 bound_hi) {
+    u128 a = i128_abs_u(v);
+    return a.hi < bound_hi || (a.hi == bound_hi && a.lo < bound_lo);
+}
+CB_HD bool dec_fits_p(i128 v, int p) { u128 b = pow10_u128(p); return dec_fits(v, b.lo, b.hi); }
+
+// ------------------------------------------------------------------------------------------------
+// plain decimal arithmetic (arrow-arith 58.4.0 `decimal_op`, reached from planner.rs:1126):
+// checked i128 operations; `err` is set when the i128 result overflows (arrow raises
+// "Overflow happened on ...", which fails the query).
+// ------------------------------------------------------------------------------------------------
+CB_HD i128 i128_mul_checked(i128 a, i128 b, bool& err) {
+    bool neg = (a.hi < 0) != (b.hi < 0);
+    u256 p = umul_128x128(i128_abs_u(a), i128_abs_u(b));
+    // magnitude must be <= 2^127-1 (or == 2^127 when negative)
+    bool big = (p.w[2] | p.w[3]) != 0 || (p.w[1] >> 63) != 0;
+    if (big) {
+        bool is_min = neg && p.w[2] == 0 && p.w[3] == 0 && p.w[1] == 0x8000000000000000ull && p.w[0] == 0;
+        if (!is_min) err = true;
+    }
+    i128 r = mk128(p.w[0], (i64)p.w[1]);
+    return neg ? i128_neg(r) : r;
+}
+CB_HD i128 i128_mul_pow10_checked(i128 a, int e, bool& err) {
+    if (e == 0) return a;
+    u128 m = pow10_u128(e);
+    return i128_mul_checked(a, mk128(m.lo, (i64)m.hi), err);
+}
+CB_HD i128 dec_add_plain(i128 l, int lup, i128 r, int rup, bool& err) {
+    i128 a = i128_mul_pow10_checked(l, lup, err), b = i128_mul_pow10_checked(r, rup, err), o;
+    if (i128_add_overflow(a, b, o)) err = true;
+    return o;
+}
+CB_HD i128 dec_sub_plain(i128 l, int lup, i128 r, int rup, bool& err) {
+    i128 a = i128_mul_pow10_checked(l, lup, err), b = i128_mul_pow10_checked(r, rup, err), o;
+    if (i128_sub_overflow(a, b, o)) err = true;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wide decimal arithmetic  (spark-expr/src/math_funcs/wide_decimal_binary_expr.rs:179-291,
+// div_round_half_up :121-144, check_overflow_and_convert :335-350).  Sign-magnitude restatement of
+// the i256 computation: |raw| < 2^254 for any Decimal128 inputs, so magnitudes never wrap.
+// Returns false when the result is out of the output precision (NULL in Legacy/Try, error in ANSI).
+//   scale_diff = natural_scale - s_out (>0: divide by 10^d HALF_UP, <0: multiply by 10^-d)
+// ------------------------------------------------------------------------------------------------
+CB_HD bool wide_finish(u256 mag, bool neg, int scale_diff, int p_out, i128& out) {
+    if (scale_diff > 0) {
+        // q = floor((|raw| + 10^d/2) / 10^d)  ==  truncated quotient rounded away from zero at >= half
+        u256 half = u256_pow10(scale_diff - 1);
+        u256_mul_small(half, 5);
+        u256_add(mag, half);
+        u256_div_pow10(mag, scale_diff);
+    } else if (scale_diff < 0) {
+        if (u256_mul_pow10(mag, -scale_diff)) return false; // astronomically out of range
+    }
+    u128 b = pow10_u128(p_out);
+    if ((mag.w[2] | mag.w[3]) != 0) return false;
+    if (!(mag.w[1] < b.hi || (mag.w[1] == b.hi && mag.w[0] < b.lo))) return false;
+    i128 r = mk128(mag.w[0], (i64)mag.w[1]);
+    out = neg ? i128_neg(r) : r;
+    return true;
+}
+CB_HD bool wide_mul(i128 l, i128 r, int scale_diff, int p_out, i128& out) {
+    bool neg = (l.hi < 0) != (r.hi < 0);
+    u256 mag = umul_128x128(i128_abs_u(l), i128_abs_u(r));
+    return wide_finish(mag, neg, scale_diff, p_out, out);
+}
+// l*10^lup (+/-) r*10^rup, then rescale by scale_diff
+CB_HD bool wide_addsub(i128 l, int lup, i128 r, int rup, bool subtract, int scale_diff, int p_out, i128& out) {
+    u256 a = u256_from_u128(i128_abs_u(l)), b = u256_from_u128(i128_abs_u(r));
+    u256_mul_pow10(a, lup);
+    u256_mul_pow10(b, rup);
+    bool na = l.hi < 0, nb = (r.hi < 0) != subtract;
+    bool neg;
+    if (na == nb) { u256_add(a, b); neg = na; }
+    else {
+        int c = u256_cmp(a, b);
+        if (c >= 0) { u256_sub(a, b); neg = na; }
+        else { u256_sub(b, a); a = b; neg = nb; }
+    }
+    if ((a.w[0] | a.w[1] | a.w[2] | a.w[3]) == 0) neg = false;
+    return wide_finish(a, neg, scale_diff, p_out, out);
+}
+
+// DecimalRescaleCheckOverflow (math_funcs/internal/decimal_rescale_check.rs:111-150):
+// delta = s_out - s_in;  >0 multiply (checked), <0 divide HALF_UP via (v + sign*half)/divisor.
+CB_HD bool dec_rescale_check(i128 v, int delta, int p_out, i128& out) {
+    bool neg = v.hi < 0;
+    u256 mag = u256_from_u128(i128_abs_u(v));
+    return wide_finish(mag, neg, -delta, p_out, out);
+}
+
+// 128 / 64 signed division used by AVG(decimal).evaluate (agg_funcs/avg_decimal.rs:670-689):
+//   value = sum*scaler (checked); (div, rem) = value.div_rem(count); half = div_ceil(count,2);
+//   value>=0 && rem>=half -> div+1 ; value<0 && rem<=-half -> div-1.  NULL if out of target range.
+CB_HD bool avg_decimal_eval(i128 sum, i64 count, int scaler_exp, int target_p, i128& out) {
+    bool err = false;
+    i128 value = i128_mul_pow10_checked(sum, scaler_exp, err);
+    if (err) return false;
+    bool neg = value.hi < 0;
+    u128 mag = i128_abs_u(value);
+    // divide 128-bit magnitude by count (count > 0) with 32-bit digits when count < 2^32, else bitwise
+    u64 c = (u64)count;
+    u128 q; u64 rem;
+    if (c <= 0xffffffffull) {
+        u32 d = (u32)c; u64 r = 0; u64 limbs[2] = {mag.lo, mag.hi};
+        for (int i = 1; i >= 0; i--) {
+            u64 hi32 = limbs[i] >> 32, lo32 = limbs[i] & 0xffffffffull;
+            u64 cur = (r << 32) | hi32; u64 qh = cur / d; r = cur % d;
+            cur = (r << 32) | lo32; u64 ql = cur / d; r = cur % d;
+            limbs[i] = (qh << 32) | ql;
+        }
+        q.lo = limbs[0]; q.hi = limbs[1]; rem = r;
+    } else {
+        q.lo = q.hi = 0; u64 r = 0;
+        for (int bit = 127; bit >= 0; bit--) {
+            u64 top = r >> 63;
+            r = (r << 1) | ((bit >= 64 ? (mag.hi >> (bit - 64)) : (mag.lo >> bit)) & 1ull);
+            if (top || r >= c) { r -= c; if (bit >= 64) q.hi |= 1ull << (bit - 64); else q.lo |= 1ull << bit; }
+        }
+        rem = r;
+    }
+    u64 half = c / 2 + (c & 1ull);
+    if (rem >= half) { q.lo += 1; if (q.lo == 0) q.hi += 1; } // symmetric for negative values
+    i128 r128 = mk128(q.lo, (i64)q.hi);
+    if (neg) r128 = i128_neg(r128);
+    if (!dec_fits_p(r128, target_p)) return false;
+    out = r128;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spark murmur3  (spark-expr/src/hash_funcs/murmur3.rs:73-137; per-type rules hash_funcs/utils.rs)
+// ------------------------------------------------------------------------------------------------
+CB_HD u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
+CB_HD u32 mm3_mix_k1(u32 k1) { k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u; return k1; }
+CB_HD u32 mm3_mix_h1(u32 h1, u32 k1) { h1 ^= k1; h1 = rotl32(h1, 13); return h1 * 5u + 0xe6546b64u; }
+CB_HD u32 mm3_fmix(u32 h1, u32 len) {
+    h1 ^= len; h1 ^= h1 >> 16; h1 *= 0x85ebca6bu; h1 ^= h1 >> 13; h1 *= 0xc2b2ae35u; h1 ^= h1 >> 16;
+    return h1;
+}
+CB_HD u32 mm3_i32(i32 v, u32 seed) { return mm3_fmix(mm3_mix_h1(seed, mm3_mix_k1((u32)v)), 4u); }
+CB_HD u32 mm3_i64(i64 v, u32 seed) {
+    u32 h = mm3_mix_h1(seed, mm3_mix_k1((u32)(u64)v));
+    h = mm3_mix_h1(h, mm3_mix_k1((u32)((u64)v >> 32)));
+    return mm3_fmix(h, 8u);
+}
+CB_HD u32 mm3_i128(i128 v, u32 seed) { // d(p>18): 16 little-endian bytes (utils.rs:199-226)
+    u32 h = mm3_mix_h1(seed, mm3_mix_k1((u32)v.lo));
+    h = mm3_mix_h1(h, mm3_mix_k1((u32)(v.lo >> 32)));
+    h = mm3_mix_h1(h, mm3_mix_k1((u32)(u64)v.hi));
+    h = mm3_mix_h1(h, mm3_mix_k1((u32)((u64)v.hi >> 32)));
+    return mm3_fmix(h, 16u);
+}
+CB_HD u32 mm3_bytes(const u8* data, i32 len, u32 seed) {
+    i32 aligned = len - len % 4;
+    u32 h1 = seed;
+    for (i32 i = 0; i < aligned; i += 4) {
+        u32 w = (u32)data[i] | ((u32)data[i + 1] << 8) | ((u32)data[i + 2] << 16) | ((u32)data[i + 3] << 24);
+        h1 = mm3_mix_h1(h1, mm3_mix_k1(w));
+    }
+    for (i32 i = aligned; i < len; i++) h1 = mm3_mix_h1(h1, mm3_mix_k1((u32)(i32)(signed char)data[i]));
+    return mm3_fmix(h1, (u32)len);
+}
+CB_HD u32 pmod_u32(u32 hash, u32 n) { // shuffle/src/comet_partitioning.rs:51-57
+    i32 h = (i32)hash, m = (i32)n;
+    i32 r = h % m;
+    return (u32)(r < 0 ? (r + m) % m : r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IEEE-754 totalOrder keys: arrow-ord 58.4.0 `cmp` compares floats by totalOrder
+// (reached from planner/macros.rs:96-98 via DataFusion BinaryExpr).
+// ------------------------------------------------------------------------------------------------
+CB_HD i64 f64_total_key(u64 bits) { i64 b = (i64)bits; return b ^ (i64)(((u64)(b >> 63)) >> 1); }
+CB_HD i32 f32_total_key(u32 bits) { i32 b = (i32)bits; return b ^ (i32)(((u32)(b >> 31)) >> 1); }
+
+// ------------------------------------------------------------------------------------------------
+// double-double accumulation (float aggregates: result within 1 ULP of the exact sum)
+// ------------------------------------------------------------------------------------------------
+struct dd { double hi, lo; };
+CB_HD void dd_add_double(dd& a, double x) { // Knuth TwoSum + renormalise
+    double s = a.hi + x;
+    if (s - s != 0.0) { a.hi = s; a.lo = 0.0; return; } // inf / NaN: plain IEEE propagation
+    double bb = s - a.hi;
+    double e = (a.hi - (s - bb)) + (x - bb);
+    e += a.lo;
+    double hi = s + e;
+    a.lo = e - (hi - s);
+    a.hi = hi;
+}
+CB_HD void dd_add_dd(dd& a, dd b) {
+    double s = a.hi + b.hi;
+    if (s - s != 0.0) { a.hi = s; a.lo = 0.0; return; }
+    double bb = s - a.hi;
+    double e = (a.hi - (s - bb)) + (b.hi - bb);
+    e += a.lo + b.lo;
+    double hi = s + e;
+    a.lo = e - (hi - s);
+    a.hi = hi;
+}
+
+} // namespace cb
+#endif // CB_MATH_H
