@@ -1,0 +1,256 @@
+"""ctypes binding of libcomet_b200.so -- the Python stand-in for the reference's JVM caller.
+
+Mirrors `org.apache.comet.Native` (spark/src/main/scala/org/apache/comet/Native.scala:60-103):
+createPlan / executePlan / releasePlan, driven the way `CometExecIterator`
+(CometExecIterator.scala:109-210) drives them: serialized plan bytes in, Arrow C Data structs out.
+
+The library is the product; this module only marshals.  It fails loudly if the shared library is
+missing -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import pyarrow as pa
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.path.join(_PKG, "libcomet_b200.so")
+_lib = None
+
+
+class CometB200Error(RuntimeError):
+    def __init__(self, code, error_class, message):
+        super().__init__(f"[{code}{' ' + error_class if error_class else ''}] {message}")
+        self.code, self.error_class, self.message = code, error_class, message
+
+
+class Unsupported(CometB200Error):
+    """The plan is outside the GPU hot path; a caller keeps its CPU path (CB200_ERR_UNSUPPORTED)."""
+
+
+class _Error(C.Structure):
+    _fields_ = [("code", C.c_int32), ("error_class", C.c_char * 64), ("message", C.c_char * 952)]
+
+
+class ArrowSchema(C.Structure):
+    pass
+
+
+class ArrowArray(C.Structure):
+    pass
+
+
+ArrowSchema._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                        ("n_children", C.c_int64), ("children", C.POINTER(C.POINTER(ArrowSchema))),
+                        ("dictionary", C.POINTER(ArrowSchema)), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                       ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)),
+                       ("children", C.POINTER(C.POINTER(ArrowArray))), ("dictionary", C.POINTER(ArrowArray)),
+                       ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArrayStream(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class DeviceColumn(C.Structure):
+    _fields_ = [("type_id", C.c_int32), ("precision", C.c_int32), ("scale", C.c_int32), ("value_width", C.c_int32),
+                ("values", C.c_void_p), ("validity", C.c_void_p), ("host_values", C.c_void_p),
+                ("host_validity_bytes", C.c_void_p)]
+
+
+EXPORTED = ["cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
+            "cb200_release", "cb200_table_create", "cb200_table_add_column", "cb200_plan_bind_table",
+            "cb200_table_release", "cb200_execute_device", "cb200_plan_kernel_launches", "cb200_compile_plan",
+            "cb200_plan_kernel_source"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C datafusion-comet_b200/csrc).  comet_b200 has no CPU fallback.")
+        l = C.CDLL(_LIB_PATH)
+        l.cb200_version.restype = C.c_char_p
+        l.cb200_supports.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Error)]
+        l.cb200_create_plan.restype = C.c_void_p
+        l.cb200_create_plan.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_Error)]
+        l.cb200_plan_num_columns.argtypes = [C.c_void_p]
+        l.cb200_execute.restype = C.c_int64
+        l.cb200_execute.argtypes = [C.c_void_p, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.c_int32, C.POINTER(_Error)]
+        l.cb200_release.argtypes = [C.c_void_p]
+        l.cb200_table_create.restype = C.c_void_p
+        l.cb200_table_create.argtypes = [C.c_int64]
+        l.cb200_table_add_column.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_int64, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(_Error)]
+        l.cb200_plan_bind_table.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(_Error)]
+        l.cb200_table_release.argtypes = [C.c_void_p]
+        l.cb200_execute_device.restype = C.c_int64
+        l.cb200_execute_device.argtypes = [C.c_void_p, C.POINTER(DeviceColumn), C.c_int32, C.POINTER(_Error)]
+        l.cb200_plan_kernel_launches.restype = C.c_int64
+        l.cb200_plan_kernel_launches.argtypes = [C.c_void_p]
+        l.cb200_compile_plan.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(_Error)]
+        l.cb200_plan_kernel_source.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(_Error)]
+        _lib = l
+    return _lib
+
+
+def _raise(err):
+    cls = Unsupported if err.code == 1 else CometB200Error
+    raise cls(err.code, err.error_class.decode(), err.message.decode(errors="replace"))
+
+
+def version():
+    return lib().cb200_version().decode()
+
+
+def supports(op_bytes):
+    err = _Error()
+    ok = lib().cb200_supports(op_bytes, len(op_bytes), C.byref(err))
+    return bool(ok), err.message.decode(errors="replace")
+
+
+def compile_plan(op_bytes):
+    """NVRTC-compile (no GPU needed) every pipeline kernel of the plan; returns the kernel keys."""
+    err = _Error()
+    buf = C.create_string_buffer(4096)
+    n = lib().cb200_compile_plan(op_bytes, len(op_bytes), buf, 4096, C.byref(err))
+    if n < 0:
+        _raise(err)
+    return [k for k in buf.value.decode().split(",") if k]
+
+
+def kernel_source(op_bytes, index=0):
+    err = _Error()
+    cap = 1 << 20
+    buf = C.create_string_buffer(cap)
+    n = lib().cb200_plan_kernel_source(op_bytes, len(op_bytes), index, buf, cap, C.byref(err))
+    if n < 0:
+        _raise(err)
+    return buf.value.decode()
+
+
+class DeviceTable:
+    """Device-resident input columns (torch CUDA tensors or raw pointers) bound to a Scan."""
+
+    def __init__(self, n_rows):
+        self.handle = lib().cb200_table_create(n_rows)
+        self.n_rows = n_rows
+        self._keep = []
+
+    def add(self, dt, values_ptr, value_width, validity_ptr=None, null_count=0, dictionary=None, keep=None):
+        from . import proto
+        err = _Error()
+        if dictionary is not None:
+            arr = (C.c_char_p * len(dictionary))(*[d.encode() if isinstance(d, str) else d for d in dictionary])
+            nd = len(dictionary)
+        else:
+            arr, nd = None, 0
+        rc = lib().cb200_table_add_column(self.handle, proto.DATA_TYPE_ID[dt.name], dt.precision, dt.scale, value_width,
+                                          values_ptr, validity_ptr, null_count, arr, nd, C.byref(err))
+        if rc != 0:
+            _raise(err)
+        self._keep.append(keep)
+        return self
+
+    def release(self):
+        if self.handle:
+            lib().cb200_table_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.release()
+
+
+class Plan:
+    """One native plan handle = one Spark task's `CometExecIterator` (CometExecIterator.scala:64)."""
+
+    def __init__(self, op_bytes, inputs=(), config=None, batch_size=8192, device=0, partition=0, partition_count=1):
+        from . import proto
+        self._lib = lib()
+        self.handle = None
+        cfg = proto.config_map(config) if config else b""
+        n = len(inputs)
+        self._streams = (ArrowArrayStream * max(n, 1))()
+        ptrs = (C.c_void_p * max(n, 1))()
+        self._tables = []
+        for i, inp in enumerate(inputs):
+            if isinstance(inp, DeviceTable):
+                ptrs[i] = None
+                self._tables.append((i, inp))
+                continue
+            if isinstance(inp, pa.Table):
+                inp = inp.to_reader()
+            elif isinstance(inp, (list, tuple)):
+                inp = pa.RecordBatchReader.from_batches(inp[0].schema, inp)
+            elif isinstance(inp, pa.RecordBatch):
+                inp = pa.RecordBatchReader.from_batches(inp.schema, [inp])
+            inp._export_to_c(C.addressof(self._streams[i]))  # ownership moves to native (ffi.md:60-150)
+            ptrs[i] = C.addressof(self._streams[i])
+        err = _Error()
+        self.handle = self._lib.cb200_create_plan(op_bytes, len(op_bytes), cfg or None, len(cfg), ptrs, n, partition,
+                                                  partition_count, batch_size, device, C.byref(err))
+        if not self.handle:
+            _raise(err)
+        for i, t in self._tables:
+            if self._lib.cb200_plan_bind_table(self.handle, i, t.handle, C.byref(err)) != 0:
+                _raise(err)
+        self.n_cols = self._lib.cb200_plan_num_columns(self.handle)
+
+    def execute(self):
+        """Next output batch as a pyarrow RecordBatch, or None at end of stream (executePlan == -1)."""
+        arrays = (ArrowArray * self.n_cols)()
+        schemas = (ArrowSchema * self.n_cols)()
+        err = _Error()
+        rows = self._lib.cb200_execute(self.handle, arrays, schemas, self.n_cols, C.byref(err))
+        if rows == -1:
+            return None
+        if rows < 0:
+            _raise(err)
+        cols = [pa.Array._import_from_c(C.addressof(arrays[i]), C.addressof(schemas[i])) for i in range(self.n_cols)]
+        return pa.RecordBatch.from_arrays(cols, names=[f"col_{i}" for i in range(self.n_cols)])
+
+    def execute_device(self):
+        """Next output batch left on the device: (rows, [DeviceColumn...]) or None."""
+        cols = (DeviceColumn * self.n_cols)()
+        err = _Error()
+        rows = self._lib.cb200_execute_device(self.handle, cols, self.n_cols, C.byref(err))
+        if rows == -1:
+            return None
+        if rows < 0:
+            _raise(err)
+        return rows, cols
+
+    def collect(self):
+        batches = []
+        while True:
+            b = self.execute()
+            if b is None:
+                break
+            batches.append(b)
+        if not batches:
+            return None
+        return pa.Table.from_batches(batches)
+
+    @property
+    def kernel_launches(self):
+        return self._lib.cb200_plan_kernel_launches(self.handle)
+
+    def release(self):
+        if self.handle:
+            self._lib.cb200_release(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

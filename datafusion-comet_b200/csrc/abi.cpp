@@ -1,0 +1,282 @@
+// abi.cpp -- extern "C" surface of libcomet_b200.so (include/comet_b200.h).
+#include "../../include/comet_b200.h"
+
+#include "exec.h"
+#include "jit.h"
+#include "plan.h"
+#include "proto_wire.h"
+
+#include <cstring>
+#include <functional>
+#include <mutex>
+
+using namespace cb200;
+
+struct cb200_table {
+    std::shared_ptr<DeviceTable> t;
+};
+
+struct cb200_plan {
+    OperatorP op;
+    ExecContext ctx;
+    PlanInputs inputs;
+    ExecNodeP root;
+    Batch last; // keeps device results alive for cb200_execute_device
+    bool started = false, finished = false;
+    int partition = 0, partition_count = 1;
+};
+
+namespace {
+
+void set_error(cb200_error* e, int code, const std::string& cls, const std::string& msg) {
+    if (!e) return;
+    e->code = code;
+    snprintf(e->error_class, sizeof(e->error_class), "%s", cls.c_str());
+    snprintf(e->message, sizeof(e->message), "%s", msg.c_str());
+}
+void clear_error(cb200_error* e) {
+    if (e) { e->code = 0; e->error_class[0] = 0; e->message[0] = 0; }
+}
+
+template <typename F> auto guarded(cb200_error* err, F&& f, decltype(f()) on_error) -> decltype(f()) {
+    clear_error(err);
+    try {
+        return f();
+    } catch (const Unsupported& e) {
+        set_error(err, CB200_ERR_UNSUPPORTED, "", e.what());
+    } catch (const PlanError& e) {
+        set_error(err, CB200_ERR_PLAN, "", e.what());
+    } catch (const JitError& e) {
+        set_error(err, CB200_ERR_JIT, "", e.what());
+    } catch (const ExecError& e) {
+        set_error(err, e.code >= 10 ? CB200_ERR_SPARK : e.code, e.error_class, e.what());
+    } catch (const std::exception& e) { // the reference turns panics into a pending exception (errors.rs:832-850)
+        set_error(err, CB200_ERR_PLAN, "", std::string("native panic: ") + e.what());
+    } catch (...) {
+        set_error(err, CB200_ERR_PLAN, "", "native panic: unknown exception");
+    }
+    return on_error;
+}
+
+void parse_config(const uint8_t* cfg, size_t len, ExecContext& ctx) { // config.proto ConfigMap
+    if (!cfg || !len) return;
+    PbReader r(cfg, len);
+    while (r.next()) {
+        if (r.field != 1 || r.wire != 2) { r.skip(); continue; }
+        PbReader e = r.sub();
+        std::string k, v;
+        while (e.next()) {
+            if (e.field == 1) k = e.bytes();
+            else if (e.field == 2) v = e.bytes();
+            else e.skip();
+        }
+        if (k == "spark.comet.b200.chunkRows") ctx.chunk_rows = std::max<int64_t>(1024, atoll(v.c_str()));
+        else if (k == "spark.comet.batchSize") ctx.batch_size = atoi(v.c_str()); // CometConf.scala:539
+    }
+}
+
+void start(cb200_plan* p) {
+    if (p->started) return;
+    ExecContext& ctx = p->ctx;
+    cuda_check(cudaSetDevice(ctx.device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    cuda_check(cudaGetDeviceProperties(&prop, ctx.device), "cudaGetDeviceProperties");
+    if (prop.major < 10) throw ExecError(CB200_ERR_CUDA, "", "comet_b200 kernels are built for sm_100a; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    ctx.num_sms = prop.multiProcessorCount;
+    cuda_check(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cuda_check(cudaMalloc((void**)&ctx.d_err, 64), "cudaMalloc err");
+    cuda_check(cudaMemsetAsync(ctx.d_err, 0, 64, ctx.stream), "memset err");
+    cuda_check(cudaMallocHost((void**)&ctx.h_err, 64), "cudaMallocHost err");
+    p->root = build_exec(p->op, &ctx, &p->inputs);
+    p->started = true;
+}
+
+DType dtype_from_ids(int type_id, int precision, int scale) {
+    if (type_id < 0 || type_id > 13) throw Unsupported("type id " + std::to_string(type_id));
+    DType d;
+    d.id = (TypeId)type_id;
+    d.precision = precision;
+    d.scale = scale;
+    return d;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* cb200_version(void) { return "comet_b200 0.1.0 (sm_100a; reference apache/datafusion-comet 1.1.0 @2699f59b)"; }
+
+int cb200_supports(const uint8_t* op_proto, size_t op_len, cb200_error* why) {
+    return guarded(why, [&]() -> int {
+        OperatorP op = decode_plan(op_proto, op_len);
+        plan_kernels_for_build(op); // exercises fusion + code generation rules
+        return 1;
+    }, 0);
+}
+
+cb200_plan* cb200_create_plan(const uint8_t* op_proto, size_t op_len, const uint8_t* cfg_proto, size_t cfg_len, struct ArrowArrayStream** inputs,
+                              int32_t n_inputs, int32_t partition, int32_t partition_count, int32_t batch_size, int32_t device_ordinal, cb200_error* err) {
+    return guarded(err, [&]() -> cb200_plan* {
+        auto p = std::unique_ptr<cb200_plan>(new cb200_plan());
+        p->op = decode_plan(op_proto, op_len);
+        p->ctx.device = device_ordinal;
+        if (batch_size > 0) p->ctx.batch_size = batch_size;
+        parse_config(cfg_proto, cfg_len, p->ctx);
+        p->partition = partition;
+        p->partition_count = partition_count;
+        for (int i = 0; i < n_inputs; i++) {
+            p->inputs.streams.push_back(inputs ? inputs[i] : nullptr);
+            p->inputs.tables.push_back(nullptr);
+        }
+        return p.release();
+    }, (cb200_plan*)nullptr);
+}
+
+int32_t cb200_plan_num_columns(cb200_plan* plan) { return plan ? (int32_t)plan->op->schema.size() : -1; }
+
+static int64_t execute_common(cb200_plan* plan, cb200_error* err, const std::function<void(Batch&)>& sink) {
+    return guarded(err, [&]() -> int64_t {
+        if (!plan) throw PlanError("null plan handle");
+        if (plan->finished) return -1;
+        start(plan);
+        cuda_check(cudaSetDevice(plan->ctx.device), "cudaSetDevice");
+        Batch b;
+        if (!plan->root->next(b)) { plan->finished = true; return -1; }
+        plan->last = std::move(b);
+        sink(plan->last);
+        return plan->last.n_rows;
+    }, (int64_t)-2);
+}
+
+int64_t cb200_execute(cb200_plan* plan, struct ArrowArray* out_arrays, struct ArrowSchema* out_schemas, int32_t n_cols, cb200_error* err) {
+    return execute_common(plan, err, [&](Batch& b) { export_batch(b, &plan->ctx, out_arrays, out_schemas, n_cols); });
+}
+
+int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_t n_cols, cb200_error* err) {
+    return execute_common(plan, err, [&](Batch& b) {
+        if ((int)b.cols.size() != n_cols) throw PlanError("execute_device: plan produces " + std::to_string(b.cols.size()) + " columns");
+        for (int i = 0; i < n_cols; i++) {
+            Column& c = b.cols[(size_t)i];
+            cb200_device_column& o = cols[i];
+            memset(&o, 0, sizeof(o));
+            o.type_id = (int)c.type.id;
+            o.precision = c.type.precision;
+            o.scale = c.type.scale;
+            o.value_width = c.type.id == TypeId::Bool ? 1 : c.type.arrow_width();
+            if (c.on_host) {
+                o.host_values = c.h_data.data();
+                o.host_validity_bytes = c.h_valid.empty() ? nullptr : c.h_valid.data();
+            } else {
+                o.values = c.data ? c.data->ptr : nullptr;
+                o.validity = c.validity ? c.validity->ptr : nullptr;
+            }
+        }
+    });
+}
+
+void cb200_release(cb200_plan* plan) {
+    if (!plan) return;
+    try {
+        if (plan->started) cudaSetDevice(plan->ctx.device);
+        plan->last = Batch();
+        plan->root.reset();
+        // streams that were never handed to a source still belong to us
+        for (auto* s : plan->inputs.streams) if (s && s->release) s->release(s);
+        if (plan->ctx.stream) cudaStreamDestroy(plan->ctx.stream);
+        if (plan->ctx.d_err) cudaFree(plan->ctx.d_err);
+        if (plan->ctx.h_err) cudaFreeHost(plan->ctx.h_err);
+    } catch (...) {
+    }
+    delete plan;
+}
+
+cb200_table* cb200_table_create(int64_t n_rows) {
+    auto* t = new cb200_table();
+    t->t = std::make_shared<DeviceTable>();
+    t->t->n_rows = n_rows;
+    return t;
+}
+
+int cb200_table_add_column(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width, const void* dev_values,
+                           const void* dev_validity, int64_t null_count, const char* const* dict_values, int32_t n_dict, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        if (!t) throw PlanError("null table handle");
+        Column c;
+        c.type = dtype_from_ids(type_id, precision, scale);
+        size_t n = (size_t)t->t->n_rows;
+        if (n_dict > 0) {
+            if (!c.type.is_string()) throw PlanError("dictionary values on a non-string column");
+            c.is_dict = true;
+            c.dict = std::make_shared<Dictionary>();
+            for (int i = 0; i < n_dict; i++) c.dict->values.push_back(dict_values[i]);
+            c.phys = value_width == 1 ? Phys::I8 : value_width == 2 ? Phys::I16 : Phys::I32;
+            if (value_width != 1 && value_width != 2 && value_width != 4) throw PlanError("dictionary codes must be 1, 2 or 4 bytes wide");
+        } else if (c.type.is_string()) {
+            throw Unsupported("device string columns must be dictionary-encoded");
+        } else if (c.type.is_decimal() && value_width == 8) {
+            if (c.type.precision > 18) throw PlanError("8-byte decimals need precision <= 18");
+            c.phys = Phys::I64;
+        } else {
+            int w = c.type.arrow_width();
+            if (value_width != w) throw PlanError("value_width " + std::to_string(value_width) + " does not match " + c.type.str());
+            switch (c.type.id) {
+            case TypeId::Bool: c.phys = Phys::Bitmap; break;
+            case TypeId::Int8: c.phys = Phys::I8; break;
+            case TypeId::Int16: c.phys = Phys::I16; break;
+            case TypeId::Int32: case TypeId::Date: c.phys = Phys::I32; break;
+            case TypeId::Float32: c.phys = Phys::F32; break;
+            case TypeId::Float64: c.phys = Phys::F64; break;
+            case TypeId::Decimal: c.phys = Phys::I128; break;
+            default: c.phys = Phys::I64; break;
+            }
+        }
+        if (((uintptr_t)dev_values & 15) || ((uintptr_t)dev_validity & 15)) throw PlanError("device buffers must be 16-byte aligned");
+        size_t bytes = value_width == 0 ? (n + 7) / 8 : n * (size_t)value_width;
+        c.data = std::make_shared<DeviceBuf>((void*)dev_values, bytes);
+        if (dev_validity && null_count != 0) c.validity = std::make_shared<DeviceBuf>((void*)dev_validity, (n + 7) / 8);
+        c.null_count = null_count;
+        t->t->cols.push_back(c);
+        return 0;
+    }, -1);
+}
+
+int cb200_plan_bind_table(cb200_plan* plan, int32_t input_index, cb200_table* t, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        if (!plan || !t) throw PlanError("null handle");
+        if (plan->started) throw PlanError("tables must be bound before the first execute");
+        if (input_index < 0 || input_index >= (int)plan->inputs.tables.size()) throw PlanError("input index out of range");
+        plan->inputs.tables[(size_t)input_index] = t->t;
+        return 0;
+    }, -1);
+}
+
+void cb200_table_release(cb200_table* t) { delete t; }
+
+int64_t cb200_plan_kernel_launches(cb200_plan* plan) { return plan ? plan->ctx.kernel_launches : -1; }
+
+int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, size_t keys_cap, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        OperatorP op = decode_plan(op_proto, op_len);
+        auto ks = plan_kernels_for_build(op);
+        std::string keys;
+        for (auto& g : ks) {
+            jit_get(g, false);
+            keys += (keys.empty() ? "" : ",") + g.key;
+        }
+        if (keys_out && keys_cap) snprintf(keys_out, keys_cap, "%s", keys.c_str());
+        return (int)ks.size();
+    }, -1);
+}
+
+int cb200_plan_kernel_source(const uint8_t* op_proto, size_t op_len, int32_t index, char* out, size_t cap, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        OperatorP op = decode_plan(op_proto, op_len);
+        auto ks = plan_kernels_for_build(op);
+        if (index < 0 || index >= (int)ks.size()) throw PlanError("kernel index out of range");
+        const std::string& s = ks[(size_t)index].source;
+        if (out && cap) snprintf(out, cap, "%s", s.c_str());
+        return (int)s.size();
+    }, -1);
+}
+
+} // extern "C"

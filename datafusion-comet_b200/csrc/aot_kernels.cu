@@ -1,0 +1,128 @@
+// aot_kernels.cu -- ahead-of-time sm_100a kernels that do not depend on the plan: Arrow buffer
+// normalisation (bitmap append at arbitrary bit offsets, byte->bitmap packing), dictionary code
+// remapping and the device-side string dictionary builder used to turn Utf8 group keys into dense
+// codes.  (Plan-dependent kernels are JIT-specialised: device/cb_kernels.cuh.)
+#include "aot_kernels.h"
+#include "device/cb_math.h"
+
+namespace cb200 {
+using namespace cb;
+
+// ---- bitmap append: dst[dst_off .. dst_off+n) = src[src_off ..) (src == nullptr -> ones) -----------
+// dst must be zero-initialised; one thread per 32 destination bits, boundary words via atomicOr.
+__global__ void k_bitmap_append(u32* dst, i64 dst_off, const u8* src, i64 src_off, i64 n) {
+    i64 first_word = dst_off >> 5, last_word = (dst_off + n - 1) >> 5;
+    i64 w = first_word + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > last_word) return;
+    u32 bits = 0;
+    i64 lo = w << 5;
+    for (int b = 0; b < 32; b++) {
+        i64 d = lo + b;
+        if (d < dst_off || d >= dst_off + n) continue;
+        i64 s = src_off + (d - dst_off);
+        u32 bit = src ? ((src[s >> 3] >> (s & 7)) & 1u) : 1u;
+        bits |= bit << b;
+    }
+    if (w == first_word || w == last_word) atomicOr(&dst[w], bits);
+    else dst[w] = bits;
+}
+void launch_bitmap_append(u32* dst, i64 dst_off, const u8* src, i64 src_off, i64 n, cudaStream_t st) {
+    if (n <= 0) return;
+    i64 words = ((dst_off + n - 1) >> 5) - (dst_off >> 5) + 1;
+    int threads = 256;
+    k_bitmap_append<<<(unsigned)((words + threads - 1) / threads), threads, 0, st>>>(dst, dst_off, src, src_off, n);
+}
+
+// ---- validity bytes (1 per row) -> Arrow bitmap -------------------------------------------------
+__global__ void k_bytes_to_bitmap(const u8* bytes, i64 n, u32* out) {
+    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32 >= n) return;
+    u32 bits = 0;
+    for (int b = 0; b < 32; b++) {
+        i64 i = w * 32 + b;
+        if (i < n && bytes[i]) bits |= 1u << b;
+    }
+    out[w] = bits;
+}
+void launch_bytes_to_bitmap(const u8* bytes, i64 n, u32* out, cudaStream_t st) {
+    if (n <= 0) return;
+    i64 words = (n + 31) / 32;
+    k_bytes_to_bitmap<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(bytes, n, out);
+}
+
+// ---- dictionary code remap (batch dictionary -> plan-global dictionary) ------------------------------
+template <typename T> __global__ void k_remap_codes(const T* in, i64 n, const i32* table, i32 table_len, i32* out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i32 c = (i32)in[i];
+    out[i] = (c >= 0 && c < table_len) ? table[c] : 0;
+}
+void launch_remap_codes(const void* in, int in_width, i64 n, const i32* table, i32 table_len, i32* out, cudaStream_t st) {
+    if (n <= 0) return;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (in_width == 1) k_remap_codes<signed char><<<blocks, 256, 0, st>>>((const signed char*)in, n, table, table_len, out);
+    else if (in_width == 2) k_remap_codes<short><<<blocks, 256, 0, st>>>((const short*)in, n, table, table_len, out);
+    else k_remap_codes<i32><<<blocks, 256, 0, st>>>((const i32*)in, n, table, table_len, out);
+}
+
+// ---- device string dictionary -----------------------------------------------------------------------
+// Open-addressing table keyed by a 64-bit hash of the bytes; each claimed slot owns a dense code and
+// a copy of the string.  Pass 1 claims / finds slots (codes handed out by atomicAdd), pass 2 verifies
+// the bytes against the stored copy (a 64-bit hash collision between different strings raises
+// CB_DICT_COLLISION instead of silently merging two groups) and writes the code column.
+__device__ __forceinline__ u64 hash_bytes64(const u8* p, i32 len) {
+    u32 a = mm3_bytes(p, len, 42u), b = mm3_bytes(p, len, 0x9747b28cu);
+    u64 h = ((u64)a << 32) | b;
+    return h == 0 ? 1 : h; // 0 = empty slot
+}
+__global__ void k_dict_insert(StringDictDev d, const i32* offsets, const u8* chars, const u8* validity, i64 n, i32* row_slot) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (validity && !((validity[i >> 3] >> (i & 7)) & 1)) { row_slot[i] = -1; return; }
+    const u8* p = chars + offsets[i];
+    i32 len = offsets[i + 1] - offsets[i];
+    u64 h = hash_bytes64(p, len);
+    u32 mask = (u32)d.capacity - 1;
+    u32 s = (u32)(h ^ (h >> 32)) & mask;
+    for (u32 probe = 0; probe <= mask; probe++, s = (s + 1) & mask) {
+        u64 prev = atomicCAS((unsigned long long*)&d.tags[s], 0ull, (unsigned long long)h);
+        if (prev == 0) { // claimed: allocate a code and copy the bytes
+            i32 code = atomicAdd(d.n_codes, 1);
+            if (code >= d.max_codes) { atomicOr(d.err, CB_DICT_FULL); row_slot[i] = -1; return; }
+            i64 off = (i64)atomicAdd((unsigned long long*)d.bytes_used, (unsigned long long)len);
+            if (off + len > d.bytes_cap) { atomicOr(d.err, CB_DICT_FULL); row_slot[i] = -1; return; }
+            for (i32 k = 0; k < len; k++) d.bytes[off + k] = p[k];
+            d.code_off[code] = off;
+            d.code_len[code] = len;
+            d.slot_code[s] = code;
+            row_slot[i] = (i32)s;
+            return;
+        }
+        if (prev == h) { row_slot[i] = (i32)s; return; }
+    }
+    atomicOr(d.err, CB_DICT_FULL);
+    row_slot[i] = -1;
+}
+__global__ void k_dict_resolve(StringDictDev d, const i32* offsets, const u8* chars, i64 n, const i32* row_slot, i32* codes) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i32 s = row_slot[i];
+    if (s < 0) { codes[i] = 0; return; }
+    i32 code = d.slot_code[s];
+    i32 len = offsets[i + 1] - offsets[i];
+    const u8* p = chars + offsets[i];
+    bool same = d.code_len[code] == len;
+    const u8* q = d.bytes + d.code_off[code];
+    for (i32 k = 0; same && k < len; k++) same = p[k] == q[k];
+    if (!same) atomicOr(d.err, CB_DICT_COLLISION);
+    codes[i] = code;
+}
+void launch_dict_encode(const StringDictDev& d, const i32* offsets, const u8* chars, const u8* validity, i64 n, i32* row_slot, i32* codes,
+                        cudaStream_t st) {
+    if (n <= 0) return;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    k_dict_insert<<<blocks, 256, 0, st>>>(d, offsets, chars, validity, n, row_slot);
+    k_dict_resolve<<<blocks, 256, 0, st>>>(d, offsets, chars, n, row_slot, codes);
+}
+
+} // namespace cb200

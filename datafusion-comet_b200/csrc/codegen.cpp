@@ -1,0 +1,892 @@
+// codegen.cpp -- expression tree -> straight-line CUDA, spliced into device/cb_kernels.cuh.
+//
+// Every emitted operation names the reference rule it implements; the arithmetic itself is the
+// hand-written device library device/cb_math.h (host-tested against the oracle).
+#include "codegen.h"
+
+#include <climits>
+#include <cstring>
+#include <functional>
+#include <sstream>
+
+namespace cb200 {
+
+int phys_bytes(Phys p) {
+    switch (p) {
+    case Phys::Bitmap: return 0;
+    case Phys::I8: return 1;
+    case Phys::I16: return 2;
+    case Phys::I32: case Phys::F32: case Phys::Dict32: return 4;
+    case Phys::I64: case Phys::F64: return 8;
+    case Phys::I128: return 16;
+    }
+    return 0;
+}
+
+size_t GeneratedKernel::dyn_smem(int n_groups) const {
+    size_t s = 128 + (size_t)stages * stage_bytes;
+    if (!word_kinds.empty() && n_groups > 1) s += (size_t)n_groups * n_words * threads * 8;
+    else if (!word_kinds.empty() && n_groups == 1 && n_words > 0) s += 0;
+    return s;
+}
+
+namespace {
+
+struct Val {
+    std::string v;   // C expression / variable holding the value
+    std::string n;   // C expression for "is null" ("" = never null)
+    DType type;
+    bool nullable() const { return !n.empty(); }
+};
+
+std::string ctype(const DType& t) {
+    switch (t.id) {
+    case TypeId::Bool: return "bool";
+    case TypeId::Int8: case TypeId::Int16: case TypeId::Int32: case TypeId::Date: return "cb::i32";
+    case TypeId::Int64: case TypeId::Timestamp: case TypeId::TimestampNtz: return "cb::i64";
+    case TypeId::Float32: return "float";
+    case TypeId::Float64: return "double";
+    case TypeId::Decimal: return "cb::i128";
+    default: throw Unsupported("no device representation for " + t.str());
+    }
+}
+
+std::string u64lit(uint64_t v) {
+    std::ostringstream o;
+    o << v << "ull";
+    return o.str();
+}
+std::string i128lit(unsigned __int128 v) {
+    std::ostringstream o;
+    o << "cb::mk128(" << u64lit((uint64_t)v) << ", (cb::i64)" << u64lit((uint64_t)(v >> 64)) << ")";
+    return o.str();
+}
+unsigned __int128 pow10_128(int e) {
+    unsigned __int128 r = 1;
+    for (int i = 0; i < e; i++) r *= 10;
+    return r;
+}
+std::string bound_args(int precision) { // (lo, hi) of 10^p
+    unsigned __int128 b = pow10_128(precision);
+    return u64lit((uint64_t)b) + ", " + u64lit((uint64_t)(b >> 64));
+}
+std::string f64lit(double d) {
+    uint64_t bits;
+    memcpy(&bits, &d, 8);
+    return "__longlong_as_double((cb::i64)" + u64lit(bits) + ")";
+}
+std::string f32lit(float f) {
+    uint32_t bits;
+    memcpy(&bits, &f, 4);
+    std::ostringstream o;
+    o << "__uint_as_float(" << bits << "u)";
+    return o.str();
+}
+
+struct Emitter {
+    const PipelineSpec& spec;
+    std::ostringstream body;
+    std::map<std::string, Val> cse;
+    int next_id = 0;
+    bool uses_err = false;
+
+    explicit Emitter(const PipelineSpec& s) : spec(s) {}
+
+    std::string fresh(const char* prefix = "v") { return std::string(prefix) + std::to_string(next_id++); }
+
+    static std::string or_null(const std::string& a, const std::string& b) {
+        if (a.empty()) return b;
+        if (b.empty()) return a;
+        return "(" + a + " || " + b + ")";
+    }
+    std::string key_of(const Expr& e) {
+        std::ostringstream o;
+        o << (int)e.kind << "|" << e.type.str() << "|" << e.index << "|" << e.lit_null << "|" << e.lit_i64 << "|";
+        uint64_t fb;
+        memcpy(&fb, &e.lit_f64, 8);
+        o << fb << "|" << (uint64_t)e.lit_dec << "," << (uint64_t)(e.lit_dec >> 64) << "|" << (int)e.eval_mode << "|"
+          << e.fail_on_error << "|" << e.negated << "|" << e.wide_decimal << "|" << e.return_type.str() << "(";
+        for (auto& c : e.children) o << key_of(*c) << ",";
+        o << ")";
+        return o.str();
+    }
+
+    // declare `type name = init;` and return name
+    std::string decl(const DType& t, const std::string& init) {
+        std::string name = fresh();
+        body << "    " << ctype(t) << " " << name << " = " << init << ";\n";
+        return name;
+    }
+    std::string declb(const std::string& init) {
+        std::string name = fresh("b");
+        body << "    bool " << name << " = " << init << ";\n";
+        return name;
+    }
+
+    Val emit(const Expr& e) {
+        std::string k = key_of(e);
+        auto it = cse.find(k);
+        if (it != cse.end()) return it->second;
+        Val r = emit_uncached(e);
+        cse[k] = r;
+        return r;
+    }
+
+    Val load_col(int slot) {
+        const SourceCol& c = spec.cols.at(slot);
+        Val r;
+        r.type = c.type;
+        std::string s = std::to_string(slot);
+        std::string init;
+        switch (c.phys) {
+        case Phys::Bitmap: init = "cb::ldv(t.col[" + s + "], r)"; break;
+        case Phys::I8: init = "(cb::i32)cb::ld<signed char>(t.col[" + s + "], r)"; break;
+        case Phys::I16: init = "(cb::i32)cb::ld<short>(t.col[" + s + "], r)"; break;
+        case Phys::I32: case Phys::Dict32: init = "cb::ld<cb::i32>(t.col[" + s + "], r)"; break;
+        case Phys::I64: init = "cb::ld<cb::i64>(t.col[" + s + "], r)"; break;
+        case Phys::F32: init = "cb::ld<float>(t.col[" + s + "], r)"; break;
+        case Phys::F64: init = "cb::ld<double>(t.col[" + s + "], r)"; break;
+        case Phys::I128: init = "cb::ld<cb::i128>(t.col[" + s + "], r)"; break;
+        }
+        if (c.type.is_decimal() && c.phys == Phys::I64) init = "cb::i128_from_i64(" + init + ")";
+        if (c.type.is_decimal() && c.phys == Phys::I32) init = "cb::i128_from_i64((cb::i64)" + init + ")";
+        if (c.phys == Phys::Dict32) {
+            r.v = fresh("k");
+            body << "    cb::i32 " << r.v << " = " << init << ";\n";
+        } else {
+            r.v = decl(c.type, init);
+        }
+        if (c.has_validity) r.n = declb("!cb::ldv(t.val[" + s + "], r)");
+        return r;
+    }
+
+    Val emit_uncached(const Expr& e) {
+        switch (e.kind) {
+        case ExprKind::Bound: return load_col(e.index);
+        case ExprKind::Unbound: throw PlanError("unbound reference reached code generation");
+        case ExprKind::Literal: return emit_literal(e);
+        case ExprKind::Add: case ExprKind::Sub: case ExprKind::Mul: case ExprKind::Div: return emit_arith(e);
+        case ExprKind::Eq: case ExprKind::Neq: case ExprKind::Gt: case ExprKind::GtEq: case ExprKind::Lt: case ExprKind::LtEq:
+            return emit_cmp(e);
+        case ExprKind::And: case ExprKind::Or: return emit_logic(e);
+        case ExprKind::Not: {
+            Val c = emit(*e.children[0]);
+            Val r;
+            r.type = e.type;
+            r.v = declb("!" + c.v);
+            r.n = c.n;
+            return r;
+        }
+        case ExprKind::IsNull: case ExprKind::IsNotNull: {
+            Val c = emit(*e.children[0]);
+            Val r;
+            r.type = e.type;
+            std::string isnull = c.n.empty() ? "false" : c.n;
+            r.v = declb(e.kind == ExprKind::IsNull ? isnull : "!(" + isnull + ")");
+            return r;
+        }
+        case ExprKind::Cast: return emit_cast(e);
+        case ExprKind::CheckOverflow: return emit_check_overflow(e);
+        case ExprKind::UnaryMinus: return emit_neg(e);
+        case ExprKind::If: {
+            Val c = emit(*e.children[0]), a = emit(*e.children[1]), b = emit(*e.children[2]);
+            Val r;
+            r.type = e.type;
+            std::string ct = c.n.empty() ? c.v : declb("!" + c.n + " && " + c.v); // NULL condition -> else branch
+            r.v = decl(e.type, ct + " ? " + a.v + " : " + b.v);
+            if (a.nullable() || b.nullable())
+                r.n = declb(ct + " ? " + (a.n.empty() ? "false" : a.n) + " : " + (b.n.empty() ? "false" : b.n));
+            return r;
+        }
+        case ExprKind::In: return emit_in(e);
+        }
+        throw PlanError("unhandled expression kind");
+    }
+
+    Val emit_literal(const Expr& e) {
+        Val r;
+        r.type = e.type;
+        if (e.lit_null) {
+            if (e.type.id == TypeId::Null) throw Unsupported("untyped NULL literal");
+            r.v = decl(e.type, e.type.is_decimal() ? "cb::mk128(0, 0)" : "0");
+            r.n = "true";
+            return r;
+        }
+        switch (e.type.id) {
+        case TypeId::Bool: r.v = e.lit_i64 ? "true" : "false"; break;
+        case TypeId::Int8: case TypeId::Int16: case TypeId::Int32: case TypeId::Date:
+            r.v = "((cb::i32)" + std::to_string((int32_t)e.lit_i64) + ")";
+            if ((int32_t)e.lit_i64 == INT32_MIN) r.v = "((cb::i32)0x80000000u)";
+            break;
+        case TypeId::Int64: case TypeId::Timestamp: case TypeId::TimestampNtz:
+            r.v = "((cb::i64)" + u64lit((uint64_t)e.lit_i64) + ")";
+            break;
+        case TypeId::Float32: r.v = f32lit((float)e.lit_f64); break;
+        case TypeId::Float64: r.v = f64lit(e.lit_f64); break;
+        case TypeId::Decimal: r.v = decl(e.type, i128lit(e.lit_dec)); break;
+        default: throw Unsupported("literal of type " + e.type.str());
+        }
+        return r;
+    }
+
+    void raise(const std::string& cond, int bit) {
+        uses_err = true;
+        body << "    if (" << cond << ") cb::set_err(p, " << bit << ");\n";
+    }
+
+    // ---- arithmetic --------------------------------------------------------------------------------
+    Val emit_arith(const Expr& e) {
+        Val l = emit(*e.children[0]), rr = emit(*e.children[1]);
+        Val r;
+        r.type = e.type;
+        std::string nn = or_null(l.n, rr.n);
+        std::string valid = nn.empty() ? "true" : "!" + nn;
+        const DType &lt = l.type, &rt = rr.type;
+        if (lt.is_decimal()) {
+            int op = e.kind == ExprKind::Add ? 0 : e.kind == ExprKind::Sub ? 1 : 2;
+            if (e.wide_decimal) {
+                // wide_decimal_binary_expr.rs:179-291
+                std::string ok = fresh("b");
+                r.v = fresh();
+                body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = false;\n";
+                body << "    if (" << valid << ") " << ok << " = ";
+                if (op == 2)
+                    body << "cb::wide_mul_fast(" << l.v << ", " << rr.v << ", " << (lt.scale + rt.scale - e.type.scale) << ", "
+                         << e.type.precision << ", " << r.v << ");\n";
+                else {
+                    int ms = std::max(lt.scale, rt.scale);
+                    body << "cb::wide_addsub(" << l.v << ", " << (ms - lt.scale) << ", " << rr.v << ", " << (ms - rt.scale) << ", "
+                         << (op == 1 ? "true" : "false") << ", " << (ms - e.type.scale) << ", " << e.type.precision << ", " << r.v
+                         << ");\n";
+                }
+                if (e.eval_mode == EvalMode::Ansi) raise(valid + " && !" + ok, 1);
+                r.n = declb("!" + ok); // overflow -> NULL (Legacy/Try); null inputs -> NULL
+                return r;
+            }
+            // arrow-arith decimal_op (planner.rs:1126 fallthrough): checked i128, evaluated only on valid rows
+            std::string err = fresh("e");
+            r.v = fresh();
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << err << " = false;\n";
+            body << "    if (" << valid << ") " << r.v << " = ";
+            if (op == 2) body << "cb::dec_mul_plain(" << l.v << ", " << rr.v << ", " << err << ");\n";
+            else {
+                int rs = std::max(lt.scale, rt.scale);
+                body << (op == 0 ? "cb::dec_add_plain(" : "cb::dec_sub_plain(") << l.v << ", " << (rs - lt.scale) << ", " << rr.v
+                     << ", " << (rs - rt.scale) << ", " << err << ");\n";
+            }
+            raise(err, 0); // arrow: "Overflow happened on ..." fails the query
+            r.n = nn;
+            return r;
+        }
+        if (lt.is_float()) {
+            const char* opc = e.kind == ExprKind::Add ? "+" : e.kind == ExprKind::Sub ? "-" : e.kind == ExprKind::Mul ? "*" : "/";
+            // IEEE arithmetic, no contraction: each node rounds once like the reference's per-node arrays
+            std::string fn = lt.id == TypeId::Float64
+                                 ? (e.kind == ExprKind::Add ? "__dadd_rn" : e.kind == ExprKind::Sub ? "__dsub_rn" : e.kind == ExprKind::Mul ? "__dmul_rn" : "__ddiv_rn")
+                                 : (e.kind == ExprKind::Add ? "__fadd_rn" : e.kind == ExprKind::Sub ? "__fsub_rn" : e.kind == ExprKind::Mul ? "__fmul_rn" : "__fdiv_rn");
+            (void)opc;
+            r.v = decl(e.type, fn + "(" + l.v + ", " + rr.v + ")");
+            r.n = nn;
+            return r;
+        }
+        // integers: Legacy wraps (arrow-arith *_wrapping); Try -> NULL, Ansi -> error (checked_arithmetic.rs:53-128)
+        int bits = lt.id == TypeId::Int8 ? 8 : lt.id == TypeId::Int16 ? 16 : lt.id == TypeId::Int32 ? 32 : 64;
+        std::string wide = fresh("w");
+        const char* opc = e.kind == ExprKind::Add ? "+" : e.kind == ExprKind::Sub ? "-" : "*";
+        if (bits < 64) {
+            body << "    cb::i64 " << wide << " = (cb::i64)" << l.v << " " << opc << " (cb::i64)" << rr.v << ";\n";
+            std::string wrapped = bits == 8 ? "(cb::i32)(signed char)" + wide : bits == 16 ? "(cb::i32)(short)" + wide : "(cb::i32)" + wide;
+            r.v = decl(e.type, wrapped);
+            if (e.eval_mode != EvalMode::Legacy) {
+                std::string ovf = declb("(cb::i64)" + r.v + " != " + wide);
+                if (e.eval_mode == EvalMode::Ansi) { raise(valid + " && " + ovf, 1); r.n = nn; }
+                else r.n = or_null(nn, ovf);
+            } else r.n = nn;
+        } else {
+            if (e.eval_mode == EvalMode::Legacy) {
+                r.v = decl(e.type, "(cb::i64)((cb::u64)" + l.v + " " + opc + " (cb::u64)" + rr.v + ")");
+                r.n = nn;
+            } else {
+                std::string ovf = fresh("b");
+                r.v = fresh();
+                body << "    cb::i64 " << r.v << "; bool " << ovf << " = cb::i64_" << (e.kind == ExprKind::Add ? "add" : e.kind == ExprKind::Sub ? "sub" : "mul")
+                     << "_overflow(" << l.v << ", " << rr.v << ", " << r.v << ");\n";
+                if (e.eval_mode == EvalMode::Ansi) { raise(valid + " && " + ovf, 1); r.n = nn; }
+                else r.n = or_null(nn, ovf);
+            }
+        }
+        return r;
+    }
+
+    // ---- comparisons (arrow-ord cmp; floats by IEEE totalOrder) -------------------------------------
+    Val emit_cmp(const Expr& e) {
+        Val l = emit(*e.children[0]), rr = emit(*e.children[1]);
+        Val r;
+        r.type = e.type;
+        r.n = or_null(l.n, rr.n);
+        std::string a = l.v, b = rr.v;
+        const DType& t = l.type;
+        std::string expr;
+        if (t.is_decimal()) {
+            switch (e.kind) {
+            case ExprKind::Eq: expr = "cb::i128_eq(" + a + ", " + b + ")"; break;
+            case ExprKind::Neq: expr = "!cb::i128_eq(" + a + ", " + b + ")"; break;
+            case ExprKind::Lt: expr = "cb::i128_lt(" + a + ", " + b + ")"; break;
+            case ExprKind::LtEq: expr = "cb::i128_le(" + a + ", " + b + ")"; break;
+            case ExprKind::Gt: expr = "cb::i128_lt(" + b + ", " + a + ")"; break;
+            default: expr = "cb::i128_le(" + b + ", " + a + ")"; break;
+            }
+        } else {
+            if (t.id == TypeId::Float64) {
+                a = "cb::f64_total_key((cb::u64)__double_as_longlong(" + a + "))";
+                b = "cb::f64_total_key((cb::u64)__double_as_longlong(" + b + "))";
+            } else if (t.id == TypeId::Float32) {
+                a = "cb::f32_total_key(__float_as_uint(" + a + "))";
+                b = "cb::f32_total_key(__float_as_uint(" + b + "))";
+            }
+            const char* opc = e.kind == ExprKind::Eq ? "==" : e.kind == ExprKind::Neq ? "!=" : e.kind == ExprKind::Lt ? "<" : e.kind == ExprKind::LtEq ? "<=" : e.kind == ExprKind::Gt ? ">" : ">=";
+            expr = "(" + a + " " + opc + " " + b + ")";
+        }
+        r.v = declb(expr);
+        return r;
+    }
+
+    // ---- Kleene AND / OR (arrow and_kleene / or_kleene) ---------------------------------------------
+    Val emit_logic(const Expr& e) {
+        Val l = emit(*e.children[0]), rr = emit(*e.children[1]);
+        Val r;
+        r.type = e.type;
+        bool is_and = e.kind == ExprKind::And;
+        if (!l.nullable() && !rr.nullable()) {
+            r.v = declb(l.v + (is_and ? " && " : " || ") + rr.v);
+            return r;
+        }
+        std::string ln = l.n.empty() ? "false" : l.n, rn = rr.n.empty() ? "false" : rr.n;
+        std::string lt = declb("!" + ln + " && " + l.v), lf = declb("!" + ln + " && !" + l.v);
+        std::string rt = declb("!" + rn + " && " + rr.v), rf = declb("!" + rn + " && !" + rr.v);
+        std::string T = declb(is_and ? lt + " && " + rt : lt + " || " + rt);
+        std::string F = declb(is_and ? lf + " || " + rf : lf + " && " + rf);
+        r.v = T;
+        r.n = declb("!" + T + " && !" + F);
+        return r;
+    }
+
+    Val emit_cast(const Expr& e) {
+        Val c = emit(*e.children[0]);
+        const DType &from = c.type, &to = e.type;
+        Val r;
+        r.type = to;
+        r.n = c.n;
+        if (from == to) { r.v = c.v; return r; }
+        if ((from.is_integer() || from.is_float()) && (to.is_integer() || to.is_float())) {
+            r.v = decl(to, "(" + ctype(to) + ")" + c.v);
+            return r;
+        }
+        std::string valid = c.n.empty() ? "true" : "!" + c.n;
+        if (from.is_integer() && to.is_decimal()) {
+            // Spark Cast(int -> decimal(p,s)): value * 10^s, out of precision -> NULL (Legacy/Try) / error (ANSI)
+            std::string ok = fresh("b");
+            r.v = fresh();
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(cb::i128_from_i64((cb::i64)" << c.v
+                 << "), " << to.scale << ", " << to.precision << ", " << r.v << ");\n";
+            if (e.eval_mode == EvalMode::Ansi) raise(valid + " && !" + ok, 1);
+            r.n = or_null(c.n, "!" + ok);
+            return r;
+        }
+        if (from.is_decimal() && to.is_decimal()) {
+            std::string ok = fresh("b");
+            r.v = fresh();
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(" << c.v << ", "
+                 << (to.scale - from.scale) << ", " << to.precision << ", " << r.v << ");\n";
+            if (e.eval_mode == EvalMode::Ansi) raise(valid + " && !" + ok, 1);
+            r.n = or_null(c.n, "!" + ok);
+            return r;
+        }
+        throw Unsupported("cast " + from.str() + " -> " + to.str());
+    }
+
+    Val emit_check_overflow(const Expr& e) {
+        const Expr& ch = *e.children[0];
+        // planner.rs:606-613: WideDecimalBinaryExpr already checked -> skip when the types agree
+        if ((ch.kind == ExprKind::Add || ch.kind == ExprKind::Sub || ch.kind == ExprKind::Mul) && ch.wide_decimal && ch.type == e.type)
+            return emit(ch);
+        // planner.rs:617-637: Cast(decimal->decimal) + CheckOverflow fuse into DecimalRescaleCheckOverflow
+        if (ch.kind == ExprKind::Cast && ch.children[0]->type.is_decimal() && ch.type == e.type) {
+            Val c = emit(*ch.children[0]);
+            std::string valid = c.n.empty() ? "true" : "!" + c.n;
+            Val r;
+            r.type = e.type;
+            std::string ok = fresh("b");
+            r.v = fresh();
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(" << c.v << ", "
+                 << (e.type.scale - ch.children[0]->type.scale) << ", " << e.type.precision << ", " << r.v << ");\n";
+            if (e.fail_on_error) raise(valid + " && !" + ok, 1);
+            r.n = or_null(c.n, "!" + ok);
+            return r;
+        }
+        // checkoverflow.rs:105-200: bound check only
+        Val c = emit(ch);
+        std::string valid = c.n.empty() ? "true" : "!" + c.n;
+        Val r;
+        r.type = e.type;
+        r.v = c.v;
+        std::string ok = declb("cb::dec_fits(" + c.v + ", " + bound_args(e.type.precision) + ")");
+        if (e.fail_on_error) { raise(valid + " && !" + ok, 1); r.n = c.n; }
+        else r.n = or_null(c.n, "!" + ok);
+        return r;
+    }
+
+    Val emit_neg(const Expr& e) {
+        Val c = emit(*e.children[0]);
+        Val r;
+        r.type = e.type;
+        r.n = c.n;
+        const DType& t = c.type;
+        if (t.is_decimal()) r.v = decl(t, "cb::i128_neg(" + c.v + ")");
+        else if (t.is_float()) r.v = decl(t, "-" + c.v);
+        else if (t.id == TypeId::Int64) r.v = decl(t, "(cb::i64)(0ull - (cb::u64)" + c.v + ")");
+        else {
+            int bits = t.id == TypeId::Int8 ? 8 : t.id == TypeId::Int16 ? 16 : 32;
+            r.v = decl(t, bits == 8 ? "(cb::i32)(signed char)(0u - (cb::u32)" + c.v + ")" : bits == 16 ? "(cb::i32)(short)(0u - (cb::u32)" + c.v + ")" : "(cb::i32)(0u - (cb::u32)" + c.v + ")");
+        }
+        if (e.fail_on_error && t.is_integer()) { // negative.rs: ANSI overflow on MIN
+            std::string valid = c.n.empty() ? "true" : "!" + c.n;
+            raise(valid + " && " + c.v + " != 0 && " + r.v + " == " + c.v, 1);
+        }
+        return r;
+    }
+
+    Val emit_in(const Expr& e) { // Spark In: NULL value -> NULL; match -> TRUE; else NULL if list has NULL, else FALSE
+        Val v = emit(*e.children[0]);
+        bool list_has_null = false;
+        std::string any = "false";
+        for (size_t i = 1; i < e.children.size(); i++) {
+            const Expr& m = *e.children[i];
+            if (m.lit_null) { list_has_null = true; continue; }
+            Val mv = emit(m);
+            if (v.type.is_decimal()) any += " || cb::i128_eq(" + v.v + ", " + mv.v + ")";
+            else if (v.type.id == TypeId::Float64) any += " || (__double_as_longlong(" + v.v + ") == __double_as_longlong(" + mv.v + "))";
+            else any += " || (" + v.v + " == " + mv.v + ")";
+        }
+        Val r;
+        r.type = e.type;
+        std::string hit = declb(any);
+        r.v = e.negated ? declb("!" + hit) : hit;
+        if (list_has_null) r.n = or_null(v.n, "!" + hit);
+        else r.n = v.n;
+        return r;
+    }
+};
+
+// ---- aggregate slot planning ----------------------------------------------------------------------
+struct SlotPlan {
+    std::vector<int> kinds;                 // per word
+    std::map<std::string, int> dedup;       // (kind|expr|cond) -> first word
+    int add(int kind, const std::string& key, int n_words = 1) {
+        std::string k = std::to_string(kind) + "|" + key;
+        auto it = dedup.find(k);
+        if (it != dedup.end()) return it->second;
+        int w = (int)kinds.size();
+        kinds.push_back(kind);
+        if (n_words == 2) kinds.push_back(W_DD_LO);
+        dedup[k] = w;
+        return w;
+    }
+};
+
+struct AggLayout { // where each aggregate finds its totals at finalize time
+    int w_sum = -1, w_cnt = -1, w_bits = -1, w_bad = -1, w_minmax = -1;
+    bool is_f64_sum = false;
+};
+
+std::string header(const PipelineSpec& s, const std::string& defs) {
+    std::ostringstream o;
+    o << "// generated by comet_b200 codegen -- do not edit\n";
+    o << defs;
+    o << "#define CB_NCOLS " << s.cols.size() << "\n#define CB_TILE " << s.tile << "\n#define CB_STAGES " << s.stages
+      << "\n#define CB_THREADS " << s.threads << "\n";
+    o << "#include \"cb_math.h\"\n";
+    o << "constexpr __host__ __device__ int cb_col_bytes(int c) { return ";
+    for (size_t i = 0; i < s.cols.size(); i++) o << "c == " << i << " ? " << phys_bytes(s.cols[i].phys) << " : ";
+    o << "0; }\n";
+    o << "constexpr __host__ __device__ bool cb_col_has_val(int c) { return ";
+    for (size_t i = 0; i < s.cols.size(); i++) o << "c == " << i << " ? " << (s.cols[i].has_validity ? "true" : "false") << " : ";
+    o << "false; }\n";
+    return o.str();
+}
+
+uint64_t fnv1a(const std::string& s) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+
+int stage_bytes_of(const PipelineSpec& s) {
+    int b = 0;
+    for (auto& c : s.cols) {
+        int w = phys_bytes(c.phys);
+        int colb = w == 0 ? s.tile / 8 : s.tile * w;
+        b += (colb + 127) / 128 * 128;
+        if (c.has_validity) b += (s.tile / 8 + 127) / 128 * 128;
+    }
+    return b;
+}
+
+int out_width(const DType& t) { return t.id == TypeId::Bool ? 1 : t.arrow_width(); }
+
+// store a value into a raw 16-byte output slot
+std::string to_slot(const Val& v, const std::string& dst) {
+    const DType& t = v.type;
+    std::ostringstream o;
+    if (t.is_decimal()) o << dst << "[0] = " << v.v << ".lo; " << dst << "[1] = (cb::u64)" << v.v << ".hi;";
+    else if (t.id == TypeId::Float64) o << dst << "[0] = (cb::u64)__double_as_longlong(" << v.v << ");";
+    else if (t.id == TypeId::Float32) o << dst << "[0] = (cb::u64)__float_as_uint(" << v.v << ");";
+    else if (t.id == TypeId::Bool) o << dst << "[0] = " << v.v << " ? 1ull : 0ull;";
+    else o << dst << "[0] = (cb::u64)(cb::i64)" << v.v << ";";
+    return o.str();
+}
+
+} // namespace
+
+// =================================================================================================
+GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
+    GeneratedKernel g;
+    g.threads = spec.threads;
+    g.tile = spec.tile;
+    g.stages = spec.stages;
+    g.stage_bytes = stage_bytes_of(spec);
+    if (spec.cols.empty()) throw Unsupported("pipeline without input columns");
+    if (spec.cols.size() > 24) throw Unsupported("more than 24 staged input columns");
+
+    Emitter em(spec);
+    // predicates first: `keep` = every predicate TRUE (FilterExec drops NULL and FALSE)
+    std::string keep = "true";
+    for (auto& p : spec.predicates) {
+        Val v = em.emit(*p);
+        keep += " && " + (v.n.empty() ? v.v : "(!" + v.n + " && " + v.v + ")");
+    }
+    std::ostringstream tu;
+
+    if (spec.sink == SinkKind::Select) {
+        if (spec.outputs.size() > 16) throw Unsupported("more than 16 output columns");
+        em.body << "    if (!(" << keep << ")) return false;\n";
+        std::ostringstream defs;
+        defs << "#define CB_KERNEL_SELECT 1\n#define CB_NOUT " << spec.outputs.size() << "\n";
+        std::vector<Val> outs;
+        for (size_t i = 0; i < spec.outputs.size(); i++) {
+            Val v = em.emit(*spec.outputs[i]);
+            if (v.type.is_string()) throw Unsupported("string columns in a fused projection");
+            outs.push_back(v);
+            em.body << "    " << to_slot(v, "o.v[" + std::to_string(i) + "]") << " o.valid[" << i << "] = "
+                    << (v.n.empty() ? "true" : "!" + v.n) << ";\n";
+            OutCol oc;
+            oc.type = v.type;
+            oc.nullable = v.nullable();
+            g.out_cols.push_back(oc);
+            g.out_bytes.push_back(out_width(v.type));
+        }
+        em.body << "    return true;\n";
+        tu << header(spec, defs.str());
+        tu << "constexpr __host__ __device__ int cb_out_bytes(int c) { return ";
+        for (size_t i = 0; i < outs.size(); i++) tu << "c == " << i << " ? " << g.out_bytes[i] << " : ";
+        tu << "0; }\n";
+        tu << "constexpr __host__ __device__ bool cb_out_nullable(int c) { return ";
+        for (size_t i = 0; i < outs.size(); i++) tu << "c == " << i << " ? " << (g.out_cols[i].nullable ? "true" : "false") << " : ";
+        tu << "false; }\n";
+        tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
+        tu << "CB_D bool cb_row_select(const Tile& t, int r, i64 grow, const PipeParams& p, SelOut& o) {\n    (void)grow; (void)p;\n"
+           << em.body.str() << "}\n} // namespace cb\n";
+        g.entry = "cb_pipeline_select";
+    } else {
+        // ---------------- aggregate ----------------
+        em.body << "    if (!(" << keep << ")) return;\n";
+        SlotPlan slots;
+        std::vector<AggLayout> layout(spec.aggs.size());
+        // group id (dense): mixed radix over key codes; NULL key -> last slot of that key
+        std::string gid = "0";
+        if (!spec.ungrouped) {
+            for (size_t k = 0; k < spec.keys.size(); k++) {
+                Val kv = em.emit(*spec.keys[k]);
+                std::string code = kv.type.id == TypeId::Bool && spec.cols[spec.keys[k]->index].phys == Phys::Bitmap ? "(" + kv.v + " ? 1 : 0)" : kv.v;
+                if (kv.nullable()) code = "(" + kv.n + " ? p.key_card[" + std::to_string(k) + "] - 1 : " + code + ")";
+                gid = "(" + gid + ") * p.key_card[" + std::to_string(k) + "] + " + code;
+            }
+        }
+        em.body << "    const int g = " << gid << ";\n";
+        int w_rows = slots.add(W_WRAP64, "rows");
+        em.body << "    acc.add_i64_wrap(g, " << w_rows << ", 1);\n";
+
+        for (size_t ai = 0; ai < spec.aggs.size(); ai++) {
+            const AggExpr& a = spec.aggs[ai];
+            AggLayout& L = layout[ai];
+            if (spec.mode == AggMode::Partial) {
+                // per-aggregate FILTER clause: NULL/FALSE excludes the row (sum_decimal.rs:452-458)
+                std::string cond = "true";
+                if (a.filter) {
+                    Val f = em.emit(*a.filter);
+                    cond = f.n.empty() ? f.v : "(!" + f.n + " && " + f.v + ")";
+                }
+                std::vector<Val> cv;
+                for (auto& c : a.children) cv.push_back(em.emit(*c));
+                for (auto& v : cv) if (v.nullable()) cond += " && !" + v.n;
+                std::string condkey = cond;
+                const Val& v = cv[0];
+                std::string use = em.declb(cond);
+                // non-null (and filter-passing) row count of this input: COUNT, AVG count, !is_empty
+                auto cnt_slot = [&]() {
+                    std::string k = "cnt|" + condkey;
+                    bool first = slots.dedup.count(std::to_string((int)W_WRAP64) + "|" + k) == 0;
+                    int w = slots.add(W_WRAP64, k);
+                    if (first) em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << w << ", 1);\n";
+                    return w;
+                };
+                switch (a.kind) {
+                case AggKind::Count:
+                    L.w_cnt = cnt_slot();
+                    break;
+                case AggKind::Sum: case AggKind::Avg: {
+                    bool dec = a.datatype.is_decimal();
+                    bool f64 = !dec && (a.kind == AggKind::Avg || a.datatype.is_float());
+                    L.w_cnt = cnt_slot();
+                    if (dec) {
+                        bool first = slots.dedup.count(std::to_string((int)W_SUM128) + "|sum|" + v.v + "|" + condkey) == 0;
+                        L.w_sum = slots.add(W_SUM128, "sum|" + v.v + "|" + condkey);
+                        if (first) em.body << "    if (" << use << ") acc.add_i128(g, " << L.w_sum << ", " << v.v << ");\n";
+                        // overflow certificate only when the type alone cannot exclude overflow:
+                        // n * (10^p_in - 1) < 10^(p_in + 10) for any n <= 10^10 rows
+                        int sp = a.kind == AggKind::Avg ? a.sum_datatype.precision : a.datatype.precision;
+                        if (sp - v.type.precision < 10) {
+                            bool firstb = slots.dedup.count(std::to_string((int)W_MAX) + "|bits|" + v.v + "|" + condkey) == 0;
+                            L.w_bits = slots.add(W_MAX, "bits|" + v.v + "|" + condkey);
+                            if (firstb) em.body << "    if (" << use << ") acc.max_i64(g, " << L.w_bits << ", cb::i128_bitlen(" << v.v << "));\n";
+                        }
+                    } else if (f64) {
+                        L.is_f64_sum = true;
+                        std::string dv = v.type.id == TypeId::Float64 ? v.v : "(double)" + v.v;
+                        bool first = slots.dedup.count(std::to_string((int)W_DD_HI) + "|dd|" + dv + "|" + condkey) == 0;
+                        L.w_sum = slots.add(W_DD_HI, "dd|" + dv + "|" + condkey, 2);
+                        if (first) em.body << "    if (" << use << ") acc.add_f64(g, " << L.w_sum << ", " << dv << ");\n";
+                    } else { // SumInt Legacy: wrapping i64 (sum_int.rs:432)
+                        bool first = slots.dedup.count(std::to_string((int)W_WRAP64) + "|isum|" + v.v + "|" + condkey) == 0;
+                        L.w_sum = slots.add(W_WRAP64, "isum|" + v.v + "|" + condkey);
+                        if (first) em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << L.w_sum << ", (cb::i64)" << v.v << ");\n";
+                    }
+                    break;
+                }
+                case AggKind::Min: case AggKind::Max: {
+                    L.w_cnt = cnt_slot();
+                    std::string key = v.type.is_decimal() ? "(cb::i64)" + v.v + ".lo"
+                                      : v.type.id == TypeId::Float64 ? "cb::f64_total_key((cb::u64)__double_as_longlong(" + v.v + "))"
+                                                                     : "(cb::i64)" + v.v;
+                    bool mn = a.kind == AggKind::Min;
+                    std::string sk = std::string(mn ? "min|" : "max|") + v.v + "|" + condkey;
+                    bool first = slots.dedup.count(std::to_string((int)(mn ? W_MIN : W_MAX)) + "|" + sk) == 0;
+                    L.w_minmax = slots.add(mn ? W_MIN : W_MAX, sk);
+                    if (first) em.body << "    if (" << use << ") acc." << (mn ? "min_i64" : "max_i64") << "(g, " << L.w_minmax << ", " << key << ");\n";
+                    break;
+                }
+                }
+            } else {
+                // ---- Final: merge state columns (merge_batch semantics) ----
+                const std::vector<int>& sc = spec.state_slots.at(ai);
+                auto col = [&](int i) { Expr b; b.kind = ExprKind::Bound; b.index = sc[i]; b.type = spec.cols[sc[i]].type; return em.emit(b); };
+                std::string tag = "agg" + std::to_string(ai);
+                switch (a.kind) {
+                case AggKind::Count: { // count merge = sum of partial counts
+                    Val c = col(0);
+                    L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                    em.body << "    if (" << (c.n.empty() ? "true" : "!" + c.n) << ") acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
+                    break;
+                }
+                case AggKind::Sum:
+                    if (a.datatype.is_decimal()) { // sum_decimal.rs:540-607
+                        Val s = col(0), e = col(1);
+                        std::string snull = s.n.empty() ? "false" : s.n;
+                        L.w_sum = slots.add(W_SUM128, tag + "sum");
+                        L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                        L.w_bad = slots.add(W_WRAP64, tag + "bad");
+                        L.w_bits = slots.add(W_MAX, tag + "bits");
+                        em.body << "    if (!" << e.v << " && " << snull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
+                        em.body << "    else if (!" << e.v << ") { acc.add_i128(g, " << L.w_sum << ", " << s.v << "); acc.add_i64_wrap(g, " << L.w_cnt
+                                << ", 1); acc.max_i64(g, " << L.w_bits << ", cb::i128_bitlen(" << s.v << ")); }\n";
+                    } else if (a.datatype.is_integer()) { // sum_int.rs:497-528
+                        Val s = col(0);
+                        L.w_sum = slots.add(W_WRAP64, tag + "sum");
+                        L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                        em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc.add_i64_wrap(g, " << L.w_sum << ", " << s.v
+                                << "); acc.add_i64_wrap(g, " << L.w_cnt << ", 1); }\n";
+                    } else {
+                        Val s = col(0);
+                        L.is_f64_sum = true;
+                        L.w_sum = slots.add(W_DD_HI, tag + "sum", 2);
+                        L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                        em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc.add_f64(g, " << L.w_sum << ", (double)" << s.v
+                                << "); acc.add_i64_wrap(g, " << L.w_cnt << ", 1); }\n";
+                    }
+                    break;
+                case AggKind::Avg:
+                    if (a.datatype.is_decimal()) { // avg_decimal.rs:542-595
+                        Val s = col(0), c = col(1);
+                        L.w_sum = slots.add(W_SUM128, tag + "sum");
+                        L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                        L.w_bad = slots.add(W_WRAP64, tag + "bad");
+                        L.w_bits = slots.add(W_MAX, tag + "bits");
+                        std::string cnull = c.n.empty() ? "false" : c.n, snull = s.n.empty() ? "false" : s.n;
+                        em.body << "    if (!" << cnull << ") acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
+                        em.body << "    if (" << snull << " || " << cnull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
+                        em.body << "    if (!" << snull << ") { acc.add_i128(g, " << L.w_sum << ", " << s.v << "); acc.max_i64(g, " << L.w_bits
+                                << ", cb::i128_bitlen(" << s.v << ")); }\n";
+                    } else { // avg.rs:279-309
+                        Val s = col(0), c = col(1);
+                        L.is_f64_sum = true;
+                        L.w_sum = slots.add(W_DD_HI, tag + "sum", 2);
+                        L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                        em.body << "    acc.add_f64(g, " << L.w_sum << ", " << s.v << "); acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
+                    }
+                    break;
+                case AggKind::Min: case AggKind::Max: {
+                    Val s = col(0);
+                    bool mn = a.kind == AggKind::Min;
+                    L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                    L.w_minmax = slots.add(mn ? W_MIN : W_MAX, tag + "mm");
+                    std::string key = s.type.is_decimal() ? "(cb::i64)" + s.v + ".lo"
+                                      : s.type.id == TypeId::Float64 ? "cb::f64_total_key((cb::u64)__double_as_longlong(" + s.v + "))"
+                                                                     : "(cb::i64)" + s.v;
+                    em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc." << (mn ? "min_i64" : "max_i64") << "(g, " << L.w_minmax << ", "
+                            << key << "); acc.add_i64_wrap(g, " << L.w_cnt << ", 1); }\n";
+                    break;
+                }
+                }
+            }
+        }
+        g.n_words = (int)slots.kinds.size();
+        g.word_kinds = slots.kinds;
+
+        // ---------------- finalize program: totals -> state columns (Partial) / results (Final) -------
+        std::ostringstream fin;
+        int oc = 0;
+        auto add_out = [&](const DType& t, bool nullable) {
+            OutCol o;
+            o.type = t;
+            o.nullable = nullable;
+            g.out_cols.push_back(o);
+            g.out_bytes.push_back(out_width(t));
+            return oc++;
+        };
+        auto T128 = [](int w) { return "cb::fin_i128(T, " + std::to_string(w) + ")"; };
+        auto T64 = [](int w) { return "(cb::i64)T[" + std::to_string(w) + " * 2]"; };
+        auto TDD = [](int w) { return "cb::fin_dd(T, " + std::to_string(w) + ")"; };
+        for (size_t ai = 0; ai < spec.aggs.size(); ai++) {
+            const AggExpr& a = spec.aggs[ai];
+            const AggLayout& L = layout[ai];
+            bool partial = spec.mode == AggMode::Partial;
+            std::string A = "a" + std::to_string(ai);
+            fin << "    { // aggregate " << ai << "\n";
+            switch (a.kind) {
+            case AggKind::Count: {
+                int c = add_out(mk_type(TypeId::Int64), false);
+                fin << "      cb::fin_store_i64(fp, " << c << ", g, " << T64(L.w_cnt) << ", true);\n";
+                break;
+            }
+            case AggKind::Sum:
+                if (a.datatype.is_decimal()) {
+                    // exact total; overflow decided by the certificate (see DESIGN.md "decimal sums")
+                    fin << "      cb::i128 s = " << T128(L.w_sum) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
+                    fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
+                    fin << "      int cert = " << (L.w_bits >= 0 ? "cb::sum_certificate(n, " + T64(L.w_bits) + ", s, " + std::to_string(a.datatype.precision) + ")"
+                                                               : "(cb::dec_fits_p(s, " + std::to_string(a.datatype.precision) + ") ? 0 : 1)")
+                        << "; // 0 fits, 1 overflow, 2 order-dependent\n";
+                    fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
+                    fin << "      bool ovf = bad || (n > 0 && cert != 0);\n";
+                    if (a.eval_mode == EvalMode::Ansi) fin << "      if (ovf && !bad) cb::set_err_raw(fp.err, 1);\n";
+                    if (partial) {
+                        int c0 = add_out(a.datatype, true), c1 = add_out(mk_type(TypeId::Bool), false);
+                        // state(): sum = Some(0) while empty, None after overflow (sum_decimal.rs:526-538)
+                        fin << "      cb::fin_store_i128(fp, " << c0 << ", g, ovf ? cb::mk128(0, 0) : s, !ovf);\n";
+                        fin << "      cb::fin_store_u8(fp, " << c1 << ", g, (n == 0 && !bad) ? 1 : 0, true);\n";
+                    } else {
+                        int c0 = add_out(a.datatype, true);
+                        fin << "      bool ok = !ovf && n > 0;\n";
+                        fin << "      cb::fin_store_i128(fp, " << c0 << ", g, ok ? s : cb::mk128(0, 0), ok);\n";
+                    }
+                } else if (a.datatype.is_integer()) {
+                    int c0 = add_out(mk_type(TypeId::Int64), true);
+                    fin << "      cb::i64 n = " << T64(L.w_cnt) << ";\n";
+                    fin << "      cb::fin_store_i64(fp, " << c0 << ", g, n > 0 ? " << T64(L.w_sum) << " : 0, n > 0);\n";
+                } else {
+                    int c0 = add_out(a.datatype, true);
+                    fin << "      cb::i64 n = " << T64(L.w_cnt) << "; double s = " << TDD(L.w_sum) << ";\n";
+                    if (a.datatype.id == TypeId::Float32) fin << "      cb::fin_store_f32(fp, " << c0 << ", g, n > 0 ? (float)s : 0.0f, n > 0);\n";
+                    else fin << "      cb::fin_store_f64(fp, " << c0 << ", g, n > 0 ? s : 0.0, n > 0);\n";
+                }
+                break;
+            case AggKind::Avg:
+                if (a.datatype.is_decimal()) {
+                    int sp = a.sum_datatype.precision;
+                    fin << "      cb::i128 s = " << T128(L.w_sum) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
+                    fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
+                    fin << "      int cert = " << (L.w_bits >= 0 ? "cb::sum_certificate(n, " + T64(L.w_bits) + ", s, " + std::to_string(sp) + ")"
+                                                               : "(cb::dec_fits_p(s, " + std::to_string(sp) + ") ? 0 : 1)")
+                        << ";\n";
+                    fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
+                    fin << "      bool notnull = !bad && !(n > 0 && cert != 0);\n";
+                    if (partial) { // state(): sums and counts share is_not_null as validity (avg_decimal.rs:640-656)
+                        int c0 = add_out(a.sum_datatype, true), c1 = add_out(mk_type(TypeId::Int64), true);
+                        fin << "      cb::fin_store_i128(fp, " << c0 << ", g, s, notnull);\n";
+                        fin << "      cb::fin_store_i64(fp, " << c1 << ", g, n, notnull);\n";
+                    } else {
+                        int c0 = add_out(a.datatype, true);
+                        if (a.eval_mode == EvalMode::Ansi) fin << "      if (!notnull && n > 0) cb::set_err_raw(fp.err, 1);\n";
+                        int d = a.datatype.scale - a.sum_datatype.scale;
+                        if (d < 0) d = 0;
+                        fin << "      cb::i128 r = cb::mk128(0, 0); bool ok = notnull && n > 0 && cb::avg_decimal_eval(s, n, " << d << ", "
+                            << a.datatype.precision << ", r);\n";
+                        fin << "      cb::fin_store_i128(fp, " << c0 << ", g, ok ? r : cb::mk128(0, 0), ok);\n";
+                    }
+                } else {
+                    fin << "      cb::i64 n = " << T64(L.w_cnt) << "; double s = " << TDD(L.w_sum) << ";\n";
+                    if (partial) {
+                        int c0 = add_out(mk_type(TypeId::Float64), false), c1 = add_out(mk_type(TypeId::Int64), false);
+                        fin << "      cb::fin_store_f64(fp, " << c0 << ", g, s, true);\n      cb::fin_store_i64(fp, " << c1 << ", g, n, true);\n";
+                    } else {
+                        int c0 = add_out(mk_type(TypeId::Float64), true);
+                        fin << "      cb::fin_store_f64(fp, " << c0 << ", g, n != 0 ? __ddiv_rn(s, (double)n) : 0.0, n != 0);\n";
+                    }
+                }
+                break;
+            case AggKind::Min: case AggKind::Max: {
+                int c0 = add_out(a.datatype, true);
+                fin << "      cb::i64 n = " << T64(L.w_cnt) << "; cb::i64 k = " << T64(L.w_minmax) << ";\n";
+                if (a.datatype.is_decimal()) fin << "      cb::fin_store_i128(fp, " << c0 << ", g, cb::i128_from_i64(k), n > 0);\n";
+                else if (a.datatype.id == TypeId::Float64)
+                    fin << "      cb::fin_store_f64(fp, " << c0 << ", g, __longlong_as_double(cb::f64_total_key((cb::u64)k)), n > 0);\n";
+                else if (a.datatype.arrow_width() == 8) fin << "      cb::fin_store_i64(fp, " << c0 << ", g, k, n > 0);\n";
+                else fin << "      cb::fin_store_i32(fp, " << c0 << ", g, (cb::i32)k, n > 0, " << a.datatype.arrow_width() << ");\n";
+                break;
+            }
+            }
+            fin << "    }\n";
+        }
+
+        std::ostringstream defs;
+        defs << "#define CB_KERNEL_AGG 1\n#define CB_WORDS " << g.n_words << "\n#define CB_G1 " << (spec.ungrouped ? 1 : 0) << "\n#define CB_W_ROWS " << w_rows
+             << "\n";
+        tu << header(spec, defs.str());
+        tu << "constexpr __host__ __device__ int cb_word_kind(int w) { return ";
+        for (size_t i = 0; i < slots.kinds.size(); i++) tu << "w == " << i << " ? " << slots.kinds[i] << " : ";
+        tu << "0; }\n";
+        tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
+        tu << "CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc) {\n    (void)grow;\n" << em.body.str() << "}\n";
+        tu << "CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T) {\n" << fin.str() << "}\n";
+        tu << "} // namespace cb\n";
+        g.entry = "cb_pipeline_agg";
+        g.finalize_entry = "cb_finalize";
+    }
+    g.source = tu.str();
+    std::ostringstream k;
+    k << std::hex << fnv1a(g.source) << "_" << g.source.size();
+    g.key = k.str();
+    return g;
+}
+
+} // namespace cb200

@@ -1,0 +1,573 @@
+// cb_kernels.cuh -- hand-written sm_100a kernel skeletons for the fused scan -> filter -> project
+// -> {compact | aggregate} pipelines.  A pipeline kernel = this file + one generated `cb_prog`
+// block (the plan's expression tree spliced into straight-line code by codegen.cpp) compiled by
+// NVRTC for sm_100a at createPlan time.  Everything that decides performance lives here:
+//
+//   * persistent CTAs (grid = #SMs x CTAs/SM), each looping over row tiles;
+//   * TMA bulk staging: one elected thread issues `cp.async.bulk.shared::cluster.global` per input
+//     column per tile into a CB_STAGES-deep shared-memory ring, completion via mbarrier tx-count;
+//     rows are then read from shared memory, so HBM traffic is exactly one read of every input
+//     column and bytes-in-flight do not cost registers;
+//   * aggregation: thread-private partial aggregates (registers for the ungrouped case, a
+//     bank-conflict-free shared-memory slice per thread for <= a few dozen groups), 64-bit fast
+//     path with an exact 128-bit escape, then a fixed-order intra-CTA tree and per-CTA partials in
+//     global memory merged by a finalize kernel => exact integer results, deterministic floats;
+//   * selection: warp-ballot + popc prefix for in-tile compaction and a decoupled look-back scan
+//     over tile descriptors for the global output offsets (single pass, stable row order).
+//
+// Replaces (reference, all CPU): DataFusion FilterExec / ProjectionExec / AggregateExec as wired by
+// native/core/src/execution/planner.rs:1230-1385 and the accumulators in
+// native/spark-expr/src/agg_funcs/{sum_decimal,avg_decimal,avg,sum_int}.rs.
+#ifndef CB_KERNELS_CUH
+#define CB_KERNELS_CUH
+
+namespace cb {
+
+} // namespace cb
+#include "cb_params.h"
+namespace cb {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA 1-D bulk copy (SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+CB_D u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+CB_D void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+CB_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+CB_D void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CB_D void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CB_DONE_%=;\n"
+        "bra CB_WAIT_%=;\n"
+        "CB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+CB_D u64 l2_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+CB_D void tma_bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar, u64 policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// staged tile view handed to the generated row program
+// ------------------------------------------------------------------------------------------------
+struct Tile {
+    const u8* col[CB_MAX_COLS]; // shared-memory slabs of the current stage
+    const u8* val[CB_MAX_COLS]; // shared-memory validity slabs (or nullptr)
+};
+template <typename T> CB_D T ld(const u8* slab, int r) { return reinterpret_cast<const T*>(slab)[r]; }
+CB_D bool ldv(const u8* vslab, int r) { return (vslab[r >> 3] >> (r & 7)) & 1; }
+
+CB_D void set_err(const PipeParams& p, int bit) { atomicOr(p.err, 1 << bit); }
+
+} // namespace cb
+
+// =================================================================================================
+// The generated program supplies (see codegen.cpp):
+//   CB_NCOLS, CB_COL_BYTES(c) (constexpr array cb_col_bytes[]), cb_col_has_val[],
+//   CB_TILE, CB_STAGES, CB_THREADS,
+//   and for the aggregate kernel: CB_WORDS (8-byte accumulator words per group), CB_G1 (ungrouped),
+//   cb_word_kind(w) (0 = i64 sum w/ 128-bit escape, 1 = f64 double-double hi, 2 = dd lo,
+//                   3 = i64 wrapping sum / count, 4 = min i64 key, 5 = max i64 key),
+//   `cb_row_agg(const cb::Tile&, int r, i64 grow, Acc&)`  or
+//   `cb_row_select(const cb::Tile&, int r, i64 grow, SelOut&) -> bool`.
+// =================================================================================================
+
+#if defined(CB_KERNEL_AGG) || defined(CB_KERNEL_SELECT)
+namespace cb {
+
+constexpr __host__ __device__ int stage_bytes() {
+    int b = 0;
+    for (int c = 0; c < CB_NCOLS; c++) {
+        b += (CB_TILE * cb_col_bytes(c) + 127) / 128 * 128;
+        if (cb_col_has_val(c)) b += (CB_TILE / 8 + 127) / 128 * 128;
+    }
+    return b;
+}
+
+// Issue the bulk copies of one tile into one stage.  Called by a single thread.
+CB_D void issue_tile(const PipeParams& p, int tile, u8* stage_base, u64* bar, u64 policy) {
+    i64 row0 = (i64)tile * CB_TILE;
+    i64 rem = p.n_rows - row0;
+    int rows = rem < CB_TILE ? (int)rem : CB_TILE;
+    u32 total = 0;
+    u32 bytes_c[CB_NCOLS], bytes_v[CB_NCOLS];
+#pragma unroll
+    for (int c = 0; c < CB_NCOLS; c++) {
+        bytes_c[c] = (u32)((rows * cb_col_bytes(c) + 15) & ~15);
+        bytes_v[c] = cb_col_has_val(c) ? (u32)((((rows + 7) >> 3) + 15) & ~15) : 0u;
+        total += bytes_c[c] + bytes_v[c];
+    }
+    mbar_expect_tx(bar, total);
+    u8* dst = stage_base;
+#pragma unroll
+    for (int c = 0; c < CB_NCOLS; c++) {
+        tma_bulk_g2s(dst, p.col[c] + row0 * cb_col_bytes(c), bytes_c[c], bar, policy);
+        dst += (CB_TILE * cb_col_bytes(c) + 127) / 128 * 128;
+        if (cb_col_has_val(c)) {
+            tma_bulk_g2s(dst, p.val[c] + (row0 >> 3), bytes_v[c], bar, policy);
+            dst += (CB_TILE / 8 + 127) / 128 * 128;
+        }
+    }
+}
+CB_D void tile_view(u8* stage_base, Tile& t) {
+    u8* ptr = stage_base;
+#pragma unroll
+    for (int c = 0; c < CB_NCOLS; c++) {
+        t.col[c] = ptr;
+        ptr += (CB_TILE * cb_col_bytes(c) + 127) / 128 * 128;
+        if (cb_col_has_val(c)) { t.val[c] = ptr; ptr += (CB_TILE / 8 + 127) / 128 * 128; }
+        else t.val[c] = nullptr;
+    }
+}
+
+} // namespace cb
+#endif
+
+// =================================================================================================
+// AGGREGATE kernel
+// =================================================================================================
+#ifdef CB_KERNEL_AGG
+namespace cb {
+struct Acc;
+CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc);
+
+// Thread-private accumulator file.  Word (g, w) of thread t lives at acc[(g*CB_WORDS + w)*CB_THREADS + t]
+// (8-byte words interleaved across threads => every warp access is bank-conflict-free no matter
+// which group each lane updates).  For the ungrouped case the words are registers.
+struct Acc {
+#if CB_G1
+    u64 r[CB_WORDS];
+#else
+    u64* base; // shared memory, already offset by threadIdx.x
+#endif
+    const PipeParams* p;
+
+    CB_D u64& word(int g, int w) {
+#if CB_G1
+        (void)g;
+        return r[w];
+#else
+        return base[(g * CB_WORDS + w) * CB_THREADS];
+#endif
+    }
+    // exact escape: add a full 128-bit value to the global spill accumulator (rare path)
+    CB_D void spill128(int g, int w, i128 v) {
+        u64* s = p->spill + ((size_t)g * CB_WORDS + w) * 2;
+        u64 old = atomicAdd((unsigned long long*)&s[0], (unsigned long long)v.lo);
+        u64 carry = (old + v.lo) < old ? 1ull : 0ull;
+        atomicAdd((unsigned long long*)&s[1], (unsigned long long)((u64)v.hi + carry));
+    }
+    // decimal / wide integer sum: 64-bit thread-private partial when |v| < 2^46, else exact escape
+    CB_D void add_i128(int g, int w, i128 v) {
+        i64 lo = (i64)v.lo;
+        bool small = (v.hi == (lo >> 63)) && (lo < (1ll << 46)) && (lo > -(1ll << 46));
+        if (small) word(g, w) += (u64)lo;
+        else spill128(g, w, v);
+    }
+    CB_D void add_i64_wide(int g, int w, i64 v) { add_i128(g, w, i128_from_i64(v)); }
+    CB_D void add_i64_wrap(int g, int w, i64 v) { word(g, w) += (u64)v; }          // SumInt Legacy, counts
+    CB_D void add_f64(int g, int w, double x) {                                     // double-double in words w, w+1
+        dd a;
+        a.hi = __longlong_as_double((i64)word(g, w));
+        a.lo = __longlong_as_double((i64)word(g, w + 1));
+        dd_add_double(a, x);
+        word(g, w) = (u64)__double_as_longlong(a.hi);
+        word(g, w + 1) = (u64)__double_as_longlong(a.lo);
+    }
+    CB_D void min_i64(int g, int w, i64 key) { i64 c = (i64)word(g, w); if (key < c) word(g, w) = (u64)key; }
+    CB_D void max_i64(int g, int w, i64 key) { i64 c = (i64)word(g, w); if (key > c) word(g, w) = (u64)key; }
+};
+
+CB_D u64 acc_identity(int kind) {
+    switch (kind) {
+    case 4: return 0x7fffffffffffffffull; // min
+    case 5: return 0x8000000000000000ull; // max
+    default: return 0ull;
+    }
+}
+
+// combine two partial words of the same kind (used in the intra-CTA tree)
+struct Pair128 { u64 a, b; };
+CB_D Pair128 shfl_xor_pair(Pair128 v, int m) {
+    Pair128 r;
+    r.a = __shfl_xor_sync(0xffffffffu, v.a, m);
+    r.b = __shfl_xor_sync(0xffffffffu, v.b, m);
+    return r;
+}
+
+extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(const __grid_constant__ PipeParams p) {
+    extern __shared__ __align__(128) u8 smem[];
+    constexpr int SB = stage_bytes();
+    u64* bars = reinterpret_cast<u64*>(smem);                 // CB_STAGES mbarriers
+    u8* stages = smem + 128;
+    u64* accmem = reinterpret_cast<u64*>(stages + (size_t)CB_STAGES * SB);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < CB_STAGES; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    Acc acc;
+    acc.p = &p;
+#if CB_G1
+#pragma unroll
+    for (int w = 0; w < CB_WORDS; w++) acc.r[w] = acc_identity(cb_word_kind(w));
+#else
+    acc.base = accmem + tid;
+    for (int g = 0; g < p.n_groups; g++)
+        for (int w = 0; w < CB_WORDS; w++) acc.word(g, w) = acc_identity(cb_word_kind(w));
+#endif
+    __syncthreads();
+
+    const int first = blockIdx.x, step = gridDim.x;
+    const int my_tiles = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;
+    u64 policy = 0;
+    if (tid == 0) {
+        policy = l2_evict_first_policy();
+        for (int k = 0; k < CB_STAGES - 1 && k < my_tiles; k++)
+            issue_tile(p, first + k * step, stages + (size_t)(k % CB_STAGES) * SB, &bars[k % CB_STAGES], policy);
+    }
+    for (int k = 0; k < my_tiles; k++) {
+        const int s = k % CB_STAGES;
+        if (tid == 0) {
+            int kn = k + CB_STAGES - 1; // refill the stage every thread released at the end of iteration k-1
+            if (kn < my_tiles) issue_tile(p, first + kn * step, stages + (size_t)(kn % CB_STAGES) * SB, &bars[kn % CB_STAGES], policy);
+        }
+        mbar_wait(&bars[s], (u32)((k / CB_STAGES) & 1));
+        Tile t;
+        tile_view(stages + (size_t)s * SB, t);
+        const int tile = first + k * step;
+        const i64 row0 = (i64)tile * CB_TILE;
+        const i64 rem = p.n_rows - row0;
+        const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
+#pragma unroll 2
+        for (int r = tid; r < rows; r += CB_THREADS) cb_row_agg(t, r, row0 + r, p, acc);
+        __syncthreads(); // stage s fully consumed
+    }
+
+    // ---- fold thread-private partials into one per-CTA partial per (group, word) -------------------
+    // fixed butterfly order inside a warp, fixed warp order across the CTA => deterministic.
+    constexpr int NW = CB_THREADS / 32;
+    __shared__ Pair128 wred[NW];
+    const int lane = tid & 31, wid = tid >> 5;
+    const int ng = p.n_groups;
+    u64* out = reinterpret_cast<u64*>(p.partials) + (size_t)blockIdx.x * ng * CB_WORDS * 2;
+    for (int g = 0; g < ng; g++) {
+#pragma unroll
+        for (int w = 0; w < CB_WORDS; w++) {
+            const int kind = cb_word_kind(w);
+            if (kind == 2) continue; // dd lo handled with its hi word
+            Pair128 v;
+            u64 x = acc.word(g, w);
+            if (kind == 0) { v.a = x; v.b = (u64)((i64)x >> 63); }              // sign-extend to 128
+            else if (kind == 1) { v.a = x; v.b = acc.word(g, w + 1); }           // (hi, lo) doubles
+            else { v.a = x; v.b = 0; }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                Pair128 o = shfl_xor_pair(v, m);
+                if (kind == 0) { i128 s = i128_add(mk128(v.a, (i64)v.b), mk128(o.a, (i64)o.b)); v.a = s.lo; v.b = (u64)s.hi; }
+                else if (kind == 1) {
+                    // butterfly: both partners must compute the same value => order operands by lane
+                    dd A, B;
+                    bool lowfirst = (lane & m) == 0;
+                    A.hi = __longlong_as_double((i64)(lowfirst ? v.a : o.a)); A.lo = __longlong_as_double((i64)(lowfirst ? v.b : o.b));
+                    B.hi = __longlong_as_double((i64)(lowfirst ? o.a : v.a)); B.lo = __longlong_as_double((i64)(lowfirst ? o.b : v.b));
+                    dd_add_dd(A, B);
+                    v.a = (u64)__double_as_longlong(A.hi); v.b = (u64)__double_as_longlong(A.lo);
+                }
+                else if (kind == 3) v.a += o.a;
+                else if (kind == 4) v.a = (u64)(((i64)o.a < (i64)v.a) ? (i64)o.a : (i64)v.a);
+                else v.a = (u64)(((i64)o.a > (i64)v.a) ? (i64)o.a : (i64)v.a);
+            }
+            if (lane == 0) wred[wid] = v;
+            __syncthreads();
+            if (tid == 0) {
+                Pair128 t = wred[0];
+                for (int i = 1; i < NW; i++) {
+                    Pair128 o = wred[i];
+                    if (kind == 0) { i128 s = i128_add(mk128(t.a, (i64)t.b), mk128(o.a, (i64)o.b)); t.a = s.lo; t.b = (u64)s.hi; }
+                    else if (kind == 1) {
+                        dd A, B;
+                        A.hi = __longlong_as_double((i64)t.a); A.lo = __longlong_as_double((i64)t.b);
+                        B.hi = __longlong_as_double((i64)o.a); B.lo = __longlong_as_double((i64)o.b);
+                        dd_add_dd(A, B);
+                        t.a = (u64)__double_as_longlong(A.hi); t.b = (u64)__double_as_longlong(A.lo);
+                    }
+                    else if (kind == 3) t.a += o.a;
+                    else if (kind == 4) t.a = (u64)(((i64)o.a < (i64)t.a) ? (i64)o.a : (i64)t.a);
+                    else t.a = (u64)(((i64)o.a > (i64)t.a) ? (i64)o.a : (i64)t.a);
+                }
+                out[((size_t)g * CB_WORDS + w) * 2 + 0] = t.a;
+                out[((size_t)g * CB_WORDS + w) * 2 + 1] = t.b;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+} // namespace cb
+#endif // CB_KERNEL_AGG
+
+
+// =================================================================================================
+// fold + finalize (aggregate pipelines): per-CTA partials -> running totals -> output columns
+// =================================================================================================
+#ifdef CB_KERNEL_AGG
+namespace cb {
+
+
+CB_D void set_err_raw(i32* err, int bit) { atomicOr(err, 1 << bit); }
+CB_D i128 fin_i128(const u64* T, int w) { return mk128(T[w * 2], (i64)T[w * 2 + 1]); }
+CB_D double fin_dd(const u64* T, int w) { return __longlong_as_double((i64)T[w * 2]); } // normalised: hi = round(hi + lo)
+CB_D void fin_store_i128(const FinParams& fp, int c, int g, i128 v, bool valid) {
+    reinterpret_cast<i128*>(fp.out[c])[g] = v; fp.outv[c][g] = valid ? 1 : 0;
+}
+CB_D void fin_store_i64(const FinParams& fp, int c, int g, i64 v, bool valid) {
+    reinterpret_cast<i64*>(fp.out[c])[g] = v; fp.outv[c][g] = valid ? 1 : 0;
+}
+CB_D void fin_store_f64(const FinParams& fp, int c, int g, double v, bool valid) {
+    reinterpret_cast<double*>(fp.out[c])[g] = v; fp.outv[c][g] = valid ? 1 : 0;
+}
+CB_D void fin_store_f32(const FinParams& fp, int c, int g, float v, bool valid) {
+    reinterpret_cast<float*>(fp.out[c])[g] = v; fp.outv[c][g] = valid ? 1 : 0;
+}
+CB_D void fin_store_u8(const FinParams& fp, int c, int g, int v, bool valid) {
+    fp.out[c][g] = (u8)v; fp.outv[c][g] = valid ? 1 : 0;
+}
+CB_D void fin_store_i32(const FinParams& fp, int c, int g, i32 v, bool valid, int width) {
+    if (width == 4) reinterpret_cast<i32*>(fp.out[c])[g] = v;
+    else if (width == 2) reinterpret_cast<short*>(fp.out[c])[g] = (short)v;
+    else reinterpret_cast<signed char*>(fp.out[c])[g] = (signed char)v;
+    fp.outv[c][g] = valid ? 1 : 0;
+}
+
+CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T);
+
+// one thread per (group, word): fixed CTA order => deterministic
+extern "C" __global__ void cb_fold(const __grid_constant__ FinParams fp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = fp.n_groups * CB_WORDS;
+    if (idx >= total) return;
+    int w = idx % CB_WORDS;
+    int kind = cb_word_kind(w);
+    if (kind == 2) return;
+    u64 a, b;
+    if (fp.first) { a = acc_identity(kind); b = 0; if (kind == 0) b = 0; }
+    else { a = fp.totals[idx * 2]; b = fp.totals[idx * 2 + 1]; }
+    for (int c = 0; c < fp.n_ctas; c++) {
+        const u64* P = fp.partials + ((size_t)c * total + idx) * 2;
+        u64 pa = P[0], pb = P[1];
+        if (kind == 0) { i128 s = i128_add(mk128(a, (i64)b), mk128(pa, (i64)pb)); a = s.lo; b = (u64)s.hi; }
+        else if (kind == 1) {
+            dd A, B;
+            A.hi = __longlong_as_double((i64)a); A.lo = __longlong_as_double((i64)b);
+            B.hi = __longlong_as_double((i64)pa); B.lo = __longlong_as_double((i64)pb);
+            dd_add_dd(A, B);
+            a = (u64)__double_as_longlong(A.hi); b = (u64)__double_as_longlong(A.lo);
+        }
+        else if (kind == 3) a += pa;
+        else if (kind == 4) a = (u64)(((i64)pa < (i64)a) ? (i64)pa : (i64)a);
+        else a = (u64)(((i64)pa > (i64)a) ? (i64)pa : (i64)a);
+    }
+    if (kind == 0) {
+        i128 s = i128_add(mk128(a, (i64)b), mk128(fp.spill[idx * 2], (i64)fp.spill[idx * 2 + 1]));
+        a = s.lo; b = (u64)s.hi;
+        fp.spill[idx * 2] = 0; fp.spill[idx * 2 + 1] = 0;
+    }
+    fp.totals[idx * 2] = a;
+    fp.totals[idx * 2 + 1] = b;
+}
+
+extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= fp.n_groups) return;
+    const u64* T = fp.totals + (size_t)g * CB_WORDS * 2;
+    fp.present[g] = (i64)T[CB_W_ROWS * 2] > 0 ? 1 : 0;
+    cb_finalize_group(fp, g, T);
+}
+
+} // namespace cb
+#endif // CB_KERNEL_AGG (fold/finalize)
+
+// =================================================================================================
+// SELECT kernel: filter + project + stable compaction (single pass, decoupled look-back)
+// =================================================================================================
+#ifdef CB_KERNEL_SELECT
+namespace cb {
+
+// tile descriptor: bits 63..62 status (0 invalid, 1 aggregate-only, 2 inclusive prefix), low 62 bits count
+#define CB_ST_AGG (1ull << 62)
+#define CB_ST_PREFIX (2ull << 62)
+#define CB_ST_MASK (3ull << 62)
+
+struct SelOut {
+    // filled by the generated program for one row: CB_NOUT values (raw 16-byte slots) + validity
+    u64 v[CB_NOUT][2];
+    bool valid[CB_NOUT];
+};
+
+CB_D bool cb_row_select(const Tile& t, int r, i64 grow, const PipeParams& p, SelOut& o);
+
+CB_D void store_out(u8* base, int bytes, i64 idx, const u64* v) {
+    if (bytes == 16) { ulonglong2 x; x.x = v[0]; x.y = v[1]; reinterpret_cast<ulonglong2*>(base)[idx] = x; }
+    else if (bytes == 8) reinterpret_cast<u64*>(base)[idx] = v[0];
+    else if (bytes == 4) reinterpret_cast<u32*>(base)[idx] = (u32)v[0];
+    else if (bytes == 2) reinterpret_cast<u16*>(base)[idx] = (u16)v[0];
+    else base[idx] = (u8)v[0];
+}
+
+extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_select(const __grid_constant__ PipeParams p) {
+    extern __shared__ __align__(128) u8 smem[];
+    constexpr int SB = stage_bytes();
+    constexpr int NW = CB_THREADS / 32;
+    constexpr int ROUNDS = CB_TILE / CB_THREADS;
+    static_assert(CB_TILE % CB_THREADS == 0, "tile must be a multiple of the CTA size");
+    u64* bars = reinterpret_cast<u64*>(smem);
+    u8* stages = smem + 128;
+    __shared__ i32 s_tile[CB_STAGES];
+    __shared__ i32 s_wcount[ROUNDS][NW];
+    __shared__ i64 s_tile_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < CB_STAGES; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    u64 policy = 0;
+    // tiles are handed out in increasing order by a global ticket so that every predecessor of a
+    // tile is already owned by a resident CTA (forward progress of the look-back).
+    if (tid == 0) {
+        policy = l2_evict_first_policy();
+        for (int k = 0; k < CB_STAGES - 1; k++) {
+            int t = atomicAdd(p.tile_counter, 1);
+            s_tile[k] = t;
+            if (t < p.n_tiles) issue_tile(p, t, stages + (size_t)k * SB, &bars[k], policy);
+        }
+    }
+    __syncthreads();
+    for (int k = 0;; k++) {
+        const int s = k % CB_STAGES;
+        if (tid == 0) {
+            int kn = k + CB_STAGES - 1, sn = kn % CB_STAGES;
+            int t = atomicAdd(p.tile_counter, 1);
+            s_tile[sn] = t;
+            if (t < p.n_tiles) issue_tile(p, t, stages + (size_t)sn * SB, &bars[sn], policy);
+        }
+        const int tile = s_tile[s]; // written >= one __syncthreads ago
+        if (tile >= p.n_tiles) break;
+        mbar_wait(&bars[s], (u32)((k / CB_STAGES) & 1));
+        Tile t;
+        tile_view(stages + (size_t)s * SB, t);
+        const i64 row0 = (i64)tile * CB_TILE;
+        const i64 rem = p.n_rows - row0;
+        const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
+
+        // evaluate: row = round*CB_THREADS + tid keeps (round, warp, lane) order == row order
+        SelOut o[ROUNDS];
+        bool keep[ROUNDS];
+        u32 bal[ROUNDS];
+#pragma unroll
+        for (int q = 0; q < ROUNDS; q++) {
+            int r = q * CB_THREADS + tid;
+            keep[q] = (r < rows) ? cb_row_select(t, r, row0 + r, p, o[q]) : false;
+            bal[q] = __ballot_sync(0xffffffffu, keep[q]);
+            if (lane == 0) s_wcount[q][wid] = __popc(bal[q]);
+        }
+        __syncthreads(); // also: stage s fully consumed
+        // exclusive prefix over (round, warp) -- tiny, every thread recomputes what it needs
+        int tile_total = 0, my_base[ROUNDS];
+#pragma unroll
+        for (int q = 0; q < ROUNDS; q++) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                if (w == wid) my_base[q] = tile_total;
+                tile_total += s_wcount[q][w];
+            }
+        }
+        // decoupled look-back (one warp)
+        if (wid == 0) {
+            i64 excl = 0;
+            if (tile == 0) {
+                if (lane == 0) { __threadfence(); atomicExch((unsigned long long*)&p.tile_state[0], CB_ST_PREFIX | (u64)tile_total); }
+            } else {
+                if (lane == 0) { atomicExch((unsigned long long*)&p.tile_state[tile], CB_ST_AGG | (u64)tile_total); }
+                int look = tile - 1;
+                while (true) {
+                    int idx = look - lane;
+                    u64 d = idx >= 0 ? *((volatile u64*)&p.tile_state[idx]) : CB_ST_PREFIX; // before tile 0: prefix 0
+                    u32 invalid = __ballot_sync(0xffffffffu, (d & CB_ST_MASK) == 0);
+                    if (invalid) continue; // spin until the 32-window is published
+                    u32 isprefix = __ballot_sync(0xffffffffu, (d & CB_ST_MASK) == CB_ST_PREFIX);
+                    int firstp = isprefix ? __ffs(isprefix) - 1 : 32;
+                    i64 c = (lane <= firstp) ? (i64)(d & ~CB_ST_MASK) : 0;
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+                    excl += c;
+                    if (isprefix) break;
+                    look -= 32;
+                }
+                if (lane == 0) { __threadfence(); atomicExch((unsigned long long*)&p.tile_state[tile], CB_ST_PREFIX | (u64)(excl + tile_total)); }
+            }
+            if (lane == 0) {
+                s_tile_base = excl;
+                if (tile == p.n_tiles - 1) *p.out_count = excl + tile_total;
+            }
+        }
+        __syncthreads();
+        const i64 base = s_tile_base;
+#pragma unroll
+        for (int q = 0; q < ROUNDS; q++) {
+            i64 wbase = base + my_base[q];
+            if (keep[q]) {
+                i64 idx = wbase + __popc(bal[q] & ((1u << lane) - 1u));
+#pragma unroll
+                for (int c = 0; c < CB_NOUT; c++) store_out(p.out[c], cb_out_bytes(c), idx, o[q].v[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < CB_NOUT; c++) {
+                if (!cb_out_nullable(c)) continue;
+                // this warp's kept rows occupy output bits [wbase, wbase + popc): scatter their validity
+                // compress vb by the keep mask (order-preserving) -- lane j owns kept-rank j
+                u32 packed = 0;
+                {
+                    u32 km = bal[q];
+                    int rank = __popc(km & ((1u << lane) - 1u));
+                    u32 bit = (keep[q] && o[q].valid[c]) ? (1u << rank) : 0u;
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) bit |= __shfl_xor_sync(0xffffffffu, bit, m);
+                    packed = bit;
+                }
+                int cnt = __popc(bal[q]);
+                if (lane == 0 && cnt > 0) {
+                    u64 bits = (u64)packed << (wbase & 31);
+                    atomicOr(&p.out_valid[c][wbase >> 5], (u32)bits);
+                    if ((bits >> 32) != 0) atomicOr(&p.out_valid[c][(wbase >> 5) + 1], (u32)(bits >> 32));
+                }
+            }
+        }
+        __syncthreads(); // s_wcount / s_tile_base reuse
+    }
+}
+
+} // namespace cb
+#endif // CB_KERNEL_SELECT
+
+#endif // CB_KERNELS_CUH

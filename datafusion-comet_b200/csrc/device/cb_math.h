@@ -311,6 +311,55 @@ CB_HD bool avg_decimal_eval(i128 sum, i64 count, int scaler_exp, int target_p, i
     return true;
 }
 
+
+// ---- fast paths: both operands fit in 64 bits (every d(p<=18) value does) ----------------------------
+CB_HD i128 dec_mul_plain(i128 a, i128 b, bool& err) {
+    if (i128_fits_i64(a) && i128_fits_i64(b)) return mul_i64_i64((i64)a.lo, (i64)b.lo); // cannot overflow i128
+    return i128_mul_checked(a, b, err);
+}
+CB_HD bool wide_mul_fast(i128 l, i128 r, int scale_diff, int p_out, i128& out) {
+    if (scale_diff == 0 && i128_fits_i64(l) && i128_fits_i64(r)) {
+        i128 p = mul_i64_i64((i64)l.lo, (i64)r.lo);
+        if (!dec_fits_p(p, p_out)) return false;
+        out = p;
+        return true;
+    }
+    return wide_mul(l, r, scale_diff, p_out, out);
+}
+CB_HD bool i64_add_overflow(i64 a, i64 b, i64& r) { r = (i64)((u64)a + (u64)b); return ((a ^ r) & (b ^ r)) < 0; }
+CB_HD bool i64_sub_overflow(i64 a, i64 b, i64& r) { r = (i64)((u64)a - (u64)b); return ((a ^ b) & (a ^ r)) < 0; }
+CB_HD bool i64_mul_overflow(i64 a, i64 b, i64& r) { i128 p = mul_i64_i64(a, b); r = (i64)p.lo; return !i128_fits_i64(p); }
+
+// ---- overflow certificate for decimal sums ------------------------------------------------------
+// The reference adds row by row and nulls the sum as soon as a running prefix leaves the precision
+// (agg_funcs/sum_decimal.rs:418-439).  A parallel sum reproduces that exactly whenever no ordering
+// of the addends can overflow: n * max|v| <= 10^p - 1.  bitlen(v) bounds |v| <= 2^bitlen.
+CB_HD int clz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+CB_HD i64 i128_bitlen(i128 v) {
+    u64 s = (u64)(v.hi >> 63);
+    u64 hi = (u64)v.hi ^ s, lo = v.lo ^ s;
+    return hi ? 128 - clz64(hi) : 64 - clz64(lo);
+}
+// 0: the sum fits for every ordering (result = exact total); 1: it overflows for every ordering
+// (same-sign certificate not needed: the total itself is out of range); 2: order-dependent.
+CB_HD int sum_certificate(i64 n, i64 max_bitlen, i128 total, int precision) {
+    if (n <= 0) return 0;
+    u128 bound = pow10_u128(precision); // 10^p
+    // bit length of 10^p - 1
+    u64 bhi = bound.hi, blo = bound.lo - 1; if (bound.lo == 0) bhi -= 1;
+    int blen = bhi ? 128 - clz64(bhi) : 64 - clz64(blo);
+    int nb = 64 - clz64((u64)n);           // n <= 2^nb
+    if (nb + (int)max_bitlen <= blen - 1) return 0;
+    if (nb + (int)max_bitlen <= 126 && !dec_fits_p(total, precision)) return 1;
+    return 2;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Spark murmur3  (spark-expr/src/hash_funcs/murmur3.rs:73-137; per-type rules hash_funcs/utils.rs)
 // ------------------------------------------------------------------------------------------------

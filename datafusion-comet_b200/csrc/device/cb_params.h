@@ -1,0 +1,44 @@
+// cb_params.h -- kernel parameter blocks shared by the device skeletons (cb_kernels.cuh) and the host
+// executor (exec.cpp).  Plain structs over the cb_math.h typedefs so both sides agree on layout.
+#ifndef CB_PARAMS_H
+#define CB_PARAMS_H
+#include "cb_math.h"
+namespace cb {
+
+// pipeline kernels (filled by exec.cpp; passed __grid_constant__)
+#define CB_MAX_COLS 24
+#define CB_MAX_OUT 16
+#define CB_MAX_KEYS 4
+
+struct PipeParams {
+    const u8* col[CB_MAX_COLS];      // input column value buffers (16-byte aligned, padded)
+    const u8* val[CB_MAX_COLS];      // validity bitmaps (LSB order) or nullptr
+    i64 n_rows;
+    i32 n_tiles;
+    i32 n_groups;                    // dense aggregate: number of group slots (>=1)
+    i32 key_card[CB_MAX_KEYS];       // dense aggregate: cardinality of each key (incl. null slot)
+    u8* out[CB_MAX_OUT];             // select: output value buffers
+    u32* out_valid[CB_MAX_OUT];      // select: output validity bitmap words (zeroed) or nullptr
+    u64* tile_state;                 // select: look-back descriptors [n_tiles]
+    i32* tile_counter;               // select: dynamic tile ticket
+    i64* out_count;                  // select: total rows kept
+    u8* partials;                    // agg: per-CTA partial slots [grid][n_groups][CB_WORDS] x 16 B
+    u64* spill;                      // agg: exact 128-bit escape accumulators [n_groups][CB_WORDS][2]
+    i32* err;                        // error flags (bit 0: arithmetic overflow, bit1: ansi error...)
+};
+
+
+// fold / finalize kernels of aggregate pipelines
+struct FinParams {
+    const u64* partials; // [n_ctas][n_groups][CB_WORDS][2]
+    u64* spill;          // [n_groups][CB_WORDS][2]  (zeroed again after folding)
+    u64* totals;         // [n_groups][CB_WORDS][2]
+    i32 n_ctas, n_groups, first;
+    u8* out[CB_MAX_OUT];   // finalize: value buffers, one element per group
+    u8* outv[CB_MAX_OUT];  // finalize: validity, one byte per group
+    u8* present;           // finalize: 1 if the group saw at least one row
+    i32* err;
+};
+
+} // namespace cb
+#endif

@@ -1,0 +1,1090 @@
+// exec.cpp -- executor: sources, fused pipelines, dense aggregation, Arrow export.
+#include "exec.h"
+
+#include "aot_kernels.h"
+#include "device/cb_params.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <set>
+#include <sstream>
+
+namespace cb200 {
+
+// error bits raised by kernels (device/cb_kernels.cuh set_err)
+enum { ERR_I128_OVERFLOW = 0, ERR_ANSI_OVERFLOW = 1, ERR_ORDER_DEPENDENT = 2 };
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw ExecError(2, "", std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+DeviceBuf::DeviceBuf(size_t n) {
+    bytes = (n + 255) / 256 * 256 + 256; // padded: TMA bulk copies round sizes up to 16 B
+    cuda_check(cudaMalloc(&ptr, bytes), "cudaMalloc");
+}
+DeviceBuf::~DeviceBuf() {
+    if (owned && ptr) cudaFree(ptr);
+}
+
+void ExecContext::check_device_errors() {
+    cuda_check(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream), "error flag copy");
+    cuda_check(cudaStreamSynchronize(stream), "stream sync");
+    int e = *h_err;
+    if (!e) return;
+    cudaMemsetAsync(d_err, 0, sizeof(int), stream);
+    if (e & (1 << ERR_ANSI_OVERFLOW))
+        throw ExecError(10, "ARITHMETIC_OVERFLOW", "[ARITHMETIC_OVERFLOW] overflow in ANSI mode");
+    if (e & (1 << ERR_I128_OVERFLOW))
+        throw ExecError(11, "", "Arrow error: Arithmetic overflow: Overflow happened on decimal arithmetic"); // arrow-arith checked ops
+    if (e & (1 << ERR_ORDER_DEPENDENT))
+        throw ExecError(12, "", "decimal SUM/AVG may overflow depending on row order; the row-ordered fallback is not built yet");
+    throw ExecError(13, "", "device error flags " + std::to_string(e));
+}
+
+// =================================================================================================
+// expression helpers
+// =================================================================================================
+static ExprP clone_expr(const ExprP& e) {
+    auto c = std::make_shared<Expr>(*e);
+    for (auto& ch : c->children) ch = clone_expr(ch);
+    return c;
+}
+// replace Bound(i) by cur[i]
+static ExprP substitute(const ExprP& e, const std::vector<ExprP>& cur) {
+    if (e->kind == ExprKind::Bound) {
+        if (e->index < 0 || e->index >= (int)cur.size()) throw PlanError("bound reference out of range while fusing");
+        return clone_expr(cur[e->index]);
+    }
+    auto c = std::make_shared<Expr>(*e);
+    for (auto& ch : c->children) ch = substitute(ch, cur);
+    return c;
+}
+static void collect_bound(const ExprP& e, std::vector<int>& order, std::set<int>& seen) {
+    if (e->kind == ExprKind::Bound) {
+        if (!seen.count(e->index)) { seen.insert(e->index); order.push_back(e->index); }
+        return;
+    }
+    for (auto& c : e->children) collect_bound(c, order, seen);
+}
+static void rewrite_bound(const ExprP& e, const std::map<int, int>& slot_of) {
+    if (e->kind == ExprKind::Bound) { e->index = slot_of.at(e->index); return; }
+    for (auto& c : e->children) rewrite_bound(c, slot_of);
+}
+
+// =================================================================================================
+// sources
+// =================================================================================================
+static Phys phys_of(const DType& t) {
+    switch (t.id) {
+    case TypeId::Bool: return Phys::Bitmap;
+    case TypeId::Int8: return Phys::I8;
+    case TypeId::Int16: return Phys::I16;
+    case TypeId::Int32: case TypeId::Date: return Phys::I32;
+    case TypeId::Int64: case TypeId::Timestamp: case TypeId::TimestampNtz: return Phys::I64;
+    case TypeId::Float32: return Phys::F32;
+    case TypeId::Float64: return Phys::F64;
+    case TypeId::Decimal: return Phys::I128;
+    default: return Phys::I32;
+    }
+}
+
+static DType dtype_from_format(const char* f) {
+    std::string s = f ? f : "";
+    if (s == "b") return mk_type(TypeId::Bool);
+    if (s == "c") return mk_type(TypeId::Int8);
+    if (s == "s") return mk_type(TypeId::Int16);
+    if (s == "i") return mk_type(TypeId::Int32);
+    if (s == "l") return mk_type(TypeId::Int64);
+    if (s == "f") return mk_type(TypeId::Float32);
+    if (s == "g") return mk_type(TypeId::Float64);
+    if (s == "u") return mk_type(TypeId::String);
+    if (s == "z") return mk_type(TypeId::Binary);
+    if (s == "tdD") return mk_type(TypeId::Date);
+    if (s.rfind("tsu:", 0) == 0) return mk_type(s.size() > 4 ? TypeId::Timestamp : TypeId::TimestampNtz);
+    if (s.rfind("d:", 0) == 0) {
+        int p = 0, sc = 0, bits = 128;
+        if (sscanf(s.c_str(), "d:%d,%d,%d", &p, &sc, &bits) < 2) throw PlanError("bad decimal format " + s);
+        if (bits != 128) throw Unsupported("decimal bit width " + std::to_string(bits));
+        return mk_decimal(p, sc);
+    }
+    throw Unsupported("Arrow format '" + s + "' is outside the GPU hot path");
+}
+
+struct SchemaOnlySource : ExecNode { // build-time stand-in: no data
+    bool next(Batch&) override { return false; }
+};
+
+// ---- Arrow C stream -> device chunks (ScanExec: operators/scan.rs:46-170) -------------------------
+struct StreamSource : ExecNode {
+    ExecContext* ctx;
+    ArrowArrayStream* stream;
+    bool schema_checked = false, eof = false;
+    std::vector<bool> col_is_dict;
+    std::vector<int> dict_index_width;
+    std::vector<DictionaryP> dicts; // plan-global dictionary per dict column
+
+    StreamSource(ExecContext* c, ArrowArrayStream* s, const std::vector<DType>& fields) : ctx(c), stream(s) { schema = fields; }
+    ~StreamSource() override {
+        if (stream && stream->release) stream->release(stream); // ownership was transferred to native (planner.rs:1725-1737)
+    }
+
+    void check_schema() {
+        ArrowSchema sc;
+        memset(&sc, 0, sizeof(sc));
+        if (stream->get_schema(stream, &sc) != 0) {
+            const char* m = stream->get_last_error ? stream->get_last_error(stream) : nullptr;
+            throw ExecError(3, "", std::string("Failed to import ArrowArrayStream schema: ") + (m ? m : "?"));
+        }
+        if (sc.n_children != (int64_t)schema.size()) {
+            int64_t n = sc.n_children;
+            if (sc.release) sc.release(&sc);
+            throw PlanError("scan declares " + std::to_string(schema.size()) + " fields but the stream has " + std::to_string(n));
+        }
+        col_is_dict.assign(schema.size(), false);
+        dict_index_width.assign(schema.size(), 4);
+        dicts.assign(schema.size(), nullptr);
+        for (size_t i = 0; i < schema.size(); i++) {
+            ArrowSchema* ch = sc.children[i];
+            if (ch->dictionary) {
+                DType vt = dtype_from_format(ch->dictionary->format);
+                DType it = dtype_from_format(ch->format);
+                if (!vt.is_string() || !it.is_integer()) throw Unsupported("dictionary column that is not int -> utf8");
+                if (!schema[i].is_string()) throw PlanError("scan field " + std::to_string(i) + " is " + schema[i].str() + " but the stream column is a string dictionary");
+                col_is_dict[i] = true;
+                dict_index_width[i] = it.arrow_width();
+                if (it.arrow_width() == 8) throw Unsupported("int64 dictionary indices");
+                dicts[i] = std::make_shared<Dictionary>();
+            } else {
+                DType t = dtype_from_format(ch->format);
+                bool ok = t == schema[i] || (t.is_decimal() && schema[i].is_decimal() && t.scale == schema[i].scale) ||
+                          (t.id == TypeId::Timestamp && schema[i].id == TypeId::TimestampNtz) || (t.id == TypeId::TimestampNtz && schema[i].id == TypeId::Timestamp);
+                if (!ok) throw PlanError("scan field " + std::to_string(i) + " is " + schema[i].str() + " but the stream column is " + t.str());
+            }
+        }
+        if (sc.release) sc.release(&sc);
+        schema_checked = true;
+    }
+
+    bool next(Batch& out) override {
+        if (!schema_checked) check_schema();
+        if (eof) return false;
+        std::vector<ArrowArray> arrs;
+        int64_t total = 0;
+        while (total < ctx->chunk_rows) {
+            ArrowArray a;
+            memset(&a, 0, sizeof(a));
+            if (stream->get_next(stream, &a) != 0) {
+                const char* m = stream->get_last_error ? stream->get_last_error(stream) : nullptr;
+                for (auto& x : arrs) if (x.release) x.release(&x);
+                throw ExecError(3, "", std::string("ArrowArrayStream get_next failed: ") + (m ? m : "?"));
+            }
+            if (!a.release) { eof = true; break; } // end of stream
+            if (a.length > 0) { total += a.length; arrs.push_back(a); }
+            else a.release(&a);
+        }
+        if (arrs.empty()) return false;
+        try {
+            upload(arrs, total, out);
+        } catch (...) {
+            for (auto& x : arrs) if (x.release) x.release(&x);
+            throw;
+        }
+        cuda_check(cudaStreamSynchronize(ctx->stream), "H2D copies"); // host buffers are released right after
+        for (auto& x : arrs) if (x.release) x.release(&x);
+        return true;
+    }
+
+    // unify a batch dictionary with the plan-global one; returns remap table (empty = identity)
+    std::vector<int32_t> unify_dict(size_t col, const ArrowArray* d) {
+        Dictionary& g = *dicts[col];
+        const int32_t* off = (const int32_t*)d->buffers[1] + d->offset;
+        const char* chars = (const char*)d->buffers[2];
+        std::vector<int32_t> remap((size_t)d->length);
+        bool identity = true;
+        for (int64_t k = 0; k < d->length; k++) {
+            std::string v(chars + off[k], (size_t)(off[k + 1] - off[k]));
+            auto it = std::find(g.values.begin(), g.values.end(), v);
+            int32_t code;
+            if (it == g.values.end()) { code = (int32_t)g.values.size(); g.values.push_back(v); }
+            else code = (int32_t)(it - g.values.begin());
+            remap[(size_t)k] = code;
+            if (code != k) identity = false;
+        }
+        if (identity) remap.clear();
+        return remap;
+    }
+
+    void upload(std::vector<ArrowArray>& arrs, int64_t total, Batch& out) {
+        out.n_rows = total;
+        out.cols.clear();
+        out.cols.resize(schema.size());
+        cudaStream_t st = ctx->stream;
+        for (size_t c = 0; c < schema.size(); c++) {
+            Column& col = out.cols[c];
+            col.type = schema[c];
+            bool any_nulls = false;
+            for (auto& a : arrs) {
+                ArrowArray* ch = a.children[c];
+                if (ch->null_count != 0 && ch->buffers[0]) any_nulls = true;
+            }
+            if (any_nulls) {
+                col.validity = std::make_shared<DeviceBuf>((size_t)(total + 7) / 8 + 8);
+                cuda_check(cudaMemsetAsync(col.validity->ptr, 0, col.validity->bytes, st), "memset validity");
+            }
+            std::vector<DeviceBufP> temps;
+            if (col_is_dict[c]) {
+                col.is_dict = true;
+                col.dict = dicts[c];
+                int w = dict_index_width[c];
+                bool need_remap = false;
+                std::vector<std::vector<int32_t>> remaps;
+                for (auto& a : arrs) {
+                    remaps.push_back(unify_dict(c, a.children[c]->dictionary));
+                    if (!remaps.back().empty()) need_remap = true;
+                }
+                if (!need_remap) {
+                    col.phys = w == 1 ? Phys::I8 : w == 2 ? Phys::I16 : Phys::I32;
+                    col.data = std::make_shared<DeviceBuf>((size_t)total * w);
+                } else {
+                    col.phys = Phys::I32;
+                    col.data = std::make_shared<DeviceBuf>((size_t)total * 4);
+                }
+                int64_t row = 0;
+                for (size_t k = 0; k < arrs.size(); k++) {
+                    ArrowArray* ch = arrs[k].children[c];
+                    const char* src = (const char*)ch->buffers[1] + ch->offset * w;
+                    if (!need_remap) {
+                        cuda_check(cudaMemcpyAsync((char*)col.data->ptr + row * w, src, (size_t)ch->length * w, cudaMemcpyHostToDevice, st), "H2D dict codes");
+                    } else {
+                        auto tmp = std::make_shared<DeviceBuf>((size_t)ch->length * w);
+                        temps.push_back(tmp);
+                        cuda_check(cudaMemcpyAsync(tmp->ptr, src, (size_t)ch->length * w, cudaMemcpyHostToDevice, st), "H2D dict codes");
+                        std::vector<int32_t> table = remaps[k];
+                        if (table.empty()) { table.resize((size_t)ch->dictionary->length); for (size_t i = 0; i < table.size(); i++) table[i] = (int32_t)i; }
+                        auto dt = std::make_shared<DeviceBuf>(table.size() * 4 + 4);
+                        temps.push_back(dt);
+                        cuda_check(cudaMemcpyAsync(dt->ptr, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st), "H2D remap table");
+                        cuda_check(cudaStreamSynchronize(st), "remap table copy"); // table is a stack temporary
+                        launch_remap_codes(tmp->ptr, w, ch->length, (const int*)dt->ptr, (int)table.size(), (int*)col.data->ptr + row, st);
+                    }
+                    row += ch->length;
+                }
+            } else if (schema[c].is_string()) {
+                // plain Utf8: ship offsets + chars; key columns are dictionary-encoded on the device
+                int64_t total_chars = 0;
+                for (auto& a : arrs) {
+                    ArrowArray* ch = a.children[c];
+                    const int32_t* off = (const int32_t*)ch->buffers[1] + ch->offset;
+                    total_chars += off[ch->length] - off[0];
+                }
+                if (total_chars > INT32_MAX) throw Unsupported("more than 2 GiB of string data in one chunk");
+                col.offsets = std::make_shared<DeviceBuf>((size_t)(total + 1) * 4);
+                col.chars = std::make_shared<DeviceBuf>((size_t)total_chars + 16);
+                std::vector<int32_t> offs((size_t)total + 1);
+                int64_t row = 0;
+                int32_t base = 0;
+                for (auto& a : arrs) {
+                    ArrowArray* ch = a.children[c];
+                    const int32_t* off = (const int32_t*)ch->buffers[1] + ch->offset;
+                    for (int64_t i = 0; i < ch->length; i++) offs[(size_t)(row + i)] = base + (off[i] - off[0]);
+                    int32_t nchars = off[ch->length] - off[0];
+                    if (nchars) cuda_check(cudaMemcpyAsync((char*)col.chars->ptr + base, (const char*)ch->buffers[2] + off[0], (size_t)nchars, cudaMemcpyHostToDevice, st), "H2D chars");
+                    base += nchars;
+                    row += ch->length;
+                }
+                offs[(size_t)total] = base;
+                cuda_check(cudaMemcpyAsync(col.offsets->ptr, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st), "H2D offsets");
+                cuda_check(cudaStreamSynchronize(st), "offsets copy");
+                col.phys = Phys::I32;
+            } else {
+                col.phys = phys_of(schema[c]);
+                int w = schema[c].arrow_width();
+                if (w == 0) { // boolean values: bitmap
+                    col.data = std::make_shared<DeviceBuf>((size_t)(total + 7) / 8 + 8);
+                    cuda_check(cudaMemsetAsync(col.data->ptr, 0, col.data->bytes, st), "memset bool");
+                    int64_t row = 0;
+                    for (auto& a : arrs) {
+                        ArrowArray* ch = a.children[c];
+                        append_bits((uint32_t*)col.data->ptr, row, (const uint8_t*)ch->buffers[1], ch->offset, ch->length, temps);
+                        row += ch->length;
+                    }
+                } else {
+                    col.data = std::make_shared<DeviceBuf>((size_t)total * w);
+                    int64_t row = 0;
+                    for (auto& a : arrs) {
+                        ArrowArray* ch = a.children[c];
+                        cuda_check(cudaMemcpyAsync((char*)col.data->ptr + row * w, (const char*)ch->buffers[1] + ch->offset * w, (size_t)ch->length * w,
+                                                   cudaMemcpyHostToDevice, st), "H2D column");
+                        row += ch->length;
+                    }
+                }
+            }
+            if (any_nulls) {
+                int64_t row = 0, nulls = 0;
+                for (auto& a : arrs) {
+                    ArrowArray* ch = a.children[c];
+                    bool has = ch->null_count != 0 && ch->buffers[0];
+                    append_bits((uint32_t*)col.validity->ptr, row, has ? (const uint8_t*)ch->buffers[0] : nullptr, ch->offset, ch->length, temps);
+                    nulls += has ? (ch->null_count < 0 ? 1 : ch->null_count) : 0;
+                    row += ch->length;
+                }
+                col.null_count = nulls;
+            }
+            if (!temps.empty()) cuda_check(cudaStreamSynchronize(st), "temp buffers");
+        }
+    }
+
+    // append n bits of a host bitmap (nullptr = ones) at dst bit offset `row`
+    void append_bits(uint32_t* dst, int64_t row, const uint8_t* src, int64_t src_off, int64_t n, std::vector<DeviceBufP>& temps) {
+        if (n <= 0) return;
+        if (src && (row & 7) == 0 && (src_off & 7) == 0 && ((n & 7) == 0)) {
+            cuda_check(cudaMemcpyAsync((char*)dst + (row >> 3), src + (src_off >> 3), (size_t)(n >> 3), cudaMemcpyHostToDevice, ctx->stream), "H2D bitmap");
+            return;
+        }
+        const uint8_t* dsrc = nullptr;
+        int64_t doff = 0;
+        if (src) {
+            int64_t b0 = src_off >> 3, b1 = (src_off + n + 7) >> 3;
+            auto tmp = std::make_shared<DeviceBuf>((size_t)(b1 - b0) + 8);
+            temps.push_back(tmp);
+            cuda_check(cudaMemcpyAsync(tmp->ptr, src + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, ctx->stream), "H2D bitmap");
+            dsrc = (const uint8_t*)tmp->ptr;
+            doff = src_off & 7;
+        }
+        launch_bitmap_append(dst, row, dsrc, doff, n, ctx->stream);
+    }
+};
+
+// ---- caller-owned device-resident table -------------------------------------------------------------
+struct TableSource : ExecNode {
+    std::shared_ptr<DeviceTable> table;
+    bool done = false;
+    TableSource(std::shared_ptr<DeviceTable> t, const std::vector<DType>& fields) : table(std::move(t)) {
+        schema = fields;
+        if (table->cols.size() != fields.size()) throw PlanError("bound device table has " + std::to_string(table->cols.size()) + " columns, scan declares " + std::to_string(fields.size()));
+    }
+    bool next(Batch& out) override {
+        if (done) return false;
+        done = true;
+        out.n_rows = table->n_rows;
+        out.cols = table->cols;
+        return out.n_rows > 0;
+    }
+};
+
+// =================================================================================================
+// fused pipeline nodes
+// =================================================================================================
+struct FusedBase : ExecNode {
+    ExecContext* ctx;
+    ExecNodeP child;
+    std::vector<ExprP> predicates;   // over child columns (Bound.index = child column)
+    std::vector<int> used_cols;      // child columns staged, in slot order
+    std::map<int, int> slot_of;
+
+    // build the staged-column list for one batch signature
+    std::vector<SourceCol> stage_cols(const Batch* b) const {
+        std::vector<SourceCol> cols;
+        for (int ci : used_cols) {
+            SourceCol sc;
+            sc.src_index = ci;
+            sc.type = child->schema[ci];
+            if (b) {
+                const Column& c = b->cols[ci];
+                sc.phys = c.phys;
+                sc.has_validity = c.validity != nullptr;
+                if (c.is_dict) sc.phys = c.phys == Phys::I8 ? Phys::I8 : c.phys == Phys::I16 ? Phys::I16 : Phys::Dict32;
+            } else {
+                sc.phys = sc.type.is_string() ? Phys::Dict32 : phys_of(sc.type);
+                sc.has_validity = false;
+            }
+            cols.push_back(sc);
+        }
+        return cols;
+    }
+    void assign_slots(const std::vector<ExprP>& roots) {
+        std::set<int> seen;
+        for (auto& e : roots) collect_bound(e, used_cols, seen);
+        for (size_t i = 0; i < used_cols.size(); i++) slot_of[used_cols[i]] = (int)i;
+    }
+    static std::vector<ExprP> to_slots(const std::vector<ExprP>& es, const std::map<int, int>& slot_of) {
+        std::vector<ExprP> out;
+        for (auto& e : es) {
+            ExprP c = clone_expr(e);
+            rewrite_bound(c, slot_of);
+            out.push_back(c);
+        }
+        return out;
+    }
+    void fill_inputs(cb::PipeParams& p, const Batch& b, int tile) const {
+        memset(&p, 0, sizeof(p));
+        for (size_t i = 0; i < used_cols.size(); i++) {
+            const Column& c = b.cols[used_cols[i]];
+            if (!c.data) throw Unsupported("column " + std::to_string(used_cols[i]) + " (" + c.type.str() + ") has no fixed-width device representation");
+            p.col[i] = (const cb::u8*)c.data->ptr;
+            p.val[i] = c.validity ? (const cb::u8*)c.validity->ptr : nullptr;
+        }
+        p.n_rows = b.n_rows;
+        p.n_tiles = (int)((b.n_rows + tile - 1) / tile);
+        p.err = ctx->d_err;
+    }
+    void launch(cudaKernel_t k, dim3 grid, dim3 block, size_t smem, void* params) {
+        cuda_check(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
+        void* args[] = {params};
+        cuda_check(cudaLaunchKernel((const void*)k, grid, block, args, smem, ctx->stream), "kernel launch");
+        ctx->kernel_launches++;
+    }
+};
+
+static const size_t SMEM_BUDGET = 200 * 1024;
+
+// ---- filter + project -> compacted batch ----------------------------------------------------------------
+struct SelectNode : FusedBase {
+    std::vector<ExprP> outputs;
+    DeviceBufP tile_state, counters; // reused across batches
+
+    PipelineSpec make_spec(const Batch* b) const {
+        PipelineSpec s;
+        s.cols = stage_cols(b);
+        s.predicates = to_slots(predicates, slot_of);
+        s.outputs = to_slots(outputs, slot_of);
+        s.sink = SinkKind::Select;
+        s.threads = 256;
+        s.tile = 1024;
+        int sb = 0;
+        for (auto& c : s.cols) {
+            int w = phys_bytes(c.phys);
+            sb += ((w == 0 ? s.tile / 8 : s.tile * w) + 127) / 128 * 128;
+            if (c.has_validity) sb += (s.tile / 8 + 127) / 128 * 128;
+        }
+        s.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (SMEM_BUDGET - 1024) / (size_t)sb));
+        return s;
+    }
+
+    bool next(Batch& out) override {
+        Batch in;
+        while (child->next(in)) {
+            if (in.n_rows == 0) continue;
+            run(in, out);
+            return true; // a batch with zero kept rows is still a (possibly empty) batch
+        }
+        return false;
+    }
+
+    void run(const Batch& in, Batch& out) {
+        PipelineSpec spec = make_spec(&in);
+        GeneratedKernel g = generate_pipeline(spec);
+        auto mod = jit_get(g, true);
+        ctx->last_kernel_key = g.key;
+        cb::PipeParams p;
+        fill_inputs(p, in, g.tile);
+        out.cols.clear();
+        out.cols.resize(g.out_cols.size());
+        cudaStream_t st = ctx->stream;
+        for (size_t i = 0; i < g.out_cols.size(); i++) {
+            Column& c = out.cols[i];
+            c.type = g.out_cols[i].type;
+            c.phys = c.type.id == TypeId::Bool ? Phys::I8 : phys_of(c.type);
+            c.data = std::make_shared<DeviceBuf>((size_t)in.n_rows * g.out_bytes[i]);
+            p.out[i] = (cb::u8*)c.data->ptr;
+            if (g.out_cols[i].nullable) {
+                c.validity = std::make_shared<DeviceBuf>((size_t)(in.n_rows + 31) / 32 * 4 + 8);
+                cuda_check(cudaMemsetAsync(c.validity->ptr, 0, c.validity->bytes, st), "memset out validity");
+                p.out_valid[i] = (cb::u32*)c.validity->ptr;
+                c.null_count = -1;
+            }
+        }
+        size_t need = (size_t)p.n_tiles * 8;
+        if (!tile_state || tile_state->bytes < need) tile_state = std::make_shared<DeviceBuf>(need);
+        if (!counters) counters = std::make_shared<DeviceBuf>(64);
+        cuda_check(cudaMemsetAsync(tile_state->ptr, 0, need, st), "memset tile state");
+        cuda_check(cudaMemsetAsync(counters->ptr, 0, 64, st), "memset counters");
+        p.tile_state = (cb::u64*)tile_state->ptr;
+        p.tile_counter = (cb::i32*)counters->ptr;
+        p.out_count = (cb::i64*)((char*)counters->ptr + 16);
+        int grid = std::min(ctx->num_sms, p.n_tiles);
+        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(0), &p);
+        int64_t kept = 0;
+        cuda_check(cudaMemcpyAsync(&kept, p.out_count, 8, cudaMemcpyDeviceToHost, st), "read kept count");
+        ctx->check_device_errors(); // also synchronises
+        out.n_rows = kept;
+        // boolean outputs were written one byte per row; repack lazily at export
+    }
+};
+
+// ---- dense / ungrouped aggregation --------------------------------------------------------------------
+struct AggNode : FusedBase {
+    std::vector<ExprP> keys;          // over child columns; each must be a plain column reference
+    std::vector<AggExpr> aggs;        // children/filter over child columns (Partial)
+    std::vector<std::vector<int>> state_cols; // Final: child column index of each state column
+    AggMode mode = AggMode::Partial;
+    bool ungrouped = false;
+    bool emitted = false;
+
+    // running state
+    std::vector<int> cards;                       // current cardinality per key (incl. null slot)
+    std::vector<bool> key_has_null;
+    std::vector<DictionaryP> key_dicts;           // strings per key (dict columns); empty for bool keys
+    DeviceBufP totals, spill, partials;
+    int totals_groups = 0, n_words = 0;
+    std::vector<int> word_kinds;
+    bool have_totals = false;
+    GeneratedKernel last_gen;
+    std::shared_ptr<CompiledModule> last_mod;
+    // device string dictionaries for plain Utf8 keys
+    struct DevDict { StringDictDev d; std::vector<DeviceBufP> bufs; DeviceBufP row_slot; int host_known = 0; };
+    std::vector<std::shared_ptr<DevDict>> dev_dicts;
+
+    PipelineSpec make_spec(const Batch* b, int n_groups) const {
+        PipelineSpec s;
+        s.cols = stage_cols(b);
+        s.predicates = to_slots(predicates, slot_of);
+        s.sink = SinkKind::Agg;
+        s.mode = mode;
+        s.ungrouped = ungrouped;
+        s.keys = to_slots(keys, slot_of);
+        for (size_t k = 0; k < keys.size(); k++) s.key_nullable.push_back(b ? key_has_null[k] : false);
+        for (auto& a : aggs) {
+            AggExpr c = a;
+            if (mode == AggMode::Partial) {
+                c.children = to_slots(a.children, slot_of);
+                if (a.filter) c.filter = to_slots({a.filter}, slot_of)[0];
+            }
+            s.aggs.push_back(c);
+        }
+        for (auto& sc : state_cols) {
+            std::vector<int> v;
+            for (int ci : sc) v.push_back(slot_of.at(ci));
+            s.state_slots.push_back(v);
+        }
+        s.threads = 256;
+        s.tile = 512;
+        s.stages = 3;
+        // first pass to learn the accumulator footprint, then size the ring to the remaining smem
+        GeneratedKernel probe = generate_pipeline(s);
+        size_t acc = n_groups > 1 ? (size_t)n_groups * probe.n_words * s.threads * 8 : 0;
+        while (acc + 2 * (size_t)probe.stage_bytes + 1024 > SMEM_BUDGET && s.threads > 32) {
+            s.threads /= 2; // shrink the thread-private accumulator file (wide Final-mode merges are tiny inputs)
+            acc /= 2;
+        }
+        if (acc + 2 * (size_t)probe.stage_bytes + 1024 > SMEM_BUDGET)
+            throw Unsupported("too many groups x aggregates for the dense path (hash aggregation path pending)");
+        s.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (SMEM_BUDGET - 1024 - acc) / (size_t)probe.stage_bytes));
+        return s;
+    }
+
+    // make key column k of batch `b` a code column; returns cardinality (without null slot)
+    int prepare_key(Batch& b, size_t k) {
+        int ci = keys[k]->index;
+        Column& c = b.cols[ci];
+        if (c.type.id == TypeId::Bool) return 2;
+        if (!c.type.is_string()) throw Unsupported("group key of type " + c.type.str() + " needs the hash aggregation path (pending)");
+        if (c.is_dict) {
+            key_dicts[k] = c.dict;
+            return (int)c.dict->values.size();
+        }
+        // plain Utf8 -> device dictionary builder
+        if (!dev_dicts[k]) {
+            auto dd = std::make_shared<DevDict>();
+            const int64_t cap = 1 << 16;
+            const int max_codes = 4096;
+            const int64_t bytes_cap = 1 << 20;
+            auto alloc = [&](size_t n) { auto bfr = std::make_shared<DeviceBuf>(n); cuda_check(cudaMemsetAsync(bfr->ptr, 0, bfr->bytes, ctx->stream), "memset dict"); dd->bufs.push_back(bfr); return bfr->ptr; };
+            dd->d.tags = (unsigned long long*)alloc((size_t)cap * 8);
+            dd->d.slot_code = (int*)alloc((size_t)cap * 4);
+            dd->d.capacity = cap;
+            dd->d.n_codes = (int*)alloc(64);
+            dd->d.bytes_used = (unsigned long long*)((char*)dd->d.n_codes + 16);
+            dd->d.err = (int*)((char*)dd->d.n_codes + 32);
+            dd->d.max_codes = max_codes;
+            dd->d.code_off = (long long*)alloc((size_t)max_codes * 8);
+            dd->d.code_len = (int*)alloc((size_t)max_codes * 4);
+            dd->d.bytes = (unsigned char*)alloc((size_t)bytes_cap);
+            dd->d.bytes_cap = bytes_cap;
+            dev_dicts[k] = dd;
+            key_dicts[k] = std::make_shared<Dictionary>();
+        }
+        DevDict& dd = *dev_dicts[k];
+        if (!c.offsets || !c.chars) throw Unsupported("string key column without offsets/chars buffers");
+        auto row_slot = std::make_shared<DeviceBuf>((size_t)b.n_rows * 4);
+        auto codes = std::make_shared<DeviceBuf>((size_t)b.n_rows * 4);
+        launch_dict_encode(dd.d, (const int*)c.offsets->ptr, (const unsigned char*)c.chars->ptr, c.validity ? (const unsigned char*)c.validity->ptr : nullptr,
+                           b.n_rows, (int*)row_slot->ptr, (int*)codes->ptr, ctx->stream);
+        ctx->kernel_launches += 2;
+        int hdr[12];
+        cuda_check(cudaMemcpyAsync(hdr, dd.d.n_codes, sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream), "dict header");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "dict encode");
+        int n_codes = hdr[0], derr = hdr[8];
+        if (derr & CB_DICT_FULL) throw Unsupported("string key cardinality exceeds the dense dictionary (hash aggregation path pending)");
+        if (derr & CB_DICT_COLLISION) throw ExecError(14, "", "64-bit hash collision between distinct group key strings");
+        // fetch newly added dictionary strings (metadata-sized)
+        if (n_codes > dd.host_known) {
+            std::vector<long long> off((size_t)n_codes);
+            std::vector<int> len((size_t)n_codes);
+            cuda_check(cudaMemcpy(off.data(), dd.d.code_off, (size_t)n_codes * 8, cudaMemcpyDeviceToHost), "dict offsets");
+            cuda_check(cudaMemcpy(len.data(), dd.d.code_len, (size_t)n_codes * 4, cudaMemcpyDeviceToHost), "dict lengths");
+            for (int i = dd.host_known; i < n_codes; i++) {
+                std::string s((size_t)len[(size_t)i], '\0');
+                if (len[(size_t)i]) cuda_check(cudaMemcpy(&s[0], dd.d.bytes + off[(size_t)i], (size_t)len[(size_t)i], cudaMemcpyDeviceToHost), "dict bytes");
+                key_dicts[k]->values.push_back(s);
+            }
+            dd.host_known = n_codes;
+        }
+        c.data = codes;
+        c.phys = Phys::I32;
+        c.is_dict = true;
+        c.dict = key_dicts[k];
+        return n_codes;
+    }
+
+    void regroup(const std::vector<int>& new_cards) { // cardinalities grew: move totals to the new mixed-radix layout
+        int old_groups = totals_groups, new_groups = 1;
+        for (int c : new_cards) new_groups *= c;
+        std::vector<uint64_t> oldt((size_t)old_groups * n_words * 2), newt((size_t)new_groups * n_words * 2);
+        cuda_check(cudaMemcpy(oldt.data(), totals->ptr, oldt.size() * 8, cudaMemcpyDeviceToHost), "regroup D2H");
+        for (int g = 0; g < new_groups; g++)
+            for (int w = 0; w < n_words; w++) {
+                uint64_t id = word_kinds[(size_t)w] == W_MIN ? 0x7fffffffffffffffull : word_kinds[(size_t)w] == W_MAX ? 0x8000000000000000ull : 0;
+                newt[((size_t)g * n_words + w) * 2] = id;
+                newt[((size_t)g * n_words + w) * 2 + 1] = 0;
+            }
+        for (int g = 0; g < old_groups; g++) {
+            int rem = g, ng = 0, mul = 1;
+            std::vector<int> code(cards.size());
+            for (int k = (int)cards.size() - 1; k >= 0; k--) { code[(size_t)k] = rem % cards[(size_t)k]; rem /= cards[(size_t)k]; }
+            for (int k = (int)cards.size() - 1; k >= 0; k--) {
+                int cd = code[(size_t)k];
+                // the null slot is always the last one of its key
+                if (key_has_null_prev[(size_t)k] && cd == cards[(size_t)k] - 1) cd = new_cards[(size_t)k] - 1;
+                ng += cd * mul;
+                mul *= new_cards[(size_t)k];
+            }
+            memcpy(&newt[(size_t)ng * n_words * 2], &oldt[(size_t)g * n_words * 2], (size_t)n_words * 16);
+        }
+        totals = std::make_shared<DeviceBuf>(newt.size() * 8);
+        cuda_check(cudaMemcpy(totals->ptr, newt.data(), newt.size() * 8, cudaMemcpyHostToDevice), "regroup H2D");
+        totals_groups = new_groups;
+    }
+    std::vector<bool> key_has_null_prev;
+
+    void consume(Batch& b) {
+        std::vector<int> nc(keys.size());
+        std::vector<bool> hn(keys.size());
+        for (size_t k = 0; k < keys.size(); k++) {
+            int card = prepare_key(b, k);
+            const Column& c = b.cols[keys[k]->index];
+            hn[k] = key_has_null[k] || c.validity != nullptr;
+            nc[k] = std::max(card, 1) + (hn[k] ? 1 : 0);
+            if (!cards.empty()) nc[k] = std::max(nc[k], cards[k]);
+        }
+        int n_groups = 1;
+        for (int c : nc) n_groups *= c;
+        if (n_groups > 4096) throw Unsupported("more than 4096 dense groups (hash aggregation path pending)");
+        key_has_null_prev = key_has_null;
+        key_has_null = hn;
+        PipelineSpec spec = make_spec(&b, n_groups);
+        GeneratedKernel g = generate_pipeline(spec);
+        auto mod = jit_get(g, true);
+        ctx->last_kernel_key = g.key;
+        if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds))
+            throw ExecError(15, "", "internal: accumulator layout changed between batches");
+        n_words = g.n_words;
+        word_kinds = g.word_kinds;
+        if (have_totals && nc != cards) regroup(nc);
+        cards = nc;
+        cudaStream_t st = ctx->stream;
+        size_t tot_bytes = (size_t)n_groups * n_words * 16;
+        if (!have_totals) {
+            totals = std::make_shared<DeviceBuf>(tot_bytes);
+            totals_groups = n_groups;
+        }
+        if (!spill || spill->bytes < tot_bytes) {
+            spill = std::make_shared<DeviceBuf>(tot_bytes);
+            cuda_check(cudaMemsetAsync(spill->ptr, 0, spill->bytes, st), "memset spill");
+        }
+        cb::PipeParams p;
+        fill_inputs(p, b, g.tile);
+        int grid = std::max(1, std::min(ctx->num_sms, p.n_tiles));
+        size_t part_bytes = (size_t)grid * tot_bytes;
+        if (!partials || partials->bytes < part_bytes) partials = std::make_shared<DeviceBuf>(part_bytes);
+        p.n_groups = n_groups;
+        for (size_t k = 0; k < cards.size() && k < CB_MAX_KEYS; k++) p.key_card[k] = cards[k];
+        p.partials = (cb::u8*)partials->ptr;
+        p.spill = (cb::u64*)spill->ptr;
+        // per-thread 64-bit partials are exact for < 2^16 rows per thread (|v| < 2^46 fast path)
+        if (b.n_rows > (int64_t)grid * g.threads * 65000ll) throw ExecError(16, "", "chunk too large for the 64-bit partial-sum fast path; lower chunkRows");
+        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(n_groups), &p);
+        cb::FinParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.partials = (const cb::u64*)partials->ptr;
+        fp.spill = (cb::u64*)spill->ptr;
+        fp.totals = (cb::u64*)totals->ptr;
+        fp.n_ctas = grid;
+        fp.n_groups = n_groups;
+        fp.first = have_totals ? 0 : 1;
+        fp.err = ctx->d_err;
+        int total_words = n_groups * n_words;
+        void* args[] = {&fp};
+        cuda_check(cudaLaunchKernel((const void*)mod->kernel("cb_fold"), dim3((total_words + 127) / 128), dim3(128), args, 0, st), "fold launch");
+        ctx->kernel_launches++;
+        have_totals = true;
+        last_gen = g;
+        last_mod = mod;
+    }
+
+    bool next(Batch& out) override {
+        if (emitted) return false;
+        if (keys.size() > CB_MAX_KEYS) throw Unsupported("more than 4 group keys");
+        key_has_null.assign(keys.size(), false);
+        key_dicts.assign(keys.size(), nullptr);
+        dev_dicts.assign(keys.size(), nullptr);
+        Batch in;
+        while (child->next(in)) {
+            if (in.n_rows == 0) continue;
+            consume(in);
+            ctx->check_device_errors();
+        }
+        emitted = true;
+        if (!have_totals) {
+            if (!ungrouped) return false; // grouped aggregate over no rows: no output rows
+            // ungrouped aggregate over an empty input still emits one row: run finalize over identities
+            PipelineSpec spec = make_spec(nullptr, 1);
+            last_gen = generate_pipeline(spec);
+            last_mod = jit_get(last_gen, true);
+            n_words = last_gen.n_words;
+            word_kinds = last_gen.word_kinds;
+            std::vector<uint64_t> id((size_t)n_words * 2, 0);
+            for (int w = 0; w < n_words; w++) id[(size_t)w * 2] = word_kinds[(size_t)w] == W_MIN ? 0x7fffffffffffffffull : word_kinds[(size_t)w] == W_MAX ? 0x8000000000000000ull : 0;
+            totals = std::make_shared<DeviceBuf>(id.size() * 8);
+            cuda_check(cudaMemcpy(totals->ptr, id.data(), id.size() * 8, cudaMemcpyHostToDevice), "identity totals");
+            totals_groups = 1;
+        }
+        finalize(out);
+        return true;
+    }
+
+    void finalize(Batch& out) {
+        const GeneratedKernel& g = last_gen;
+        int ng = totals_groups;
+        cb::FinParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.totals = (cb::u64*)totals->ptr;
+        fp.n_groups = ng;
+        fp.err = ctx->d_err;
+        std::vector<DeviceBufP> bufs, vbufs;
+        for (size_t i = 0; i < g.out_cols.size(); i++) {
+            bufs.push_back(std::make_shared<DeviceBuf>((size_t)ng * g.out_bytes[i]));
+            vbufs.push_back(std::make_shared<DeviceBuf>((size_t)ng));
+            fp.out[i] = (cb::u8*)bufs.back()->ptr;
+            fp.outv[i] = (cb::u8*)vbufs.back()->ptr;
+        }
+        auto present = std::make_shared<DeviceBuf>((size_t)ng);
+        fp.present = (cb::u8*)present->ptr;
+        void* args[] = {&fp};
+        cuda_check(cudaLaunchKernel((const void*)last_mod->kernel(g.finalize_entry), dim3((ng + 127) / 128), dim3(128), args, 0, ctx->stream), "finalize launch");
+        ctx->kernel_launches++;
+        ctx->check_device_errors();
+        // dense results are tiny: assemble the output batch on the host
+        std::vector<uint8_t> pres((size_t)ng);
+        cuda_check(cudaMemcpy(pres.data(), present->ptr, (size_t)ng, cudaMemcpyDeviceToHost), "present");
+        std::vector<int> rows;
+        for (int gi = 0; gi < ng; gi++) if (ungrouped || pres[(size_t)gi]) rows.push_back(gi);
+        out.n_rows = (int64_t)rows.size();
+        out.cols.clear();
+        // key columns
+        for (size_t k = 0; k < keys.size(); k++) {
+            Column c;
+            c.type = schema[k];
+            c.on_host = true;
+            bool any_null = false;
+            std::vector<int> codes;
+            for (int gi : rows) {
+                int rem = gi;
+                std::vector<int> code(cards.size());
+                for (int kk = (int)cards.size() - 1; kk >= 0; kk--) { code[(size_t)kk] = rem % cards[(size_t)kk]; rem /= cards[(size_t)kk]; }
+                codes.push_back(code[k]);
+            }
+            c.h_valid.assign(rows.size(), 1);
+            if (c.type.id == TypeId::Bool) {
+                c.h_data.resize(rows.size());
+                for (size_t r = 0; r < rows.size(); r++) {
+                    bool isnull = key_has_null[k] && codes[r] == cards[k] - 1;
+                    c.h_data[r] = isnull ? 0 : (uint8_t)codes[r];
+                    if (isnull) { c.h_valid[r] = 0; any_null = true; }
+                }
+            } else {
+                c.h_offsets.push_back(0);
+                for (size_t r = 0; r < rows.size(); r++) {
+                    bool isnull = key_has_null[k] && codes[r] == cards[k] - 1;
+                    if (isnull) { c.h_valid[r] = 0; any_null = true; }
+                    else {
+                        const std::string& s = key_dicts[k]->values.at((size_t)codes[r]);
+                        c.h_data.insert(c.h_data.end(), s.begin(), s.end());
+                    }
+                    c.h_offsets.push_back((int32_t)c.h_data.size());
+                }
+            }
+            if (!any_null) c.h_valid.clear();
+            out.cols.push_back(c);
+        }
+        for (size_t i = 0; i < g.out_cols.size(); i++) {
+            Column c;
+            c.type = g.out_cols[i].type;
+            c.on_host = true;
+            int w = g.out_bytes[i];
+            std::vector<uint8_t> all((size_t)ng * w), allv((size_t)ng);
+            cuda_check(cudaMemcpy(all.data(), bufs[i]->ptr, all.size(), cudaMemcpyDeviceToHost), "agg out");
+            cuda_check(cudaMemcpy(allv.data(), vbufs[i]->ptr, allv.size(), cudaMemcpyDeviceToHost), "agg out validity");
+            c.h_data.resize(rows.size() * w);
+            c.h_valid.resize(rows.size());
+            bool any_null = false;
+            for (size_t r = 0; r < rows.size(); r++) {
+                memcpy(&c.h_data[r * w], &all[(size_t)rows[r] * w], (size_t)w);
+                c.h_valid[r] = allv[(size_t)rows[r]];
+                if (!c.h_valid[r]) any_null = true;
+            }
+            if (!any_null) c.h_valid.clear();
+            out.cols.push_back(c);
+        }
+    }
+};
+
+// =================================================================================================
+// plan -> executor tree
+// =================================================================================================
+static ExprP bound_ref(int i, const DType& t) {
+    auto e = std::make_shared<Expr>();
+    e->kind = ExprKind::Bound;
+    e->index = i;
+    e->type = t;
+    return e;
+}
+
+static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs, bool build_only);
+
+static ExecNodeP build_source(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs, bool build_only) {
+    if (op->kind == OpKind::Scan || op->kind == OpKind::ShuffleScan) {
+        if (build_only) {
+            auto s = std::make_shared<SchemaOnlySource>();
+            s->schema = op->schema;
+            return s;
+        }
+        if (inputs->streams.empty() && inputs->tables.empty()) throw PlanError("No input for scan");
+        ArrowArrayStream* st = inputs->streams.empty() ? nullptr : inputs->streams.front();
+        std::shared_ptr<DeviceTable> tb = inputs->tables.empty() ? nullptr : inputs->tables.front();
+        if (!inputs->streams.empty()) inputs->streams.erase(inputs->streams.begin());
+        if (!inputs->tables.empty()) inputs->tables.erase(inputs->tables.begin());
+        if (tb) return std::make_shared<TableSource>(tb, op->schema);
+        if (!st) throw PlanError("No input for scan");
+        return std::make_shared<StreamSource>(ctx, st, op->schema);
+    }
+    if (op->kind == OpKind::NativeScan) throw Unsupported("NativeScan (device Parquet decode) is wired in a later milestone");
+    return build_node(op, ctx, inputs, build_only);
+}
+
+static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs, bool build_only) {
+    OperatorP cur = op;
+    OperatorP agg_op;
+    if (cur->kind == OpKind::ShuffleWriter) throw Unsupported("ShuffleWriter is executed through cb200_partition (see include/comet_b200.h)");
+    if (cur->kind == OpKind::HashAgg) { agg_op = cur; cur = cur->children[0]; }
+    std::vector<OperatorP> chain; // top-down
+    while (cur->kind == OpKind::Filter || cur->kind == OpKind::Projection) { chain.push_back(cur); cur = cur->children[0]; }
+    if (!agg_op && chain.empty()) return build_source(cur, ctx, inputs, build_only);
+    ExecNodeP src = build_source(cur, ctx, inputs, build_only);
+    // compose bottom-up
+    std::vector<ExprP> cols;
+    for (size_t i = 0; i < src->schema.size(); i++) cols.push_back(bound_ref((int)i, src->schema[i]));
+    std::vector<ExprP> preds;
+    for (auto it = chain.rbegin(); it != chain.rend(); ++it) {
+        const OperatorP& o = *it;
+        if (o->kind == OpKind::Filter) preds.push_back(substitute(o->predicate, cols));
+        else {
+            std::vector<ExprP> nc;
+            for (auto& e : o->project_list) nc.push_back(substitute(e, cols));
+            cols = nc;
+        }
+    }
+    if (agg_op) {
+        auto n = std::make_shared<AggNode>();
+        n->ctx = ctx;
+        n->child = src;
+        n->schema = agg_op->schema;
+        n->predicates = preds;
+        n->mode = agg_op->mode;
+        n->ungrouped = agg_op->grouping.empty();
+        std::vector<ExprP> roots = preds;
+        for (auto& gexp : agg_op->grouping) {
+            ExprP k = substitute(gexp, cols);
+            if (k->kind != ExprKind::Bound) throw Unsupported("computed group keys (only plain column keys are fused)");
+            n->keys.push_back(k);
+            roots.push_back(k);
+        }
+        size_t state_at = agg_op->grouping.size();
+        for (auto& a : agg_op->aggs) {
+            AggExpr c = a;
+            if (agg_op->mode == AggMode::Partial) {
+                for (auto& ch : c.children) { ch = substitute(ch, cols); roots.push_back(ch); }
+                if (c.filter) { c.filter = substitute(c.filter, cols); roots.push_back(c.filter); }
+            } else {
+                std::vector<int> sc;
+                for (size_t k = 0; k < agg_state_types(a).size(); k++) {
+                    ExprP e = cols.at(state_at++);
+                    if (e->kind != ExprKind::Bound) throw Unsupported("final aggregate over computed state columns");
+                    sc.push_back(e->index);
+                    roots.push_back(e);
+                }
+                n->state_cols.push_back(sc);
+            }
+            n->aggs.push_back(c);
+        }
+        n->assign_slots(roots);
+        if (n->used_cols.empty()) throw Unsupported("aggregate that reads no input column (COUNT(*) only) -- pending");
+        return n;
+    }
+    auto n = std::make_shared<SelectNode>();
+    n->ctx = ctx;
+    n->child = src;
+    n->schema = op->schema;
+    n->predicates = preds;
+    n->outputs = cols;
+    for (auto& e : cols) if (e->type.is_string()) throw Unsupported("string columns through a fused filter/projection");
+    std::vector<ExprP> roots = preds;
+    for (auto& e : cols) roots.push_back(e);
+    n->assign_slots(roots);
+    if (n->used_cols.empty()) throw Unsupported("projection of constants only");
+    return n;
+}
+
+ExecNodeP build_exec(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs) { return build_node(op, ctx, inputs, false); }
+
+std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op) {
+    std::vector<GeneratedKernel> out;
+    ExecNodeP root = build_node(op, nullptr, nullptr, true);
+    std::function<void(const ExecNodeP&)> walk = [&](const ExecNodeP& n) {
+        if (auto s = std::dynamic_pointer_cast<SelectNode>(n)) {
+            out.push_back(generate_pipeline(s->make_spec(nullptr)));
+            walk(s->child);
+        } else if (auto a = std::dynamic_pointer_cast<AggNode>(n)) {
+            a->key_has_null.assign(a->keys.size(), false);
+            out.push_back(generate_pipeline(a->make_spec(nullptr, a->ungrouped ? 1 : 6)));
+            walk(a->child);
+        }
+    };
+    walk(root);
+    return out;
+}
+
+// =================================================================================================
+// Arrow C Data export (prepare_output jni_api.rs:674-742, move_to_spark execution/utils.rs:32-62)
+// =================================================================================================
+namespace {
+struct ArrayHolder {
+    std::vector<std::vector<uint8_t>> bufs;
+    const void* ptrs[3] = {nullptr, nullptr, nullptr};
+};
+void release_array(ArrowArray* a) {
+    delete (ArrayHolder*)a->private_data;
+    a->release = nullptr;
+}
+struct SchemaHolder {
+    std::string format, name;
+};
+void release_schema(ArrowSchema* s) {
+    delete (SchemaHolder*)s->private_data;
+    s->release = nullptr;
+}
+std::string arrow_format(const DType& t) {
+    switch (t.id) {
+    case TypeId::Bool: return "b";
+    case TypeId::Int8: return "c";
+    case TypeId::Int16: return "s";
+    case TypeId::Int32: return "i";
+    case TypeId::Int64: return "l";
+    case TypeId::Float32: return "f";
+    case TypeId::Float64: return "g";
+    case TypeId::String: return "u";
+    case TypeId::Binary: return "z";
+    case TypeId::Date: return "tdD";
+    case TypeId::Timestamp: return "tsu:UTC";
+    case TypeId::TimestampNtz: return "tsu:";
+    case TypeId::Decimal: return "d:" + std::to_string(t.precision) + "," + std::to_string(t.scale);
+    default: throw Unsupported("export of " + t.str());
+    }
+}
+std::vector<uint8_t> pack_bits(const uint8_t* bytes, size_t n) {
+    std::vector<uint8_t> out((n + 7) / 8 + 8, 0);
+    for (size_t i = 0; i < n; i++) if (bytes[i]) out[i >> 3] |= (uint8_t)(1u << (i & 7));
+    return out;
+}
+} // namespace
+
+void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols) {
+    if ((int)b.cols.size() != n_cols) throw PlanError("executePlan: caller passed " + std::to_string(n_cols) + " output slots, plan produces " + std::to_string(b.cols.size()) + " columns");
+    size_t n = (size_t)b.n_rows;
+    for (int i = 0; i < n_cols; i++) {
+        Column& c = b.cols[(size_t)i];
+        auto* h = new ArrayHolder();
+        int64_t null_count = 0;
+        std::vector<uint8_t> validity, data, offs;
+        if (c.on_host) {
+            if (!c.h_valid.empty()) {
+                validity = pack_bits(c.h_valid.data(), n);
+                for (size_t r = 0; r < n; r++) null_count += c.h_valid[r] ? 0 : 1;
+            }
+            if (c.type.is_string()) {
+                offs.resize((n + 1) * 4);
+                memcpy(offs.data(), c.h_offsets.data(), (n + 1) * 4);
+                data = c.h_data;
+                data.resize(data.size() + 8);
+            } else if (c.type.id == TypeId::Bool) data = pack_bits(c.h_data.data(), n);
+            else { data = c.h_data; data.resize(data.size() + 8); }
+        } else {
+            if (c.type.is_string()) throw Unsupported("export of device string columns");
+            int w = c.type.id == TypeId::Bool ? 1 : c.type.arrow_width();
+            std::vector<uint8_t> raw(n * (size_t)w + 8);
+            if (n) cuda_check(cudaMemcpyAsync(raw.data(), c.data->ptr, n * (size_t)w, cudaMemcpyDeviceToHost, ctx->stream), "D2H output");
+            if (c.validity) {
+                validity.resize((n + 7) / 8 + 8);
+                if (n) cuda_check(cudaMemcpyAsync(validity.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity");
+            }
+            cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
+            if (c.validity) {
+                for (size_t r = 0; r < n; r++) null_count += ((validity[r >> 3] >> (r & 7)) & 1) ? 0 : 1;
+                if (null_count == 0) validity.clear();
+            }
+            if (c.type.id == TypeId::Bool) data = pack_bits(raw.data(), n);
+            else data = std::move(raw);
+        }
+        bool is_str = c.type.is_string();
+        h->bufs.push_back(std::move(validity));
+        if (is_str) h->bufs.push_back(std::move(offs));
+        h->bufs.push_back(std::move(data));
+        h->ptrs[0] = h->bufs[0].empty() ? nullptr : h->bufs[0].data();
+        h->ptrs[1] = h->bufs[1].data();
+        if (is_str) h->ptrs[2] = h->bufs[2].data();
+        ArrowArray& a = out_arrays[i];
+        memset(&a, 0, sizeof(a));
+        a.length = (int64_t)n;
+        a.null_count = null_count;
+        a.offset = 0; // zero offset only (jni_api.rs:716-732)
+        a.n_buffers = is_str ? 3 : 2;
+        a.buffers = h->ptrs;
+        a.release = release_array;
+        a.private_data = h;
+        auto* sh = new SchemaHolder();
+        sh->format = arrow_format(c.type);
+        sh->name = "col_" + std::to_string(i); // projection.rs:60
+        ArrowSchema& s = out_schemas[i];
+        memset(&s, 0, sizeof(s));
+        s.format = sh->format.c_str();
+        s.name = sh->name.c_str();
+        s.flags = ARROW_FLAG_NULLABLE;
+        s.release = release_schema;
+        s.private_data = sh;
+    }
+}
+
+} // namespace cb200

@@ -1,0 +1,104 @@
+// exec.h -- executor: pull-based operator tree over device batches.
+//
+// Mirrors what the reference builds in PhysicalPlanner::create_plan (native/core/src/execution/
+// planner.rs:1211) but with pipeline fusion: every maximal chain Scan -> (Filter|Projection)* ->
+// {output | HashAggregate} becomes ONE JIT-specialised kernel launch per device chunk.
+#pragma once
+#include "arrow_abi.h"
+#include "codegen.h"
+#include "jit.h"
+#include "plan.h"
+
+#include <cuda_runtime.h>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace cb200 {
+
+struct ExecError : std::runtime_error {
+    int code;
+    std::string error_class;
+    ExecError(int c, const std::string& cls, const std::string& msg) : std::runtime_error(msg), code(c), error_class(cls) {}
+};
+
+void cuda_check(cudaError_t e, const char* what);
+
+struct DeviceBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+    DeviceBuf() {}
+    DeviceBuf(size_t n);                       // cudaMalloc, padded
+    DeviceBuf(void* p, size_t n) : ptr(p), bytes(n), owned(false) {}
+    ~DeviceBuf();
+    DeviceBuf(const DeviceBuf&) = delete;
+    DeviceBuf& operator=(const DeviceBuf&) = delete;
+};
+using DeviceBufP = std::shared_ptr<DeviceBuf>;
+
+struct Dictionary { // string dictionary of a key column (host copy; tiny)
+    std::vector<std::string> values;
+};
+using DictionaryP = std::shared_ptr<Dictionary>;
+
+struct Column {
+    DType type;
+    Phys phys = Phys::I32;          // physical encoding of `data` (device) -- see codegen.h
+    bool is_dict = false;           // data holds dictionary codes (type = String)
+    DictionaryP dict;
+    DeviceBufP data, validity;      // device (validity: Arrow bitmap) ...
+    DeviceBufP offsets, chars;      // ... device Utf8 (offsets int32[n+1], chars)
+    int64_t null_count = 0;
+    // host-resident alternative (small aggregate results)
+    bool on_host = false;
+    std::vector<uint8_t> h_data;        // fixed-width values or chars
+    std::vector<uint8_t> h_valid;       // one byte per row; empty = all valid
+    std::vector<int32_t> h_offsets;     // Utf8
+};
+
+struct Batch {
+    int64_t n_rows = 0;
+    std::vector<Column> cols;
+};
+
+struct ExecContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    int64_t chunk_rows = 1ll << 26;
+    int batch_size = 8192;
+    int* d_err = nullptr;   // device error flags
+    int* h_err = nullptr;   // pinned host mirror
+    int64_t kernel_launches = 0;
+    std::string last_kernel_key;
+    void check_device_errors();
+};
+
+struct ExecNode {
+    std::vector<DType> schema;
+    virtual ~ExecNode() {}
+    virtual bool next(Batch& out) = 0; // false = end of stream
+};
+using ExecNodeP = std::shared_ptr<ExecNode>;
+
+struct DeviceTable { // caller-owned device-resident columns bound as a plan input (bench "value" path)
+    int64_t n_rows = 0;
+    std::vector<Column> cols;
+};
+
+// Build the executor tree for a decoded plan.  `inputs` are consumed in Scan order.
+struct PlanInputs {
+    std::vector<ArrowArrayStream*> streams;
+    std::vector<std::shared_ptr<DeviceTable>> tables; // parallel to streams; non-null entry overrides
+};
+ExecNodeP build_exec(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs);
+
+// Export helpers (host-visible Arrow C Data)
+void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols);
+
+// Debug / build-time: generate (and NVRTC-compile, no device needed) the kernels a plan would use,
+// assuming inputs without nulls and dictionary-encoded string keys.
+std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op);
+
+} // namespace cb200

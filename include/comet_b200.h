@@ -1,0 +1,114 @@
+/*
+ * comet_b200.h -- C ABI of libcomet_b200.so: the B200-native drop-in for the hot path of
+ * apache/datafusion-comet's native layer (scan -> filter -> project -> hash aggregate).
+ *
+ * The entry points are exactly what the reference's JNI surface binds for this path; each one names
+ * the reference interface it replaces (paths relative to the reference tree).  Plain pointers and
+ * sizes only: a Rust `ExecutionPlan` shim (extern "C"), a JNI stub or ctypes can call it directly.
+ * INTEGRATION.md shows the reference-side bindings.
+ *
+ * Threading (same contract as the reference, jni_api.rs:194-223): one plan handle is driven by one
+ * thread at a time; any number of handles may run concurrently (each owns a CUDA stream + arena).
+ * Errors never unwind across the ABI: calls return a code and fill `cb200_error`
+ * (jni-bridge/src/errors.rs:832-850 `try_unwrap_or_throw` is the reference's equivalent).
+ */
+#ifndef COMET_B200_H
+#define COMET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct ArrowArray;       /* Arrow C Data interface  */
+struct ArrowSchema;
+struct ArrowArrayStream; /* Arrow C Stream interface */
+
+typedef struct cb200_plan cb200_plan;
+typedef struct cb200_table cb200_table;
+
+/* error codes */
+#define CB200_OK 0
+#define CB200_ERR_UNSUPPORTED 1  /* plan uses an operator/expression outside the GPU hot path: fall back */
+#define CB200_ERR_CUDA 2
+#define CB200_ERR_INPUT 3        /* Arrow stream / schema problem */
+#define CB200_ERR_PLAN 4         /* malformed plan */
+#define CB200_ERR_JIT 5
+#define CB200_ERR_SPARK 10       /* Spark-visible runtime error; error_class carries the Spark error class */
+
+typedef struct cb200_error {
+    int32_t code;
+    char error_class[64];  /* e.g. "ARITHMETIC_OVERFLOW" (errors.rs:507-519 carries the same class to the JVM) */
+    char message[952];
+} cb200_error;
+
+const char* cb200_version(void);
+
+/* 1 if the serialized `spark.spark_operator.Operator` can run on the GPU path, 0 otherwise (`why`
+ * explains).  Lets the caller keep the CPU path for everything else -- the role CometExecRule's
+ * fallback tagging plays on the JVM side (spark/src/main/scala/org/apache/comet/rules/). */
+int cb200_supports(const uint8_t* op_proto, size_t op_len, cb200_error* why);
+
+/* Replaces Native.createPlan (spark/src/main/scala/org/apache/comet/Native.scala:60-79,
+ * native/core/src/execution/jni_api.rs:371-394).  `op_proto` is the same prost-encoded
+ * spark.spark_operator.Operator the JVM sends; `cfg_proto` the spark.spark_config.ConfigMap (may be
+ * NULL).  `inputs[i]` feeds the i-th Scan in plan order; ownership of each stream moves to the plan
+ * (planner.rs:1725-1737).  An entry may be NULL if a device table is bound before the first execute.
+ * Returns NULL on error. */
+cb200_plan* cb200_create_plan(const uint8_t* op_proto, size_t op_len, const uint8_t* cfg_proto, size_t cfg_len,
+                              struct ArrowArrayStream** inputs, int32_t n_inputs, int32_t partition,
+                              int32_t partition_count, int32_t batch_size, int32_t device_ordinal, cb200_error* err);
+
+/* number of columns every output batch has */
+int32_t cb200_plan_num_columns(cb200_plan* plan);
+
+/* Replaces Native.executePlan (Native.scala:98-103, jni_api.rs:767-775): produce the next output
+ * batch into caller-allocated ArrowArray/ArrowSchema structs (moved, release callbacks set).  Returns
+ * the row count, -1 at end of stream (jni_api.rs:891,933), -2 on error. */
+int64_t cb200_execute(cb200_plan* plan, struct ArrowArray* out_arrays, struct ArrowSchema* out_schemas,
+                      int32_t n_cols, cb200_error* err);
+
+/* Replaces Native.releasePlan (jni_api.rs:961).  Safe mid-stream. */
+void cb200_release(cb200_plan* plan);
+
+/* ---- device-resident inputs / outputs (no reference equivalent: the reference has no device) --------
+ * Columns already in HBM can be bound as the input of a Scan instead of an Arrow stream; this is the
+ * "inputs resident in HBM" leg of bench.py.  Buffers stay owned by the caller, must be 16-byte aligned
+ * and readable 16 bytes past the last element (TMA bulk copies round sizes up to 16 B). */
+cb200_table* cb200_table_create(int64_t n_rows);
+/* type_id: spark_expression.DataType.DataTypeId (types.proto:43-66).  value_width: bytes per value in
+ * `dev_values` (0 = bit-packed booleans; 1/2/4 for dictionary codes of a STRING column when
+ * n_dict > 0; 8 allowed for DECIMAL with precision <= 18).  dev_validity: Arrow bitmap or NULL. */
+int cb200_table_add_column(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width,
+                           const void* dev_values, const void* dev_validity, int64_t null_count,
+                           const char* const* dict_values, int32_t n_dict, cb200_error* err);
+int cb200_plan_bind_table(cb200_plan* plan, int32_t input_index, cb200_table* t, cb200_error* err);
+void cb200_table_release(cb200_table* t);
+
+typedef struct cb200_device_column {
+    int32_t type_id, precision, scale, value_width;
+    const void* values;    /* device pointer (NULL when the column lives on the host: small aggregate results) */
+    const void* validity;  /* device Arrow bitmap or NULL */
+    const void* host_values;
+    const uint8_t* host_validity_bytes; /* one byte per row, or NULL */
+} cb200_device_column;
+/* Like cb200_execute but leaves fixed-width results where they are (valid until the next call on the
+ * plan).  Returns rows, -1 at end, -2 on error. */
+int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_t n_cols, cb200_error* err);
+
+/* kernels launched so far by this plan (bench.py reports it as gpu_launches) */
+int64_t cb200_plan_kernel_launches(cb200_plan* plan);
+
+/* Build-time: generate and NVRTC-compile (sm_100a; needs no GPU) every pipeline kernel the plan would
+ * use for null-free inputs; cubins land in the JIT cache that ships with the library.  Writes the
+ * comma-separated kernel keys to `keys_out`.  Returns the number of kernels, <0 on error. */
+int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, size_t keys_cap, cb200_error* err);
+/* Same, but returns the generated CUDA source of kernel `index` (for inspection / nvcc -Xptxas -v). */
+int cb200_plan_kernel_source(const uint8_t* op_proto, size_t op_len, int32_t index, char* out, size_t cap, cb200_error* err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
