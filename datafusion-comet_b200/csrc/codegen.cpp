@@ -150,7 +150,7 @@ struct Emitter {
         }
         if (c.type.is_decimal() && c.phys == Phys::I64) init = "cb::i128_from_i64(" + init + ")";
         if (c.type.is_decimal() && c.phys == Phys::I32) init = "cb::i128_from_i64((cb::i64)" + init + ")";
-        if (c.phys == Phys::Dict32) {
+        if (c.phys == Phys::Dict32 || c.type.is_string()) { // dictionary codes of a string column
             r.v = fresh("k");
             body << "    cb::i32 " << r.v << " = " << init << ";\n";
         } else {

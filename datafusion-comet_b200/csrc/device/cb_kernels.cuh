@@ -92,10 +92,14 @@ CB_D void set_err(const PipeParams& p, int bit) { atomicOr(p.err, 1 << bit); }
 #if defined(CB_KERNEL_AGG) || defined(CB_KERNEL_SELECT)
 namespace cb {
 
+// bytes of one column slab in a stage (cb_col_bytes == 0: bit-packed booleans)
+constexpr __host__ __device__ int slab_bytes(int c) {
+    return ((cb_col_bytes(c) == 0 ? CB_TILE / 8 : CB_TILE * cb_col_bytes(c)) + 127) / 128 * 128;
+}
 constexpr __host__ __device__ int stage_bytes() {
     int b = 0;
     for (int c = 0; c < CB_NCOLS; c++) {
-        b += (CB_TILE * cb_col_bytes(c) + 127) / 128 * 128;
+        b += slab_bytes(c);
         if (cb_col_has_val(c)) b += (CB_TILE / 8 + 127) / 128 * 128;
     }
     return b;
@@ -110,7 +114,7 @@ CB_D void issue_tile(const PipeParams& p, int tile, u8* stage_base, u64* bar, u6
     u32 bytes_c[CB_NCOLS], bytes_v[CB_NCOLS];
 #pragma unroll
     for (int c = 0; c < CB_NCOLS; c++) {
-        bytes_c[c] = (u32)((rows * cb_col_bytes(c) + 15) & ~15);
+        bytes_c[c] = cb_col_bytes(c) == 0 ? (u32)((((rows + 7) >> 3) + 15) & ~15) : (u32)((rows * cb_col_bytes(c) + 15) & ~15);
         bytes_v[c] = cb_col_has_val(c) ? (u32)((((rows + 7) >> 3) + 15) & ~15) : 0u;
         total += bytes_c[c] + bytes_v[c];
     }
@@ -118,8 +122,8 @@ CB_D void issue_tile(const PipeParams& p, int tile, u8* stage_base, u64* bar, u6
     u8* dst = stage_base;
 #pragma unroll
     for (int c = 0; c < CB_NCOLS; c++) {
-        tma_bulk_g2s(dst, p.col[c] + row0 * cb_col_bytes(c), bytes_c[c], bar, policy);
-        dst += (CB_TILE * cb_col_bytes(c) + 127) / 128 * 128;
+        tma_bulk_g2s(dst, p.col[c] + (cb_col_bytes(c) == 0 ? (row0 >> 3) : row0 * cb_col_bytes(c)), bytes_c[c], bar, policy);
+        dst += slab_bytes(c);
         if (cb_col_has_val(c)) {
             tma_bulk_g2s(dst, p.val[c] + (row0 >> 3), bytes_v[c], bar, policy);
             dst += (CB_TILE / 8 + 127) / 128 * 128;
@@ -131,7 +135,7 @@ CB_D void tile_view(u8* stage_base, Tile& t) {
 #pragma unroll
     for (int c = 0; c < CB_NCOLS; c++) {
         t.col[c] = ptr;
-        ptr += (CB_TILE * cb_col_bytes(c) + 127) / 128 * 128;
+        ptr += slab_bytes(c);
         if (cb_col_has_val(c)) { t.val[c] = ptr; ptr += (CB_TILE / 8 + 127) / 128 * 128; }
         else t.val[c] = nullptr;
     }

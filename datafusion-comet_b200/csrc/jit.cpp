@@ -45,6 +45,20 @@ std::string jit_cache_dir() {
     return "/tmp/cb200_jitcache";
 }
 
+// cubins depend on the device headers as much as on the generated translation unit
+static std::string headers_tag() {
+    static std::string tag;
+    if (tag.empty()) {
+        uint64_t h = 1469598103934665603ull;
+        for (const char* src : {cb_math_src, cb_params_src, cb_kernels_src})
+            for (const char* c = src; *c; c++) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
+        char buf[32];
+        snprintf(buf, sizeof(buf), "%016llx", (unsigned long long)h);
+        tag = buf;
+    }
+    return tag;
+}
+
 static std::mutex g_mu;
 static std::map<std::string, std::shared_ptr<CompiledModule>> g_cache;
 
@@ -83,7 +97,7 @@ std::shared_ptr<CompiledModule> jit_get(const GeneratedKernel& g, bool load) {
     if (it != g_cache.end()) m = it->second;
     if (!m) {
         m = std::make_shared<CompiledModule>();
-        std::string dir = jit_cache_dir(), path = dir + "/" + g.key + ".cubin";
+        std::string dir = jit_cache_dir(), path = dir + "/" + g.key + "_" + headers_tag() + ".cubin";
         std::ifstream in(path, std::ios::binary);
         if (in) {
             m->cubin.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());

@@ -752,8 +752,9 @@ int co_q1_f64(int64_t n, const double *qty, const double *price, const double *d
 }
 
 int co_q6_dec(int64_t n, const i128 *qty, const i128 *price, const i128 *disc,
-              const int32_t *shipdate, int32_t dlo, int32_t dhi, i128 disc_lo, i128 disc_hi,
-              i128 qty_max, int n_threads, i128 *out, uint8_t *out_valid) {
+              const int32_t *shipdate, int32_t dlo, int32_t dhi, const i128 *p_disc_lo,
+              const i128 *p_disc_hi, const i128 *p_qty_max, int n_threads, i128 *out, uint8_t *out_valid) {
+    const i128 disc_lo = *p_disc_lo, disc_hi = *p_disc_hi, qty_max = *p_qty_max;
     int T = nthreads_or_default(n_threads);
     i128 *ps = (i128 *)calloc((size_t)T, sizeof(i128));
     uint8_t *pv = (uint8_t *)malloc((size_t)T), *pe = (uint8_t *)malloc((size_t)T);

@@ -172,8 +172,9 @@ int co_q1_f64(int64_t n, const double *qty, const double *price, const double *d
 /* TPC-H Q6: sum(l_extendedprice*l_discount) where shipdate in [lo,hi), discount in [dlo,dhi],
  * quantity < qmax.  DEC: d(12,2)*d(12,2) -> d(25,4) plain mul + CheckOverflow, sum -> d(35,4). */
 int co_q6_dec(int64_t n, const co_i128 *qty, const co_i128 *price, const co_i128 *disc,
-              const int32_t *shipdate, int32_t date_lo, int32_t date_hi, co_i128 disc_lo,
-              co_i128 disc_hi, co_i128 qty_max, int n_threads, co_i128 *out, uint8_t *out_valid);
+              const int32_t *shipdate, int32_t date_lo, int32_t date_hi, const co_i128 *disc_lo,
+              const co_i128 *disc_hi, const co_i128 *qty_max, int n_threads, co_i128 *out,
+              uint8_t *out_valid);
 int co_q6_f64(int64_t n, const double *qty, const double *price, const double *disc,
               const int32_t *shipdate, int32_t date_lo, int32_t date_hi, double disc_lo,
               double disc_hi, double qty_max, int n_threads, double *out, uint8_t *out_valid);

@@ -442,9 +442,8 @@ def q6_dec(qty, price, disc, shipdate, date_lo, date_hi, disc_lo, disc_hi, qty_m
     n = shipdate.shape[0]
     out = np.zeros((1, 2), dtype=np.uint64)
     outv = np.zeros(1, dtype=np.uint8)
-    # __int128 by value follows the SysV ABI of a two-INTEGER-class struct
     _chk(lib().co_q6_dec(C.c_int64(n), _p(qty), _p(price), _p(disc), _p(shipdate), C.c_int32(date_lo),
-                         C.c_int32(date_hi), _i128_byval(disc_lo), _i128_byval(disc_hi), _i128_byval(qty_max),
+                         C.c_int32(date_hi), _p(dec_from_ints([disc_lo])), _p(dec_from_ints([disc_hi])), _p(dec_from_ints([qty_max])),
                          C.c_int(n_threads), _p(out), _p(outv)))
     return dec_to_ints(out, outv)[0]
 

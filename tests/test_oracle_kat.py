@@ -379,3 +379,49 @@ def test_q1_pipeline_small(oracle):
     assert r["count"] == 3
     # avg qty = 61.00/3 = 20.333333 at scale 6
     assert r["avg_qty"] == 20333333
+
+
+# ---- whole-pipeline baselines vs plain python ---------------------------------------------------
+def _lineitem(n, seed):
+    import sys, os
+    from comet_b200 import tpch
+    return tpch, tpch.gen_lineitem(n, seed=seed)
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_q6_dec_pipeline(oracle, threads):
+    tpch, c = _lineitem(20000, 5)
+    d = oracle.dec_from_i64
+    got = oracle.q6_dec(d(c["l_quantity"]), d(c["l_extendedprice"]), d(c["l_discount"]), c["l_shipdate"], tpch.DATE_1994_01_01,
+                        tpch.DATE_1995_01_01, 5, 7, 2400, threads)
+    m = (c["l_shipdate"] >= tpch.DATE_1994_01_01) & (c["l_shipdate"] < tpch.DATE_1995_01_01) & (c["l_discount"] >= 5) & \
+        (c["l_discount"] <= 7) & (c["l_quantity"] < 2400)
+    assert got == int((c["l_extendedprice"][m].astype(object) * c["l_discount"][m].astype(object)).sum())
+
+
+def test_q6_f64_and_config1_pipelines(oracle):
+    import math
+    tpch, c = _lineitem(30000, 6)
+    q, p, dsc = (c[k].astype(np.float64) / 100.0 for k in ("l_quantity", "l_extendedprice", "l_discount"))
+    got = oracle.q6_f64(q, p, dsc, c["l_shipdate"], tpch.DATE_1994_01_01, tpch.DATE_1995_01_01, 0.05, 0.07, 24.0, 1)
+    m = (c["l_shipdate"] >= tpch.DATE_1994_01_01) & (c["l_shipdate"] < tpch.DATE_1995_01_01) & (dsc >= 0.05) & (dsc <= 0.07) & (q < 24.0)
+    assert abs(got - math.fsum((p * dsc)[m])) <= 1e-9 * abs(got)
+    out = oracle.filter_project_f64(q, p, c["l_shipdate"], tpch.DATE_1998_09_02, 3)
+    keep = c["l_shipdate"] < tpch.DATE_1998_09_02
+    assert (out == (q * p)[keep]).all()
+    d = oracle.dec_from_i64
+    o, ov = oracle.filter_project_dec(d(c["l_quantity"]), d(c["l_extendedprice"]), c["l_shipdate"], tpch.DATE_1998_09_02, 2)
+    assert oracle.dec_to_ints(o[:50]) == [int(a) * int(b) for a, b in zip(c["l_quantity"][keep][:50], c["l_extendedprice"][keep][:50])]
+    assert ov.all() and o.shape[0] == int(keep.sum())
+
+
+def test_q1_dec_threads_agree(oracle):
+    tpch, c = _lineitem(50000, 8)
+    d = oracle.dec_from_i64
+    args = (d(c["l_quantity"]), d(c["l_extendedprice"]), d(c["l_discount"]), d(c["l_tax"]), c["l_shipdate"], c["l_returnflag"],
+            c["l_linestatus"], 3, 2, tpch.DATE_1998_09_02)
+    a, b = oracle.q1_dec(*args, 1), oracle.q1_dec(*args, 5)
+    assert a == b
+    keep = c["l_shipdate"] <= tpch.DATE_1998_09_02
+    k0 = keep & (c["l_returnflag"] == 0) & (c["l_linestatus"] == 0)
+    assert a[0]["sum_qty"] == int(c["l_quantity"][k0].sum()) and a[0]["count"] == int(k0.sum())
