@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- TPC-H Q1 (filter + 2-key group-by, 4 sums, 3 avgs, count) over synthetic SF100 lineitem.
+
+One "step" = one full pass of the hot path over the rank's lineitem partition:
+  HashAggregate(Partial) over [Scan -> Filter -> Project] as ONE fused sm_100a kernel launch per
+  device chunk (+ fold/finalize), then the partial states of all ranks are gathered on rank 0 and
+  merged by HashAggregate(Final) (merge_batch semantics) -- the same two plans Spark + Comet run on
+  either side of the shuffle.
+
+`value`  : rows/s with the Arrow columns already resident in HBM (bound through cb200_table_*).
+`e2e`    : the same plans through cb200_create_plan / cb200_execute with HOST Arrow buffers handed over
+           as an ArrowArrayStream (pinned host memory; H2D inside the timed region; result D2H).
+`roofline`: algorithmic bytes of the fused Q1 kernel / its CUDA-event duration (events recorded by the
+           library on the stream it launches on) against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/comet_oracle.c, OpenMP, all host
+           cores) -- the reference's Rust/DataFusion path cannot be built in this image (no Rust).
+
+Launch: python bench.py [--gpus N --steps K --warmup W]   (torchrun for N>1, one rank per GPU)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "datafusion-comet_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SF100_ROWS = 600_037_902
+METRIC = "rows/sec on TPC-H Q1 filter+agg"
+# bytes the fused kernel must read per row (Arrow layout, dictionary-coded flags):
+#   l_shipdate date32 4 + returnflag/linestatus codes 1+1 + 4 x Decimal128 16  (DESIGN.md "algorithmic bytes")
+BYTES_PER_ROW = {"dec": 4 + 1 + 1 + 4 * 16, "f64": 4 + 1 + 1 + 4 * 8}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        self.path = tempfile.mktemp(prefix="cb200_clocks_", suffix=".csv")
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ---- data ---------------------------------------------------------------------------------------
+def gen_device(torch, n, seed, device):
+    """TPC-H-shaped lineitem columns on the device (SURVEY.md 8d distribution; torch Philox, seeded)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def ri(lo, hi, dtype=torch.int64):
+        return torch.randint(lo, hi, (n,), generator=g, device=device, dtype=dtype)
+
+    qty_units = ri(1, 51)
+    price = qty_units * ri(90000, 210001)          # cents
+    qty = qty_units * 100
+    disc = ri(0, 11)
+    tax = ri(0, 9)
+    ship = ri(8036, 10562, torch.int32)
+    receipt = ship + ri(1, 31, torch.int32)
+    ar = (ri(0, 2, torch.int8) * 2)
+    rf = torch.where(receipt <= 9298, ar, torch.ones_like(ar)).contiguous()
+    ls = (ship > 9298).to(torch.int8).contiguous()
+    del receipt, ar, qty_units
+    return dict(l_quantity=qty, l_extendedprice=price, l_discount=disc, l_tax=tax, l_shipdate=ship, l_returnflag=rf, l_linestatus=ls)
+
+
+def to_dec128(torch, cents):
+    """int64 unscaled -> Arrow Decimal128 layout (n,2) int64 (lo, sign-extended hi)"""
+    out = torch.empty((cents.shape[0], 2), dtype=torch.int64, device=cents.device)
+    out[:, 0] = cents
+    out[:, 1] = cents >> 63
+    return out
+
+
+def build_columns(torch, cols, variant):
+    money = {}
+    for k in ("l_quantity", "l_extendedprice", "l_discount", "l_tax"):
+        money[k] = to_dec128(torch, cols[k]) if variant == "dec" else (cols[k].to(torch.float64) / 100.0)
+    return money
+
+
+def bind_table(native, P, tpch, variant, n, money, cols):
+    m = tpch.D12 if variant == "dec" else P.DOUBLE
+    w = 16 if variant == "dec" else 8
+    t = native.DeviceTable(n)
+    for k in ("l_quantity", "l_extendedprice", "l_discount", "l_tax"):
+        t.add(m, money[k].data_ptr(), w, keep=money[k])
+    t.add(P.STRING, cols["l_returnflag"].data_ptr(), 1, dictionary=tpch.RETURNFLAGS, keep=cols["l_returnflag"])
+    t.add(P.STRING, cols["l_linestatus"].data_ptr(), 1, dictionary=tpch.LINESTATUS, keep=cols["l_linestatus"])
+    t.add(P.DATE, cols["l_shipdate"].data_ptr(), 4, keep=cols["l_shipdate"])
+    return t
+
+
+def host_arrow_batches(torch, pa, tpch, variant, money, cols, batch_rows):
+    """Copy the device columns into PINNED host memory and wrap them as zero-copy Arrow batches."""
+    host = {}
+    for k, t in list(money.items()) + [(k, cols[k]) for k in ("l_returnflag", "l_linestatus", "l_shipdate")]:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        host[k] = h
+    torch.cuda.synchronize()
+    n = cols["l_shipdate"].shape[0]
+
+    def buf(t):
+        return pa.foreign_buffer(t.data_ptr(), t.numel() * t.element_size(), base=t)
+
+    arrays = []
+    for k in ("l_quantity", "l_extendedprice", "l_discount", "l_tax"):
+        typ = pa.decimal128(12, 2) if variant == "dec" else pa.float64()
+        arrays.append(pa.Array.from_buffers(typ, n, [None, buf(host[k])]))
+    for k, vals in (("l_returnflag", tpch.RETURNFLAGS), ("l_linestatus", tpch.LINESTATUS)):
+        idx = pa.Array.from_buffers(pa.int8(), n, [None, buf(host[k])])
+        arrays.append(pa.DictionaryArray.from_arrays(idx, pa.array(vals)))
+    arrays.append(pa.Array.from_buffers(pa.date32(), n, [None, buf(host["l_shipdate"])]))
+    names = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+    tbl = pa.table(arrays, names=names)
+    return tbl.to_batches(max_chunksize=batch_rows), host
+
+
+# ---- one step -----------------------------------------------------------------------------------
+def run_partial(native, plan_bytes, inp, chunk_rows):
+    with native.Plan(plan_bytes, [inp], config={"spark.comet.b200.chunkRows": str(chunk_rows)}) as p:
+        state = p.collect()
+        st = p.stats()
+    return state, st
+
+
+def run_final(native, pa, plan_bytes, states):
+    tbl = pa.concat_tables(states)
+    with native.Plan(plan_bytes, [tbl]) as p:
+        res = p.collect()
+        st = p.stats()
+    return res, st
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the CPU port of the reference path (oracle) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    from comet_b200 import tpch
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    n = args.ref_rows
+    cols = tpch.gen_lineitem(n, seed=42)
+    d = oracle.dec_from_i64
+    a = (d(cols["l_quantity"]), d(cols["l_extendedprice"]), d(cols["l_discount"]), d(cols["l_tax"]), cols["l_shipdate"],
+         cols["l_returnflag"], cols["l_linestatus"], 3, 2, tpch.DATE_1998_09_02)
+    for _ in range(args.warmup):
+        oracle.q1_dec(*a, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.q1_dec(*a, cores)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i128",
+            "data": "synthetic", "config": {"workload": f"TPC-H Q1 DECIMAL(12,2), bounded sample of {n} rows of the SF100 lineitem shape per step", "rows": n},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} rows/step, oracle/comet_oracle.c co_q1_dec, OpenMP {cores} threads (reference Rust path not buildable here)"},
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variant", default="dec", choices=["dec", "f64"])
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("CB200_BENCH_ROWS", SF100_ROWS)))
+    ap.add_argument("--ref-rows", type=int, default=60_000_000)
+    ap.add_argument("--chunk-rows", type=int, default=1 << 30)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-batch-rows", type=int, default=1 << 22)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import pyarrow as pa
+    import torch
+    import torch.distributed as dist
+    from comet_b200 import native, proto as P, tpch
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    variant, n = args.variant, args.rows
+    cols = gen_device(torch, n, 42 + rank, device)
+    money = build_columns(torch, cols, variant)
+    partial_plan, final_plan = tpch.q1_partial_plan(variant), tpch.q1_final_plan(variant)
+    chunk_rows = min(args.chunk_rows, 2_000_000_000)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def gather_states(state):
+        if world == 1:
+            return [state]
+        objs = [None] * world if rank == 0 else None
+        dist.gather_object(state, objs, dst=0)
+        return objs
+
+    def step_resident():
+        table = bind_table(native, P, tpch, variant, n, money, cols)
+        state, st = run_partial(native, partial_plan, table, chunk_rows)
+        states = gather_states(state)
+        res, st2 = (run_final(native, pa, final_plan, states) if rank == 0 else (None, None))
+        return res, st, st2
+
+    # ---- device-resident leg -----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    pipe_ms, pipe_launches, launches = 0.0, 0, 0
+    res = None
+    for _ in range(args.steps):
+        res, st, st2 = step_resident()
+        pipe_ms += st["pipeline_ms"]
+        pipe_launches += st["pipeline_launches"]
+        launches += st["kernel_launches"] + (st2["kernel_launches"] if st2 else 0)
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+
+    # cheap full-size check (rank 0's partition): count(*) per group and sum(l_quantity) are exact integers
+    checked = None
+    if rank == 0 and world == 1:
+        keep = cols["l_shipdate"] <= tpch.DATE_1998_09_02
+        gid = cols["l_returnflag"].to(torch.int64) * 2 + cols["l_linestatus"].to(torch.int64)
+        cnt = torch.bincount(gid[keep], minlength=6).cpu().tolist()
+        sq = torch.zeros(6, dtype=torch.int64, device=device).scatter_add_(0, gid[keep], cols["l_quantity"][keep]).cpu().tolist()
+        got = {(r["col_0"], r["col_1"]): r for r in res.to_pylist()}
+        checked = True
+        for k in range(6):
+            if cnt[k] == 0:
+                continue
+            g = got[(tpch.RETURNFLAGS[k // 2], tpch.LINESTATUS[k % 2])]
+            if variant == "dec":
+                checked &= int(g["col_2"].scaleb(2)) == sq[k]
+            checked &= g["col_9"] == cnt[k]
+        del keep, gid
+
+    # ---- end-to-end leg: host Arrow buffers -> C ABI -> result (per rank; rank 0 merges) -------------
+    e2e = None
+    host = None
+    if not args.no_e2e:
+        batches, host = host_arrow_batches(torch, pa, tpch, variant, money, cols, args.e2e_batch_rows)
+        e2e_chunk = 1 << 26
+
+        def step_e2e():
+            state, st = run_partial(native, partial_plan, batches, e2e_chunk)
+            states = gather_states(state)
+            r, st2 = (run_final(native, pa, final_plan, states) if rank == 0 else (None, None))
+            return st, st2
+
+        step_e2e()  # warm-up (JIT variants, pinned-page faults)
+        barrier()
+        t1 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(args.e2e_steps):
+            st, st2 = step_e2e()
+            h2d += st["h2d_bytes"] + (st2["h2d_bytes"] if st2 else 0)
+            d2h += st["d2h_bytes"] + (st2["d2h_bytes"] if st2 else 0)
+        barrier()
+        e2e_elapsed = time.perf_counter() - t1
+        if world > 1:
+            t = torch.tensor([e2e_elapsed], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_elapsed = float(t.item())
+        e2e = {"value": world * n * args.e2e_steps / e2e_elapsed, "unit": "rows/s", "h2d_bytes_per_step": h2d // args.e2e_steps,
+               "d2h_bytes_per_step": max(d2h // args.e2e_steps, 1), "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
+               "input": f"pinned host Arrow batches of {args.e2e_batch_rows} rows via ArrowArrayStream, 64 Mi-row device chunks"}
+
+    # ---- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded sample -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and variant == "dec":
+        from oracle import oracle
+        oracle.build()
+        cores = os.cpu_count() or 1
+        m = min(n, 200_000_000)
+        if host is None:
+            _, host = host_arrow_batches(torch, pa, tpch, variant, {k: v[:m] for k, v in money.items()}, {k: v[:m] for k, v in cols.items()}, m)
+        hv = lambda k: host[k].numpy()[:m]
+        a = (hv("l_quantity").view(np.uint64), hv("l_extendedprice").view(np.uint64), hv("l_discount").view(np.uint64), hv("l_tax").view(np.uint64),
+             hv("l_shipdate"), hv("l_returnflag").view(np.uint8), hv("l_linestatus").view(np.uint8), 3, 2, tpch.DATE_1998_09_02)
+        oracle.q1_dec(*a, cores)
+        reps, tc = 0, time.perf_counter()
+        while reps < 3 or time.perf_counter() - tc < 5.0:
+            oracle.q1_dec(*a, cores)
+            reps += 1
+            if time.perf_counter() - tc > 30.0:
+                break
+        dtc = time.perf_counter() - tc
+        cpu = {"value": m * reps / dtc, "unit": "rows/s", "cores": cores, "kind": "port",
+               "sample": f"{m} rows x {reps} passes, oracle/comet_oracle.c co_q1_dec (OpenMP, partial per thread + final merge)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        rows_per_launch = n  # one fused launch per chunk; chunk >= partition
+        ms_per_launch = pipe_ms / max(pipe_launches, 1)
+        achieved = BYTES_PER_ROW[variant] * (n * args.steps / max(pipe_launches, 1)) / (ms_per_launch * 1e-3) / 1e9 if pipe_launches else 0.0
+        line = {
+            "metric": METRIC, "value": world * n * args.steps / elapsed, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i128" if variant == "dec" else "f64", "data": "synthetic",
+            "config": {"workload": f"TPC-H Q1 (filter + group-by 2 keys, 4 sum + 3 avg + count) over SF100-shaped lineitem, "
+                                   f"{'DECIMAL(12,2)' if variant == 'dec' else 'DOUBLE'} money columns, Arrow columns resident in HBM",
+                       "rows_per_gpu": n, "variant": variant, "parallelism": f"round-robin partitions x{world}, partial state gathered to rank 0",
+                       "l2": f"inputs ({BYTES_PER_ROW[variant] * n / 1e9:.1f} GB per GPU) exceed L2; no flush needed",
+                       "checked_against_torch_int64": checked},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "cb_pipeline_agg (fused scan+filter+project+partial aggregate)", "ms_per_launch": ms_per_launch,
+                         "algorithmic_bytes_per_row": BYTES_PER_ROW[variant], "peak_source": peak_src},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

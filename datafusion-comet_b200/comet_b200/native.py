@@ -59,7 +59,12 @@ class DeviceColumn(C.Structure):
                 ("host_validity_bytes", C.c_void_p)]
 
 
-EXPORTED = ["cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("pipeline_launches", C.c_int64), ("pipeline_ms", C.c_double),
+                ("pipeline_rows", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+EXPORTED = ["cb200_plan_stats", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
             "cb200_release", "cb200_table_create", "cb200_table_add_column", "cb200_plan_bind_table",
             "cb200_table_release", "cb200_execute_device", "cb200_plan_kernel_launches", "cb200_compile_plan",
             "cb200_plan_kernel_source"]
@@ -91,6 +96,7 @@ def lib():
         l.cb200_execute_device.argtypes = [C.c_void_p, C.POINTER(DeviceColumn), C.c_int32, C.POINTER(_Error)]
         l.cb200_plan_kernel_launches.restype = C.c_int64
         l.cb200_plan_kernel_launches.argtypes = [C.c_void_p]
+        l.cb200_plan_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         l.cb200_compile_plan.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(_Error)]
         l.cb200_plan_kernel_source.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(_Error)]
         _lib = l
@@ -120,6 +126,19 @@ def compile_plan(op_bytes):
     if n < 0:
         _raise(err)
     return [k for k in buf.value.decode().split(",") if k]
+
+
+def compile_plan_assume(op_bytes, assume_bits, source_index=-1):
+    """Pre-compile the range-specialised kernels for decimal columns assumed to satisfy |v| < 2^bits."""
+    err = _Error()
+    arr = (C.c_int32 * len(assume_bits))(*assume_bits)
+    cap = 1 << 20
+    buf = C.create_string_buffer(cap)
+    lib().cb200_compile_plan_assume.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(_Error)]
+    n = lib().cb200_compile_plan_assume(op_bytes, len(op_bytes), arr, len(assume_bits), source_index, buf, cap, C.byref(err))
+    if n < 0:
+        _raise(err)
+    return buf.value.decode()
 
 
 def kernel_source(op_bytes, index=0):
@@ -233,6 +252,11 @@ class Plan:
         if not batches:
             return None
         return pa.Table.from_batches(batches)
+
+    def stats(self):
+        st = Stats()
+        self._lib.cb200_plan_stats(self.handle, C.byref(st))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
 
     @property
     def kernel_launches(self):

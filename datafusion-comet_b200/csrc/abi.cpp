@@ -84,9 +84,25 @@ void start(cb200_plan* p) {
     if (prop.major < 10) throw ExecError(CB200_ERR_CUDA, "", "comet_b200 kernels are built for sm_100a; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
     ctx.num_sms = prop.multiProcessorCount;
     cuda_check(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    {
+        static std::mutex mu;
+        static bool pool_set[64] = {false};
+        std::lock_guard<std::mutex> lk(mu);
+        if (ctx.device < 64 && !pool_set[ctx.device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, ctx.device) == cudaSuccess) {
+                unsigned long long keep = ~0ull; // keep freed blocks cached in the pool
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_set[ctx.device] = true;
+        }
+    }
+    set_alloc_stream(ctx.stream);
     cuda_check(cudaMalloc((void**)&ctx.d_err, 64), "cudaMalloc err");
     cuda_check(cudaMemsetAsync(ctx.d_err, 0, 64, ctx.stream), "memset err");
     cuda_check(cudaMallocHost((void**)&ctx.h_err, 64), "cudaMallocHost err");
+    cuda_check(cudaEventCreate(&ctx.ev0), "cudaEventCreate");
+    cuda_check(cudaEventCreate(&ctx.ev1), "cudaEventCreate");
     p->root = build_exec(p->op, &ctx, &p->inputs);
     p->started = true;
 }
@@ -140,6 +156,7 @@ static int64_t execute_common(cb200_plan* plan, cb200_error* err, const std::fun
         if (plan->finished) return -1;
         start(plan);
         cuda_check(cudaSetDevice(plan->ctx.device), "cudaSetDevice");
+        set_alloc_stream(plan->ctx.stream);
         Batch b;
         if (!plan->root->next(b)) { plan->finished = true; return -1; }
         plan->last = std::move(b);
@@ -180,11 +197,14 @@ void cb200_release(cb200_plan* plan) {
         if (plan->started) cudaSetDevice(plan->ctx.device);
         plan->last = Batch();
         plan->root.reset();
+        if (plan->ctx.stream) cudaStreamSynchronize(plan->ctx.stream); // stream-ordered frees above
         // streams that were never handed to a source still belong to us
         for (auto* s : plan->inputs.streams) if (s && s->release) s->release(s);
         if (plan->ctx.stream) cudaStreamDestroy(plan->ctx.stream);
         if (plan->ctx.d_err) cudaFree(plan->ctx.d_err);
         if (plan->ctx.h_err) cudaFreeHost(plan->ctx.h_err);
+        if (plan->ctx.ev0) cudaEventDestroy(plan->ctx.ev0);
+        if (plan->ctx.ev1) cudaEventDestroy(plan->ctx.ev1);
     } catch (...) {
     }
     delete plan;
@@ -254,6 +274,18 @@ void cb200_table_release(cb200_table* t) { delete t; }
 
 int64_t cb200_plan_kernel_launches(cb200_plan* plan) { return plan ? plan->ctx.kernel_launches : -1; }
 
+int cb200_plan_stats(cb200_plan* plan, cb200_stats* out) {
+    if (!plan || !out) return -1;
+    const ExecContext& c = plan->ctx;
+    out->kernel_launches = c.kernel_launches;
+    out->pipeline_launches = c.pipeline_launches;
+    out->pipeline_ms = c.pipeline_ms;
+    out->pipeline_rows = c.pipeline_rows;
+    out->h2d_bytes = c.h2d_bytes;
+    out->d2h_bytes = c.d2h_bytes;
+    return 0;
+}
+
 int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, size_t keys_cap, cb200_error* err) {
     return guarded(err, [&]() -> int {
         OperatorP op = decode_plan(op_proto, op_len);
@@ -264,6 +296,18 @@ int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, s
             keys += (keys.empty() ? "" : ",") + g.key;
         }
         if (keys_out && keys_cap) snprintf(keys_out, keys_cap, "%s", keys.c_str());
+        return (int)ks.size();
+    }, -1);
+}
+
+int cb200_compile_plan_assume(const uint8_t* op_proto, size_t op_len, const int32_t* assume_bits, int32_t n_assume, int32_t source_index,
+                              char* src_out, size_t src_cap, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        OperatorP op = decode_plan(op_proto, op_len);
+        std::vector<int> as(assume_bits, assume_bits + n_assume);
+        auto ks = plan_kernels_for_build(op, as);
+        for (auto& g : ks) jit_get(g, false);
+        if (src_out && src_cap && source_index >= 0 && source_index < (int)ks.size()) snprintf(src_out, src_cap, "%s", ks[(size_t)source_index].source.c_str());
         return (int)ks.size();
     }, -1);
 }

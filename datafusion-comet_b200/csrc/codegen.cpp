@@ -3,6 +3,7 @@
 // Every emitted operation names the reference rule it implements; the arithmetic itself is the
 // hand-written device library device/cb_math.h (host-tested against the oracle).
 #include "codegen.h"
+#include "ranges.h"
 
 #include <climits>
 #include <cstring>
@@ -36,8 +37,10 @@ struct Val {
     std::string v;   // C expression / variable holding the value
     std::string n;   // C expression for "is null" ("" = never null)
     DType type;
+    bool narrow = false; // decimal held in a cb::i64 (its proven bound is < 2^63)
     bool nullable() const { return !n.empty(); }
 };
+const u128r R63 = (u128r)1 << 63;
 
 std::string ctype(const DType& t) {
     switch (t.id) {
@@ -89,8 +92,24 @@ struct Emitter {
     std::map<std::string, Val> cse;
     int next_id = 0;
     bool uses_err = false;
+    std::vector<u128r> col_bounds; // assumed (kernel-validated) magnitude bound per staged column
+    std::vector<bool> col_masked;  // columns whose value mask is accumulated (decimal inputs of aggregate pipelines)
 
-    explicit Emitter(const PipelineSpec& s) : spec(s) {}
+    explicit Emitter(const PipelineSpec& s) : spec(s) {
+        for (auto& c : s.cols) {
+            u128r b = RSAT;
+            if (c.type.is_decimal()) {
+                if (c.assume_bits > 0 && c.assume_bits < 127) b = (u128r)1 << c.assume_bits; // (v ^ sign) < 2^k  =>  |v| <= 2^k
+                if (c.phys == Phys::I64 || c.phys == Phys::I32) b = std::min(b, R63 - 1); // narrow storage always fits
+            }
+            col_bounds.push_back(b);
+            col_masked.push_back(s.sink == SinkKind::Agg && c.type.is_decimal());
+        }
+    }
+    u128r bound_of(const Expr& e) const { return expr_maxabs(e, col_bounds); }
+    static std::string W(const Val& v) { return v.narrow ? "cb::i128_from_i64(" + v.v + ")" : v.v; } // as cb::i128
+    std::string declw(const std::string& init) { std::string n = fresh(); body << "    cb::i128 " << n << " = " << init << ";\n"; return n; }
+    std::string decln(const std::string& init) { std::string n = fresh(); body << "    cb::i64 " << n << " = " << init << ";\n"; return n; }
 
     std::string fresh(const char* prefix = "v") { return std::string(prefix) + std::to_string(next_id++); }
 
@@ -137,6 +156,23 @@ struct Emitter {
         Val r;
         r.type = c.type;
         std::string s = std::to_string(slot);
+        if (c.has_validity) r.n = declb("!cb::ldv(t.val[" + s + "], r)");
+        std::string notnull = r.n.empty() ? "" : "if (!" + r.n + ") ";
+        if (c.type.is_decimal()) {
+            bool narrow = col_bounds[slot] < R63;
+            if (c.phys == Phys::I128) {
+                std::string raw = declw("cb::ld<cb::i128>(t.col[" + s + "], r)");
+                if (col_masked[slot]) body << "    " << notnull << "acc.vm_or(" << s << ", " << raw << ");\n";
+                if (narrow) { r.v = decln("(cb::i64)" + raw + ".lo"); r.narrow = true; }
+                else r.v = raw;
+            } else { // decimal stored as int64 / int32 (Parquet physical types)
+                std::string raw = decln(c.phys == Phys::I64 ? "cb::ld<cb::i64>(t.col[" + s + "], r)" : "(cb::i64)cb::ld<cb::i32>(t.col[" + s + "], r)");
+                if (col_masked[slot]) body << "    " << notnull << "acc.vm_or64(" << s << ", " << raw << ");\n";
+                r.v = raw;
+                r.narrow = true;
+            }
+            return r;
+        }
         std::string init;
         switch (c.phys) {
         case Phys::Bitmap: init = "cb::ldv(t.col[" + s + "], r)"; break;
@@ -148,15 +184,12 @@ struct Emitter {
         case Phys::F64: init = "cb::ld<double>(t.col[" + s + "], r)"; break;
         case Phys::I128: init = "cb::ld<cb::i128>(t.col[" + s + "], r)"; break;
         }
-        if (c.type.is_decimal() && c.phys == Phys::I64) init = "cb::i128_from_i64(" + init + ")";
-        if (c.type.is_decimal() && c.phys == Phys::I32) init = "cb::i128_from_i64((cb::i64)" + init + ")";
         if (c.phys == Phys::Dict32 || c.type.is_string()) { // dictionary codes of a string column
             r.v = fresh("k");
             body << "    cb::i32 " << r.v << " = " << init << ";\n";
         } else {
             r.v = decl(c.type, init);
         }
-        if (c.has_validity) r.n = declb("!cb::ldv(t.val[" + s + "], r)");
         return r;
     }
 
@@ -193,6 +226,10 @@ struct Emitter {
             Val r;
             r.type = e.type;
             std::string ct = c.n.empty() ? c.v : declb("!" + c.n + " && " + c.v); // NULL condition -> else branch
+            if (e.type.is_decimal()) {
+                if (a.narrow && b.narrow) { r.v = decln(ct + " ? " + a.v + " : " + b.v); r.narrow = true; }
+                else r.v = declw(ct + " ? " + W(a) + " : " + W(b));
+            } else
             r.v = decl(e.type, ct + " ? " + a.v + " : " + b.v);
             if (a.nullable() || b.nullable())
                 r.n = declb(ct + " ? " + (a.n.empty() ? "false" : a.n) + " : " + (b.n.empty() ? "false" : b.n));
@@ -208,7 +245,8 @@ struct Emitter {
         r.type = e.type;
         if (e.lit_null) {
             if (e.type.id == TypeId::Null) throw Unsupported("untyped NULL literal");
-            r.v = decl(e.type, e.type.is_decimal() ? "cb::mk128(0, 0)" : "0");
+            if (e.type.is_decimal()) { r.v = "((cb::i64)0)"; r.narrow = true; }
+            else r.v = decl(e.type, "0");
             r.n = "true";
             return r;
         }
@@ -223,7 +261,10 @@ struct Emitter {
             break;
         case TypeId::Float32: r.v = f32lit((float)e.lit_f64); break;
         case TypeId::Float64: r.v = f64lit(e.lit_f64); break;
-        case TypeId::Decimal: r.v = decl(e.type, i128lit(e.lit_dec)); break;
+        case TypeId::Decimal:
+            if (bound_of(e) < R63) { r.v = "((cb::i64)" + u64lit((uint64_t)e.lit_dec) + ")"; r.narrow = true; }
+            else r.v = declw(i128lit(e.lit_dec));
+            break;
         default: throw Unsupported("literal of type " + e.type.str());
         }
         return r;
@@ -244,6 +285,15 @@ struct Emitter {
         const DType &lt = l.type, &rt = rr.type;
         if (lt.is_decimal()) {
             int op = e.kind == ExprKind::Add ? 0 : e.kind == ExprKind::Sub ? 1 : 2;
+            const u128r raw = r_binary_raw(e, bound_of(*e.children[0]), bound_of(*e.children[1]));
+            const int natural = op == 2 ? lt.scale + rt.scale : std::max(lt.scale, rt.scale);
+            // Range proof: when the exact result provably stays inside i128 (plain) / the output precision
+            // (wide, no rescale) the checks of the reference can never fire and are not emitted.
+            bool unchecked = e.wide_decimal ? (natural == e.type.scale && raw <= r_prec_max(e.type.precision)) : raw < RSAT;
+            if (unchecked) {
+                Val u = emit_unchecked(op, l, rr, lt, rt, raw);
+                if (!u.v.empty()) { u.type = e.type; u.n = nn; return u; }
+            }
             if (e.wide_decimal) {
                 // wide_decimal_binary_expr.rs:179-291
                 std::string ok = fresh("b");
@@ -251,14 +301,11 @@ struct Emitter {
                 body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = false;\n";
                 body << "    if (" << valid << ") " << ok << " = ";
                 if (op == 2)
-                    body << "cb::wide_mul_fast(" << l.v << ", " << rr.v << ", " << (lt.scale + rt.scale - e.type.scale) << ", "
-                         << e.type.precision << ", " << r.v << ");\n";
-                else {
-                    int ms = std::max(lt.scale, rt.scale);
-                    body << "cb::wide_addsub(" << l.v << ", " << (ms - lt.scale) << ", " << rr.v << ", " << (ms - rt.scale) << ", "
-                         << (op == 1 ? "true" : "false") << ", " << (ms - e.type.scale) << ", " << e.type.precision << ", " << r.v
+                    body << "cb::wide_mul_fast(" << W(l) << ", " << W(rr) << ", " << (natural - e.type.scale) << ", " << e.type.precision << ", " << r.v
                          << ");\n";
-                }
+                else
+                    body << "cb::wide_addsub(" << W(l) << ", " << (natural - lt.scale) << ", " << W(rr) << ", " << (natural - rt.scale) << ", "
+                         << (op == 1 ? "true" : "false") << ", " << (natural - e.type.scale) << ", " << e.type.precision << ", " << r.v << ");\n";
                 if (e.eval_mode == EvalMode::Ansi) raise(valid + " && !" + ok, 1);
                 r.n = declb("!" + ok); // overflow -> NULL (Legacy/Try); null inputs -> NULL
                 return r;
@@ -268,12 +315,10 @@ struct Emitter {
             r.v = fresh();
             body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << err << " = false;\n";
             body << "    if (" << valid << ") " << r.v << " = ";
-            if (op == 2) body << "cb::dec_mul_plain(" << l.v << ", " << rr.v << ", " << err << ");\n";
-            else {
-                int rs = std::max(lt.scale, rt.scale);
-                body << (op == 0 ? "cb::dec_add_plain(" : "cb::dec_sub_plain(") << l.v << ", " << (rs - lt.scale) << ", " << rr.v
-                     << ", " << (rs - rt.scale) << ", " << err << ");\n";
-            }
+            if (op == 2) body << "cb::dec_mul_plain(" << W(l) << ", " << W(rr) << ", " << err << ");\n";
+            else
+                body << (op == 0 ? "cb::dec_add_plain(" : "cb::dec_sub_plain(") << W(l) << ", " << (natural - lt.scale) << ", " << W(rr) << ", "
+                     << (natural - rt.scale) << ", " << err << ");\n";
             raise(err, 0); // arrow: "Overflow happened on ..." fails the query
             r.n = nn;
             return r;
@@ -318,6 +363,35 @@ struct Emitter {
         return r;
     }
 
+    // exact decimal op whose result magnitude is proven < 2^127 (`raw`): no overflow handling needed.
+    // Returns an empty Val when no cheap form exists (caller falls back to the checked path).
+    Val emit_unchecked(int op, const Val& l, const Val& rr, const DType& lt, const DType& rt, u128r raw) {
+        Val r;
+        if (op == 2) {
+            if (l.narrow && rr.narrow) {
+                if (raw < R63) { r.v = decln(l.v + " * " + rr.v); r.narrow = true; }
+                else r.v = declw("cb::mul_i64_i64(" + l.v + ", " + rr.v + ")");
+            } else if (l.narrow || rr.narrow) {
+                const Val &w = l.narrow ? rr : l, &nv = l.narrow ? l : rr;
+                r.v = declw("cb::mul_i128_i64(" + w.v + ", " + nv.v + ")");
+            } else r.v = declw("cb::mul_i128_wrap(" + l.v + ", " + rr.v + ")");
+            return r;
+        }
+        int ms = std::max(lt.scale, rt.scale), lup = ms - lt.scale, rup = ms - rt.scale;
+        if (lup > 18 || rup > 18) return r; // scale factors beyond i64: keep the generic path
+        std::string F1 = "((cb::i64)" + u64lit((uint64_t)pow10_128(lup)) + ")", F2 = "((cb::i64)" + u64lit((uint64_t)pow10_128(rup)) + ")";
+        const char* o = op == 0 ? " + " : " - ";
+        if (raw < R63 && l.narrow && rr.narrow) {
+            std::string a = lup ? l.v + " * " + F1 : l.v, b = rup ? rr.v + " * " + F2 : rr.v;
+            r.v = decln(a + o + b);
+            r.narrow = true;
+            return r;
+        }
+        std::string a = lup ? "cb::mul_i128_i64(" + W(l) + ", " + F1 + ")" : W(l), b = rup ? "cb::mul_i128_i64(" + W(rr) + ", " + F2 + ")" : W(rr);
+        r.v = declw(std::string(op == 0 ? "cb::i128_add(" : "cb::i128_sub(") + a + ", " + b + ")");
+        return r;
+    }
+
     // ---- comparisons (arrow-ord cmp; floats by IEEE totalOrder) -------------------------------------
     Val emit_cmp(const Expr& e) {
         Val l = emit(*e.children[0]), rr = emit(*e.children[1]);
@@ -327,7 +401,11 @@ struct Emitter {
         std::string a = l.v, b = rr.v;
         const DType& t = l.type;
         std::string expr;
-        if (t.is_decimal()) {
+        if (t.is_decimal() && l.narrow && rr.narrow) {
+            const char* opc = e.kind == ExprKind::Eq ? "==" : e.kind == ExprKind::Neq ? "!=" : e.kind == ExprKind::Lt ? "<" : e.kind == ExprKind::LtEq ? "<=" : e.kind == ExprKind::Gt ? ">" : ">=";
+            expr = "(" + a + " " + opc + " " + b + ")";
+        } else if (t.is_decimal()) {
+            a = W(l); b = W(rr);
             switch (e.kind) {
             case ExprKind::Eq: expr = "cb::i128_eq(" + a + ", " + b + ")"; break;
             case ExprKind::Neq: expr = "!cb::i128_eq(" + a + ", " + b + ")"; break;
@@ -377,7 +455,7 @@ struct Emitter {
         Val r;
         r.type = to;
         r.n = c.n;
-        if (from == to) { r.v = c.v; return r; }
+        if (from == to) { r.v = c.v; r.narrow = c.narrow; return r; }
         if ((from.is_integer() || from.is_float()) && (to.is_integer() || to.is_float())) {
             r.v = decl(to, "(" + ctype(to) + ")" + c.v);
             return r;
@@ -396,7 +474,7 @@ struct Emitter {
         if (from.is_decimal() && to.is_decimal()) {
             std::string ok = fresh("b");
             r.v = fresh();
-            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(" << c.v << ", "
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(" << W(c) << ", "
                  << (to.scale - from.scale) << ", " << to.precision << ", " << r.v << ");\n";
             if (e.eval_mode == EvalMode::Ansi) raise(valid + " && !" + ok, 1);
             r.n = or_null(c.n, "!" + ok);
@@ -418,7 +496,7 @@ struct Emitter {
             r.type = e.type;
             std::string ok = fresh("b");
             r.v = fresh();
-            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(" << c.v << ", "
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = cb::dec_rescale_check(" << W(c) << ", "
                  << (e.type.scale - ch.children[0]->type.scale) << ", " << e.type.precision << ", " << r.v << ");\n";
             if (e.fail_on_error) raise(valid + " && !" + ok, 1);
             r.n = or_null(c.n, "!" + ok);
@@ -426,11 +504,11 @@ struct Emitter {
         }
         // checkoverflow.rs:105-200: bound check only
         Val c = emit(ch);
-        std::string valid = c.n.empty() ? "true" : "!" + c.n;
-        Val r;
+        Val r = c;
         r.type = e.type;
-        r.v = c.v;
-        std::string ok = declb("cb::dec_fits(" + c.v + ", " + bound_args(e.type.precision) + ")");
+        if (bound_of(ch) <= r_prec_max(e.type.precision)) return r; // range proof: the check can never fire
+        std::string valid = c.n.empty() ? "true" : "!" + c.n;
+        std::string ok = declb("cb::dec_fits(" + W(c) + ", " + bound_args(e.type.precision) + ")");
         if (e.fail_on_error) { raise(valid + " && !" + ok, 1); r.n = c.n; }
         else r.n = or_null(c.n, "!" + ok);
         return r;
@@ -442,7 +520,10 @@ struct Emitter {
         r.type = e.type;
         r.n = c.n;
         const DType& t = c.type;
-        if (t.is_decimal()) r.v = decl(t, "cb::i128_neg(" + c.v + ")");
+        if (t.is_decimal()) {
+            if (c.narrow) { r.v = decln("-" + c.v); r.narrow = true; } // |v| < 2^63: cannot overflow
+            else r.v = declw("cb::i128_neg(" + c.v + ")");
+        }
         else if (t.is_float()) r.v = decl(t, "-" + c.v);
         else if (t.id == TypeId::Int64) r.v = decl(t, "(cb::i64)(0ull - (cb::u64)" + c.v + ")");
         else {
@@ -464,7 +545,7 @@ struct Emitter {
             const Expr& m = *e.children[i];
             if (m.lit_null) { list_has_null = true; continue; }
             Val mv = emit(m);
-            if (v.type.is_decimal()) any += " || cb::i128_eq(" + v.v + ", " + mv.v + ")";
+            if (v.type.is_decimal()) any += (v.narrow && mv.narrow) ? " || (" + v.v + " == " + mv.v + ")" : " || cb::i128_eq(" + W(v) + ", " + W(mv) + ")";
             else if (v.type.id == TypeId::Float64) any += " || (__double_as_longlong(" + v.v + ") == __double_as_longlong(" + mv.v + "))";
             else any += " || (" + v.v + " == " + mv.v + ")";
         }
@@ -509,6 +590,9 @@ std::string header(const PipelineSpec& s, const std::string& defs) {
     o << "constexpr __host__ __device__ int cb_col_bytes(int c) { return ";
     for (size_t i = 0; i < s.cols.size(); i++) o << "c == " << i << " ? " << phys_bytes(s.cols[i].phys) << " : ";
     o << "0; }\n";
+    o << "constexpr __host__ __device__ bool cb_col_masked(int c) { return ";
+    for (size_t i = 0; i < s.cols.size(); i++) o << "c == " << i << " ? " << (s.sink == SinkKind::Agg && s.cols[i].type.is_decimal() ? "true" : "false") << " : ";
+    o << "false; }\n";
     o << "constexpr __host__ __device__ bool cb_col_has_val(int c) { return ";
     for (size_t i = 0; i < s.cols.size(); i++) o << "c == " << i << " ? " << (s.cols[i].has_validity ? "true" : "false") << " : ";
     o << "false; }\n";
@@ -538,7 +622,8 @@ int out_width(const DType& t) { return t.id == TypeId::Bool ? 1 : t.arrow_width(
 std::string to_slot(const Val& v, const std::string& dst) {
     const DType& t = v.type;
     std::ostringstream o;
-    if (t.is_decimal()) o << dst << "[0] = " << v.v << ".lo; " << dst << "[1] = (cb::u64)" << v.v << ".hi;";
+    if (t.is_decimal() && v.narrow) o << dst << "[0] = (cb::u64)" << v.v << "; " << dst << "[1] = (cb::u64)(" << v.v << " >> 63);";
+    else if (t.is_decimal()) o << dst << "[0] = " << v.v << ".lo; " << dst << "[1] = (cb::u64)" << v.v << ".hi;";
     else if (t.id == TypeId::Float64) o << dst << "[0] = (cb::u64)__double_as_longlong(" << v.v << ");";
     else if (t.id == TypeId::Float32) o << dst << "[0] = (cb::u64)__float_as_uint(" << v.v << ");";
     else if (t.id == TypeId::Bool) o << dst << "[0] = " << v.v << " ? 1ull : 0ull;";
@@ -613,7 +698,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
             }
         }
         em.body << "    const int g = " << gid << ";\n";
-        int w_rows = slots.add(W_WRAP64, "rows");
+        int w_rows = slots.add(W_WRAP64, "cnt|true"); // rows passing the filter == COUNT(*) == non-null count of never-null inputs
         em.body << "    acc.add_i64_wrap(g, " << w_rows << ", 1);\n";
 
         for (size_t ai = 0; ai < spec.aggs.size(); ai++) {
@@ -631,7 +716,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                 for (auto& v : cv) if (v.nullable()) cond += " && !" + v.n;
                 std::string condkey = cond;
                 const Val& v = cv[0];
-                std::string use = em.declb(cond);
+                std::string use = cond == "true" ? "true" : em.declb(cond);
                 // non-null (and filter-passing) row count of this input: COUNT, AVG count, !is_empty
                 auto cnt_slot = [&]() {
                     std::string k = "cnt|" + condkey;
@@ -651,14 +736,15 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                     if (dec) {
                         bool first = slots.dedup.count(std::to_string((int)W_SUM128) + "|sum|" + v.v + "|" + condkey) == 0;
                         L.w_sum = slots.add(W_SUM128, "sum|" + v.v + "|" + condkey);
-                        if (first) em.body << "    if (" << use << ") acc.add_i128(g, " << L.w_sum << ", " << v.v << ");\n";
-                        // overflow certificate only when the type alone cannot exclude overflow:
-                        // n * (10^p_in - 1) < 10^(p_in + 10) for any n <= 10^10 rows
-                        int sp = a.kind == AggKind::Avg ? a.sum_datatype.precision : a.datatype.precision;
-                        if (sp - v.type.precision < 10) {
-                            bool firstb = slots.dedup.count(std::to_string((int)W_MAX) + "|bits|" + v.v + "|" + condkey) == 0;
-                            L.w_bits = slots.add(W_MAX, "bits|" + v.v + "|" + condkey);
-                            if (firstb) em.body << "    if (" << use << ") acc.max_i64(g, " << L.w_bits << ", cb::i128_bitlen(" << v.v << "));\n";
+                        if (first) {
+                            // per-thread 64-bit partials are exact while rows/thread * |v| < 2^63 (host caps rows/thread at 2^CB_RPT_LOG2)
+                            u128r vb = em.bound_of(*a.children[0]);
+                            if (v.narrow && vb < (R63 >> CB_RPT_LOG2))
+                                em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << L.w_sum << ", " << v.v << ");\n";
+                            else if (v.narrow)
+                                em.body << "    if (" << use << ") acc.add_i64_wide(g, " << L.w_sum << ", " << v.v << ");\n";
+                            else
+                                em.body << "    if (" << use << ") acc.add_i128(g, " << L.w_sum << ", " << v.v << ");\n";
                         }
                     } else if (f64) {
                         L.is_f64_sum = true;
@@ -675,7 +761,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                 }
                 case AggKind::Min: case AggKind::Max: {
                     L.w_cnt = cnt_slot();
-                    std::string key = v.type.is_decimal() ? "(cb::i64)" + v.v + ".lo"
+                    std::string key = v.type.is_decimal() ? (v.narrow ? v.v : "(cb::i64)" + v.v + ".lo")
                                       : v.type.id == TypeId::Float64 ? "cb::f64_total_key((cb::u64)__double_as_longlong(" + v.v + "))"
                                                                      : "(cb::i64)" + v.v;
                     bool mn = a.kind == AggKind::Min;
@@ -705,10 +791,9 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                         L.w_sum = slots.add(W_SUM128, tag + "sum");
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
                         L.w_bad = slots.add(W_WRAP64, tag + "bad");
-                        L.w_bits = slots.add(W_MAX, tag + "bits");
                         em.body << "    if (!" << e.v << " && " << snull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
-                        em.body << "    else if (!" << e.v << ") { acc.add_i128(g, " << L.w_sum << ", " << s.v << "); acc.add_i64_wrap(g, " << L.w_cnt
-                                << ", 1); acc.max_i64(g, " << L.w_bits << ", cb::i128_bitlen(" << s.v << ")); }\n";
+                        em.body << "    else if (!" << e.v << ") { acc.add_i128(g, " << L.w_sum << ", " << Emitter::W(s) << "); acc.add_i64_wrap(g, " << L.w_cnt
+                                << ", 1); }\n";
                     } else if (a.datatype.is_integer()) { // sum_int.rs:497-528
                         Val s = col(0);
                         L.w_sum = slots.add(W_WRAP64, tag + "sum");
@@ -730,12 +815,10 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                         L.w_sum = slots.add(W_SUM128, tag + "sum");
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
                         L.w_bad = slots.add(W_WRAP64, tag + "bad");
-                        L.w_bits = slots.add(W_MAX, tag + "bits");
                         std::string cnull = c.n.empty() ? "false" : c.n, snull = s.n.empty() ? "false" : s.n;
                         em.body << "    if (!" << cnull << ") acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
                         em.body << "    if (" << snull << " || " << cnull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
-                        em.body << "    if (!" << snull << ") { acc.add_i128(g, " << L.w_sum << ", " << s.v << "); acc.max_i64(g, " << L.w_bits
-                                << ", cb::i128_bitlen(" << s.v << ")); }\n";
+                        em.body << "    if (!" << snull << ") acc.add_i128(g, " << L.w_sum << ", " << Emitter::W(s) << ");\n";
                     } else { // avg.rs:279-309
                         Val s = col(0), c = col(1);
                         L.is_f64_sum = true;
@@ -749,7 +832,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                     bool mn = a.kind == AggKind::Min;
                     L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
                     L.w_minmax = slots.add(mn ? W_MIN : W_MAX, tag + "mm");
-                    std::string key = s.type.is_decimal() ? "(cb::i64)" + s.v + ".lo"
+                    std::string key = s.type.is_decimal() ? (s.narrow ? s.v : "(cb::i64)" + s.v + ".lo")
                                       : s.type.id == TypeId::Float64 ? "cb::f64_total_key((cb::u64)__double_as_longlong(" + s.v + "))"
                                                                      : "(cb::i64)" + s.v;
                     em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc." << (mn ? "min_i64" : "max_i64") << "(g, " << L.w_minmax << ", "
@@ -793,9 +876,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                     // exact total; overflow decided by the certificate (see DESIGN.md "decimal sums")
                     fin << "      cb::i128 s = " << T128(L.w_sum) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
                     fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
-                    fin << "      int cert = " << (L.w_bits >= 0 ? "cb::sum_certificate(n, " + T64(L.w_bits) + ", s, " + std::to_string(a.datatype.precision) + ")"
-                                                               : "(cb::dec_fits_p(s, " + std::to_string(a.datatype.precision) + ") ? 0 : 1)")
-                        << "; // 0 fits, 1 overflow, 2 order-dependent\n";
+                    fin << "      int cert = cb::sum_cert(fp.cert[" << ai << "], cb::dec_fits_p(s, " << a.datatype.precision << ")); // 0 fits, 1 overflow, 2 order-dependent\n";
                     fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
                     fin << "      bool ovf = bad || (n > 0 && cert != 0);\n";
                     if (a.eval_mode == EvalMode::Ansi) fin << "      if (ovf && !bad) cb::set_err_raw(fp.err, 1);\n";
@@ -825,9 +906,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                     int sp = a.sum_datatype.precision;
                     fin << "      cb::i128 s = " << T128(L.w_sum) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
                     fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
-                    fin << "      int cert = " << (L.w_bits >= 0 ? "cb::sum_certificate(n, " + T64(L.w_bits) + ", s, " + std::to_string(sp) + ")"
-                                                               : "(cb::dec_fits_p(s, " + std::to_string(sp) + ") ? 0 : 1)")
-                        << ";\n";
+                    fin << "      int cert = cb::sum_cert(fp.cert[" << ai << "], cb::dec_fits_p(s, " << sp << "));\n";
                     fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
                     fin << "      bool notnull = !bad && !(n > 0 && cert != 0);\n";
                     if (partial) { // state(): sums and counts share is_not_null as validity (avg_decimal.rs:640-656)

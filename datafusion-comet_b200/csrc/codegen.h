@@ -19,7 +19,11 @@ struct SourceCol {
     DType type;      // logical type
     Phys phys;
     bool has_validity;
+    int assume_bits = 0; // decimal columns: kernel may assume |v| < 2^assume_bits (validated by the value masks); 0 = no assumption
 };
+
+// thread-private 64-bit partial sums are exact while rows/thread <= 2^CB_RPT_LOG2 (host enforces it per launch)
+#define CB_RPT_LOG2 14
 
 enum class SinkKind { Select, Agg };
 

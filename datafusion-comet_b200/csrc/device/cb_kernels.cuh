@@ -162,6 +162,10 @@ struct Acc {
     u64* base; // shared memory, already offset by threadIdx.x
 #endif
     const PipeParams* p;
+    u64 vm[2 * CB_NCOLS]; // OR of (value ^ sign) per staged column: validates range assumptions, feeds the host certificate
+
+    CB_D void vm_or(int c, i128 raw) { u64 s = (u64)(raw.hi >> 63); vm[2 * c] |= raw.lo ^ s; vm[2 * c + 1] |= (u64)raw.hi ^ s; }
+    CB_D void vm_or64(int c, i64 raw) { vm[2 * c] |= (u64)raw ^ (u64)(raw >> 63); }
 
     CB_D u64& word(int g, int w) {
 #if CB_G1
@@ -230,6 +234,8 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
     }
     Acc acc;
     acc.p = &p;
+#pragma unroll
+    for (int c = 0; c < 2 * CB_NCOLS; c++) acc.vm[c] = 0;
 #if CB_G1
 #pragma unroll
     for (int w = 0; w < CB_WORDS; w++) acc.r[w] = acc_identity(cb_word_kind(w));
@@ -264,6 +270,15 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
 #pragma unroll 2
         for (int r = tid; r < rows; r += CB_THREADS) cb_row_agg(t, r, row0 + r, p, acc);
         __syncthreads(); // stage s fully consumed
+    }
+
+    // ---- publish the value masks (warp OR-reduce, one atomic per warp and word) ----------------------
+#pragma unroll
+    for (int c = 0; c < 2 * CB_NCOLS; c++) {
+        if (!cb_col_masked(c >> 1)) continue;
+        u32 lo = __reduce_or_sync(0xffffffffu, (u32)acc.vm[c]), hi = __reduce_or_sync(0xffffffffu, (u32)(acc.vm[c] >> 32));
+        u64 m = ((u64)hi << 32) | lo;
+        if ((tid & 31) == 0 && m) atomicOr((unsigned long long*)&p.vmask[c], (unsigned long long)m);
     }
 
     // ---- fold thread-private partials into one per-CTA partial per (group, word) -------------------

@@ -326,6 +326,19 @@ CB_HD bool wide_mul_fast(i128 l, i128 r, int scale_diff, int p_out, i128& out) {
     }
     return wide_mul(l, r, scale_diff, p_out, out);
 }
+// wrapping 128-bit products: exact whenever the true product is known to fit (range-proved by codegen)
+CB_HD i128 mul_i128_i64(i128 a, i64 b) {
+    u64 ub = (u64)b;
+    u64 lo = a.lo * ub;
+    u64 hi = umulhi64(a.lo, ub) + (u64)a.hi * ub;
+    if (b < 0) hi -= a.lo; // signed correction for the multiplier
+    return mk128(lo, (i64)hi);
+}
+CB_HD i128 mul_i128_wrap(i128 a, i128 b) {
+    u64 lo = a.lo * b.lo;
+    u64 hi = umulhi64(a.lo, b.lo) + a.lo * (u64)b.hi + (u64)a.hi * b.lo;
+    return mk128(lo, (i64)hi);
+}
 CB_HD bool i64_add_overflow(i64 a, i64 b, i64& r) { r = (i64)((u64)a + (u64)b); return ((a ^ r) & (b ^ r)) < 0; }
 CB_HD bool i64_sub_overflow(i64 a, i64 b, i64& r) { r = (i64)((u64)a - (u64)b); return ((a ^ b) & (a ^ r)) < 0; }
 CB_HD bool i64_mul_overflow(i64 a, i64 b, i64& r) { i128 p = mul_i64_i64(a, b); r = (i64)p.lo; return !i128_fits_i64(p); }
@@ -333,30 +346,16 @@ CB_HD bool i64_mul_overflow(i64 a, i64 b, i64& r) { i128 p = mul_i64_i64(a, b); 
 // ---- overflow certificate for decimal sums ------------------------------------------------------
 // The reference adds row by row and nulls the sum as soon as a running prefix leaves the precision
 // (agg_funcs/sum_decimal.rs:418-439).  A parallel sum reproduces that exactly whenever no ordering
-// of the addends can overflow: n * max|v| <= 10^p - 1.  bitlen(v) bounds |v| <= 2^bitlen.
-CB_HD int clz64(u64 x) {
-#if defined(__CUDA_ARCH__)
-    return __clzll((long long)x);
-#else
-    return x ? __builtin_clzll(x) : 64;
-#endif
-}
-CB_HD i64 i128_bitlen(i128 v) {
-    u64 s = (u64)(v.hi >> 63);
-    u64 hi = (u64)v.hi ^ s, lo = v.lo ^ s;
-    return hi ? 128 - clz64(hi) : 64 - clz64(lo);
-}
-// 0: the sum fits for every ordering (result = exact total); 1: it overflows for every ordering
-// (same-sign certificate not needed: the total itself is out of range); 2: order-dependent.
-CB_HD int sum_certificate(i64 n, i64 max_bitlen, i128 total, int precision) {
-    if (n <= 0) return 0;
-    u128 bound = pow10_u128(precision); // 10^p
-    // bit length of 10^p - 1
-    u64 bhi = bound.hi, blo = bound.lo - 1; if (bound.lo == 0) bhi -= 1;
-    int blen = bhi ? 128 - clz64(bhi) : 64 - clz64(blo);
-    int nb = 64 - clz64((u64)n);           // n <= 2^nb
-    if (nb + (int)max_bitlen <= blen - 1) return 0;
-    if (nb + (int)max_bitlen <= 126 && !dec_fits_p(total, precision)) return 1;
+// of the addends can overflow: n * max|v| <= 10^p - 1.
+// host certificate h (exec.cpp AggNode::certificate, from the observed input ranges):
+//   0: n * max|v| <= 10^p - 1          -> no ordering can overflow, the exact total is the answer
+//   1: n * max|v| <  2^127             -> the 128-bit total is exact; if IT is out of range every ordering
+//                                         overflows (the last prefix is the total), otherwise order-dependent
+//   2: the 128-bit total may have wrapped
+// returns 0 fits, 1 overflows (NULL / ANSI error), 2 order-dependent (cannot be decided without row order)
+CB_HD int sum_cert(int h, bool total_fits) {
+    if (h == 0) return total_fits ? 0 : 1;
+    if (h == 1 && !total_fits) return 1;
     return 2;
 }
 

@@ -25,6 +25,7 @@ struct PipeParams {
     u8* partials;                    // agg: per-CTA partial slots [grid][n_groups][CB_WORDS] x 16 B
     u64* spill;                      // agg: exact 128-bit escape accumulators [n_groups][CB_WORDS][2]
     i32* err;                        // error flags (bit 0: arithmetic overflow, bit1: ansi error...)
+    u64* vmask;                      // agg: per staged column OR of (value ^ sign) over valid rows [CB_MAX_COLS][2] (lo, hi)
 };
 
 
@@ -38,6 +39,7 @@ struct FinParams {
     u8* outv[CB_MAX_OUT];  // finalize: validity, one byte per group
     u8* present;           // finalize: 1 if the group saw at least one row
     i32* err;
+    i32 cert[CB_MAX_OUT];  // per aggregate: 0 = host certified that the decimal sum cannot overflow for any row order, 2 = not certified
 };
 
 } // namespace cb

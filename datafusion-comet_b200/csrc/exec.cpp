@@ -3,6 +3,7 @@
 
 #include "aot_kernels.h"
 #include "device/cb_params.h"
+#include "ranges.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -21,17 +22,31 @@ void cuda_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw ExecError(2, "", std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
 }
 
+// Stream-ordered allocation from the device's default pool (kept warm: cudaFree on a process that holds
+// tens of GB costs milliseconds and synchronises the device; cudaFreeAsync does neither).
+static thread_local cudaStream_t tl_alloc_stream = nullptr;
+void set_alloc_stream(cudaStream_t s) { tl_alloc_stream = s; }
+
 DeviceBuf::DeviceBuf(size_t n) {
     bytes = (n + 255) / 256 * 256 + 256; // padded: TMA bulk copies round sizes up to 16 B
-    cuda_check(cudaMalloc(&ptr, bytes), "cudaMalloc");
+    stream = tl_alloc_stream;
+    cuda_check(cudaMallocAsync(&ptr, bytes, stream), "cudaMallocAsync");
 }
 DeviceBuf::~DeviceBuf() {
-    if (owned && ptr) cudaFree(ptr);
+    if (owned && ptr) cudaFreeAsync(ptr, stream);
+}
+
+void ExecContext::collect_timing() {
+    if (!ev_pending) return;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) { pipeline_ms += ms; pipeline_launches++; }
+    ev_pending = false;
 }
 
 void ExecContext::check_device_errors() {
     cuda_check(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream), "error flag copy");
     cuda_check(cudaStreamSynchronize(stream), "stream sync");
+    collect_timing();
     int e = *h_err;
     if (!e) return;
     cudaMemsetAsync(d_err, 0, sizeof(int), stream);
@@ -217,6 +232,11 @@ struct StreamSource : ExecNode {
         return remap;
     }
 
+    cudaError_t h2d(void* dst, const void* src, size_t n) {
+        ctx->h2d_bytes += (int64_t)n;
+        return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream);
+    }
+
     void upload(std::vector<ArrowArray>& arrs, int64_t total, Batch& out) {
         out.n_rows = total;
         out.cols.clear();
@@ -257,16 +277,16 @@ struct StreamSource : ExecNode {
                     ArrowArray* ch = arrs[k].children[c];
                     const char* src = (const char*)ch->buffers[1] + ch->offset * w;
                     if (!need_remap) {
-                        cuda_check(cudaMemcpyAsync((char*)col.data->ptr + row * w, src, (size_t)ch->length * w, cudaMemcpyHostToDevice, st), "H2D dict codes");
+                        cuda_check(h2d((char*)col.data->ptr + row * w, src, (size_t)ch->length * w), "H2D dict codes");
                     } else {
                         auto tmp = std::make_shared<DeviceBuf>((size_t)ch->length * w);
                         temps.push_back(tmp);
-                        cuda_check(cudaMemcpyAsync(tmp->ptr, src, (size_t)ch->length * w, cudaMemcpyHostToDevice, st), "H2D dict codes");
+                        cuda_check(h2d(tmp->ptr, src, (size_t)ch->length * w), "H2D dict codes");
                         std::vector<int32_t> table = remaps[k];
                         if (table.empty()) { table.resize((size_t)ch->dictionary->length); for (size_t i = 0; i < table.size(); i++) table[i] = (int32_t)i; }
                         auto dt = std::make_shared<DeviceBuf>(table.size() * 4 + 4);
                         temps.push_back(dt);
-                        cuda_check(cudaMemcpyAsync(dt->ptr, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st), "H2D remap table");
+                        cuda_check(h2d(dt->ptr, table.data(), table.size() * 4), "H2D remap table");
                         cuda_check(cudaStreamSynchronize(st), "remap table copy"); // table is a stack temporary
                         launch_remap_codes(tmp->ptr, w, ch->length, (const int*)dt->ptr, (int)table.size(), (int*)col.data->ptr + row, st);
                     }
@@ -291,12 +311,12 @@ struct StreamSource : ExecNode {
                     const int32_t* off = (const int32_t*)ch->buffers[1] + ch->offset;
                     for (int64_t i = 0; i < ch->length; i++) offs[(size_t)(row + i)] = base + (off[i] - off[0]);
                     int32_t nchars = off[ch->length] - off[0];
-                    if (nchars) cuda_check(cudaMemcpyAsync((char*)col.chars->ptr + base, (const char*)ch->buffers[2] + off[0], (size_t)nchars, cudaMemcpyHostToDevice, st), "H2D chars");
+                    if (nchars) cuda_check(h2d((char*)col.chars->ptr + base, (const char*)ch->buffers[2] + off[0], (size_t)nchars), "H2D chars");
                     base += nchars;
                     row += ch->length;
                 }
                 offs[(size_t)total] = base;
-                cuda_check(cudaMemcpyAsync(col.offsets->ptr, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st), "H2D offsets");
+                cuda_check(h2d(col.offsets->ptr, offs.data(), offs.size() * 4), "H2D offsets");
                 cuda_check(cudaStreamSynchronize(st), "offsets copy");
                 col.phys = Phys::I32;
             } else {
@@ -316,8 +336,7 @@ struct StreamSource : ExecNode {
                     int64_t row = 0;
                     for (auto& a : arrs) {
                         ArrowArray* ch = a.children[c];
-                        cuda_check(cudaMemcpyAsync((char*)col.data->ptr + row * w, (const char*)ch->buffers[1] + ch->offset * w, (size_t)ch->length * w,
-                                                   cudaMemcpyHostToDevice, st), "H2D column");
+                        cuda_check(h2d((char*)col.data->ptr + row * w, (const char*)ch->buffers[1] + ch->offset * w, (size_t)ch->length * w), "H2D column");
                         row += ch->length;
                     }
                 }
@@ -341,7 +360,7 @@ struct StreamSource : ExecNode {
     void append_bits(uint32_t* dst, int64_t row, const uint8_t* src, int64_t src_off, int64_t n, std::vector<DeviceBufP>& temps) {
         if (n <= 0) return;
         if (src && (row & 7) == 0 && (src_off & 7) == 0 && ((n & 7) == 0)) {
-            cuda_check(cudaMemcpyAsync((char*)dst + (row >> 3), src + (src_off >> 3), (size_t)(n >> 3), cudaMemcpyHostToDevice, ctx->stream), "H2D bitmap");
+            cuda_check(h2d((char*)dst + (row >> 3), src + (src_off >> 3), (size_t)(n >> 3)), "H2D bitmap");
             return;
         }
         const uint8_t* dsrc = nullptr;
@@ -350,7 +369,7 @@ struct StreamSource : ExecNode {
             int64_t b0 = src_off >> 3, b1 = (src_off + n + 7) >> 3;
             auto tmp = std::make_shared<DeviceBuf>((size_t)(b1 - b0) + 8);
             temps.push_back(tmp);
-            cuda_check(cudaMemcpyAsync(tmp->ptr, src + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, ctx->stream), "H2D bitmap");
+            cuda_check(h2d(tmp->ptr, src + b0, (size_t)(b1 - b0)), "H2D bitmap");
             dsrc = (const uint8_t*)tmp->ptr;
             doff = src_off & 7;
         }
@@ -419,22 +438,29 @@ struct FusedBase : ExecNode {
         }
         return out;
     }
-    void fill_inputs(cb::PipeParams& p, const Batch& b, int tile) const {
+    void fill_inputs(cb::PipeParams& p, const Batch& b, int tile, int64_t row0 = 0, int64_t row1 = -1) const {
         memset(&p, 0, sizeof(p));
+        if (row1 < 0) row1 = b.n_rows;
+        if (row0 & 1023) throw ExecError(15, "", "internal: launch range must start on a 1024-row boundary");
         for (size_t i = 0; i < used_cols.size(); i++) {
             const Column& c = b.cols[used_cols[i]];
             if (!c.data) throw Unsupported("column " + std::to_string(used_cols[i]) + " (" + c.type.str() + ") has no fixed-width device representation");
-            p.col[i] = (const cb::u8*)c.data->ptr;
-            p.val[i] = c.validity ? (const cb::u8*)c.validity->ptr : nullptr;
+            int w = phys_bytes(c.is_dict && c.phys == Phys::I32 ? Phys::Dict32 : c.phys);
+            p.col[i] = (const cb::u8*)c.data->ptr + (w == 0 ? row0 / 8 : row0 * w);
+            p.val[i] = c.validity ? (const cb::u8*)c.validity->ptr + row0 / 8 : nullptr;
         }
-        p.n_rows = b.n_rows;
-        p.n_tiles = (int)((b.n_rows + tile - 1) / tile);
+        p.n_rows = row1 - row0;
+        p.n_tiles = (int)((p.n_rows + tile - 1) / tile);
         p.err = ctx->d_err;
     }
     void launch(cudaKernel_t k, dim3 grid, dim3 block, size_t smem, void* params) {
         cuda_check(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
         void* args[] = {params};
+        if (ctx->ev_pending) { cuda_check(cudaStreamSynchronize(ctx->stream), "stream sync"); ctx->collect_timing(); }
+        cuda_check(cudaEventRecord(ctx->ev0, ctx->stream), "event record");
         cuda_check(cudaLaunchKernel((const void*)k, grid, block, args, smem, ctx->stream), "kernel launch");
+        cuda_check(cudaEventRecord(ctx->ev1, ctx->stream), "event record");
+        ctx->ev_pending = true;
         ctx->kernel_launches++;
     }
 };
@@ -507,6 +533,7 @@ struct SelectNode : FusedBase {
         p.out_count = (cb::i64*)((char*)counters->ptr + 16);
         int grid = std::min(ctx->num_sms, p.n_tiles);
         launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(0), &p);
+        ctx->pipeline_rows += in.n_rows;
         int64_t kept = 0;
         cuda_check(cudaMemcpyAsync(&kept, p.out_count, 8, cudaMemcpyDeviceToHost, st), "read kept count");
         ctx->check_device_errors(); // also synchronises
@@ -514,6 +541,10 @@ struct SelectNode : FusedBase {
         // boolean outputs were written one byte per row; repack lazily at export
     }
 };
+
+// build-time only (cb200_compile_plan_assume): value-range assumptions per source column, so the specialised
+// kernels of known workloads can be compiled ahead of time
+std::vector<int> g_build_assume;
 
 // ---- dense / ungrouped aggregation --------------------------------------------------------------------
 struct AggNode : FusedBase {
@@ -538,9 +569,26 @@ struct AggNode : FusedBase {
     struct DevDict { StringDictDev d; std::vector<DeviceBufP> bufs; DeviceBufP row_slot; int host_known = 0; };
     std::vector<std::shared_ptr<DevDict>> dev_dicts;
 
-    PipelineSpec make_spec(const Batch* b, int n_groups) const {
+    // ---- range assumptions (see ranges.h) ----------------------------------------------------------------
+    enum Level { SAFE = 0, TYPE = 1, TIGHT = 2 };
+    std::vector<int> observed_bits; // per child column: max bit length of (v ^ sign) over every valid row scanned so far (-1: none)
+    int64_t rows_scanned = 0;
+    DeviceBufP vmask;
+
+    static int type_bits(const DType& t) { return r_bitlen(r_prec_max(t.precision)); }
+    int assume_for(int child_col, Level lv) const {
+        const DType& t = child->schema[(size_t)child_col];
+        if (!t.is_decimal() || lv == SAFE || mode != AggMode::Partial) return 0;
+        int k = type_bits(t);
+        if (!ctx && (size_t)child_col < g_build_assume.size() && g_build_assume[(size_t)child_col] > 0) k = std::min(k, g_build_assume[(size_t)child_col]);
+        if (lv == TIGHT && !observed_bits.empty() && observed_bits[(size_t)child_col] >= 0) k = std::min(k, observed_bits[(size_t)child_col] + 2);
+        return std::min(k, 126);
+    }
+
+    PipelineSpec make_spec(const Batch* b, int n_groups, Level lv = TYPE) const {
         PipelineSpec s;
         s.cols = stage_cols(b);
+        for (auto& c : s.cols) c.assume_bits = assume_for(c.src_index, lv);
         s.predicates = to_slots(predicates, slot_of);
         s.sink = SinkKind::Agg;
         s.mode = mode;
@@ -665,7 +713,8 @@ struct AggNode : FusedBase {
             memcpy(&newt[(size_t)ng * n_words * 2], &oldt[(size_t)g * n_words * 2], (size_t)n_words * 16);
         }
         totals = std::make_shared<DeviceBuf>(newt.size() * 8);
-        cuda_check(cudaMemcpy(totals->ptr, newt.data(), newt.size() * 8, cudaMemcpyHostToDevice), "regroup H2D");
+        cuda_check(cudaMemcpyAsync(totals->ptr, newt.data(), newt.size() * 8, cudaMemcpyHostToDevice, ctx->stream), "regroup H2D");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "regroup sync");
         totals_groups = new_groups;
     }
     std::vector<bool> key_has_null_prev;
@@ -685,16 +734,53 @@ struct AggNode : FusedBase {
         if (n_groups > 4096) throw Unsupported("more than 4096 dense groups (hash aggregation path pending)");
         key_has_null_prev = key_has_null;
         key_has_null = hn;
-        PipelineSpec spec = make_spec(&b, n_groups);
-        GeneratedKernel g = generate_pipeline(spec);
-        auto mod = jit_get(g, true);
-        ctx->last_kernel_key = g.key;
-        if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds))
-            throw ExecError(15, "", "internal: accumulator layout changed between batches");
-        n_words = g.n_words;
-        word_kinds = g.word_kinds;
-        if (have_totals && nc != cards) regroup(nc);
+        if (have_totals && nc != cards) {
+            if (n_words == 0) throw ExecError(15, "", "internal: regroup before layout");
+            regroup(nc);
+        }
         cards = nc;
+        if (observed_bits.empty()) observed_bits.assign(child->schema.size(), -1);
+        const int64_t SAMPLE = 1 << 20;
+        bool have_obs = false;
+        for (int ci : used_cols) if (child->schema[(size_t)ci].is_decimal() && observed_bits[(size_t)ci] >= 0) have_obs = true;
+        if (mode != AggMode::Partial) {
+            run_range(b, 0, b.n_rows, n_groups, SAFE);
+        } else if (!have_obs && b.n_rows > 2 * SAMPLE) {
+            // sample-then-specialise: a short launch measures the value ranges, the bulk launch runs the kernel
+            // specialised to them (64-bit arithmetic, unconditional accumulation); every launch validates its
+            // assumptions through the value masks, so a violated guess only costs a re-run.
+            run_range(b, 0, SAMPLE, n_groups, TYPE);
+            run_range(b, SAMPLE, b.n_rows, n_groups, TIGHT);
+        } else {
+            run_range(b, 0, b.n_rows, n_groups, have_obs ? TIGHT : TYPE);
+        }
+    }
+
+    // one (possibly split) launch over rows [row0,row1) at assumption level lv, escalating on violated assumptions
+    void run_range(Batch& b, int64_t row0, int64_t row1, int n_groups, Level lv) {
+        while (true) {
+            PipelineSpec spec = make_spec(&b, n_groups, lv);
+            GeneratedKernel g = generate_pipeline(spec);
+            auto mod = jit_get(g, true);
+            ctx->last_kernel_key = g.key;
+            if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds))
+                throw ExecError(15, "", "internal: accumulator layout changed between launches");
+            n_words = g.n_words;
+            word_kinds = g.word_kinds;
+            const int64_t max_rows = (int64_t)ctx->num_sms * g.threads * (1ll << CB_RPT_LOG2) / 1024 * 1024;
+            bool ok = true;
+            for (int64_t r0 = row0; r0 < row1 && ok; r0 += max_rows) ok = launch_one(b, r0, std::min(row1, r0 + max_rows), n_groups, spec, g, mod);
+            if (ok) return;
+            if (lv == SAFE) throw ExecError(15, "", "internal: value-mask validation failed without assumptions");
+            lv = lv == TIGHT ? TYPE : SAFE; // widen: observed ranges -> declared precision -> no assumption (fully checked code)
+            // partial sub-launches of the failed attempt were already folded only if they validated; restart the remainder
+            row0 = failed_from;
+        }
+    }
+    int64_t failed_from = 0;
+
+    bool launch_one(Batch& b, int64_t r0, int64_t r1, int n_groups, const PipelineSpec& spec, const GeneratedKernel& g,
+                    const std::shared_ptr<CompiledModule>& mod) {
         cudaStream_t st = ctx->stream;
         size_t tot_bytes = (size_t)n_groups * n_words * 16;
         if (!have_totals) {
@@ -705,8 +791,10 @@ struct AggNode : FusedBase {
             spill = std::make_shared<DeviceBuf>(tot_bytes);
             cuda_check(cudaMemsetAsync(spill->ptr, 0, spill->bytes, st), "memset spill");
         }
+        if (!vmask) vmask = std::make_shared<DeviceBuf>(CB_MAX_COLS * 16);
+        cuda_check(cudaMemsetAsync(vmask->ptr, 0, CB_MAX_COLS * 16, st), "memset vmask");
         cb::PipeParams p;
-        fill_inputs(p, b, g.tile);
+        fill_inputs(p, b, g.tile, r0, r1);
         int grid = std::max(1, std::min(ctx->num_sms, p.n_tiles));
         size_t part_bytes = (size_t)grid * tot_bytes;
         if (!partials || partials->bytes < part_bytes) partials = std::make_shared<DeviceBuf>(part_bytes);
@@ -714,9 +802,34 @@ struct AggNode : FusedBase {
         for (size_t k = 0; k < cards.size() && k < CB_MAX_KEYS; k++) p.key_card[k] = cards[k];
         p.partials = (cb::u8*)partials->ptr;
         p.spill = (cb::u64*)spill->ptr;
-        // per-thread 64-bit partials are exact for < 2^16 rows per thread (|v| < 2^46 fast path)
-        if (b.n_rows > (int64_t)grid * g.threads * 65000ll) throw ExecError(16, "", "chunk too large for the 64-bit partial-sum fast path; lower chunkRows");
+        p.vmask = (cb::u64*)vmask->ptr;
         launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(n_groups), &p);
+        ctx->pipeline_rows += r1 - r0;
+        uint64_t masks[CB_MAX_COLS * 2];
+        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, st), "read value masks");
+        ctx->check_device_errors(); // synchronises
+        // validate the assumptions this kernel was specialised for
+        std::vector<int> seen(spec.cols.size(), -1);
+        bool ok = true;
+        for (size_t i = 0; i < spec.cols.size(); i++) {
+            if (!spec.cols[i].type.is_decimal()) continue;
+            uint64_t lo = masks[2 * i], hi = masks[2 * i + 1];
+            int bl = hi ? 64 + r_bitlen(hi) : r_bitlen(lo);
+            seen[i] = bl;
+            if (spec.cols[i].assume_bits > 0 && bl > spec.cols[i].assume_bits) ok = false;
+        }
+        if (!ok) {
+            // discard this launch: partials are simply not folded; the exact-escape accumulators must be cleared
+            cuda_check(cudaMemsetAsync(spill->ptr, 0, spill->bytes, st), "memset spill");
+            // remember what we saw so the retry is specialised correctly
+            for (size_t i = 0; i < spec.cols.size(); i++)
+                if (seen[i] >= 0) observed_bits[(size_t)used_cols[i]] = std::max(observed_bits[(size_t)used_cols[i]], seen[i]);
+            failed_from = r0;
+            return false;
+        }
+        for (size_t i = 0; i < spec.cols.size(); i++)
+            if (seen[i] >= 0) observed_bits[(size_t)used_cols[i]] = std::max(observed_bits[(size_t)used_cols[i]], seen[i]);
+        rows_scanned += r1 - r0;
         cb::FinParams fp;
         memset(&fp, 0, sizeof(fp));
         fp.partials = (const cb::u64*)partials->ptr;
@@ -733,6 +846,23 @@ struct AggNode : FusedBase {
         have_totals = true;
         last_gen = g;
         last_mod = mod;
+        return true;
+    }
+
+    // host certificate: can the decimal sum of aggregate `ai` overflow for ANY row order, given the observed input ranges?
+    int certificate(size_t ai) const {
+        const AggExpr& a = aggs[ai];
+        if (!(a.kind == AggKind::Sum || a.kind == AggKind::Avg) || !a.datatype.is_decimal()) return 0;
+        std::vector<u128r> bounds(child->schema.size(), RSAT);
+        for (size_t c = 0; c < bounds.size(); c++)
+            if (child->schema[c].is_decimal() && !observed_bits.empty())
+                bounds[c] = observed_bits[c] < 0 ? 0 : (observed_bits[c] >= 127 ? RSAT : (u128r)1 << observed_bits[c]);
+        u128r B;
+        if (mode == AggMode::Partial) B = expr_maxabs(*a.children[0], bounds);
+        else B = bounds[(size_t)state_cols[ai][0]];
+        int sp = a.kind == AggKind::Avg ? a.sum_datatype.precision : a.datatype.precision;
+        u128r total = r_mul((u128r)std::max<int64_t>(rows_scanned, 1), B);
+        return total <= r_prec_max(sp) ? 0 : total < RSAT ? 1 : 2; // see cb::sum_cert
     }
 
     bool next(Batch& out) override {
@@ -759,7 +889,8 @@ struct AggNode : FusedBase {
             std::vector<uint64_t> id((size_t)n_words * 2, 0);
             for (int w = 0; w < n_words; w++) id[(size_t)w * 2] = word_kinds[(size_t)w] == W_MIN ? 0x7fffffffffffffffull : word_kinds[(size_t)w] == W_MAX ? 0x8000000000000000ull : 0;
             totals = std::make_shared<DeviceBuf>(id.size() * 8);
-            cuda_check(cudaMemcpy(totals->ptr, id.data(), id.size() * 8, cudaMemcpyHostToDevice), "identity totals");
+            cuda_check(cudaMemcpyAsync(totals->ptr, id.data(), id.size() * 8, cudaMemcpyHostToDevice, ctx->stream), "identity totals");
+            cuda_check(cudaStreamSynchronize(ctx->stream), "identity totals sync");
             totals_groups = 1;
         }
         finalize(out);
@@ -774,6 +905,7 @@ struct AggNode : FusedBase {
         fp.totals = (cb::u64*)totals->ptr;
         fp.n_groups = ng;
         fp.err = ctx->d_err;
+        for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) fp.cert[ai] = certificate(ai);
         std::vector<DeviceBufP> bufs, vbufs;
         for (size_t i = 0; i < g.out_cols.size(); i++) {
             bufs.push_back(std::make_shared<DeviceBuf>((size_t)ng * g.out_bytes[i]));
@@ -960,7 +1092,8 @@ static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* i
 
 ExecNodeP build_exec(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs) { return build_node(op, ctx, inputs, false); }
 
-std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op) {
+std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const std::vector<int>& assume) {
+    g_build_assume = assume;
     std::vector<GeneratedKernel> out;
     ExecNodeP root = build_node(op, nullptr, nullptr, true);
     std::function<void(const ExecNodeP&)> walk = [&](const ExecNodeP& n) {
@@ -1046,6 +1179,7 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
             int w = c.type.id == TypeId::Bool ? 1 : c.type.arrow_width();
             std::vector<uint8_t> raw(n * (size_t)w + 8);
             if (n) cuda_check(cudaMemcpyAsync(raw.data(), c.data->ptr, n * (size_t)w, cudaMemcpyDeviceToHost, ctx->stream), "D2H output");
+            ctx->d2h_bytes += (int64_t)(n * (size_t)w);
             if (c.validity) {
                 validity.resize((n + 7) / 8 + 8);
                 if (n) cuda_check(cudaMemcpyAsync(validity.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity");

@@ -23,11 +23,13 @@ struct ExecError : std::runtime_error {
 };
 
 void cuda_check(cudaError_t e, const char* what);
+void set_alloc_stream(cudaStream_t s); // stream used by DeviceBuf allocations made on this thread
 
 struct DeviceBuf {
     void* ptr = nullptr;
     size_t bytes = 0;
     bool owned = true;
+    cudaStream_t stream = nullptr;
     DeviceBuf() {}
     DeviceBuf(size_t n);                       // cudaMalloc, padded
     DeviceBuf(void* p, size_t n) : ptr(p), bytes(n), owned(false) {}
@@ -72,7 +74,16 @@ struct ExecContext {
     int* h_err = nullptr;   // pinned host mirror
     int64_t kernel_launches = 0;
     std::string last_kernel_key;
+    // measurement (bench.py / cb200_plan_stats): CUDA events around each fused pipeline kernel, on the
+    // stream the kernel is launched on
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
+    double pipeline_ms = 0;       // sum of fused-pipeline kernel durations
+    int64_t pipeline_launches = 0;
+    int64_t pipeline_rows = 0;    // rows those launches scanned
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
     void check_device_errors();
+    void collect_timing();
 };
 
 struct ExecNode {
@@ -99,6 +110,6 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
 
 // Debug / build-time: generate (and NVRTC-compile, no device needed) the kernels a plan would use,
 // assuming inputs without nulls and dictionary-encoded string keys.
-std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op);
+std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const std::vector<int>& assume_bits = {});
 
 } // namespace cb200

@@ -57,6 +57,12 @@ uint32_t hm_pmod(uint32_t h, uint32_t n) { return pmod_u32(h, n); }
 void hm_mul_i64(int64_t n, const int64_t* a, const int64_t* b, i128* out) {
     for (int64_t i = 0; i < n; i++) out[i] = mul_i64_i64(a[i], b[i]);
 }
+void hm_mul_i128_i64(int64_t n, const i128* a, const int64_t* b, i128* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = mul_i128_i64(a[i], b[i]);
+}
+void hm_mul_i128_wrap(int64_t n, const i128* a, const i128* b, i128* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = mul_i128_wrap(a[i], b[i]);
+}
 void hm_f64_total_lt(int64_t n, const uint64_t* a, const uint64_t* b, uint8_t* out) {
     for (int64_t i = 0; i < n; i++) out[i] = f64_total_key(a[i]) < f64_total_key(b[i]);
 }

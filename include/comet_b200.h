@@ -101,10 +101,26 @@ int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_
 /* kernels launched so far by this plan (bench.py reports it as gpu_launches) */
 int64_t cb200_plan_kernel_launches(cb200_plan* plan);
 
+/* Measurement: the library times every fused pipeline kernel with CUDA events on its own stream. */
+typedef struct cb200_stats {
+    int64_t kernel_launches;   /* all kernels (pipelines, fold/finalize, helpers) */
+    int64_t pipeline_launches; /* fused pipeline kernels only */
+    double pipeline_ms;        /* sum of their device durations */
+    int64_t pipeline_rows;     /* input rows those launches scanned */
+    int64_t h2d_bytes;         /* host->device bytes copied by Arrow-stream sources */
+    int64_t d2h_bytes;         /* device->host bytes copied by cb200_execute */
+} cb200_stats;
+int cb200_plan_stats(cb200_plan* plan, cb200_stats* out);
+
 /* Build-time: generate and NVRTC-compile (sm_100a; needs no GPU) every pipeline kernel the plan would
  * use for null-free inputs; cubins land in the JIT cache that ships with the library.  Writes the
  * comma-separated kernel keys to `keys_out`.  Returns the number of kernels, <0 on error. */
 int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, size_t keys_cap, cb200_error* err);
+/* Same with value-range assumptions for the scan's decimal columns (assume_bits[i] > 0: |column i| < 2^bits,
+ * validated at run time by the kernels' value masks): pre-compiles the range-specialised variant a known
+ * workload will select after sampling.  Optionally returns the source of kernel `source_index`. */
+int cb200_compile_plan_assume(const uint8_t* op_proto, size_t op_len, const int32_t* assume_bits, int32_t n_assume,
+                              int32_t source_index, char* src_out, size_t src_cap, cb200_error* err);
 /* Same, but returns the generated CUDA source of kernel `index` (for inspection / nvcc -Xptxas -v). */
 int cb200_plan_kernel_source(const uint8_t* op_proto, size_t op_len, int32_t index, char* out, size_t cap, cb200_error* err);
 

@@ -97,11 +97,24 @@ static i128 pow10_i128(int e) { i128 r = 1; for (int i = 0; i < e; i++) r *= 10;
 #define I128_MAX ((i128)(((u128)1 << 127) - 1))
 #define I128_MIN (-I128_MAX - 1)
 
-int co_is_valid_decimal_precision(i128 v, int precision) { /* spark-expr/src/utils.rs:332-336 */
+/* 10^p table (arrow MAX_DECIMAL128_FOR_EACH_PRECISION is 10^p - 1): built once */
+static i128 POW10_TAB[39];
+static int pow10_ready = 0;
+static void pow10_init(void) {
+    if (pow10_ready) return;
+    i128 r = 1;
+    for (int i = 0; i <= 38; i++) { POW10_TAB[i] = r; if (i < 38) r *= 10; }
+    pow10_ready = 1;
+}
+__attribute__((constructor)) static void co_init(void) { pow10_init(); }
+static inline int valid_p(i128 v, int precision) { /* spark-expr/src/utils.rs:332-336 */
+    i128 b = POW10_TAB[precision];
+    return v < b && v > -b;
+}
+int co_is_valid_decimal_precision(i128 v, int precision) {
     if (precision > 38 || precision < 0) return 0;
     if (precision == 0) return v == 0; /* arrow table entry 0 is 0 */
-    i128 b = pow10_i128(precision) - 1;
-    return v >= -b && v <= b;
+    return valid_p(v, precision);
 }
 static int rowvalid(const uint8_t *v, int64_t i) { return v == NULL || v[i]; }
 
@@ -327,17 +340,25 @@ static int keep(const uint8_t *valid, const uint8_t *filter, int64_t i) {
 }
 
 /* sum_decimal.rs:418-439 update_single */
-static int sum_decimal_update_single(i128 value, i128 *sum, uint8_t *sum_valid, uint8_t *is_empty,
-                                     int precision, int eval_mode) {
+static inline int sum_decimal_update_single(i128 value, i128 *sum, uint8_t *sum_valid, uint8_t *is_empty,
+                                            int precision, int eval_mode) {
     if (!*is_empty && !*sum_valid) return CO_OK; /* sticky overflow */
     i128 running = *sum_valid ? *sum : 0, ns;
     int ovf = __builtin_add_overflow(running, value, &ns);
-    if (ovf || !co_is_valid_decimal_precision(ns, precision)) {
+    if (ovf || !valid_p(ns, precision)) {
         if (eval_mode == CO_ANSI) return CO_ERR_ARITHMETIC_OVERFLOW;
         *sum_valid = 0; *sum = 0;
     } else { *sum = ns; *sum_valid = 1; }
     *is_empty = 0;
     return CO_OK;
+}
+/* avg_decimal.rs:483-495 update_single */
+static inline void avg_decimal_update_single(i128 v, i128 *sum, int64_t *count, uint8_t *is_not_null, int sum_precision) {
+    i128 ns;
+    int ovf = __builtin_add_overflow(*sum, v, &ns);
+    if (ovf) ns = (i128)((u128)*sum + (u128)v);
+    *count += 1; *sum = ns;
+    if (ovf || !valid_p(ns, sum_precision)) *is_not_null = 0;
 }
 int co_sum_decimal_update(int64_t n, const i128 *v, const uint8_t *valid, const uint8_t *filter,
                           const int64_t *g, i128 *sum, uint8_t *sum_valid, uint8_t *is_empty,
@@ -401,11 +422,7 @@ int co_avg_decimal_update(int64_t n, const i128 *v, const uint8_t *valid, const 
     for (int64_t i = 0; i < n; i++) {
         if (!keep(valid, filter, i)) continue;
         int64_t k = g ? g[i] : 0;
-        i128 ns;
-        int ovf = __builtin_add_overflow(sums[k], v[i], &ns);
-        if (ovf) ns = (i128)((u128)sums[k] + (u128)v[i]); /* overflowing_add keeps the wrapped value */
-        counts[k] += 1; sums[k] = ns;
-        if (ovf || !co_is_valid_decimal_precision(ns, sum_precision)) is_not_null[k] = 0;
+        avg_decimal_update_single(v[i], &sums[k], &counts[k], &is_not_null[k], sum_precision); /* overflowing_add keeps the wrapped value */
     }
     return CO_OK;
 }
@@ -615,17 +632,17 @@ static inline int q1_row_dec(i128 price, i128 disc, i128 tax, i128 *disc_price, 
                              i128 *charge, int *ch_valid) {
     static const i128 one = 100;          /* Literal 1 (d(1,0)) brought to scale 2 by arrow-arith add/sub */
     i128 om = one - disc;                 /* d(13,2) plain sub + CheckOverflow(13) */
-    int om_valid = co_is_valid_decimal_precision(om, 13);
+    int om_valid = valid_p(om, 13);
     i128 dp = 0; int dpv = 0;
-    if (om_valid) { dp = price * om; dpv = co_is_valid_decimal_precision(dp, 26); } /* |.| < 10^25 < 2^127 */
-    i128 op = one + tax; int op_valid = co_is_valid_decimal_precision(op, 13);
+    if (om_valid) { dp = price * om; dpv = valid_p(dp, 26); } /* |.| < 10^25 < 2^127 */
+    i128 op = one + tax; int op_valid = valid_p(op, 13);
     *disc_price = dpv ? dp : 0; *dp_valid = dpv;
     if (dpv && op_valid) {
         /* WideDecimal mul d(26,4)*d(13,2)->d(38,6): natural scale == output scale, so the i256
          * product is only bound-checked.  An i128-overflowing product has |x| >= 2^127 > 10^38-1,
          * i.e. it is out of bound too, so the checked i128 multiply is an exact restatement. */
         i128 o;
-        if (__builtin_mul_overflow(dp, op, &o) || !co_is_valid_decimal_precision(o, 38)) { *charge = 0; *ch_valid = 0; }
+        if (__builtin_mul_overflow(dp, op, &o) || !valid_p(o, 38)) { *charge = 0; *ch_valid = 0; }
         else { *charge = o; *ch_valid = 1; }
     } else { *charge = 0; *ch_valid = 0; }
     return 0;
@@ -667,10 +684,9 @@ int co_q1_dec(int64_t n, const i128 *qty, const i128 *price, const i128 *disc, c
             sum_decimal_update_single(price[i], &s->s_base, &s->v_base, &s->e_base, 22, CO_LEGACY);
             if (dpv) sum_decimal_update_single(dp, &s->s_dp, &s->v_dp, &s->e_dp, 36, CO_LEGACY);
             if (chv) sum_decimal_update_single(ch, &s->s_ch, &s->v_ch, &s->e_ch, 38, CO_LEGACY);
-            int64_t z = 0;
-            co_avg_decimal_update(1, &qty[i], NULL, NULL, &z, &s->a_qty, &s->c_qty, &s->nn_qty, 22);
-            co_avg_decimal_update(1, &price[i], NULL, NULL, &z, &s->a_price, &s->c_price, &s->nn_price, 22);
-            co_avg_decimal_update(1, &disc[i], NULL, NULL, &z, &s->a_disc, &s->c_disc, &s->nn_disc, 22);
+            avg_decimal_update_single(qty[i], &s->a_qty, &s->c_qty, &s->nn_qty, 22);
+            avg_decimal_update_single(price[i], &s->a_price, &s->c_price, &s->nn_price, 22);
+            avg_decimal_update_single(disc[i], &s->a_disc, &s->c_disc, &s->nn_disc, 22);
             s->count++;
         }
     }
@@ -771,7 +787,7 @@ int co_q6_dec(int64_t n, const i128 *qty, const i128 *price, const i128 *disc,
         for (int64_t i = lo; i < hi; i++) {
             if (!(shipdate[i] >= dlo && shipdate[i] < dhi && disc[i] >= disc_lo && disc[i] <= disc_hi && qty[i] < qty_max)) continue;
             i128 rev = price[i] * disc[i]; /* d(25,4) plain mul, CheckOverflow(25) */
-            if (!co_is_valid_decimal_precision(rev, 25)) continue; /* NULL input to sum is skipped */
+            if (!valid_p(rev, 25)) continue; /* NULL input to sum is skipped */
             sum_decimal_update_single(rev, &s, &v, &e, 35, CO_LEGACY);
         }
         ps[t] = s; pv[t] = v; pe[t] = e;
@@ -833,7 +849,7 @@ int64_t co_filter_project_dec(int64_t n, const i128 *qty, const i128 *price,
         for (int64_t i = lo; i < hi; i++) {
             if (!(shipdate[i] < cutoff)) continue;
             i128 v = qty[i] * price[i]; /* d(25,4) plain mul + CheckOverflow(25) */
-            int ok = co_is_valid_decimal_precision(v, 25);
+            int ok = valid_p(v, 25);
             out[o] = ok ? v : 0; if (outv) outv[o] = (uint8_t)ok; o++;
         }
     }

@@ -173,3 +173,18 @@ def test_dd_sum_within_1ulp_of_exact(hm, oracle):
             out = C.c_double(0)
             fn(C.c_int64(v.shape[0]), _p(v), *args, C.byref(out))
             assert abs(out.value - exact) <= math.ulp(exact)
+
+
+def test_wrapping_products(hm, oracle):
+    rng = np.random.default_rng(31)
+    a = rand_dec(rng, 2000, 30)
+    b64 = [int(x) for x in rng.integers(-2**63, 2**63, 2000)]
+    b = rand_dec(rng, 2000, 30)
+    A, B = oracle.dec_from_ints(a), oracle.dec_from_ints(b)
+    B64 = np.array(b64, dtype=np.int64)
+    out = np.zeros((2000, 2), dtype=np.uint64)
+    hm.hm_mul_i128_i64(C.c_int64(2000), _p(A), _p(B64), _p(out))
+    wrap = lambda v: ((v + (1 << 127)) % (1 << 128)) - (1 << 127)
+    assert oracle.dec_to_ints(out) == [wrap(x * y) for x, y in zip(a, b64)]
+    hm.hm_mul_i128_wrap(C.c_int64(2000), _p(A), _p(B), _p(out))
+    assert oracle.dec_to_ints(out) == [wrap(x * y) for x, y in zip(a, b)]
