@@ -8,6 +8,7 @@
 
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
 
 using namespace cb200;
@@ -27,6 +28,15 @@ struct cb200_plan {
 };
 
 namespace {
+
+struct CtxRes {
+    cudaStream_t stream;
+    int* d_err;
+    int* h_err;
+    cudaEvent_t ev0, ev1;
+};
+std::mutex g_pool_mu;
+std::map<int, std::vector<CtxRes>> g_pool;
 
 void set_error(cb200_error* e, int code, const std::string& cls, const std::string& msg) {
     if (!e) return;
@@ -77,32 +87,38 @@ void parse_config(const uint8_t* cfg, size_t len, ExecContext& ctx) { // config.
 
 void start(cb200_plan* p) {
     if (p->started) return;
+    TraceSpan ts("plan.start");
     ExecContext& ctx = p->ctx;
     cuda_check(cudaSetDevice(ctx.device), "cudaSetDevice");
     cudaDeviceProp prop;
     cuda_check(cudaGetDeviceProperties(&prop, ctx.device), "cudaGetDeviceProperties");
     if (prop.major < 10) throw ExecError(CB200_ERR_CUDA, "", "comet_b200 kernels are built for sm_100a; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
     ctx.num_sms = prop.multiProcessorCount;
-    cuda_check(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking), "cudaStreamCreate");
     {
-        static std::mutex mu;
-        static bool pool_set[64] = {false};
-        std::lock_guard<std::mutex> lk(mu);
-        if (ctx.device < 64 && !pool_set[ctx.device]) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, ctx.device) == cudaSuccess) {
-                unsigned long long keep = ~0ull; // keep freed blocks cached in the pool
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            pool_set[ctx.device] = true;
+        // per-plan CUDA resources come from a per-device free list: creating a stream, events and pinned /
+        // device scratch costs ~2 ms per plan, which matters when a plan runs for 10 ms
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto& fl = g_pool[ctx.device];
+        if (!fl.empty()) {
+            CtxRes r = fl.back();
+            fl.pop_back();
+            ctx.stream = r.stream; ctx.d_err = r.d_err; ctx.h_err = r.h_err; ctx.ev0 = r.ev0; ctx.ev1 = r.ev1;
         }
     }
-    set_alloc_stream(ctx.stream);
-    cuda_check(cudaMalloc((void**)&ctx.d_err, 64), "cudaMalloc err");
+    if (!ctx.stream) {
+        cuda_check(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx.device) == cudaSuccess) {
+            unsigned long long keep = ~0ull; // keep freed blocks cached in the pool
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cuda_check(cudaMalloc((void**)&ctx.d_err, 64), "cudaMalloc err");
+        cuda_check(cudaMallocHost((void**)&ctx.h_err, 64), "cudaMallocHost err");
+        cuda_check(cudaEventCreate(&ctx.ev0), "cudaEventCreate");
+        cuda_check(cudaEventCreate(&ctx.ev1), "cudaEventCreate");
+    }
     cuda_check(cudaMemsetAsync(ctx.d_err, 0, 64, ctx.stream), "memset err");
-    cuda_check(cudaMallocHost((void**)&ctx.h_err, 64), "cudaMallocHost err");
-    cuda_check(cudaEventCreate(&ctx.ev0), "cudaEventCreate");
-    cuda_check(cudaEventCreate(&ctx.ev1), "cudaEventCreate");
+    set_alloc_stream(ctx.stream);
     p->root = build_exec(p->op, &ctx, &p->inputs);
     p->started = true;
 }
@@ -132,6 +148,7 @@ int cb200_supports(const uint8_t* op_proto, size_t op_len, cb200_error* why) {
 
 cb200_plan* cb200_create_plan(const uint8_t* op_proto, size_t op_len, const uint8_t* cfg_proto, size_t cfg_len, struct ArrowArrayStream** inputs,
                               int32_t n_inputs, int32_t partition, int32_t partition_count, int32_t batch_size, int32_t device_ordinal, cb200_error* err) {
+    TraceSpan ts("create_plan");
     return guarded(err, [&]() -> cb200_plan* {
         auto p = std::unique_ptr<cb200_plan>(new cb200_plan());
         p->op = decode_plan(op_proto, op_len);
@@ -151,6 +168,7 @@ cb200_plan* cb200_create_plan(const uint8_t* op_proto, size_t op_len, const uint
 int32_t cb200_plan_num_columns(cb200_plan* plan) { return plan ? (int32_t)plan->op->schema.size() : -1; }
 
 static int64_t execute_common(cb200_plan* plan, cb200_error* err, const std::function<void(Batch&)>& sink) {
+    TraceSpan ts("execute");
     return guarded(err, [&]() -> int64_t {
         if (!plan) throw PlanError("null plan handle");
         if (plan->finished) return -1;
@@ -193,18 +211,18 @@ int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_
 
 void cb200_release(cb200_plan* plan) {
     if (!plan) return;
+    TraceSpan ts("release");
     try {
         if (plan->started) cudaSetDevice(plan->ctx.device);
         plan->last = Batch();
         plan->root.reset();
-        if (plan->ctx.stream) cudaStreamSynchronize(plan->ctx.stream); // stream-ordered frees above
+        if (plan->ctx.stream) {
+            cudaStreamSynchronize(plan->ctx.stream); // stream-ordered frees above
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            g_pool[plan->ctx.device].push_back(CtxRes{plan->ctx.stream, plan->ctx.d_err, plan->ctx.h_err, plan->ctx.ev0, plan->ctx.ev1});
+        }
         // streams that were never handed to a source still belong to us
         for (auto* s : plan->inputs.streams) if (s && s->release) s->release(s);
-        if (plan->ctx.stream) cudaStreamDestroy(plan->ctx.stream);
-        if (plan->ctx.d_err) cudaFree(plan->ctx.d_err);
-        if (plan->ctx.h_err) cudaFreeHost(plan->ctx.h_err);
-        if (plan->ctx.ev0) cudaEventDestroy(plan->ctx.ev0);
-        if (plan->ctx.ev1) cudaEventDestroy(plan->ctx.ev1);
     } catch (...) {
     }
     delete plan;

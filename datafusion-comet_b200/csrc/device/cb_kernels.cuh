@@ -220,18 +220,46 @@ CB_D Pair128 shfl_xor_pair(Pair128 v, int m) {
     return r;
 }
 
-extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(const __grid_constant__ PipeParams p) {
+CB_D void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+CB_D void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CB_THREADS) : "memory"); }
+
+// CB_THREADS consumer threads + one producer warp.  The producer's elected lane keeps the CB_STAGES-deep
+// ring full with TMA bulk copies (full[s]: tx-count mbarrier); each consumer warp releases a stage through
+// empty[s] as soon as IT is done with it, so no CTA-wide barrier sits on the streaming path.
+extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_agg(const __grid_constant__ PipeParams p) {
     extern __shared__ __align__(128) u8 smem[];
     constexpr int SB = stage_bytes();
-    u64* bars = reinterpret_cast<u64*>(smem);                 // CB_STAGES mbarriers
+    constexpr int NW = CB_THREADS / 32;
+    u64* full = reinterpret_cast<u64*>(smem);                  // CB_STAGES mbarriers
+    u64* empty = full + CB_STAGES;                             // CB_STAGES mbarriers
     u8* stages = smem + 128;
     u64* accmem = reinterpret_cast<u64*>(stages + (size_t)CB_STAGES * SB);
     const int tid = threadIdx.x;
+    static_assert(2 * CB_STAGES * 8 <= 128, "barrier area");
 
     if (tid == 0) {
-        for (int s = 0; s < CB_STAGES; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < CB_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         mbar_fence_init();
     }
+    __syncthreads();
+
+    const int first = blockIdx.x, step = gridDim.x;
+    const int my_tiles = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;
+
+    if (tid >= CB_THREADS) { // ---------------- producer warp ----------------
+        if (tid == CB_THREADS) {
+            const u64 policy = l2_evict_first_policy();
+            for (int k = 0; k < my_tiles; k++) {
+                const int s = k % CB_STAGES, u = k / CB_STAGES;
+                if (u > 0) mbar_wait(&empty[s], (u32)((u - 1) & 1));
+                issue_tile(p, first + k * step, stages + (size_t)s * SB, &full[s], policy);
+            }
+        }
+        return;
+    }
+
     Acc acc;
     acc.p = &p;
 #pragma unroll
@@ -244,23 +272,10 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
     for (int g = 0; g < p.n_groups; g++)
         for (int w = 0; w < CB_WORDS; w++) acc.word(g, w) = acc_identity(cb_word_kind(w));
 #endif
-    __syncthreads();
 
-    const int first = blockIdx.x, step = gridDim.x;
-    const int my_tiles = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;
-    u64 policy = 0;
-    if (tid == 0) {
-        policy = l2_evict_first_policy();
-        for (int k = 0; k < CB_STAGES - 1 && k < my_tiles; k++)
-            issue_tile(p, first + k * step, stages + (size_t)(k % CB_STAGES) * SB, &bars[k % CB_STAGES], policy);
-    }
     for (int k = 0; k < my_tiles; k++) {
         const int s = k % CB_STAGES;
-        if (tid == 0) {
-            int kn = k + CB_STAGES - 1; // refill the stage every thread released at the end of iteration k-1
-            if (kn < my_tiles) issue_tile(p, first + kn * step, stages + (size_t)(kn % CB_STAGES) * SB, &bars[kn % CB_STAGES], policy);
-        }
-        mbar_wait(&bars[s], (u32)((k / CB_STAGES) & 1));
+        mbar_wait(&full[s], (u32)((k / CB_STAGES) & 1));
         Tile t;
         tile_view(stages + (size_t)s * SB, t);
         const int tile = first + k * step;
@@ -269,7 +284,8 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
         const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
 #pragma unroll 2
         for (int r = tid; r < rows; r += CB_THREADS) cb_row_agg(t, r, row0 + r, p, acc);
-        __syncthreads(); // stage s fully consumed
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[s]); // this warp is done with stage s
     }
 
     // ---- publish the value masks (warp OR-reduce, one atomic per warp and word) ----------------------
@@ -283,7 +299,6 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
 
     // ---- fold thread-private partials into one per-CTA partial per (group, word) -------------------
     // fixed butterfly order inside a warp, fixed warp order across the CTA => deterministic.
-    constexpr int NW = CB_THREADS / 32;
     __shared__ Pair128 wred[NW];
     const int lane = tid & 31, wid = tid >> 5;
     const int ng = p.n_groups;
@@ -316,7 +331,7 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
                 else v.a = (u64)(((i64)o.a > (i64)v.a) ? (i64)o.a : (i64)v.a);
             }
             if (lane == 0) wred[wid] = v;
-            __syncthreads();
+            consumer_bar();
             if (tid == 0) {
                 Pair128 t = wred[0];
                 for (int i = 1; i < NW; i++) {
@@ -336,7 +351,7 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_agg(cons
                 out[((size_t)g * CB_WORDS + w) * 2 + 0] = t.a;
                 out[((size_t)g * CB_WORDS + w) * 2 + 1] = t.b;
             }
-            __syncthreads();
+            consumer_bar();
         }
     }
 }

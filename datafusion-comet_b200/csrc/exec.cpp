@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <functional>
 #include <map>
 #include <set>
@@ -17,6 +18,21 @@ namespace cb200 {
 
 // error bits raised by kernels (device/cb_kernels.cuh set_err)
 enum { ERR_I128_OVERFLOW = 0, ERR_ANSI_OVERFLOW = 1, ERR_ORDER_DEPENDENT = 2 };
+
+static bool trace_on() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("CB200_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
+    return on == 1;
+}
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+TraceSpan::TraceSpan(const char* n) : name(n), t0(trace_on() ? now_ms() : 0) {}
+TraceSpan::~TraceSpan() {
+    if (trace_on()) fprintf(stderr, "[cb200 trace] %-28s %8.3f ms\n", name, now_ms() - t0);
+}
 
 void cuda_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw ExecError(2, "", std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
@@ -238,6 +254,7 @@ struct StreamSource : ExecNode {
     }
 
     void upload(std::vector<ArrowArray>& arrs, int64_t total, Batch& out) {
+        TraceSpan ts("source.upload");
         out.n_rows = total;
         out.cols.clear();
         out.cols.resize(schema.size());
@@ -465,7 +482,7 @@ struct FusedBase : ExecNode {
     }
 };
 
-static const size_t SMEM_BUDGET = 200 * 1024;
+static const size_t SMEM_BUDGET = 220 * 1024;
 
 // ---- filter + project -> compacted batch ----------------------------------------------------------------
 struct SelectNode : FusedBase {
@@ -758,10 +775,17 @@ struct AggNode : FusedBase {
 
     // one (possibly split) launch over rows [row0,row1) at assumption level lv, escalating on violated assumptions
     void run_range(Batch& b, int64_t row0, int64_t row1, int n_groups, Level lv) {
+        TraceSpan tsr("agg.run_range");
         while (true) {
-            PipelineSpec spec = make_spec(&b, n_groups, lv);
-            GeneratedKernel g = generate_pipeline(spec);
-            auto mod = jit_get(g, true);
+            PipelineSpec spec;
+            GeneratedKernel g;
+            std::shared_ptr<CompiledModule> mod;
+            {
+                TraceSpan ts("agg.codegen+jit");
+                spec = make_spec(&b, n_groups, lv);
+                g = generate_pipeline(spec);
+                mod = jit_get(g, true);
+            }
             ctx->last_kernel_key = g.key;
             if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds))
                 throw ExecError(15, "", "internal: accumulator layout changed between launches");
@@ -803,7 +827,7 @@ struct AggNode : FusedBase {
         p.partials = (cb::u8*)partials->ptr;
         p.spill = (cb::u64*)spill->ptr;
         p.vmask = (cb::u64*)vmask->ptr;
-        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(n_groups), &p);
+        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(n_groups), &p); // + producer warp
         ctx->pipeline_rows += r1 - r0;
         uint64_t masks[CB_MAX_COLS * 2];
         cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, st), "read value masks");
@@ -898,6 +922,7 @@ struct AggNode : FusedBase {
     }
 
     void finalize(Batch& out) {
+        TraceSpan ts("agg.finalize");
         const GeneratedKernel& g = last_gen;
         int ng = totals_groups;
         cb::FinParams fp;
@@ -906,22 +931,25 @@ struct AggNode : FusedBase {
         fp.n_groups = ng;
         fp.err = ctx->d_err;
         for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) fp.cert[ai] = certificate(ai);
-        std::vector<DeviceBufP> bufs, vbufs;
+        // all finalize outputs live in ONE device buffer so the (tiny) result comes back in a single copy
+        std::vector<size_t> off_v, off_n;
+        size_t total_bytes = 0;
+        auto take = [&](size_t n) { size_t o = total_bytes; total_bytes += (n + 15) / 16 * 16; return o; };
+        for (size_t i = 0; i < g.out_cols.size(); i++) { off_v.push_back(take((size_t)ng * g.out_bytes[i])); off_n.push_back(take((size_t)ng)); }
+        size_t off_present = take((size_t)ng);
+        auto dbuf = std::make_shared<DeviceBuf>(total_bytes);
         for (size_t i = 0; i < g.out_cols.size(); i++) {
-            bufs.push_back(std::make_shared<DeviceBuf>((size_t)ng * g.out_bytes[i]));
-            vbufs.push_back(std::make_shared<DeviceBuf>((size_t)ng));
-            fp.out[i] = (cb::u8*)bufs.back()->ptr;
-            fp.outv[i] = (cb::u8*)vbufs.back()->ptr;
+            fp.out[i] = (cb::u8*)dbuf->ptr + off_v[i];
+            fp.outv[i] = (cb::u8*)dbuf->ptr + off_n[i];
         }
-        auto present = std::make_shared<DeviceBuf>((size_t)ng);
-        fp.present = (cb::u8*)present->ptr;
+        fp.present = (cb::u8*)dbuf->ptr + off_present;
         void* args[] = {&fp};
         cuda_check(cudaLaunchKernel((const void*)last_mod->kernel(g.finalize_entry), dim3((ng + 127) / 128), dim3(128), args, 0, ctx->stream), "finalize launch");
         ctx->kernel_launches++;
-        ctx->check_device_errors();
-        // dense results are tiny: assemble the output batch on the host
-        std::vector<uint8_t> pres((size_t)ng);
-        cuda_check(cudaMemcpy(pres.data(), present->ptr, (size_t)ng, cudaMemcpyDeviceToHost), "present");
+        std::vector<uint8_t> hbuf(total_bytes);
+        cuda_check(cudaMemcpyAsync(hbuf.data(), dbuf->ptr, total_bytes, cudaMemcpyDeviceToHost, ctx->stream), "agg results D2H");
+        ctx->check_device_errors(); // synchronises
+        const uint8_t* pres = hbuf.data() + off_present;
         std::vector<int> rows;
         for (int gi = 0; gi < ng; gi++) if (ungrouped || pres[(size_t)gi]) rows.push_back(gi);
         out.n_rows = (int64_t)rows.size();
@@ -967,9 +995,8 @@ struct AggNode : FusedBase {
             c.type = g.out_cols[i].type;
             c.on_host = true;
             int w = g.out_bytes[i];
-            std::vector<uint8_t> all((size_t)ng * w), allv((size_t)ng);
-            cuda_check(cudaMemcpy(all.data(), bufs[i]->ptr, all.size(), cudaMemcpyDeviceToHost), "agg out");
-            cuda_check(cudaMemcpy(allv.data(), vbufs[i]->ptr, allv.size(), cudaMemcpyDeviceToHost), "agg out validity");
+            const uint8_t* all = hbuf.data() + off_v[i];
+            const uint8_t* allv = hbuf.data() + off_n[i];
             c.h_data.resize(rows.size() * w);
             c.h_valid.resize(rows.size());
             bool any_null = false;
@@ -1155,6 +1182,7 @@ std::vector<uint8_t> pack_bits(const uint8_t* bytes, size_t n) {
 } // namespace
 
 void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols) {
+    TraceSpan ts("export_batch");
     if ((int)b.cols.size() != n_cols) throw PlanError("executePlan: caller passed " + std::to_string(n_cols) + " output slots, plan produces " + std::to_string(b.cols.size()) + " columns");
     size_t n = (size_t)b.n_rows;
     for (int i = 0; i < n_cols; i++) {

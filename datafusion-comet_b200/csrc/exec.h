@@ -23,6 +23,15 @@ struct ExecError : std::runtime_error {
 };
 
 void cuda_check(cudaError_t e, const char* what);
+
+// CB200_TRACE=1: wall-clock spans to stderr (the reference's spark.comet.tracing.enabled analogue,
+// native/common/src/tracing.rs:27-96)
+struct TraceSpan {
+    const char* name;
+    double t0;
+    explicit TraceSpan(const char* n);
+    ~TraceSpan();
+};
 void set_alloc_stream(cudaStream_t s); // stream used by DeviceBuf allocations made on this thread
 
 struct DeviceBuf {
