@@ -264,11 +264,8 @@ def main():
             dist.barrier()
 
     def gather_states(state):
-        if world == 1:
-            return [state]
-        objs = [None] * world if rank == 0 else None
-        dist.gather_object(state, objs, dst=0)
-        return objs
+        from comet_b200.dist import gather_tables
+        return gather_tables(state, dist if world > 1 else None, 0)
 
     def step_resident():
         table = bind_table(native, P, tpch, variant, n, money, cols)
