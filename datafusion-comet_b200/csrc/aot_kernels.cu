@@ -126,3 +126,96 @@ void launch_dict_encode(const StringDictDev& d, const i32* offsets, const u8* ch
 }
 
 } // namespace cb200
+
+// ---- stream compaction of sparse (hash-table ordered) result columns ---------------------------------------------
+namespace cb200 {
+using namespace cb;
+
+__global__ void k_block_counts(const u8* present, i64 n, i32* counts) {
+    __shared__ i32 s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    i64 i = (i64)blockIdx.x * 1024 + threadIdx.x;
+    int c = 0;
+    for (int k = 0; k < 4; k++, i += 256) if (i < n && present[i]) c++;
+    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) counts[blockIdx.x] = s;
+}
+// single-CTA exclusive scan of the per-block counts (<= a few million entries); total written to *total
+__global__ void k_scan_counts(const i32* counts, i64 nb, i64* offsets, i64* total) {
+    __shared__ i64 carry;
+    __shared__ i64 wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (i64 base = 0; base < nb; base += 1024) {
+        i64 i = base + threadIdx.x;
+        i64 v = i < nb ? counts[i] : 0, x = v;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int d = 1; d < 32; d <<= 1) { i64 y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            i64 t = wsum[lane], u = t;
+            for (int d = 1; d < 32; d <<= 1) { i64 y = __shfl_up_sync(0xffffffffu, u, d); if (lane >= d) u += y; }
+            wsum[lane] = u - t; // exclusive
+        }
+        __syncthreads();
+        i64 excl = carry + wsum[w] + x - v;
+        if (i < nb) offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+// out[offsets[block] + rank within block] = in[i] for present rows; one launch per column (width bytes per row)
+__global__ void k_compact_scatter(const u8* present, i64 n, const i64* offsets, const u8* in, int width, u8* out) {
+    __shared__ i32 wcount[8];
+    i64 blk0 = (i64)blockIdx.x * 1024;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    i64 base = offsets[blockIdx.x];
+    for (int k = 0; k < 4; k++) { // rows blk0 + k*256 + tid: (k, warp, lane) order == row order
+        i64 i = blk0 + (i64)k * 256 + threadIdx.x;
+        bool keep = i < n && present[i];
+        u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcount[w] = __popc(bal);
+        __syncthreads();
+        i64 off = base;
+        int tot = 0;
+        for (int j = 0; j < 8; j++) { if (j < w) off += wcount[j]; tot += wcount[j]; }
+        if (keep) {
+            i64 o = off + __popc(bal & ((1u << lane) - 1u));
+            const u8* src = in + i * width;
+            u8* dst = out + o * width;
+            if (width == 16) *reinterpret_cast<ulonglong2*>(dst) = *reinterpret_cast<const ulonglong2*>(src);
+            else if (width == 8) *reinterpret_cast<u64*>(dst) = *reinterpret_cast<const u64*>(src);
+            else if (width == 4) *reinterpret_cast<u32*>(dst) = *reinterpret_cast<const u32*>(src);
+            else for (int b = 0; b < width; b++) dst[b] = src[b];
+        }
+        base += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void k_key_presence(const unsigned long long* keys, i64 n, u8* present) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) present[i] = keys[i] != 0xffffffffffffffffull;
+}
+void launch_key_presence(const unsigned long long* keys, i64 n, u8* present, cudaStream_t st) {
+    if (n > 0) k_key_presence<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, present);
+}
+void launch_compact_plan(const u8* present, i64 n, i32* counts, i64* offsets, i64* total, cudaStream_t st) {
+    i64 nb = (n + 1023) / 1024;
+    if (nb <= 0) return;
+    k_block_counts<<<(unsigned)nb, 256, 0, st>>>(present, n, counts);
+    k_scan_counts<<<1, 1024, 0, st>>>(counts, nb, offsets, total);
+}
+void launch_compact_scatter(const u8* present, i64 n, const i64* offsets, const void* in, int width, void* out, cudaStream_t st) {
+    i64 nb = (n + 1023) / 1024;
+    if (nb <= 0) return;
+    k_compact_scatter<<<(unsigned)nb, 256, 0, st>>>(present, n, offsets, (const u8*)in, width, (u8*)out);
+}
+
+} // namespace cb200

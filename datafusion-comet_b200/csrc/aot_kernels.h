@@ -26,4 +26,9 @@ struct StringDictDev {
 void launch_dict_encode(const StringDictDev& d, const int* offsets, const unsigned char* chars, const unsigned char* validity, long long n,
                         int* row_slot, int* codes, cudaStream_t st);
 
+// stream compaction (hash-aggregate results): per-1024-row-block counts + exclusive scan, then one scatter per column
+void launch_key_presence(const unsigned long long* keys, long long n, unsigned char* present, cudaStream_t st);
+void launch_compact_plan(const unsigned char* present, long long n, int* counts, long long* offsets, long long* total, cudaStream_t st);
+void launch_compact_scatter(const unsigned char* present, long long n, const long long* offsets, const void* in, int width, void* out, cudaStream_t st);
+
 } // namespace cb200

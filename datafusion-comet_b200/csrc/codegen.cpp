@@ -26,6 +26,7 @@ int phys_bytes(Phys p) {
 
 size_t GeneratedKernel::dyn_smem(int n_groups) const {
     size_t s = 128 + (size_t)stages * stage_bytes;
+    if (hash) return s;
     if (!word_kinds.empty() && n_groups > 1) s += (size_t)n_groups * n_words * threads * 8;
     else if (!word_kinds.empty() && n_groups == 1 && n_words > 0) s += 0;
     return s;
@@ -618,6 +619,20 @@ int stage_bytes_of(const PipelineSpec& s) {
 
 int out_width(const DType& t) { return t.id == TypeId::Bool ? 1 : t.arrow_width(); }
 
+// bits a group key occupies in the packed 64-bit hash-table key (0 = cannot be packed)
+int key_bits(const DType& t) {
+    switch (t.id) {
+    case TypeId::Bool: return 1;
+    case TypeId::Int8: return 8;
+    case TypeId::Int16: return 16;
+    case TypeId::Int32: case TypeId::Date: return 32;
+    case TypeId::String: return 32; // dictionary code
+    case TypeId::Int64: case TypeId::Timestamp: case TypeId::TimestampNtz: return 64;
+    case TypeId::Decimal: return t.precision <= 18 ? 64 : 0;
+    default: return 0;
+    }
+}
+
 // store a value into a raw 16-byte output slot
 std::string to_slot(const Val& v, const std::string& dst) {
     const DType& t = v.type;
@@ -687,9 +702,68 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
         em.body << "    if (!(" << keep << ")) return;\n";
         SlotPlan slots;
         std::vector<AggLayout> layout(spec.aggs.size());
-        // group id (dense): mixed radix over key codes; NULL key -> last slot of that key
+        // group id.  dense: mixed radix over key codes, NULL key -> last slot of that key.
+        //           hash : key columns packed into one 64-bit word -> slot of the global table.
         std::string gid = "0";
-        if (!spec.ungrouped) {
+        std::string null_group_cond;
+        std::ostringstream unpack; // hash: cb_unpack_key body (reverse of the packing)
+        if (spec.hash) {
+            int total_bits = 0;
+            std::string packed = em.fresh("pk");
+            em.body << "    cb::u64 " << packed << " = 0;\n";
+            std::vector<std::string> unpack_steps;
+            for (size_t k = 0; k < spec.keys.size(); k++) {
+                Val kv = em.emit(*spec.keys[k]);
+                const DType& kt = spec.keys[k]->type;
+                int bits = key_bits(kt);
+                bool nullable = kv.nullable();
+                if (nullable && bits == 64 && spec.keys.size() == 1) { // no spare bit: NULL rows go to the reserved NULL-key slot
+                    null_group_cond = kv.n;
+                    nullable = false;
+                }
+                if (bits == 0) throw Unsupported("group key of type " + kt.str() + " cannot be packed into the 64-bit hash key");
+                total_bits += bits + (nullable ? 1 : 0);
+                std::string raw;
+                if (kt.is_decimal()) {
+                    if (kv.narrow) raw = "(cb::u64)" + kv.v;
+                    else {
+                        em.body << "    if (!cb::i128_fits_i64(" << kv.v << ")) atomicOr(p.hflags, 4);\n";
+                        raw = kv.v + ".lo";
+                    }
+                } else if (kt.id == TypeId::Bool) raw = "(" + kv.v + " ? 1ull : 0ull)";
+                else raw = "(cb::u64)(cb::i64)" + kv.v;
+                std::string mask = bits == 64 ? "0xffffffffffffffffull" : u64lit((1ull << bits) - 1);
+                if (nullable) raw = "(" + kv.n + " ? 0ull : " + raw + ")";
+                if (bits == 64) em.body << "    " << packed << " = " << raw << ";\n";
+                else em.body << "    " << packed << " = (" << packed << " << " << bits << ") | (" << raw << " & " << mask << ");\n";
+                if (nullable) em.body << "    " << packed << " = (" << packed << " << 1) | (" << kv.n << " ? 1ull : 0ull);\n";
+                // unpack (emitted in reverse order below)
+                std::ostringstream u;
+                std::string kc = std::to_string(k);
+                u << "    {\n";
+                if (nullable) u << "      bool isnull = (key & 1ull) != 0; key >>= 1;\n";
+                else u << "      bool isnull = null_group;\n";
+                if (bits == 64) u << "      cb::u64 raw = key; key = 0;\n";
+                else u << "      cb::u64 raw = key & " << mask << "; key >>= " << bits << ";\n";
+                if (kt.is_decimal()) u << "      cb::fin_store_i128(fp, " << kc << ", g, cb::i128_from_i64((cb::i64)raw), !isnull);\n";
+                else if (kt.id == TypeId::Bool) u << "      cb::fin_store_u8(fp, " << kc << ", g, (int)raw, !isnull);\n";
+                else if (bits == 64) u << "      cb::fin_store_i64(fp, " << kc << ", g, (cb::i64)raw, !isnull);\n";
+                else {
+                    int w = kt.is_string() ? 4 : kt.arrow_width();
+                    std::string sx = bits == 8 ? "(cb::i32)(signed char)raw" : bits == 16 ? "(cb::i32)(short)raw" : "(cb::i32)raw";
+                    u << "      cb::fin_store_i32(fp, " << kc << ", g, " << sx << ", !isnull, " << w << ");\n";
+                }
+                u << "    }\n";
+                unpack_steps.push_back(u.str());
+            }
+            if (total_bits > 64) throw Unsupported("group keys need " + std::to_string(total_bits) + " bits; multi-word hash keys are pending");
+            for (auto it = unpack_steps.rbegin(); it != unpack_steps.rend(); ++it) unpack << *it;
+            gid = "acc.find_slot(" + packed + ")";
+            if (!null_group_cond.empty()) {
+                em.body << "    if (" << null_group_cond << ") atomicOr(p.hflags, 8);\n";
+                gid = "(" + null_group_cond + " ? (int)(p.hmask + 2u) : " + gid + ")";
+            }
+        } else if (!spec.ungrouped) {
             for (size_t k = 0; k < spec.keys.size(); k++) {
                 Val kv = em.emit(*spec.keys[k]);
                 std::string code = kv.type.id == TypeId::Bool && spec.cols[spec.keys[k]->index].phys == Phys::Bitmap ? "(" + kv.v + " ? 1 : 0)" : kv.v;
@@ -739,7 +813,9 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                         if (first) {
                             // per-thread 64-bit partials are exact while rows/thread * |v| < 2^63 (host caps rows/thread at 2^CB_RPT_LOG2)
                             u128r vb = em.bound_of(*a.children[0]);
-                            if (v.narrow && vb < (R63 >> CB_RPT_LOG2))
+                            if (spec.hash) // table words are full 128-bit totals: always sign-extend + carry
+                                em.body << "    if (" << use << ") acc." << (v.narrow ? "add_i64_wide" : "add_i128") << "(g, " << L.w_sum << ", " << v.v << ");\n";
+                            else if (v.narrow && vb < (R63 >> CB_RPT_LOG2))
                                 em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << L.w_sum << ", " << v.v << ");\n";
                             else if (v.narrow)
                                 em.body << "    if (" << use << ") acc.add_i64_wide(g, " << L.w_sum << ", " << v.v << ");\n";
@@ -848,6 +924,18 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
         // ---------------- finalize program: totals -> state columns (Partial) / results (Final) -------
         std::ostringstream fin;
         int oc = 0;
+        if (spec.hash) {
+            for (size_t k = 0; k < spec.keys.size(); k++) {
+                OutCol o;
+                o.type = spec.keys[k]->type;
+                o.nullable = true;
+                g.out_cols.push_back(o);
+                g.out_bytes.push_back(o.type.is_string() ? 4 : out_width(o.type));
+                oc++;
+            }
+            g.n_key_cols = (int)spec.keys.size();
+            g.hash = true;
+        }
         auto add_out = [&](const DType& t, bool nullable) {
             OutCol o;
             o.type = t;
@@ -949,7 +1037,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
 
         std::ostringstream defs;
         defs << "#define CB_KERNEL_AGG 1\n#define CB_WORDS " << g.n_words << "\n#define CB_G1 " << (spec.ungrouped ? 1 : 0) << "\n#define CB_W_ROWS " << w_rows
-             << "\n";
+             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n";
         tu << header(spec, defs.str());
         tu << "constexpr __host__ __device__ int cb_word_kind(int w) { return ";
         for (size_t i = 0; i < slots.kinds.size(); i++) tu << "w == " << i << " ? " << slots.kinds[i] << " : ";
@@ -957,6 +1045,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
         tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
         tu << "CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc) {\n    (void)grow;\n" << em.body.str() << "}\n";
         tu << "CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T) {\n" << fin.str() << "}\n";
+        if (spec.hash) tu << "CB_D void cb_unpack_key(const FinParams& fp, int g, u64 key, bool null_group) {\n" << unpack.str() << "}\n";
         tu << "} // namespace cb\n";
         g.entry = "cb_pipeline_agg";
         g.finalize_entry = "cb_finalize";

@@ -48,6 +48,7 @@ struct PipelineSpec {
     std::vector<std::vector<int>> state_slots; // Final mode: staged-col slot of each state column per agg
     AggMode mode = AggMode::Partial;
     bool ungrouped = false;
+    bool hash = false;                    // high-cardinality: global open-addressing table keyed by the packed key columns
     // tuning
     int tile = 512, stages = 3, threads = 256;
 };
@@ -63,6 +64,8 @@ struct GeneratedKernel {
     std::vector<OutCol> out_cols;     // select: outputs; agg: finalize outputs (excluding key columns)
     std::vector<int> out_bytes;       // element bytes of each output column (1 for bool-as-byte)
     int threads = 256, tile = 512, stages = 3;
+    bool hash = false;
+    int n_key_cols = 0;               // hash: leading out_cols are the group keys
     size_t dyn_smem(int n_groups) const;
 };
 

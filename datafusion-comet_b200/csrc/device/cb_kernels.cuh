@@ -155,6 +155,77 @@ CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& a
 // Thread-private accumulator file.  Word (g, w) of thread t lives at acc[(g*CB_WORDS + w)*CB_THREADS + t]
 // (8-byte words interleaved across threads => every warp access is bank-conflict-free no matter
 // which group each lane updates).  For the ungrouped case the words are registers.
+#ifndef CB_HASH
+#define CB_HASH 0
+#endif
+#define CB_EMPTY_KEY 0xffffffffffffffffull
+
+#if CB_HASH
+// ---- hash aggregation: accumulators live in a global open-addressing table, updated with atomics -------------
+struct Acc {
+    const PipeParams* p;
+    u64 vm[2 * CB_NCOLS];
+    CB_D void vm_or(int c, i128 raw) { u64 s = (u64)(raw.hi >> 63); vm[2 * c] |= raw.lo ^ s; vm[2 * c + 1] |= (u64)raw.hi ^ s; }
+    CB_D void vm_or64(int c, i64 raw) { vm[2 * c] |= (u64)raw ^ (u64)(raw >> 63); }
+
+    // slot of `key` (inserting it if new).  Linear probing; a plain L2 load first so that hits on existing keys
+    // (clustered inputs) need no CAS.
+    CB_D int find_slot(u64 key) const {
+        const u32 mask = p->hmask;
+        if (key == CB_EMPTY_KEY) { atomicOr(p->hflags, 1); return (int)(mask + 1u); }
+        u64 h = key;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        u32 s = (u32)h & mask;
+        for (u32 probe = 0; probe <= mask; probe++) {
+            u64 cur = __ldcg(&p->hkeys[s]);
+            if (cur == key) return (int)s;
+            if (cur == CB_EMPTY_KEY) {
+                u64 prev = atomicCAS((unsigned long long*)&p->hkeys[s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);
+                if (prev == CB_EMPTY_KEY || prev == key) return (int)s;
+            }
+            s = (s + 1u) & mask;
+        }
+        atomicOr(p->hflags, 2);
+        return (int)(mask + 1u);
+    }
+    CB_D u64* W(int g, int w) const { return p->htotals + ((size_t)g * CB_WORDS + w) * 2; }
+    CB_D void add_i64_wrap(int g, int w, i64 v) { atomicAdd((unsigned long long*)W(g, w), (unsigned long long)v); }
+    CB_D void add_i128(int g, int w, i128 v) {
+        u64* s = W(g, w);
+        u64 old = atomicAdd((unsigned long long*)&s[0], (unsigned long long)v.lo);
+        u64 carry = (old + v.lo) < old ? 1ull : 0ull;
+        u64 hi = (u64)v.hi + carry;
+        if (hi) atomicAdd((unsigned long long*)&s[1], (unsigned long long)hi);
+    }
+    CB_D void add_i64_wide(int g, int w, i64 v) { add_i128(g, w, i128_from_i64(v)); }
+    CB_D void add_f64(int g, int w, double x) { // double-double in one 16-byte word pair, updated with a 128-bit CAS
+        u64* s = W(g, w);
+        u64 o0 = __ldcg(&s[0]), o1 = __ldcg(&s[1]);
+        while (true) {
+            dd a;
+            a.hi = __longlong_as_double((i64)o0);
+            a.lo = __longlong_as_double((i64)o1);
+            dd_add_double(a, x);
+            u64 n0 = (u64)__double_as_longlong(a.hi), n1 = (u64)__double_as_longlong(a.lo), r0, r1;
+            asm volatile(
+                "{\n"
+                ".reg .b128 cmp, nv, res;\n"
+                "mov.b128 cmp, {%3, %4};\n"
+                "mov.b128 nv, {%5, %6};\n"
+                "atom.relaxed.gpu.global.cas.b128 res, [%2], cmp, nv;\n"
+                "mov.b128 {%0, %1}, res;\n"
+                "}\n"
+                : "=l"(r0), "=l"(r1)
+                : "l"(s), "l"(o0), "l"(o1), "l"(n0), "l"(n1)
+                : "memory");
+            if (r0 == o0 && r1 == o1) return;
+            o0 = r0; o1 = r1;
+        }
+    }
+    CB_D void min_i64(int g, int w, i64 key) { atomicMin((long long*)W(g, w), (long long)key); }
+    CB_D void max_i64(int g, int w, i64 key) { atomicMax((long long*)W(g, w), (long long)key); }
+};
+#else
 struct Acc {
 #if CB_G1
     u64 r[CB_WORDS];
@@ -202,6 +273,8 @@ struct Acc {
     CB_D void min_i64(int g, int w, i64 key) { i64 c = (i64)word(g, w); if (key < c) word(g, w) = (u64)key; }
     CB_D void max_i64(int g, int w, i64 key) { i64 c = (i64)word(g, w); if (key > c) word(g, w) = (u64)key; }
 };
+
+#endif // CB_HASH
 
 CB_D u64 acc_identity(int kind) {
     switch (kind) {
@@ -264,7 +337,9 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_agg
     acc.p = &p;
 #pragma unroll
     for (int c = 0; c < 2 * CB_NCOLS; c++) acc.vm[c] = 0;
-#if CB_G1
+#if CB_HASH
+    (void)accmem;
+#elif CB_G1
 #pragma unroll
     for (int w = 0; w < CB_WORDS; w++) acc.r[w] = acc_identity(cb_word_kind(w));
 #else
@@ -297,6 +372,9 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_agg
         if ((tid & 31) == 0 && m) atomicOr((unsigned long long*)&p.vmask[c], (unsigned long long)m);
     }
 
+#if CB_HASH
+    return; // the table is the running total: nothing to fold
+#else
     // ---- fold thread-private partials into one per-CTA partial per (group, word) -------------------
     // fixed butterfly order inside a warp, fixed warp order across the CTA => deterministic.
     __shared__ Pair128 wred[NW];
@@ -354,6 +432,7 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_agg
             consumer_bar();
         }
     }
+#endif // !CB_HASH
 }
 
 } // namespace cb
@@ -393,6 +472,33 @@ CB_D void fin_store_i32(const FinParams& fp, int c, int g, i32 v, bool valid, in
 }
 
 CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T);
+#if CB_HASH
+CB_D void cb_unpack_key(const FinParams& fp, int g, u64 key, bool null_group);
+
+// identities for every slot of a fresh table
+extern "C" __global__ void cb_hash_init(u64* keys, u64* totals, long long n_slots) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    keys[i] = CB_EMPTY_KEY;
+#pragma unroll
+    for (int w = 0; w < CB_WORDS; w++) { totals[(i * CB_WORDS + w) * 2] = acc_identity(cb_word_kind(w)); totals[(i * CB_WORDS + w) * 2 + 1] = 0; }
+}
+// move every occupied slot of an old table into a bigger one (keys are unique: plain copies after the claim)
+extern "C" __global__ void cb_hash_rehash(const u64* old_keys, const u64* old_totals, long long old_slots, const __grid_constant__ PipeParams p) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= old_slots) return;
+    u64 key = old_keys[i];
+    const bool is_sentinel = i == old_slots - 2, is_null_group = i == old_slots - 1;
+    if (is_sentinel && !(p.hpad & 1u)) return; // reserved slots only when they were used
+    if (is_null_group && !(p.hpad & 2u)) return;
+    if (!is_sentinel && !is_null_group && key == CB_EMPTY_KEY) return;
+    Acc acc;
+    acc.p = &p;
+    int g = is_sentinel ? (int)(p.hmask + 1u) : is_null_group ? (int)(p.hmask + 2u) : acc.find_slot(key);
+#pragma unroll
+    for (int w = 0; w < CB_WORDS * 2; w++) p.htotals[(size_t)g * CB_WORDS * 2 + w] = old_totals[i * CB_WORDS * 2 + w];
+}
+#endif
 
 // one thread per (group, word): fixed CTA order => deterministic
 extern "C" __global__ void cb_fold(const __grid_constant__ FinParams fp) {
@@ -433,7 +539,16 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= fp.n_groups) return;
     const u64* T = fp.totals + (size_t)g * CB_WORDS * 2;
+#if CB_HASH
+    u64 key = fp.hkeys[g];
+    const bool is_null_group = g == fp.n_groups - 1, is_sentinel = g == fp.n_groups - 2;
+    bool present = is_null_group ? (fp.null_group_used != 0) : is_sentinel ? (fp.sentinel_used != 0) : (key != CB_EMPTY_KEY);
+    fp.present[g] = present ? 1 : 0;
+    if (!present) return;
+    cb_unpack_key(fp, g, is_sentinel ? CB_EMPTY_KEY : key, is_null_group);
+#else
     fp.present[g] = (i64)T[CB_W_ROWS * 2] > 0 ? 1 : 0;
+#endif
     cb_finalize_group(fp, g, T);
 }
 

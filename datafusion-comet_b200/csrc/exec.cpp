@@ -108,6 +108,8 @@ static void rewrite_bound(const ExprP& e, const std::map<int, int>& slot_of) {
 // =================================================================================================
 // sources
 // =================================================================================================
+static Phys phys_of(const DType& t);
+static Phys phys_of_type(const DType& t) { return phys_of(t); }
 static Phys phys_of(const DType& t) {
     switch (t.id) {
     case TypeId::Bool: return Phys::Bitmap;
@@ -586,6 +588,12 @@ struct AggNode : FusedBase {
     struct DevDict { StringDictDev d; std::vector<DeviceBufP> bufs; DeviceBufP row_slot; int host_known = 0; };
     std::vector<std::shared_ptr<DevDict>> dev_dicts;
 
+    // ---- hash aggregation state ---------------------------------------------------------------------------
+    bool hash_mode = false, strategy_decided = false;
+    DeviceBufP hkeys, htotals, hflags;
+    int64_t hcap = 0;
+    static constexpr int DENSE_MAX_GROUPS = 64;
+
     // ---- range assumptions (see ranges.h) ----------------------------------------------------------------
     enum Level { SAFE = 0, TYPE = 1, TIGHT = 2 };
     std::vector<int> observed_bits; // per child column: max bit length of (v ^ sign) over every valid row scanned so far (-1: none)
@@ -610,6 +618,7 @@ struct AggNode : FusedBase {
         s.sink = SinkKind::Agg;
         s.mode = mode;
         s.ungrouped = ungrouped;
+        s.hash = hash_mode;
         s.keys = to_slots(keys, slot_of);
         for (size_t k = 0; k < keys.size(); k++) s.key_nullable.push_back(b ? key_has_null[k] : false);
         for (auto& a : aggs) {
@@ -630,7 +639,7 @@ struct AggNode : FusedBase {
         s.stages = 3;
         // first pass to learn the accumulator footprint, then size the ring to the remaining smem
         GeneratedKernel probe = generate_pipeline(s);
-        size_t acc = n_groups > 1 ? (size_t)n_groups * probe.n_words * s.threads * 8 : 0;
+        size_t acc = (n_groups > 1 && !hash_mode) ? (size_t)n_groups * probe.n_words * s.threads * 8 : 0;
         while (acc + 2 * (size_t)probe.stage_bytes + 1024 > SMEM_BUDGET && s.threads > 32) {
             s.threads /= 2; // shrink the thread-private accumulator file (wide Final-mode merges are tiny inputs)
             acc /= 2;
@@ -646,7 +655,7 @@ struct AggNode : FusedBase {
         int ci = keys[k]->index;
         Column& c = b.cols[ci];
         if (c.type.id == TypeId::Bool) return 2;
-        if (!c.type.is_string()) throw Unsupported("group key of type " + c.type.str() + " needs the hash aggregation path (pending)");
+        if (!c.type.is_string()) return -1; // integer / date / decimal keys: hash aggregation
         if (c.is_dict) {
             key_dicts[k] = c.dict;
             return (int)c.dict->values.size();
@@ -743,12 +752,25 @@ struct AggNode : FusedBase {
             int card = prepare_key(b, k);
             const Column& c = b.cols[keys[k]->index];
             hn[k] = key_has_null[k] || c.validity != nullptr;
-            nc[k] = std::max(card, 1) + (hn[k] ? 1 : 0);
-            if (!cards.empty()) nc[k] = std::max(nc[k], cards[k]);
+            nc[k] = card < 0 ? -1 : std::max(card, 1) + (hn[k] ? 1 : 0);
+            if (!cards.empty() && nc[k] >= 0) nc[k] = std::max(nc[k], cards[k]);
         }
+        bool densifiable = true;
+        for (int c : nc) if (c < 0) densifiable = false;
         int n_groups = 1;
-        for (int c : nc) n_groups *= c;
-        if (n_groups > 4096) throw Unsupported("more than 4096 dense groups (hash aggregation path pending)");
+        if (densifiable) for (int c : nc) { n_groups *= c; if (n_groups > 1 << 20) break; }
+        if (!strategy_decided) {
+            hash_mode = !ungrouped && (!densifiable || n_groups > DENSE_MAX_GROUPS);
+            strategy_decided = true;
+        } else if (!hash_mode && (!densifiable || n_groups > DENSE_MAX_GROUPS)) {
+            throw Unsupported("group cardinality grew past the dense path mid-stream (dense -> hash migration pending)");
+        }
+        if (hash_mode) {
+            key_has_null_prev = key_has_null;
+            key_has_null = hn;
+            consume_hash(b);
+            return;
+        }
         key_has_null_prev = key_has_null;
         key_has_null = hn;
         if (have_totals && nc != cards) {
@@ -771,6 +793,167 @@ struct AggNode : FusedBase {
         } else {
             run_range(b, 0, b.n_rows, n_groups, have_obs ? TIGHT : TYPE);
         }
+    }
+
+    // ---- hash aggregation: table sizing, launch, flags ------------------------------------------------------------
+    void launch_named(const std::shared_ptr<CompiledModule>& mod, const char* name, dim3 grid, dim3 block, void** args) {
+        cuda_check(cudaLaunchKernel((const void*)mod->kernel(name), grid, block, args, 0, ctx->stream), name);
+        ctx->kernel_launches++;
+    }
+    void hash_params(cb::PipeParams& p) const {
+        p.hkeys = (cb::u64*)hkeys->ptr;
+        p.htotals = (cb::u64*)htotals->ptr;
+        p.hmask = (cb::u32)(hcap - 1);
+        p.hflags = (cb::i32*)hflags->ptr;
+    }
+    // make sure the table can absorb `incoming` more distinct keys at load factor <= 0.5
+    void ensure_table(const std::shared_ptr<CompiledModule>& mod, int64_t incoming) {
+        int flags[8] = {0};
+        if (hflags) {
+            cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "hash flags");
+            cuda_check(cudaStreamSynchronize(ctx->stream), "hash flags sync");
+        } else {
+            hflags = std::make_shared<DeviceBuf>(64);
+            cuda_check(cudaMemsetAsync(hflags->ptr, 0, 64, ctx->stream), "memset hash flags");
+        }
+        int64_t occupied = hcap ? count_occupied() : 0;
+        int64_t need = 2 * (occupied + incoming);
+        int64_t cap = std::max<int64_t>(hcap, 1 << 16);
+        while (cap < need) cap <<= 1;
+        if (cap > (1ll << 31)) throw ExecError(16, "", "hash table would exceed 2^31 slots; lower spark.comet.b200.chunkRows");
+        if (cap == hcap) return;
+        auto nkeys = std::make_shared<DeviceBuf>((size_t)(cap + 2) * 8);
+        auto ntot = std::make_shared<DeviceBuf>((size_t)(cap + 2) * n_words * 16);
+        long long n_slots = cap + 2;
+        cb::u64* kp = (cb::u64*)nkeys->ptr;
+        cb::u64* tp = (cb::u64*)ntot->ptr;
+        void* a1[] = {&kp, &tp, &n_slots};
+        launch_named(mod, "cb_hash_init", dim3((unsigned)((n_slots + 255) / 256)), dim3(256), a1);
+        if (hcap) {
+            cb::PipeParams p;
+            memset(&p, 0, sizeof(p));
+            p.hkeys = kp; p.htotals = tp; p.hmask = (cb::u32)(cap - 1); p.hflags = (cb::i32*)hflags->ptr;
+            p.hpad = ((flags[0] & 1) ? 1u : 0u) | ((flags[0] & 8) ? 2u : 0u);
+            const cb::u64* ok = (const cb::u64*)hkeys->ptr;
+            const cb::u64* ot = (const cb::u64*)htotals->ptr;
+            long long old_slots = hcap + 2;
+            void* a2[] = {&ok, &ot, &old_slots, &p};
+            launch_named(mod, "cb_hash_rehash", dim3((unsigned)((old_slots + 255) / 256)), dim3(256), a2);
+        }
+        hkeys = nkeys; htotals = ntot; hcap = cap;
+    }
+    int64_t count_occupied() { // exact: scan the key array (cap x 8 bytes, tiny next to the rows that filled it)
+        auto pres = std::make_shared<DeviceBuf>((size_t)hcap + 1);
+        auto counts = std::make_shared<DeviceBuf>(((size_t)hcap / 1024 + 2) * 4);
+        auto offs = std::make_shared<DeviceBuf>(((size_t)hcap / 1024 + 2) * 8 + 16);
+        launch_key_presence((const unsigned long long*)hkeys->ptr, hcap, (unsigned char*)pres->ptr, ctx->stream);
+        long long* total = (long long*)((char*)offs->ptr + ((size_t)hcap / 1024 + 2) * 8);
+        launch_compact_plan((const unsigned char*)pres->ptr, hcap, (int*)counts->ptr, (long long*)offs->ptr, total, ctx->stream);
+        ctx->kernel_launches += 3;
+        long long t = 0;
+        cuda_check(cudaMemcpyAsync(&t, total, 8, cudaMemcpyDeviceToHost, ctx->stream), "occupied count");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "occupied sync");
+        return t;
+    }
+
+    void consume_hash(Batch& b) {
+        if (keys.size() > CB_MAX_KEYS) throw Unsupported("more than 4 group keys");
+        if (observed_bits.empty()) observed_bits.assign(child->schema.size(), -1);
+        // updates go straight into the table, so a launch cannot be discarded: no speculative assumptions here
+        PipelineSpec spec = make_spec(&b, 2, SAFE);
+        GeneratedKernel g = generate_pipeline(spec);
+        auto mod = jit_get(g, true);
+        ctx->last_kernel_key = g.key;
+        if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds)) throw ExecError(15, "", "internal: accumulator layout changed between launches");
+        n_words = g.n_words;
+        word_kinds = g.word_kinds;
+        ensure_table(mod, b.n_rows);
+        if (!vmask) vmask = std::make_shared<DeviceBuf>(CB_MAX_COLS * 16);
+        cuda_check(cudaMemsetAsync(vmask->ptr, 0, CB_MAX_COLS * 16, ctx->stream), "memset vmask");
+        cb::PipeParams p;
+        fill_inputs(p, b, g.tile);
+        hash_params(p);
+        p.vmask = (cb::u64*)vmask->ptr;
+        p.n_groups = (int)std::min<int64_t>(hcap + 2, INT32_MAX);
+        int grid = std::max(1, std::min(ctx->num_sms, p.n_tiles));
+        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(0), &p);
+        ctx->pipeline_rows += b.n_rows;
+        uint64_t masks[CB_MAX_COLS * 2];
+        int flags[8];
+        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, ctx->stream), "read value masks");
+        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags");
+        ctx->check_device_errors();
+        if (flags[0] & 2) throw ExecError(15, "", "internal: hash table full");
+        if (flags[0] & 4) throw Unsupported("decimal group key does not fit 64 bits (multi-word hash keys are pending)");
+        for (size_t i = 0; i < spec.cols.size(); i++) {
+            if (!spec.cols[i].type.is_decimal()) continue;
+            uint64_t lo = masks[2 * i], hi = masks[2 * i + 1];
+            int bl = hi ? 64 + r_bitlen(hi) : r_bitlen(lo);
+            observed_bits[(size_t)used_cols[i]] = std::max(observed_bits[(size_t)used_cols[i]], bl);
+        }
+        rows_scanned += b.n_rows;
+        have_totals = true;
+        last_gen = g;
+        last_mod = mod;
+    }
+
+    // hash results: finalize every slot, then compact the occupied ones into dense device columns
+    void finalize_hash(Batch& out) {
+        TraceSpan ts("agg.finalize_hash");
+        const GeneratedKernel& g = last_gen;
+        int64_t n_slots = hcap + 2;
+        int flags[8];
+        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "flags sync");
+        cb::FinParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.totals = (cb::u64*)htotals->ptr;
+        fp.hkeys = (const cb::u64*)hkeys->ptr;
+        fp.sentinel_used = flags[0] & 1;
+        fp.null_group_used = (flags[0] & 8) ? 1 : 0;
+        fp.n_groups = (int)n_slots;
+        fp.err = ctx->d_err;
+        for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) fp.cert[ai] = certificate(ai);
+        if (g.out_cols.size() > CB_MAX_OUT) throw Unsupported("too many output columns");
+        std::vector<DeviceBufP> sparse_v, sparse_n;
+        for (size_t i = 0; i < g.out_cols.size(); i++) {
+            sparse_v.push_back(std::make_shared<DeviceBuf>((size_t)n_slots * g.out_bytes[i]));
+            sparse_n.push_back(std::make_shared<DeviceBuf>((size_t)n_slots));
+            fp.out[i] = (cb::u8*)sparse_v.back()->ptr;
+            fp.outv[i] = (cb::u8*)sparse_n.back()->ptr;
+        }
+        auto present = std::make_shared<DeviceBuf>((size_t)n_slots);
+        fp.present = (cb::u8*)present->ptr;
+        void* args[] = {&fp};
+        launch_named(last_mod, g.finalize_entry.c_str(), dim3((unsigned)((n_slots + 127) / 128)), dim3(128), args);
+        size_t nb = (size_t)(n_slots + 1023) / 1024;
+        auto counts = std::make_shared<DeviceBuf>(nb * 4 + 16);
+        auto offs = std::make_shared<DeviceBuf>(nb * 8 + 32);
+        long long* total = (long long*)((char*)offs->ptr + nb * 8 + 8);
+        launch_compact_plan((const unsigned char*)present->ptr, n_slots, (int*)counts->ptr, (long long*)offs->ptr, total, ctx->stream);
+        ctx->kernel_launches += 2;
+        long long n_out = 0;
+        cuda_check(cudaMemcpyAsync(&n_out, total, 8, cudaMemcpyDeviceToHost, ctx->stream), "group count");
+        ctx->check_device_errors();
+        out.n_rows = n_out;
+        out.cols.clear();
+        for (size_t i = 0; i < g.out_cols.size(); i++) {
+            Column c;
+            c.type = g.out_cols[i].type;
+            int w = g.out_bytes[i];
+            c.phys = c.type.id == TypeId::Bool ? Phys::I8 : (c.type.is_string() ? Phys::I32 : phys_of_type(c.type));
+            c.data = std::make_shared<DeviceBuf>((size_t)std::max<long long>(n_out, 1) * w);
+            launch_compact_scatter((const unsigned char*)present->ptr, n_slots, (const long long*)offs->ptr, sparse_v[i]->ptr, w, c.data->ptr, ctx->stream);
+            auto vbytes = std::make_shared<DeviceBuf>((size_t)std::max<long long>(n_out, 1));
+            launch_compact_scatter((const unsigned char*)present->ptr, n_slots, (const long long*)offs->ptr, sparse_n[i]->ptr, 1, vbytes->ptr, ctx->stream);
+            c.validity = std::make_shared<DeviceBuf>((size_t)(n_out + 31) / 32 * 4 + 8);
+            launch_bytes_to_bitmap((const unsigned char*)vbytes->ptr, n_out, (uint32_t*)c.validity->ptr, ctx->stream);
+            ctx->kernel_launches += 3;
+            c.null_count = -1;
+            if ((int)i < g.n_key_cols && c.type.is_string()) { c.is_dict = true; c.dict = key_dicts[i]; }
+            out.cols.push_back(c);
+        }
+        cuda_check(cudaStreamSynchronize(ctx->stream), "compaction sync"); // temporaries die here
     }
 
     // one (possibly split) launch over rows [row0,row1) at assumption level lv, escalating on violated assumptions
@@ -917,7 +1100,8 @@ struct AggNode : FusedBase {
             cuda_check(cudaStreamSynchronize(ctx->stream), "identity totals sync");
             totals_groups = 1;
         }
-        finalize(out);
+        if (hash_mode) finalize_hash(out);
+        else finalize(out);
         return true;
     }
 
@@ -1129,6 +1313,7 @@ std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const s
             walk(s->child);
         } else if (auto a = std::dynamic_pointer_cast<AggNode>(n)) {
             a->key_has_null.assign(a->keys.size(), false);
+            for (auto& k : a->keys) if (!k->type.is_string() && k->type.id != TypeId::Bool) a->hash_mode = true;
             out.push_back(generate_pipeline(a->make_spec(nullptr, a->ungrouped ? 1 : 6)));
             walk(a->child);
         }
@@ -1202,6 +1387,25 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
                 data.resize(data.size() + 8);
             } else if (c.type.id == TypeId::Bool) data = pack_bits(c.h_data.data(), n);
             else { data = c.h_data; data.resize(data.size() + 8); }
+        } else if (c.is_dict) {
+            // dictionary-coded string keys of a hash aggregate: fetch the codes, spell the strings out on the host
+            std::vector<int32_t> codes(n + 1);
+            if (n) cuda_check(cudaMemcpyAsync(codes.data(), c.data->ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H key codes");
+            std::vector<uint8_t> vb((n + 7) / 8 + 8, 0xff);
+            if (c.validity && n) cuda_check(cudaMemcpyAsync(vb.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity");
+            cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
+            ctx->d2h_bytes += (int64_t)n * 4;
+            offs.resize((n + 1) * 4);
+            int32_t* o = (int32_t*)offs.data();
+            o[0] = 0;
+            for (size_t r = 0; r < n; r++) {
+                bool valid = (vb[r >> 3] >> (r & 7)) & 1;
+                if (valid) { const std::string& sv = c.dict->values.at((size_t)codes[r]); data.insert(data.end(), sv.begin(), sv.end()); }
+                else null_count++;
+                o[r + 1] = (int32_t)data.size();
+            }
+            data.resize(data.size() + 8);
+            if (null_count) validity = vb;
         } else {
             if (c.type.is_string()) throw Unsupported("export of device string columns");
             int w = c.type.id == TypeId::Bool ? 1 : c.type.arrow_width();

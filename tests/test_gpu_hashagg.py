@@ -1,0 +1,118 @@
+"""GPU parity: high-cardinality hash aggregation (BASELINE config 4 shape: GROUP BY l_orderkey SUM(l_extendedprice))."""
+import math
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import comet_b200
+    return comet_b200
+
+
+def run(cb, plan, inputs, chunk_rows=None):
+    cfg = {"spark.comet.b200.chunkRows": str(chunk_rows)} if chunk_rows else None
+    with cb.native.Plan(plan, inputs, config=cfg) as p:
+        return p.collect()
+
+
+def unscaled(x):
+    return None if x is None else int(x.scaleb(-x.as_tuple().exponent))
+
+
+def plans(cb, variant):
+    P = cb.proto
+    m = P.DECIMAL(12, 2) if variant == "dec" else P.DOUBLE
+    sdt = P.DECIMAL(22, 2) if variant == "dec" else P.DOUBLE
+    partial = P.hash_agg(P.scan([P.INT64, m]), [P.bound(0, P.INT64)], [P.agg_sum(P.bound(1, m), sdt)], P.PARTIAL)
+    state = [P.INT64, sdt, P.BOOL] if variant == "dec" else [P.INT64, sdt]
+    final = P.hash_agg(P.scan(state, source="shuffle"), [P.bound(0, P.INT64)], [P.agg_sum(P.unbound("c", m), sdt)], P.FINAL)
+    return partial, final
+
+
+@pytest.mark.parametrize("n,chunk", [(10, None), (100_000, None), (700_000, 200_000)])
+def test_group_by_orderkey_sum_dec(cb, n, chunk):
+    t = cb.tpch
+    cols = t.gen_lineitem(n, seed=3)
+    tbl = pa.table({"k": pa.array(cols["l_orderkey"]), "v": t._dec_array(cols["l_extendedprice"])})
+    partial, final = plans(cb, "dec")
+    state = run(cb, partial, [tbl.to_batches(max_chunksize=8192)], chunk)
+    res = run(cb, final, [state])
+    exp = {}
+    for k, v in zip(cols["l_orderkey"].tolist(), cols["l_extendedprice"].tolist()):
+        exp[k] = exp.get(k, 0) + v
+    got = {k: unscaled(v) for k, v in zip(res.column(0).to_pylist(), res.column(1).to_pylist())}
+    assert got == exp
+    # partial state: (key, sum d(22,2), is_empty bool); one row per group, unordered
+    assert state.num_rows == len(exp) and str(state.schema.field(2).type) == "bool"
+
+
+def test_group_by_orderkey_sum_f64(cb):
+    t = cb.tpch
+    n = 300_000
+    cols = t.gen_lineitem(n, seed=5)
+    price = cols["l_extendedprice"].astype(np.float64) / 100.0
+    tbl = pa.table({"k": pa.array(cols["l_orderkey"]), "v": pa.array(price)})
+    partial, final = plans(cb, "f64")
+    state = run(cb, partial, [tbl.to_batches(max_chunksize=8192)], 120_000)
+    res = run(cb, final, [state])
+    keys = np.array(res.column(0).to_pylist())
+    vals = np.array(res.column(1).to_pylist())
+    order = np.argsort(keys)
+    uk, inv = np.unique(cols["l_orderkey"], return_inverse=True)
+    assert (keys[order] == uk).all()
+    for i in range(0, len(uk), 997):
+        exact = math.fsum(price[inv == i])
+        assert abs(vals[order][i] - exact) <= math.ulp(exact)
+
+
+def test_null_and_negative_and_sentinel_keys(cb):
+    P = cb.proto
+    keys = pa.array([None, -1, 5, -1, None, 2**63 - 1, -(2**63), 5, -1], type=pa.int64())   # -1 == the table's EMPTY sentinel pattern
+    vals = pa.array([1, 2, 3, 4, 5, 6, 7, 8, None], type=pa.int64())
+    plan = P.hash_agg(P.scan([P.INT64, P.INT64]), [P.bound(0, P.INT64)],
+                      [P.agg_sum(P.bound(1, P.INT64), P.INT64), P.agg_count([P.bound(1, P.INT64)]), P.agg_min(P.bound(1, P.INT64), P.INT64),
+                       P.agg_max(P.bound(1, P.INT64), P.INT64)], P.PARTIAL)
+    out = run(cb, plan, [pa.table({"k": keys, "v": vals})])
+    got = {r["col_0"]: (r["col_1"], r["col_2"], r["col_3"], r["col_4"]) for r in out.to_pylist()}
+    assert got == {None: (6, 2, 1, 5), -1: (6, 2, 2, 4), 5: (11, 2, 3, 8), 2**63 - 1: (6, 1, 6, 6), -(2**63): (7, 1, 7, 7)}
+
+
+def test_two_keys_date_and_dict_string(cb):
+    P = cb.proto
+    n = 50_000
+    rng = np.random.default_rng(9)
+    d = rng.integers(9000, 9400, n).astype(np.int32)
+    s = rng.integers(0, 300, n)
+    names = [f"name-{i:03d}" for i in range(300)]
+    v = rng.integers(-1000, 1000, n)
+    tbl = pa.table({"d": pa.array(d, type=pa.date32()), "s": pa.DictionaryArray.from_arrays(pa.array(s.astype(np.int32)), pa.array(names)),
+                    "v": pa.array(v)})
+    plan = P.hash_agg(P.scan([P.DATE, P.STRING, P.INT64]), [P.bound(0, P.DATE), P.bound(1, P.STRING)],
+                      [P.agg_sum(P.bound(2, P.INT64), P.INT64), P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    out = run(cb, plan, [tbl.to_batches(max_chunksize=8192)], 20_000)
+    exp = {}
+    for a, b, c in zip(d.tolist(), s.tolist(), v.tolist()):
+        e = exp.setdefault((a, names[b]), [0, 0])
+        e[0] += c
+        e[1] += 1
+    import datetime
+    epoch = datetime.date(1970, 1, 1)
+    got = {((r["col_0"] - epoch).days, r["col_1"]): [r["col_2"], r["col_3"]] for r in out.to_pylist()}
+    assert got == exp
+
+
+def test_table_growth_and_rehash(cb):
+    """Many small chunks force the table to grow several times."""
+    P = cb.proto
+    n = 400_000
+    k = np.arange(n, dtype=np.int64) * 7919 % 1_000_003
+    v = np.ones(n, dtype=np.int64)
+    plan = P.hash_agg(P.scan([P.INT64, P.INT64]), [P.bound(0, P.INT64)], [P.agg_sum(P.bound(1, P.INT64), P.INT64)], P.PARTIAL)
+    out = run(cb, plan, [pa.table({"k": k, "v": v}).to_batches(max_chunksize=8192)], 16_384)
+    assert out.num_rows == len(np.unique(k))
+    assert sum(out.column(1).to_pylist()) == n
