@@ -64,7 +64,7 @@ class Stats(C.Structure):
                 ("pipeline_rows", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
-EXPORTED = ["cb200_plan_stats", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
+EXPORTED = ["cb200_plan_stats", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
             "cb200_release", "cb200_table_create", "cb200_table_add_column", "cb200_plan_bind_table",
             "cb200_table_release", "cb200_execute_device", "cb200_plan_kernel_launches", "cb200_compile_plan",
             "cb200_plan_kernel_source"]
@@ -252,6 +252,12 @@ class Plan:
         if not batches:
             return None
         return pa.Table.from_batches(batches)
+
+    def partition_starts(self):
+        buf = (C.c_int64 * 4096)()
+        self._lib.cb200_plan_partition_starts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        n = self._lib.cb200_plan_partition_starts(self.handle, buf, 4096)
+        return [buf[i] for i in range(n)]
 
     def stats(self):
         st = Stats()

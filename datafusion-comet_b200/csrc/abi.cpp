@@ -290,6 +290,13 @@ int cb200_plan_bind_table(cb200_plan* plan, int32_t input_index, cb200_table* t,
 
 void cb200_table_release(cb200_table* t) { delete t; }
 
+int32_t cb200_plan_partition_starts(cb200_plan* plan, int64_t* starts, int32_t cap) {
+    if (!plan) return -1;
+    const auto& ps = plan->ctx.partition_starts;
+    for (size_t i = 0; i < ps.size() && (int32_t)i < cap; i++) starts[i] = ps[i];
+    return (int32_t)ps.size();
+}
+
 int64_t cb200_plan_kernel_launches(cb200_plan* plan) { return plan ? plan->ctx.kernel_launches : -1; }
 
 int cb200_plan_stats(cb200_plan* plan, cb200_stats* out) {

@@ -219,3 +219,132 @@ void launch_compact_scatter(const u8* present, i64 n, const i64* offsets, const 
 }
 
 } // namespace cb200
+
+// ---- hash partitioning: Spark murmur3 (seed 42) over the key columns, pmod, stable counting sort ---------------------
+// Replaces native/shuffle/src/partitioners/multi_partition.rs:265-330 (hash + pmod) and :54-99 (counting sort).
+namespace cb200 {
+using namespace cb;
+
+__device__ __forceinline__ bool bit_at(const u8* bm, i64 i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+__global__ void k_partition_ids(HashKeyCols kc, i64 n, u32 n_parts, u32* hashes, u32* pids) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 h = 42u; // spark seed (multi_partition.rs:298)
+    for (int c = 0; c < kc.n; c++) {
+        const HashKeyCol& k = kc.col[c];
+        if (k.validity && !bit_at(k.validity, i)) continue; // NULL leaves the running hash unchanged (utils.rs:38-42)
+        const u8* d = (const u8*)k.data;
+        switch (k.kind) {
+        case HK_BOOL: h = mm3_i32(bit_at(d, i) ? 1 : 0, h); break;
+        case HK_I8: h = mm3_i32((i32)((const signed char*)d)[i], h); break;
+        case HK_I16: h = mm3_i32((i32)((const short*)d)[i], h); break;
+        case HK_I32: h = mm3_i32(((const i32*)d)[i], h); break;
+        case HK_I64: h = mm3_i64(((const i64*)d)[i], h); break;
+        case HK_F32: { float f = ((const float*)d)[i]; if (f == 0.0f) f = 0.0f; h = mm3_i32((i32)__float_as_uint(f == 0.0f ? 0.0f : f), h); break; }
+        case HK_F64: { double f = ((const double*)d)[i]; h = mm3_i64(f == 0.0 ? 0ll : __double_as_longlong(f), h); break; }
+        case HK_DEC_SMALL_128: h = mm3_i64((i64)((const i128*)d)[i].lo, h); break; // d(p<=18): hashed as i64 (utils.rs:159-196)
+        case HK_DEC_LARGE_128: h = mm3_i128(((const i128*)d)[i], h); break;        // d(p>18): 16 LE bytes (utils.rs:199-226)
+        case HK_DEC_LARGE_64: h = mm3_i128(i128_from_i64(((const i64*)d)[i]), h); break;
+        case HK_DICT8: case HK_DICT16: case HK_DICT32: {
+            i32 code = k.kind == HK_DICT8 ? (i32)((const signed char*)d)[i] : k.kind == HK_DICT16 ? (i32)((const short*)d)[i] : ((const i32*)d)[i];
+            i32 o0 = k.dict_offsets[code], o1 = k.dict_offsets[code + 1];
+            h = mm3_bytes(k.dict_chars + o0, o1 - o0, h);
+            break;
+        }
+        case HK_UTF8: {
+            i32 o0 = k.dict_offsets[i], o1 = k.dict_offsets[i + 1];
+            h = mm3_bytes(k.dict_chars + o0, o1 - o0, h);
+            break;
+        }
+        }
+    }
+    if (hashes) hashes[i] = h;
+    pids[i] = pmod_u32(h, n_parts);
+}
+
+// per-1024-row-block histogram of partition ids -> block_hist[block][n_parts]
+__global__ void k_pid_block_hist(const u32* pids, i64 n, u32 n_parts, i32* block_hist) {
+    extern __shared__ i32 sh[];
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) sh[p] = 0;
+    __syncthreads();
+    i64 i0 = (i64)blockIdx.x * 1024;
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) { i64 i = i0 + k; if (i < n) atomicAdd(&sh[pids[i]], 1); }
+    __syncthreads();
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) block_hist[(size_t)blockIdx.x * n_parts + p] = sh[p];
+}
+// exclusive scan in (partition-major, block-minor) order: out position of the first row of (block, partition)
+__global__ void k_pid_scan(const i32* block_hist, i64 n_blocks, u32 n_parts, i64* block_base, i64* starts) {
+    // one thread per partition computes its total, then a serial scan over partitions (n_parts is small), then per-block bases
+    extern __shared__ i64 totals[];
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) {
+        i64 t = 0;
+        for (i64 b = 0; b < n_blocks; b++) t += block_hist[(size_t)b * n_parts + p];
+        totals[p] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        i64 run = 0;
+        for (u32 p = 0; p < n_parts; p++) { starts[p] = run; run += totals[p]; }
+        starts[n_parts] = run;
+    }
+    __syncthreads();
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) {
+        i64 run = starts[p];
+        for (i64 b = 0; b < n_blocks; b++) { block_base[(size_t)b * n_parts + p] = run; run += block_hist[(size_t)b * n_parts + p]; }
+    }
+}
+// stable placement: rows of a block are visited in row order by ONE warp-sized sweep per 32 rows
+__global__ void k_pid_place(const u32* pids, i64 n, u32 n_parts, const i64* block_base, i64* row_idx) {
+    extern __shared__ i64 cursor[]; // [n_parts] running output position for this block
+    for (u32 p = threadIdx.x; p < n_parts; p += blockDim.x) cursor[p] = block_base[(size_t)blockIdx.x * n_parts + p];
+    __syncthreads();
+    if (threadIdx.x >= 32) return; // a single warp walks the block in row order: keeps the sort stable
+    i64 i0 = (i64)blockIdx.x * 1024;
+    int lane = threadIdx.x;
+    for (int k = 0; k < 32; k++) {
+        i64 i = i0 + k * 32 + lane;
+        bool in = i < n;
+        u32 pid = in ? pids[i] : 0xffffffffu;
+        u32 peers = __match_any_sync(0xffffffffu, pid);
+        int rank = __popc(peers & ((1u << lane) - 1u));
+        int leader = __ffs(peers) - 1;
+        i64 base = 0;
+        if (in && lane == leader) { base = cursor[pid]; cursor[pid] = base + __popc(peers); }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (in) row_idx[base + rank] = i;
+        __syncwarp();
+    }
+}
+template <typename T> __global__ void k_gather_rows(const T* in, const i64* row_idx, i64 n, T* out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[row_idx[i]];
+}
+__global__ void k_gather_bits(const u8* in_bits, const i64* row_idx, i64 n, u8* out_bytes) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out_bytes[i] = bit_at(in_bits, row_idx[i]) ? 1 : 0;
+}
+
+void launch_partition(const HashKeyCols& kc, i64 n, u32 n_parts, u32* hashes, u32* pids, i32* block_hist, i64* block_base, i64* starts, i64* row_idx,
+                      cudaStream_t st) {
+    if (n <= 0) return;
+    i64 nb = (n + 1023) / 1024;
+    k_partition_ids<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kc, n, n_parts, hashes, pids);
+    k_pid_block_hist<<<(unsigned)nb, 256, n_parts * sizeof(i32), st>>>(pids, n, n_parts, block_hist);
+    k_pid_scan<<<1, 256, n_parts * sizeof(i64), st>>>(block_hist, nb, n_parts, block_base, starts);
+    k_pid_place<<<(unsigned)nb, 64, n_parts * sizeof(i64), st>>>(pids, n, n_parts, block_base, row_idx);
+}
+void launch_gather(const void* in, int width, const i64* row_idx, i64 n, void* out, cudaStream_t st) {
+    if (n <= 0) return;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (width == 16) k_gather_rows<ulonglong2><<<blocks, 256, 0, st>>>((const ulonglong2*)in, row_idx, n, (ulonglong2*)out);
+    else if (width == 8) k_gather_rows<u64><<<blocks, 256, 0, st>>>((const u64*)in, row_idx, n, (u64*)out);
+    else if (width == 4) k_gather_rows<u32><<<blocks, 256, 0, st>>>((const u32*)in, row_idx, n, (u32*)out);
+    else if (width == 2) k_gather_rows<u16><<<blocks, 256, 0, st>>>((const u16*)in, row_idx, n, (u16*)out);
+    else k_gather_rows<u8><<<blocks, 256, 0, st>>>((const u8*)in, row_idx, n, (u8*)out);
+}
+void launch_gather_bits(const void* in_bits, const i64* row_idx, i64 n, void* out_bytes, cudaStream_t st) {
+    if (n > 0) k_gather_bits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u8*)in_bits, row_idx, n, (u8*)out_bytes);
+}
+
+} // namespace cb200

@@ -26,6 +26,25 @@ struct StringDictDev {
 void launch_dict_encode(const StringDictDev& d, const int* offsets, const unsigned char* chars, const unsigned char* validity, long long n,
                         int* row_slot, int* codes, cudaStream_t st);
 
+// hash partitioning (ShuffleWriter with HashPartition): murmur3 seed 42 chained over the key columns, pmod, stable counting sort
+enum { HK_BOOL, HK_I8, HK_I16, HK_I32, HK_I64, HK_F32, HK_F64, HK_DEC_SMALL_128, HK_DEC_LARGE_128, HK_DEC_SMALL_64 = HK_I64, HK_DEC_LARGE_64 = 9,
+       HK_DICT8 = 10, HK_DICT16, HK_DICT32, HK_UTF8 };
+struct HashKeyCol {
+    int kind;
+    const void* data;
+    const unsigned char* validity; // Arrow bitmap or nullptr
+    const int* dict_offsets;       // dictionary / utf8 offsets
+    const unsigned char* dict_chars;
+};
+struct HashKeyCols {
+    int n;
+    HashKeyCol col[8];
+};
+void launch_partition(const HashKeyCols& kc, long long n, unsigned n_parts, unsigned* hashes, unsigned* pids, int* block_hist, long long* block_base,
+                      long long* starts, long long* row_idx, cudaStream_t st);
+void launch_gather(const void* in, int width, const long long* row_idx, long long n, void* out, cudaStream_t st);
+void launch_gather_bits(const void* in_bits, const long long* row_idx, long long n, void* out_bytes, cudaStream_t st);
+
 // stream compaction (hash-aggregate results): per-1024-row-block counts + exclusive scan, then one scatter per column
 void launch_key_presence(const unsigned long long* keys, long long n, unsigned char* present, cudaStream_t st);
 void launch_compact_plan(const unsigned char* present, long long n, int* counts, long long* offsets, long long* total, cudaStream_t st);

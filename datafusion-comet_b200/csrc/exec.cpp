@@ -1195,6 +1195,156 @@ struct AggNode : FusedBase {
     }
 };
 
+
+// =================================================================================================
+// hash repartitioning (ShuffleWriterExec with HashPartition, native/shuffle/src/partitioners/multi_partition.rs)
+// =================================================================================================
+// Output: the child's rows reordered so that partition p occupies rows [starts[p], starts[p+1]) -- what the
+// reference writes as per-partition IPC blocks, kept on the device for the NVLink exchange.
+struct PartitionNode : ExecNode {
+    ExecContext* ctx;
+    ExecNodeP child;
+    std::vector<int> key_cols;
+    int n_parts = 1;
+
+    bool next(Batch& out) override {
+        Batch in;
+        if (!child->next(in)) return false;
+        TraceSpan ts("partition");
+        to_device(in);
+        int64_t n = in.n_rows;
+        cudaStream_t st = ctx->stream;
+        HashKeyCols kc;
+        memset(&kc, 0, sizeof(kc));
+        if (key_cols.size() > 8) throw Unsupported("more than 8 hash-partition keys");
+        std::vector<DeviceBufP> keep;
+        for (int ci : key_cols) {
+            const Column& c = in.cols[(size_t)ci];
+            HashKeyCol& k = kc.col[kc.n++];
+            k.data = c.data ? c.data->ptr : nullptr;
+            k.validity = c.validity ? (const unsigned char*)c.validity->ptr : nullptr;
+            switch (c.type.id) {
+            case TypeId::Bool: k.kind = HK_BOOL; break;
+            case TypeId::Int8: k.kind = HK_I8; break;
+            case TypeId::Int16: k.kind = HK_I16; break;
+            case TypeId::Int32: case TypeId::Date: k.kind = HK_I32; break;
+            case TypeId::Int64: case TypeId::Timestamp: case TypeId::TimestampNtz: k.kind = HK_I64; break;
+            case TypeId::Float32: k.kind = HK_F32; break;
+            case TypeId::Float64: k.kind = HK_F64; break;
+            case TypeId::Decimal:
+                if (c.phys == Phys::I64) k.kind = c.type.precision <= 18 ? HK_DEC_SMALL_64 : HK_DEC_LARGE_64;
+                else k.kind = c.type.precision <= 18 ? HK_DEC_SMALL_128 : HK_DEC_LARGE_128;
+                break;
+            case TypeId::String: case TypeId::Binary:
+                if (c.is_dict) {
+                    k.kind = c.phys == Phys::I8 ? HK_DICT8 : c.phys == Phys::I16 ? HK_DICT16 : HK_DICT32;
+                    std::vector<int32_t> off{0};
+                    std::string chars;
+                    for (auto& v : c.dict->values) { chars += v; off.push_back((int32_t)chars.size()); }
+                    auto doff = std::make_shared<DeviceBuf>(off.size() * 4), dch = std::make_shared<DeviceBuf>(chars.size() + 16);
+                    cuda_check(cudaMemcpyAsync(doff->ptr, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st), "dict offsets");
+                    if (!chars.empty()) cuda_check(cudaMemcpyAsync(dch->ptr, chars.data(), chars.size(), cudaMemcpyHostToDevice, st), "dict chars");
+                    cuda_check(cudaStreamSynchronize(st), "dict upload");
+                    keep.push_back(doff); keep.push_back(dch);
+                    k.dict_offsets = (const int*)doff->ptr;
+                    k.dict_chars = (const unsigned char*)dch->ptr;
+                } else {
+                    if (!c.offsets || !c.chars) throw Unsupported("string partition key without offsets/chars");
+                    k.kind = HK_UTF8;
+                    k.dict_offsets = (const int*)c.offsets->ptr;
+                    k.dict_chars = (const unsigned char*)c.chars->ptr;
+                }
+                break;
+            default: throw Unsupported("hash partitioning on " + c.type.str());
+            }
+        }
+        size_t nb = (size_t)(n + 1023) / 1024 + 1;
+        auto pids = std::make_shared<DeviceBuf>((size_t)n * 4 + 16);
+        auto hist = std::make_shared<DeviceBuf>(nb * n_parts * 4);
+        auto base = std::make_shared<DeviceBuf>(nb * n_parts * 8);
+        auto starts = std::make_shared<DeviceBuf>((size_t)(n_parts + 1) * 8);
+        auto row_idx = std::make_shared<DeviceBuf>((size_t)n * 8 + 16);
+        cuda_check(cudaMemsetAsync(starts->ptr, 0, (size_t)(n_parts + 1) * 8, st), "memset starts");
+        launch_partition(kc, n, (unsigned)n_parts, nullptr, (unsigned*)pids->ptr, (int*)hist->ptr, (long long*)base->ptr, (long long*)starts->ptr,
+                         (long long*)row_idx->ptr, st);
+        ctx->kernel_launches += 4;
+        out.n_rows = n;
+        out.cols.clear();
+        for (auto& c : in.cols) {
+            Column o = c;
+            if (c.offsets) throw Unsupported("repartitioning plain string columns (dictionary-encode them first)");
+            int w = phys_bytes(c.is_dict && c.phys == Phys::I32 ? Phys::Dict32 : c.phys);
+            if (w == 0) { // bit-packed booleans: gather to bytes, repack
+                auto bytes = std::make_shared<DeviceBuf>((size_t)n + 16);
+                launch_gather_bits(c.data->ptr, (const long long*)row_idx->ptr, n, bytes->ptr, st);
+                o.data = std::make_shared<DeviceBuf>((size_t)(n + 31) / 32 * 4 + 8);
+                launch_bytes_to_bitmap((const unsigned char*)bytes->ptr, n, (uint32_t*)o.data->ptr, st);
+                keep.push_back(bytes);
+                ctx->kernel_launches += 2;
+            } else {
+                o.data = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(n, 1) * w);
+                launch_gather(c.data->ptr, w, (const long long*)row_idx->ptr, n, o.data->ptr, st);
+                ctx->kernel_launches++;
+            }
+            if (c.validity) {
+                auto bytes = std::make_shared<DeviceBuf>((size_t)n + 16);
+                launch_gather_bits(c.validity->ptr, (const long long*)row_idx->ptr, n, bytes->ptr, st);
+                o.validity = std::make_shared<DeviceBuf>((size_t)(n + 31) / 32 * 4 + 8);
+                launch_bytes_to_bitmap((const unsigned char*)bytes->ptr, n, (uint32_t*)o.validity->ptr, st);
+                keep.push_back(bytes);
+                ctx->kernel_launches += 2;
+            }
+            out.cols.push_back(o);
+        }
+        ctx->partition_starts.assign((size_t)n_parts + 1, 0);
+        cuda_check(cudaMemcpyAsync(ctx->partition_starts.data(), starts->ptr, (size_t)(n_parts + 1) * 8, cudaMemcpyDeviceToHost, st), "starts D2H");
+        ctx->check_device_errors();
+        return true;
+    }
+
+    // small host-resident aggregate results -> device columns
+    void to_device(Batch& b) {
+        for (auto& c : b.cols) {
+            if (!c.on_host) continue;
+            size_t n = (size_t)b.n_rows;
+            if (c.type.is_string()) { // dictionary-encode on the host: these are group keys of a dense aggregate (a handful of rows)
+                auto d = std::make_shared<Dictionary>();
+                std::vector<int32_t> codes(n);
+                for (size_t r = 0; r < n; r++) {
+                    std::string v((const char*)c.h_data.data() + c.h_offsets[r], (size_t)(c.h_offsets[r + 1] - c.h_offsets[r]));
+                    auto it = std::find(d->values.begin(), d->values.end(), v);
+                    if (it == d->values.end()) { codes[r] = (int32_t)d->values.size(); d->values.push_back(v); }
+                    else codes[r] = (int32_t)(it - d->values.begin());
+                }
+                c.data = std::make_shared<DeviceBuf>(n * 4 + 16);
+                if (n) cuda_check(cudaMemcpyAsync(c.data->ptr, codes.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream), "keys H2D");
+                cuda_check(cudaStreamSynchronize(ctx->stream), "keys H2D sync");
+                c.is_dict = true; c.dict = d; c.phys = Phys::I32;
+            } else if (c.type.id == TypeId::Bool) {
+                std::vector<uint8_t> bits((n + 7) / 8 + 8, 0);
+                for (size_t r = 0; r < n; r++) if (c.h_data[r]) bits[r >> 3] |= (uint8_t)(1u << (r & 7));
+                c.data = std::make_shared<DeviceBuf>(bits.size());
+                cuda_check(cudaMemcpyAsync(c.data->ptr, bits.data(), bits.size(), cudaMemcpyHostToDevice, ctx->stream), "bool H2D");
+                cuda_check(cudaStreamSynchronize(ctx->stream), "bool H2D sync");
+                c.phys = Phys::Bitmap;
+            } else {
+                c.data = std::make_shared<DeviceBuf>(c.h_data.size() + 16);
+                if (!c.h_data.empty()) cuda_check(cudaMemcpyAsync(c.data->ptr, c.h_data.data(), c.h_data.size(), cudaMemcpyHostToDevice, ctx->stream), "col H2D");
+                cuda_check(cudaStreamSynchronize(ctx->stream), "col H2D sync");
+                c.phys = phys_of(c.type);
+            }
+            if (!c.h_valid.empty()) {
+                std::vector<uint8_t> bits((n + 7) / 8 + 8, 0);
+                for (size_t r = 0; r < n; r++) if (c.h_valid[r]) bits[r >> 3] |= (uint8_t)(1u << (r & 7));
+                c.validity = std::make_shared<DeviceBuf>(bits.size());
+                cuda_check(cudaMemcpyAsync(c.validity->ptr, bits.data(), bits.size(), cudaMemcpyHostToDevice, ctx->stream), "validity H2D");
+                cuda_check(cudaStreamSynchronize(ctx->stream), "validity H2D sync");
+            }
+            c.on_host = false;
+        }
+    }
+};
+
 // =================================================================================================
 // plan -> executor tree
 // =================================================================================================
@@ -1231,7 +1381,18 @@ static ExecNodeP build_source(const OperatorP& op, ExecContext* ctx, PlanInputs*
 static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs, bool build_only) {
     OperatorP cur = op;
     OperatorP agg_op;
-    if (cur->kind == OpKind::ShuffleWriter) throw Unsupported("ShuffleWriter is executed through cb200_partition (see include/comet_b200.h)");
+    if (cur->kind == OpKind::ShuffleWriter) {
+        auto n = std::make_shared<PartitionNode>();
+        n->ctx = ctx;
+        n->child = build_node(cur->children[0], ctx, inputs, build_only);
+        n->schema = cur->schema;
+        n->n_parts = cur->num_partitions;
+        for (auto& e : cur->hash_exprs) {
+            if (e->kind != ExprKind::Bound) throw Unsupported("computed hash-partition keys (only plain column keys)");
+            n->key_cols.push_back(e->index);
+        }
+        return n;
+    }
     if (cur->kind == OpKind::HashAgg) { agg_op = cur; cur = cur->children[0]; }
     std::vector<OperatorP> chain; // top-down
     while (cur->kind == OpKind::Filter || cur->kind == OpKind::Projection) { chain.push_back(cur); cur = cur->children[0]; }
@@ -1311,6 +1472,8 @@ std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const s
         if (auto s = std::dynamic_pointer_cast<SelectNode>(n)) {
             out.push_back(generate_pipeline(s->make_spec(nullptr)));
             walk(s->child);
+        } else if (auto pn = std::dynamic_pointer_cast<PartitionNode>(n)) {
+            walk(pn->child);
         } else if (auto a = std::dynamic_pointer_cast<AggNode>(n)) {
             a->key_has_null.assign(a->keys.size(), false);
             for (auto& k : a->keys) if (!k->type.is_string() && k->type.id != TypeId::Bool) a->hash_mode = true;

@@ -91,6 +91,7 @@ struct ExecContext {
     int64_t pipeline_launches = 0;
     int64_t pipeline_rows = 0;    // rows those launches scanned
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    std::vector<int64_t> partition_starts; // last ShuffleWriter batch: partition p = rows [starts[p], starts[p+1])
     void check_device_errors();
     void collect_timing();
 };

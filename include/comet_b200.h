@@ -98,6 +98,13 @@ typedef struct cb200_device_column {
  * plan).  Returns rows, -1 at end, -2 on error. */
 int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_t n_cols, cb200_error* err);
 
+/* Plans rooted at a ShuffleWriter with HashPartition (operator.proto:688, partitioning.proto:38) return their
+ * child's rows reordered by partition id = pmod(murmur3(keys, seed 42), num_partitions) -- the reference's
+ * multi_partition.rs:265-330 -- stable within a partition.  After each cb200_execute / cb200_execute_device
+ * this returns the num_partitions+1 row offsets of that batch (the map-side of the exchange; the reference writes
+ * the same segments as per-partition IPC blocks).  Returns the number of entries. */
+int32_t cb200_plan_partition_starts(cb200_plan* plan, int64_t* starts, int32_t cap);
+
 /* kernels launched so far by this plan (bench.py reports it as gpu_launches) */
 int64_t cb200_plan_kernel_launches(cb200_plan* plan);
 
