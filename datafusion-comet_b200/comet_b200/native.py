@@ -56,7 +56,8 @@ class ArrowArrayStream(C.Structure):
 class DeviceColumn(C.Structure):
     _fields_ = [("type_id", C.c_int32), ("precision", C.c_int32), ("scale", C.c_int32), ("value_width", C.c_int32),
                 ("values", C.c_void_p), ("validity", C.c_void_p), ("host_values", C.c_void_p),
-                ("host_validity_bytes", C.c_void_p)]
+                ("host_validity_bytes", C.c_void_p), ("validity_bytes", C.c_void_p), ("bool_bytes", C.c_void_p),
+                ("n_dict", C.c_int32), ("pad", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -64,7 +65,7 @@ class Stats(C.Structure):
                 ("pipeline_rows", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
-EXPORTED = ["cb200_plan_stats", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
+EXPORTED = ["cb200_plan_stats", "cb200_table_add_column_bytes", "cb200_plan_dict_value", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
             "cb200_release", "cb200_table_create", "cb200_table_add_column", "cb200_plan_bind_table",
             "cb200_table_release", "cb200_execute_device", "cb200_plan_kernel_launches", "cb200_compile_plan",
             "cb200_plan_kernel_source"]
@@ -174,13 +175,32 @@ class DeviceTable:
         self._keep.append(keep)
         return self
 
+    def add_bytes(self, dt, values_ptr, value_width, validity_bytes_ptr=None, dictionary=None, keep=None):
+        """Column in the exchange-friendly form: validity (and BOOL values) one byte per row."""
+        from . import proto
+        err = _Error()
+        if dictionary is not None:
+            arr = (C.c_char_p * len(dictionary))(*[d.encode() if isinstance(d, str) else d for d in dictionary])
+            nd = len(dictionary)
+        else:
+            arr, nd = None, 0
+        f = lib().cb200_table_add_column_bytes
+        f.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(_Error)]
+        if f(self.handle, proto.DATA_TYPE_ID[dt.name], dt.precision, dt.scale, value_width, values_ptr, validity_bytes_ptr, arr, nd, C.byref(err)) != 0:
+            _raise(err)
+        self._keep.append(keep)
+        return self
+
     def release(self):
-        if self.handle:
+        if self.handle and lib is not None:
             lib().cb200_table_release(self.handle)
             self.handle = None
 
     def __del__(self):
-        self.release()
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class Plan:
@@ -252,6 +272,17 @@ class Plan:
         if not batches:
             return None
         return pa.Table.from_batches(batches)
+
+    def dict_values(self, col, n):
+        f = self._lib.cb200_plan_dict_value
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        out = []
+        for i in range(n):
+            ln = C.c_int32(0)
+            ptr = f(self.handle, col, i, C.byref(ln))
+            out.append(C.string_at(ptr, ln.value).decode())
+        return out
 
     def partition_starts(self):
         buf = (C.c_int64 * 4096)()

@@ -204,6 +204,9 @@ int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_
             } else {
                 o.values = c.data ? c.data->ptr : nullptr;
                 o.validity = c.validity ? c.validity->ptr : nullptr;
+                o.validity_bytes = c.valid_bytes ? c.valid_bytes->ptr : nullptr;
+                o.bool_bytes = c.bool_bytes ? c.bool_bytes->ptr : nullptr;
+                if (c.is_dict) { o.n_dict = (int)c.dict->values.size(); o.value_width = phys_bytes(c.phys == Phys::I32 ? Phys::Dict32 : c.phys); }
             }
         }
     });
@@ -274,6 +277,39 @@ int cb200_table_add_column(cb200_table* t, int32_t type_id, int32_t precision, i
         if (dev_validity && null_count != 0) c.validity = std::make_shared<DeviceBuf>((void*)dev_validity, (n + 7) / 8);
         c.null_count = null_count;
         t->t->cols.push_back(c);
+        return 0;
+    }, -1);
+}
+
+const char* cb200_plan_dict_value(cb200_plan* plan, int32_t col, int32_t i, int32_t* len) {
+    if (!plan || col < 0 || col >= (int)plan->last.cols.size()) return nullptr;
+    const Column& c = plan->last.cols[(size_t)col];
+    if (!c.is_dict || !c.dict || i < 0 || i >= (int)c.dict->values.size()) return nullptr;
+    if (len) *len = (int32_t)c.dict->values[(size_t)i].size();
+    return c.dict->values[(size_t)i].data();
+}
+
+int cb200_table_add_column_bytes(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width, const void* dev_values,
+                                 const void* dev_validity_bytes, const char* const* dict_values, int32_t n_dict, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        if (!t) throw PlanError("null table handle");
+        size_t n = (size_t)t->t->n_rows;
+        bool is_bool = type_id == (int)TypeId::Bool;
+        // reuse the validation of the bitmap form, then swap in the byte forms
+        int rc = cb200_table_add_column(t, type_id, precision, scale, is_bool ? 0 : value_width, is_bool ? nullptr : dev_values, nullptr, 0, dict_values, n_dict, err);
+        if (rc != 0) throw PlanError(err ? err->message : "add_column failed");
+        Column& c = t->t->cols.back();
+        if (is_bool) {
+            if (value_width != 1) throw PlanError("byte-per-row booleans need value_width 1");
+            c.data = nullptr;
+            c.bool_bytes = std::make_shared<DeviceBuf>((void*)dev_values, n);
+            t->t->needs_packing = true;
+        }
+        if (dev_validity_bytes) {
+            c.valid_bytes = std::make_shared<DeviceBuf>((void*)dev_validity_bytes, n);
+            c.null_count = -1;
+            t->t->needs_packing = true;
+        }
         return 0;
     }, -1);
 }

@@ -761,7 +761,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
             gid = "acc.find_slot(" + packed + ")";
             if (!null_group_cond.empty()) {
                 em.body << "    if (" << null_group_cond << ") atomicOr(p.hflags, 8);\n";
-                gid = "(" + null_group_cond + " ? (int)(p.hmask + 2u) : " + gid + ")";
+                gid = "(" + null_group_cond + " ? p.max_groups + 1 : " + gid + ")";
             }
         } else if (!spec.ungrouped) {
             for (size_t k = 0; k < spec.keys.size(); k++) {

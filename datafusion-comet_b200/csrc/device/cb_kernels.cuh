@@ -168,25 +168,40 @@ struct Acc {
     CB_D void vm_or(int c, i128 raw) { u64 s = (u64)(raw.hi >> 63); vm[2 * c] |= raw.lo ^ s; vm[2 * c + 1] |= (u64)raw.hi ^ s; }
     CB_D void vm_or64(int c, i64 raw) { vm[2 * c] |= (u64)raw ^ (u64)(raw >> 63); }
 
-    // slot of `key` (inserting it if new).  Linear probing; a plain L2 load first so that hits on existing keys
-    // (clustered inputs) need no CAS.
+    // dense group id of `key` (inserting it if new).  Linear probing; a plain L2 load first so that hits on
+    // existing keys (clustered inputs) need no CAS.  The claimer publishes the id it drew; concurrent finders of the
+    // same key wait for the publication (independent thread scheduling keeps the claimer running).
+    // slot s = 16 bytes {key, gid}: one 128-bit L2 load answers "is it my key, and which group"
+    CB_D int wait_gid(u32 s) const {
+        int g;
+        while ((g = *((volatile i32*)&p->hkeys[2 * (size_t)s + 1])) < 0) {}
+        return g;
+    }
     CB_D int find_slot(u64 key) const {
         const u32 mask = p->hmask;
-        if (key == CB_EMPTY_KEY) { atomicOr(p->hflags, 1); return (int)(mask + 1u); }
+        if (key == CB_EMPTY_KEY) { atomicOr(p->hflags, 1); return p->max_groups; }
         u64 h = key;
         h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
         u32 s = (u32)h & mask;
         for (u32 probe = 0; probe <= mask; probe++) {
-            u64 cur = __ldcg(&p->hkeys[s]);
-            if (cur == key) return (int)s;
-            if (cur == CB_EMPTY_KEY) {
-                u64 prev = atomicCAS((unsigned long long*)&p->hkeys[s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);
-                if (prev == CB_EMPTY_KEY || prev == key) return (int)s;
+            ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2*>(p->hkeys) + s);
+            if (slot.x == key) { int g = (i32)(u32)slot.y; return g >= 0 ? g : wait_gid(s); }
+            if (slot.x == CB_EMPTY_KEY) {
+                u64 prev = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);
+                if (prev == CB_EMPTY_KEY) {
+                    int g = atomicAdd(&p->hflags[4], 1);
+                    if (g >= p->max_groups) { atomicOr(p->hflags, 2); g = p->max_groups; } // cannot happen: host sizes max_groups >= rows
+                    else p->hkey_of_gid[g] = key;
+                    __threadfence();
+                    *((volatile i32*)&p->hkeys[2 * (size_t)s + 1]) = g;
+                    return g;
+                }
+                if (prev == key) return wait_gid(s);
             }
             s = (s + 1u) & mask;
         }
         atomicOr(p->hflags, 2);
-        return (int)(mask + 1u);
+        return p->max_groups;
     }
     CB_D u64* W(int g, int w) const { return p->htotals + ((size_t)g * CB_WORDS + w) * 2; }
     CB_D void add_i64_wrap(int g, int w, i64 v) { atomicAdd((unsigned long long*)W(g, w), (unsigned long long)v); }
@@ -475,28 +490,27 @@ CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T);
 #if CB_HASH
 CB_D void cb_unpack_key(const FinParams& fp, int g, u64 key, bool null_group);
 
-// identities for every slot of a fresh table
-extern "C" __global__ void cb_hash_init(u64* keys, u64* totals, long long n_slots) {
+// non-zero identities (MIN / MAX words) for a fresh range of group ids; all-zero layouts use a memset instead
+extern "C" __global__ void cb_hash_init(u64* totals, long long first, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    keys[i] = CB_EMPTY_KEY;
+    if (i >= n) return;
+    i += first;
 #pragma unroll
     for (int w = 0; w < CB_WORDS; w++) { totals[(i * CB_WORDS + w) * 2] = acc_identity(cb_word_kind(w)); totals[(i * CB_WORDS + w) * 2 + 1] = 0; }
 }
-// move every occupied slot of an old table into a bigger one (keys are unique: plain copies after the claim)
-extern "C" __global__ void cb_hash_rehash(const u64* old_keys, const u64* old_totals, long long old_slots, const __grid_constant__ PipeParams p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= old_slots) return;
-    u64 key = old_keys[i];
-    const bool is_sentinel = i == old_slots - 2, is_null_group = i == old_slots - 1;
-    if (is_sentinel && !(p.hpad & 1u)) return; // reserved slots only when they were used
-    if (is_null_group && !(p.hpad & 2u)) return;
-    if (!is_sentinel && !is_null_group && key == CB_EMPTY_KEY) return;
-    Acc acc;
-    acc.p = &p;
-    int g = is_sentinel ? (int)(p.hmask + 1u) : is_null_group ? (int)(p.hmask + 2u) : acc.find_slot(key);
-#pragma unroll
-    for (int w = 0; w < CB_WORDS * 2; w++) p.htotals[(size_t)g * CB_WORDS * 2 + w] = old_totals[i * CB_WORDS * 2 + w];
+// re-insert every group's key into a bigger key table, keeping its id (keys are unique: a claim always succeeds)
+extern "C" __global__ void cb_hash_rehash(const u64* key_of_gid, int n_groups, u64* hkeys, u32 mask) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    u64 key = key_of_gid[g];
+    u64 h = key;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    u32 s = (u32)h & mask;
+    while (true) {
+        u64 prev = atomicCAS((unsigned long long*)&hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);
+        if (prev == CB_EMPTY_KEY) { *((i32*)&hkeys[2 * (size_t)s + 1]) = g; return; }
+        s = (s + 1u) & mask;
+    }
 }
 #endif
 
@@ -540,12 +554,20 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
     if (g >= fp.n_groups) return;
     const u64* T = fp.totals + (size_t)g * CB_WORDS * 2;
 #if CB_HASH
-    u64 key = fp.hkeys[g];
-    const bool is_null_group = g == fp.n_groups - 1, is_sentinel = g == fp.n_groups - 2;
-    bool present = is_null_group ? (fp.null_group_used != 0) : is_sentinel ? (fp.sentinel_used != 0) : (key != CB_EMPTY_KEY);
-    fp.present[g] = present ? 1 : 0;
-    if (!present) return;
-    cb_unpack_key(fp, g, is_sentinel ? CB_EMPTY_KEY : key, is_null_group);
+    // output row g: groups 0..n_hash_groups-1 in id order, then the reserved groups that were used
+    int gid = g;
+    bool is_sentinel = false, is_null_group = false;
+    if (g >= fp.n_hash_groups) {
+        int extra = g - fp.n_hash_groups;
+        if (fp.sentinel_used && extra == 0) is_sentinel = true;
+        else is_null_group = true;
+        gid = is_sentinel ? fp.max_groups : fp.max_groups + 1;
+    }
+    const u64* TH = fp.totals + (size_t)gid * CB_WORDS * 2;
+    fp.present[g] = 1;
+    cb_unpack_key(fp, g, is_sentinel ? CB_EMPTY_KEY : (is_null_group ? 0ull : fp.hkeys[gid]), is_null_group);
+    cb_finalize_group(fp, g, TH);
+    return;
 #else
     fp.present[g] = (i64)T[CB_W_ROWS * 2] > 0 ? 1 : 0;
 #endif

@@ -26,14 +26,17 @@ struct PipeParams {
     u64* spill;                      // agg: exact 128-bit escape accumulators [n_groups][CB_WORDS][2]
     i32* err;                        // error flags (bit 0: arithmetic overflow, bit1: ansi error...)
     u64* vmask;                      // agg: per staged column OR of (value ^ sign) over valid rows [CB_MAX_COLS][2] (lo, hi)
-    // hash aggregation: open-addressing table in HBM (keys[cap+2], totals[cap+2][CB_WORDS][2]); slot `cap` is
-    // reserved for the one key whose packed form equals the EMPTY sentinel, slot `cap+1` for the NULL key of a
-    // single nullable 64-bit key column (no spare bit for a null flag)
-    u64* hkeys;
+    // hash aggregation.  Key table in HBM: 16-byte slots {packed 64-bit key (all-ones = empty), dense group id handed out
+    // at claim time (-1 until published)}.  Accumulators are DENSE by group id: htotals[gid][CB_WORDS][2],
+    // hkey_of_gid[gid]; ids max_groups / max_groups+1 are reserved for the key equal to the empty pattern and for the
+    // NULL key of a single nullable 64-bit key column.
+    u64* hkeys;                      // [cap][2]: {packed key, group id in the low 32 bits (all-ones = not published)}
+    u64* hkey_of_gid;
     u64* htotals;
     u32 hmask;                       // cap - 1 (cap is a power of two)
-    u32 hpad;
-    i32* hflags;                     // bit 0: sentinel key seen, bit 1: table full, bit 2: key does not fit the 64-bit packing, bit 3: NULL-key group used
+    i32 max_groups;
+    i32* hflags;                     // [0] bit 0: sentinel key seen, bit 1: out of group ids / table full, bit 2: key does not fit
+                                     //     the 64-bit packing, bit 3: NULL-key group used;  [4] number of groups handed out
 };
 
 
@@ -47,7 +50,9 @@ struct FinParams {
     u8* outv[CB_MAX_OUT];  // finalize: validity, one byte per group
     u8* present;           // finalize: 1 if the group saw at least one row
     i32* err;
-    const u64* hkeys;      // hash aggregation: packed keys per slot (nullptr for dense aggregation)
+    const u64* hkeys;      // hash aggregation: hkey_of_gid (nullptr for dense aggregation); output row r < n_hash_groups is group r
+    i32 n_hash_groups;     // hash aggregation: groups handed out; reserved groups follow as output rows when used
+    i32 max_groups;
     i32 sentinel_used;     // hash aggregation: slot `cap` holds the key equal to the EMPTY sentinel
     i32 null_group_used;   // hash aggregation: slot `cap+1` holds the all-NULL key (single nullable 64-bit key)
     i32 cert[CB_MAX_OUT];  // per aggregate: 0 = host certified that the decimal sum cannot overflow for any row order, 2 = not certified

@@ -399,8 +399,9 @@ struct StreamSource : ExecNode {
 // ---- caller-owned device-resident table -------------------------------------------------------------
 struct TableSource : ExecNode {
     std::shared_ptr<DeviceTable> table;
+    ExecContext* ctx = nullptr;
     bool done = false;
-    TableSource(std::shared_ptr<DeviceTable> t, const std::vector<DType>& fields) : table(std::move(t)) {
+    TableSource(std::shared_ptr<DeviceTable> t, const std::vector<DType>& fields, ExecContext* c) : table(std::move(t)), ctx(c) {
         schema = fields;
         if (table->cols.size() != fields.size()) throw PlanError("bound device table has " + std::to_string(table->cols.size()) + " columns, scan declares " + std::to_string(fields.size()));
     }
@@ -409,6 +410,21 @@ struct TableSource : ExecNode {
         done = true;
         out.n_rows = table->n_rows;
         out.cols = table->cols;
+        if (table->needs_packing) { // byte-per-row validity / booleans (received from an exchange) -> Arrow bitmaps
+            size_t n = (size_t)out.n_rows;
+            for (auto& c : out.cols) {
+                if (c.valid_bytes && !c.validity) {
+                    c.validity = std::make_shared<DeviceBuf>((n + 31) / 32 * 4 + 8);
+                    launch_bytes_to_bitmap((const unsigned char*)c.valid_bytes->ptr, out.n_rows, (uint32_t*)c.validity->ptr, ctx->stream);
+                    ctx->kernel_launches++;
+                }
+                if (c.bool_bytes && !c.data) {
+                    c.data = std::make_shared<DeviceBuf>((n + 31) / 32 * 4 + 8);
+                    launch_bytes_to_bitmap((const unsigned char*)c.bool_bytes->ptr, out.n_rows, (uint32_t*)c.data->ptr, ctx->stream);
+                    ctx->kernel_launches++;
+                }
+            }
+        }
         return out.n_rows > 0;
     }
 };
@@ -590,8 +606,8 @@ struct AggNode : FusedBase {
 
     // ---- hash aggregation state ---------------------------------------------------------------------------
     bool hash_mode = false, strategy_decided = false;
-    DeviceBufP hkeys, htotals, hflags;
-    int64_t hcap = 0;
+    DeviceBufP hkeys, hkey_of_gid, htotals, hflags;
+    int64_t hcap = 0, max_groups = 0;
     static constexpr int DENSE_MAX_GROUPS = 64;
 
     // ---- range assumptions (see ranges.h) ----------------------------------------------------------------
@@ -802,58 +818,72 @@ struct AggNode : FusedBase {
     }
     void hash_params(cb::PipeParams& p) const {
         p.hkeys = (cb::u64*)hkeys->ptr;
+        p.hkey_of_gid = (cb::u64*)hkey_of_gid->ptr;
         p.htotals = (cb::u64*)htotals->ptr;
         p.hmask = (cb::u32)(hcap - 1);
+        p.max_groups = (cb::i32)max_groups;
         p.hflags = (cb::i32*)hflags->ptr;
     }
-    // make sure the table can absorb `incoming` more distinct keys at load factor <= 0.5
+    bool zero_identity() const {
+        for (int k : word_kinds) if (k == W_MIN || k == W_MAX) return false;
+        return true;
+    }
+    void init_totals(const std::shared_ptr<CompiledModule>& mod, cb::u64* totals, int64_t first, int64_t n) {
+        if (n <= 0) return;
+        if (zero_identity()) {
+            cuda_check(cudaMemsetAsync(totals + first * n_words * 2, 0, (size_t)n * n_words * 16, ctx->stream), "memset totals");
+        } else {
+            long long f = first, nn = n;
+            void* a1[] = {&totals, &f, &nn};
+            launch_named(mod, "cb_hash_init", dim3((unsigned)((n + 255) / 256)), dim3(256), a1);
+        }
+    }
+    // make sure `incoming` more rows (each possibly a new group) fit: dense accumulators by group id, key table at load <= 0.5
     void ensure_table(const std::shared_ptr<CompiledModule>& mod, int64_t incoming) {
+        cudaStream_t st = ctx->stream;
         int flags[8] = {0};
         if (hflags) {
-            cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "hash flags");
-            cuda_check(cudaStreamSynchronize(ctx->stream), "hash flags sync");
+            cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "hash flags");
+            cuda_check(cudaStreamSynchronize(st), "hash flags sync");
         } else {
             hflags = std::make_shared<DeviceBuf>(64);
-            cuda_check(cudaMemsetAsync(hflags->ptr, 0, 64, ctx->stream), "memset hash flags");
+            cuda_check(cudaMemsetAsync(hflags->ptr, 0, 64, st), "memset hash flags");
         }
-        int64_t occupied = hcap ? count_occupied() : 0;
-        int64_t need = 2 * (occupied + incoming);
+        const int64_t cur = flags[4];
+        const int64_t need = cur + incoming;
+        if (need + 2 >= INT32_MAX) throw ExecError(16, "", "more than 2^31 groups in one partition; lower spark.comet.b200.chunkRows");
+        if (need > max_groups) {
+            int64_t nm = std::max<int64_t>(need, max_groups + max_groups / 4);
+            auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
+            auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 + 16);
+            cb::u64* tp = (cb::u64*)ntot->ptr;
+            if (cur > 0) {
+                cuda_check(cudaMemcpyAsync(tp, htotals->ptr, (size_t)cur * n_words * 16, cudaMemcpyDeviceToDevice, st), "copy totals");
+                cuda_check(cudaMemcpyAsync(nkog->ptr, hkey_of_gid->ptr, (size_t)cur * 8, cudaMemcpyDeviceToDevice, st), "copy group keys");
+            }
+            init_totals(mod, tp, cur, nm + 2 - cur);
+            if (htotals) // reserved groups move to the new tail
+                cuda_check(cudaMemcpyAsync(tp + (size_t)nm * n_words * 2, (cb::u64*)htotals->ptr + (size_t)max_groups * n_words * 2, (size_t)2 * n_words * 16,
+                                           cudaMemcpyDeviceToDevice, st), "copy reserved groups");
+            cuda_check(cudaStreamSynchronize(st), "table growth"); // old buffers die below
+            htotals = ntot; hkey_of_gid = nkog; max_groups = nm;
+        }
         int64_t cap = std::max<int64_t>(hcap, 1 << 16);
-        while (cap < need) cap <<= 1;
-        if (cap > (1ll << 31)) throw ExecError(16, "", "hash table would exceed 2^31 slots; lower spark.comet.b200.chunkRows");
-        if (cap == hcap) return;
-        auto nkeys = std::make_shared<DeviceBuf>((size_t)(cap + 2) * 8);
-        auto ntot = std::make_shared<DeviceBuf>((size_t)(cap + 2) * n_words * 16);
-        long long n_slots = cap + 2;
-        cb::u64* kp = (cb::u64*)nkeys->ptr;
-        cb::u64* tp = (cb::u64*)ntot->ptr;
-        void* a1[] = {&kp, &tp, &n_slots};
-        launch_named(mod, "cb_hash_init", dim3((unsigned)((n_slots + 255) / 256)), dim3(256), a1);
-        if (hcap) {
-            cb::PipeParams p;
-            memset(&p, 0, sizeof(p));
-            p.hkeys = kp; p.htotals = tp; p.hmask = (cb::u32)(cap - 1); p.hflags = (cb::i32*)hflags->ptr;
-            p.hpad = ((flags[0] & 1) ? 1u : 0u) | ((flags[0] & 8) ? 2u : 0u);
-            const cb::u64* ok = (const cb::u64*)hkeys->ptr;
-            const cb::u64* ot = (const cb::u64*)htotals->ptr;
-            long long old_slots = hcap + 2;
-            void* a2[] = {&ok, &ot, &old_slots, &p};
-            launch_named(mod, "cb_hash_rehash", dim3((unsigned)((old_slots + 255) / 256)), dim3(256), a2);
+        while (cap < 2 * need) cap <<= 1;
+        if (cap != hcap) {
+            auto nkeys = std::make_shared<DeviceBuf>((size_t)cap * 16);
+            cuda_check(cudaMemsetAsync(nkeys->ptr, 0xff, (size_t)cap * 16, st), "memset key slots");
+            if (cur > 0) {
+                const cb::u64* kog = (const cb::u64*)hkey_of_gid->ptr;
+                int ng = (int)cur;
+                cb::u64* kp = (cb::u64*)nkeys->ptr;
+                cb::u32 mask = (cb::u32)(cap - 1);
+                void* a2[] = {&kog, &ng, &kp, &mask};
+                launch_named(mod, "cb_hash_rehash", dim3((unsigned)((cur + 255) / 256)), dim3(256), a2);
+                cuda_check(cudaStreamSynchronize(st), "rehash");
+            }
+            hkeys = nkeys; hcap = cap;
         }
-        hkeys = nkeys; htotals = ntot; hcap = cap;
-    }
-    int64_t count_occupied() { // exact: scan the key array (cap x 8 bytes, tiny next to the rows that filled it)
-        auto pres = std::make_shared<DeviceBuf>((size_t)hcap + 1);
-        auto counts = std::make_shared<DeviceBuf>(((size_t)hcap / 1024 + 2) * 4);
-        auto offs = std::make_shared<DeviceBuf>(((size_t)hcap / 1024 + 2) * 8 + 16);
-        launch_key_presence((const unsigned long long*)hkeys->ptr, hcap, (unsigned char*)pres->ptr, ctx->stream);
-        long long* total = (long long*)((char*)offs->ptr + ((size_t)hcap / 1024 + 2) * 8);
-        launch_compact_plan((const unsigned char*)pres->ptr, hcap, (int*)counts->ptr, (long long*)offs->ptr, total, ctx->stream);
-        ctx->kernel_launches += 3;
-        long long t = 0;
-        cuda_check(cudaMemcpyAsync(&t, total, 8, cudaMemcpyDeviceToHost, ctx->stream), "occupied count");
-        cuda_check(cudaStreamSynchronize(ctx->stream), "occupied sync");
-        return t;
     }
 
     void consume_hash(Batch& b) {
@@ -867,14 +897,17 @@ struct AggNode : FusedBase {
         if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds)) throw ExecError(15, "", "internal: accumulator layout changed between launches");
         n_words = g.n_words;
         word_kinds = g.word_kinds;
-        ensure_table(mod, b.n_rows);
+        {
+            TraceSpan ts("hash.ensure_table");
+            ensure_table(mod, b.n_rows);
+        }
         if (!vmask) vmask = std::make_shared<DeviceBuf>(CB_MAX_COLS * 16);
         cuda_check(cudaMemsetAsync(vmask->ptr, 0, CB_MAX_COLS * 16, ctx->stream), "memset vmask");
         cb::PipeParams p;
         fill_inputs(p, b, g.tile);
         hash_params(p);
         p.vmask = (cb::u64*)vmask->ptr;
-        p.n_groups = (int)std::min<int64_t>(hcap + 2, INT32_MAX);
+        p.n_groups = 2;
         int grid = std::max(1, std::min(ctx->num_sms, p.n_tiles));
         launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(0), &p);
         ctx->pipeline_rows += b.n_rows;
@@ -897,63 +930,59 @@ struct AggNode : FusedBase {
         last_mod = mod;
     }
 
-    // hash results: finalize every slot, then compact the occupied ones into dense device columns
+    // hash results: groups are dense by id, so finalize writes the output columns directly (no compaction)
     void finalize_hash(Batch& out) {
         TraceSpan ts("agg.finalize_hash");
         const GeneratedKernel& g = last_gen;
-        int64_t n_slots = hcap + 2;
+        cudaStream_t st = ctx->stream;
         int flags[8];
-        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags");
-        cuda_check(cudaStreamSynchronize(ctx->stream), "flags sync");
+        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "read hash flags");
+        cuda_check(cudaStreamSynchronize(st), "flags sync");
+        const int64_t ng = flags[4];
+        const int64_t n_out = ng + ((flags[0] & 1) ? 1 : 0) + ((flags[0] & 8) ? 1 : 0);
         cb::FinParams fp;
         memset(&fp, 0, sizeof(fp));
         fp.totals = (cb::u64*)htotals->ptr;
-        fp.hkeys = (const cb::u64*)hkeys->ptr;
+        fp.hkeys = (const cb::u64*)hkey_of_gid->ptr;
         fp.sentinel_used = flags[0] & 1;
         fp.null_group_used = (flags[0] & 8) ? 1 : 0;
-        fp.n_groups = (int)n_slots;
+        fp.n_hash_groups = (int)ng;
+        fp.max_groups = (int)max_groups;
+        fp.n_groups = (int)n_out;
         fp.err = ctx->d_err;
         for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) fp.cert[ai] = certificate(ai);
         if (g.out_cols.size() > CB_MAX_OUT) throw Unsupported("too many output columns");
-        std::vector<DeviceBufP> sparse_v, sparse_n;
-        for (size_t i = 0; i < g.out_cols.size(); i++) {
-            sparse_v.push_back(std::make_shared<DeviceBuf>((size_t)n_slots * g.out_bytes[i]));
-            sparse_n.push_back(std::make_shared<DeviceBuf>((size_t)n_slots));
-            fp.out[i] = (cb::u8*)sparse_v.back()->ptr;
-            fp.outv[i] = (cb::u8*)sparse_n.back()->ptr;
-        }
-        auto present = std::make_shared<DeviceBuf>((size_t)n_slots);
-        fp.present = (cb::u8*)present->ptr;
-        void* args[] = {&fp};
-        launch_named(last_mod, g.finalize_entry.c_str(), dim3((unsigned)((n_slots + 127) / 128)), dim3(128), args);
-        size_t nb = (size_t)(n_slots + 1023) / 1024;
-        auto counts = std::make_shared<DeviceBuf>(nb * 4 + 16);
-        auto offs = std::make_shared<DeviceBuf>(nb * 8 + 32);
-        long long* total = (long long*)((char*)offs->ptr + nb * 8 + 8);
-        launch_compact_plan((const unsigned char*)present->ptr, n_slots, (int*)counts->ptr, (long long*)offs->ptr, total, ctx->stream);
-        ctx->kernel_launches += 2;
-        long long n_out = 0;
-        cuda_check(cudaMemcpyAsync(&n_out, total, 8, cudaMemcpyDeviceToHost, ctx->stream), "group count");
-        ctx->check_device_errors();
         out.n_rows = n_out;
         out.cols.clear();
+        std::vector<DeviceBufP> vbytes;
+        size_t rows_alloc = (size_t)std::max<int64_t>(n_out, 1);
         for (size_t i = 0; i < g.out_cols.size(); i++) {
             Column c;
             c.type = g.out_cols[i].type;
-            int w = g.out_bytes[i];
             c.phys = c.type.id == TypeId::Bool ? Phys::I8 : (c.type.is_string() ? Phys::I32 : phys_of_type(c.type));
-            c.data = std::make_shared<DeviceBuf>((size_t)std::max<long long>(n_out, 1) * w);
-            launch_compact_scatter((const unsigned char*)present->ptr, n_slots, (const long long*)offs->ptr, sparse_v[i]->ptr, w, c.data->ptr, ctx->stream);
-            auto vbytes = std::make_shared<DeviceBuf>((size_t)std::max<long long>(n_out, 1));
-            launch_compact_scatter((const unsigned char*)present->ptr, n_slots, (const long long*)offs->ptr, sparse_n[i]->ptr, 1, vbytes->ptr, ctx->stream);
-            c.validity = std::make_shared<DeviceBuf>((size_t)(n_out + 31) / 32 * 4 + 8);
-            launch_bytes_to_bitmap((const unsigned char*)vbytes->ptr, n_out, (uint32_t*)c.validity->ptr, ctx->stream);
-            ctx->kernel_launches += 3;
-            c.null_count = -1;
+            c.data = std::make_shared<DeviceBuf>(rows_alloc * g.out_bytes[i]);
+            vbytes.push_back(std::make_shared<DeviceBuf>(rows_alloc));
+            fp.out[i] = (cb::u8*)c.data->ptr;
+            fp.outv[i] = (cb::u8*)vbytes.back()->ptr;
             if ((int)i < g.n_key_cols && c.type.is_string()) { c.is_dict = true; c.dict = key_dicts[i]; }
             out.cols.push_back(c);
         }
-        cuda_check(cudaStreamSynchronize(ctx->stream), "compaction sync"); // temporaries die here
+        auto present = std::make_shared<DeviceBuf>(rows_alloc);
+        fp.present = (cb::u8*)present->ptr;
+        if (n_out > 0) {
+            void* args[] = {&fp};
+            launch_named(last_mod, g.finalize_entry.c_str(), dim3((unsigned)((n_out + 127) / 128)), dim3(128), args);
+            for (size_t i = 0; i < out.cols.size(); i++) {
+                Column& c = out.cols[i];
+                c.valid_bytes = vbytes[i];
+                c.validity = std::make_shared<DeviceBuf>((size_t)(n_out + 31) / 32 * 4 + 8);
+                launch_bytes_to_bitmap((const unsigned char*)vbytes[i]->ptr, n_out, (uint32_t*)c.validity->ptr, st);
+                ctx->kernel_launches++;
+                c.null_count = -1;
+                if (c.type.id == TypeId::Bool) c.bool_bytes = c.data;
+            }
+        }
+        ctx->check_device_errors();
     }
 
     // one (possibly split) launch over rows [row0,row1) at assumption level lv, escalating on violated assumptions
@@ -1279,19 +1308,20 @@ struct PartitionNode : ExecNode {
                 launch_gather_bits(c.data->ptr, (const long long*)row_idx->ptr, n, bytes->ptr, st);
                 o.data = std::make_shared<DeviceBuf>((size_t)(n + 31) / 32 * 4 + 8);
                 launch_bytes_to_bitmap((const unsigned char*)bytes->ptr, n, (uint32_t*)o.data->ptr, st);
-                keep.push_back(bytes);
+                o.bool_bytes = bytes;
                 ctx->kernel_launches += 2;
             } else {
                 o.data = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(n, 1) * w);
                 launch_gather(c.data->ptr, w, (const long long*)row_idx->ptr, n, o.data->ptr, st);
                 ctx->kernel_launches++;
+                if (c.type.id == TypeId::Bool) o.bool_bytes = o.data; // aggregate outputs keep booleans one byte per row
             }
             if (c.validity) {
                 auto bytes = std::make_shared<DeviceBuf>((size_t)n + 16);
                 launch_gather_bits(c.validity->ptr, (const long long*)row_idx->ptr, n, bytes->ptr, st);
                 o.validity = std::make_shared<DeviceBuf>((size_t)(n + 31) / 32 * 4 + 8);
                 launch_bytes_to_bitmap((const unsigned char*)bytes->ptr, n, (uint32_t*)o.validity->ptr, st);
-                keep.push_back(bytes);
+                o.valid_bytes = bytes;
                 ctx->kernel_launches += 2;
             }
             out.cols.push_back(o);
@@ -1370,7 +1400,7 @@ static ExecNodeP build_source(const OperatorP& op, ExecContext* ctx, PlanInputs*
         std::shared_ptr<DeviceTable> tb = inputs->tables.empty() ? nullptr : inputs->tables.front();
         if (!inputs->streams.empty()) inputs->streams.erase(inputs->streams.begin());
         if (!inputs->tables.empty()) inputs->tables.erase(inputs->tables.begin());
-        if (tb) return std::make_shared<TableSource>(tb, op->schema);
+        if (tb) return std::make_shared<TableSource>(tb, op->schema, ctx);
         if (!st) throw PlanError("No input for scan");
         return std::make_shared<StreamSource>(ctx, st, op->schema);
     }

@@ -60,6 +60,8 @@ struct Column {
     DictionaryP dict;
     DeviceBufP data, validity;      // device (validity: Arrow bitmap) ...
     DeviceBufP offsets, chars;      // ... device Utf8 (offsets int32[n+1], chars)
+    DeviceBufP valid_bytes;         // optional byte-per-row validity (exchange-friendly form; see PartitionNode / cb200_table_add_column_bytes)
+    DeviceBufP bool_bytes;          // optional byte-per-row form of a boolean column
     int64_t null_count = 0;
     // host-resident alternative (small aggregate results)
     bool on_host = false;
@@ -106,6 +108,7 @@ using ExecNodeP = std::shared_ptr<ExecNode>;
 struct DeviceTable { // caller-owned device-resident columns bound as a plan input (bench "value" path)
     int64_t n_rows = 0;
     std::vector<Column> cols;
+    bool needs_packing = false; // some columns were given byte-per-row validity / booleans: packed to Arrow bitmaps at first use
 };
 
 // Build the executor tree for a decoded plan.  `inputs` are consumed in Scan order.

@@ -84,6 +84,12 @@ cb200_table* cb200_table_create(int64_t n_rows);
 int cb200_table_add_column(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width,
                            const void* dev_values, const void* dev_validity, int64_t null_count,
                            const char* const* dict_values, int32_t n_dict, cb200_error* err);
+/* Same, for columns in the exchange-friendly form cb200_execute_device reports for ShuffleWriter plans:
+ * validity as one byte per row (`dev_validity_bytes`, may be NULL) and BOOL values as one byte per row
+ * (value_width = 1).  The library packs them to Arrow bitmaps on the plan's stream at first use. */
+int cb200_table_add_column_bytes(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width,
+                                 const void* dev_values, const void* dev_validity_bytes, const char* const* dict_values,
+                                 int32_t n_dict, cb200_error* err);
 int cb200_plan_bind_table(cb200_plan* plan, int32_t input_index, cb200_table* t, cb200_error* err);
 void cb200_table_release(cb200_table* t);
 
@@ -93,7 +99,13 @@ typedef struct cb200_device_column {
     const void* validity;  /* device Arrow bitmap or NULL */
     const void* host_values;
     const uint8_t* host_validity_bytes; /* one byte per row, or NULL */
+    const void* validity_bytes;  /* device, one byte per row (ShuffleWriter plans: segments slice at any row) or NULL */
+    const void* bool_bytes;      /* device, BOOL values one byte per row (ShuffleWriter plans) or NULL */
+    int32_t n_dict;              /* dictionary-coded STRING column: number of dictionary entries (values = int32 codes) */
+    int32_t pad;
 } cb200_device_column;
+/* i-th dictionary string of output column `col` of the last batch (valid until the next call on the plan) */
+const char* cb200_plan_dict_value(cb200_plan* plan, int32_t col, int32_t i, int32_t* len);
 /* Like cb200_execute but leaves fixed-width results where they are (valid until the next call on the
  * plan).  Returns rows, -1 at end, -2 on error. */
 int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_t n_cols, cb200_error* err);
