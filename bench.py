@@ -173,8 +173,11 @@ def host_arrow_batches(torch, pa, tpch, variant, money, cols, batch_rows):
 
 
 # ---- one step -----------------------------------------------------------------------------------
+DEVICE = 0  # CUDA ordinal of this rank (set in main)
+
+
 def run_partial(native, plan_bytes, inp, chunk_rows):
-    with native.Plan(plan_bytes, [inp], config={"spark.comet.b200.chunkRows": str(chunk_rows)}) as p:
+    with native.Plan(plan_bytes, [inp], config={"spark.comet.b200.chunkRows": str(chunk_rows)}, device=DEVICE) as p:
         state = p.collect()
         st = p.stats()
     return state, st
@@ -182,7 +185,7 @@ def run_partial(native, plan_bytes, inp, chunk_rows):
 
 def run_final(native, pa, plan_bytes, states):
     tbl = pa.concat_tables(states)
-    with native.Plan(plan_bytes, [tbl]) as p:
+    with native.Plan(plan_bytes, [tbl], device=DEVICE) as p:
         res = p.collect()
         st = p.stats()
     return res, st
@@ -246,6 +249,8 @@ def main():
     import torch
     import torch.distributed as dist
     from comet_b200 import native, proto as P, tpch
+    global DEVICE
+    DEVICE = local_rank
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
