@@ -65,7 +65,7 @@ class Stats(C.Structure):
                 ("pipeline_rows", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
-EXPORTED = ["cb200_plan_stats", "cb200_table_add_column_bytes", "cb200_plan_dict_value", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
+EXPORTED = ["cb200_plan_stats", "cb200_register_memory_file", "cb200_parquet_describe", "cb200_table_add_column_bytes", "cb200_plan_dict_value", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
             "cb200_release", "cb200_table_create", "cb200_table_add_column", "cb200_plan_bind_table",
             "cb200_table_release", "cb200_execute_device", "cb200_plan_kernel_launches", "cb200_compile_plan",
             "cb200_plan_kernel_source"]
@@ -140,6 +140,41 @@ def compile_plan_assume(op_bytes, assume_bits, source_index=-1):
     if n < 0:
         _raise(err)
     return buf.value.decode()
+
+
+_MEMFILES = {}
+
+
+def register_memory_file(name, buf):
+    """Expose a Parquet file image held in host memory as "memory://<name>" (buf: bytes-like / numpy / torch pinned tensor)."""
+    import numpy as np
+    if buf is None:
+        lib().cb200_register_memory_file(name.encode(), None, 0)
+        _MEMFILES.pop(name, None)
+        return
+    if hasattr(buf, "data_ptr"):  # torch tensor (pinned host memory)
+        ptr, n = buf.data_ptr(), buf.numel() * buf.element_size()
+    else:
+        arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+        ptr, n = arr.ctypes.data, arr.nbytes
+        buf = arr
+    f = lib().cb200_register_memory_file
+    f.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
+    f(name.encode(), ptr, n)
+    _MEMFILES[name] = buf  # keep alive
+    return "memory://" + name
+
+
+def parquet_describe(path):
+    import json
+    err = _Error()
+    cap = 1 << 22
+    buf = C.create_string_buffer(cap)
+    f = lib().cb200_parquet_describe
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(_Error)]
+    if f(path.encode(), buf, cap, C.byref(err)) < 0:
+        _raise(err)
+    return json.loads(buf.value.decode())
 
 
 def kernel_source(op_bytes, index=0):

@@ -124,10 +124,32 @@ def q1_scan_fields(variant):
     return [m, m, m, m, P.STRING, P.STRING, P.DATE]
 
 
-def q1_partial_plan(variant="dec", cutoff=DATE_1998_09_02):
+Q1_COLUMNS = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+
+
+def q1_native_scan(variant, files):
+    """NativeScan (operator.proto:141) over Parquet files with the Q1 column projection."""
+    fields = list(zip(Q1_COLUMNS, q1_scan_fields(variant), [True] * 7))
+    return P.native_scan(fields, fields, files)
+
+
+def write_lineitem_parquet(cols, path, variant="dec", row_group_size=1 << 20, decimal_as_int=True, columns=None):
+    """SURVEY.md 8(d) fixture writer: pyarrow, data page v1, dictionary only for the flag columns, PLAIN numerics,
+    uncompressed, decimals as INT64 (Spark's layout) or FIXED_LEN_BYTE_ARRAY."""
+    import pyarrow.parquet as pq
+    tbl = lineitem_table(cols, variant, dictionary=True, columns=columns or Q1_COLUMNS)
+    kw = {}
+    if decimal_as_int:
+        kw["store_decimal_as_integer"] = True
+    pq.write_table(tbl, path, row_group_size=row_group_size, compression="NONE", use_dictionary=["l_returnflag", "l_linestatus"],
+                   data_page_version="1.0", write_statistics=True, **kw)
+    return path
+
+
+def q1_partial_plan(variant="dec", cutoff=DATE_1998_09_02, scan=None):
     """Map-stage plan of TPC-H Q1: Scan -> Filter -> Project -> HashAggregate(Partial)."""
     m = _money(variant)
-    sc = P.scan(q1_scan_fields(variant))
+    sc = scan if scan is not None else P.scan(q1_scan_fields(variant))
     ship = P.bound(6, P.DATE)
     flt = P.filter_(sc, P.and_(P.is_not_null(ship), P.lt_eq(ship, P.literal(cutoff, P.DATE))))
     proj = P.projection(flt, [P.bound(0, m), P.bound(1, m), P.bound(2, m), P.bound(3, m), P.bound(4, P.STRING), P.bound(5, P.STRING)])

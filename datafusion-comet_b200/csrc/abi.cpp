@@ -373,6 +373,20 @@ int cb200_compile_plan_assume(const uint8_t* op_proto, size_t op_len, const int3
     }, -1);
 }
 
+int cb200_register_memory_file(const char* name, const void* data, size_t len) {
+    if (!name) return -1;
+    register_memory_file(name, (const uint8_t*)data, len);
+    return 0;
+}
+
+int cb200_parquet_describe(const char* path, char* out, size_t cap, cb200_error* err) {
+    return guarded(err, [&]() -> int {
+        std::string s = describe_parquet(path ? path : "");
+        if (out && cap) snprintf(out, cap, "%s", s.c_str());
+        return (int)s.size();
+    }, -1);
+}
+
 int cb200_plan_kernel_source(const uint8_t* op_proto, size_t op_len, int32_t index, char* out, size_t cap, cb200_error* err) {
     return guarded(err, [&]() -> int {
         OperatorP op = decode_plan(op_proto, op_len);

@@ -3,6 +3,8 @@
 
 #include "aot_kernels.h"
 #include "device/cb_params.h"
+#include "parquet.h"
+#include "parquet_kernels.h"
 #include "ranges.h"
 
 #include <algorithm>
@@ -11,6 +13,7 @@
 #include <ctime>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <set>
 #include <sstream>
 
@@ -426,6 +429,289 @@ struct TableSource : ExecNode {
             }
         }
         return out.n_rows > 0;
+    }
+};
+
+
+// =================================================================================================
+// native Parquet scan (NativeScan -> DataSourceExec(ParquetSource), native/core/src/parquet/parquet_exec.rs:60-200)
+// =================================================================================================
+// Footer and page headers are parsed on the host (parquet.cpp); encoded pages cross PCIe as they sit in the
+// file and are decoded on the device (parquet_kernels.cu).  d(p<=18) / INT64 decimals stay 8 bytes wide in HBM
+// (the Parquet physical width) and the fused kernels read them as such.
+static std::mutex g_memfile_mu;
+static std::map<std::string, std::pair<const uint8_t*, size_t>> g_memfiles;
+void register_memory_file(const std::string& name, const uint8_t* p, size_t n) {
+    std::lock_guard<std::mutex> lk(g_memfile_mu);
+    if (p) g_memfiles[name] = {p, n};
+    else g_memfiles.erase(name);
+}
+static bool lookup_memory_file(const std::string& path, const uint8_t** p, size_t* n) {
+    const std::string pre = "memory://";
+    if (path.compare(0, pre.size(), pre) != 0) return false;
+    std::lock_guard<std::mutex> lk(g_memfile_mu);
+    auto it = g_memfiles.find(path.substr(pre.size()));
+    if (it == g_memfiles.end()) throw ExecError(3, "", "parquet: memory file '" + path + "' is not registered");
+    *p = it->second.first;
+    *n = it->second.second;
+    return true;
+}
+static std::string strip_file_scheme(const std::string& p) { return p.compare(0, 7, "file://") == 0 ? p.substr(7) : p; }
+
+pq::FileMeta open_parquet(const std::string& path, const uint8_t** mem, size_t* mem_len) {
+    *mem = nullptr;
+    *mem_len = 0;
+    if (lookup_memory_file(path, mem, mem_len)) return pq::parse_footer(*mem, *mem_len);
+    int64_t sz = 0;
+    return pq::read_footer(strip_file_scheme(path), &sz);
+}
+
+struct NativeScanSource : ExecNode {
+    ExecContext* ctx;
+    std::vector<std::string> files;
+    std::vector<StructField> fields;
+    size_t file_idx = 0, rg_idx = 0;
+    bool opened = false;
+    pq::FileMeta meta;
+    const uint8_t* mem = nullptr;
+    size_t mem_len = 0;
+    FILE* fh = nullptr;
+    std::vector<int> leaf_of; // per output column: leaf index in the current file
+    std::vector<DictionaryP> dicts;
+    uint8_t* staging = nullptr;
+    size_t staging_cap = 0;
+
+    ~NativeScanSource() override {
+        if (fh) fclose(fh);
+        if (staging) cudaFreeHost(staging);
+    }
+
+    void open_next_file() {
+        if (fh) { fclose(fh); fh = nullptr; }
+        const std::string& path = files[file_idx];
+        meta = open_parquet(path, &mem, &mem_len);
+        if (!mem) {
+            fh = fopen(strip_file_scheme(path).c_str(), "rb");
+            if (!fh) throw ExecError(3, "", "parquet: cannot open " + path);
+        }
+        leaf_of.clear();
+        for (auto& f : fields) {
+            int li = meta.leaf_index(f.name);
+            if (li < 0) throw Unsupported("parquet: column '" + f.name + "' missing from " + path + " (schema evolution / default values are out of scope)");
+            leaf_of.push_back(li);
+        }
+        rg_idx = 0;
+        opened = true;
+    }
+
+    struct Unit { size_t rg; int64_t rows, row0; };
+
+    bool next(Batch& out) override {
+        TraceSpan ts("parquet.next");
+        if (dicts.empty()) dicts.assign(fields.size(), nullptr);
+        // find the next file with row groups left
+        while (true) {
+            if (file_idx >= files.size()) return false;
+            if (!opened) open_next_file();
+            if (rg_idx < meta.row_groups.size()) break;
+            file_idx++;
+            opened = false;
+        }
+        std::vector<Unit> units;
+        int64_t total = 0;
+        while (rg_idx < meta.row_groups.size() && (units.empty() || total + meta.row_groups[rg_idx].num_rows <= ctx->chunk_rows)) {
+            units.push_back({rg_idx, meta.row_groups[rg_idx].num_rows, total});
+            total += meta.row_groups[rg_idx].num_rows;
+            rg_idx++;
+        }
+        out.n_rows = total;
+        out.cols.clear();
+        out.cols.resize(fields.size());
+        // staging: one pinned region for every chunk of this call (file-backed inputs only)
+        size_t need = 0;
+        std::vector<std::vector<size_t>> stage_off(fields.size(), std::vector<size_t>(units.size(), 0));
+        for (size_t c = 0; c < fields.size(); c++)
+            for (size_t u = 0; u < units.size(); u++) {
+                stage_off[c][u] = need;
+                need += ((size_t)meta.row_groups[units[u].rg].columns[(size_t)leaf_of[c]].total_compressed + 63) / 64 * 64;
+            }
+        if (!mem && need > staging_cap) {
+            if (staging) cudaFreeHost(staging);
+            cuda_check(cudaMallocHost((void**)&staging, need), "cudaMallocHost staging");
+            staging_cap = need;
+        }
+        std::vector<DeviceBufP> keep;
+        auto derr = std::make_shared<DeviceBuf>(64);
+        cuda_check(cudaMemsetAsync(derr->ptr, 0, 64, ctx->stream), "memset parquet err");
+        for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, stage_off[c], out.cols[c], keep, (int*)derr->ptr);
+        int perr = 0;
+        cuda_check(cudaMemcpyAsync(&perr, derr->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream), "parquet err");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "parquet decode sync");
+        if (perr & 2) throw Unsupported("parquet: NULL values in data pages (definition-level scatter is pending)");
+        if (perr & 4) throw ExecError(3, "", "parquet: dictionary index out of range (corrupt page)");
+        if (perr & 1) throw Unsupported("parquet: RLE stream with pathological run structure");
+        return true;
+    }
+
+    void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<size_t>& soff, Column& col, std::vector<DeviceBufP>& keep,
+                       int* derr) {
+        const DType& t = fields[c].type;
+        const pq::SchemaElement& se = meta.leaf(leaf_of[c]);
+        cudaStream_t st = ctx->stream;
+        // pick the device representation
+        int conv, out_w;
+        col.type = t;
+        col.null_count = 0;
+        switch (se.type) {
+        case pq::INT32:
+            if (!(t.is_integer() || t.id == TypeId::Date || (t.is_decimal() && t.precision <= 9))) throw Unsupported("parquet INT32 -> " + t.str());
+            if (t.id == TypeId::Int64) { conv = PQ_I32_TO_I64; out_w = 8; col.phys = Phys::I64; }
+            else { conv = PQ_COPY32; out_w = 4; col.phys = Phys::I32; }
+            break;
+        case pq::INT64:
+            if (!(t.id == TypeId::Int64 || t.id == TypeId::Timestamp || t.id == TypeId::TimestampNtz || (t.is_decimal() && t.precision <= 18)))
+                throw Unsupported("parquet INT64 -> " + t.str());
+            conv = PQ_COPY64; out_w = 8; col.phys = Phys::I64;
+            break;
+        case pq::FLOAT: if (t.id != TypeId::Float32) throw Unsupported("parquet FLOAT -> " + t.str()); conv = PQ_COPY32; out_w = 4; col.phys = Phys::F32; break;
+        case pq::DOUBLE: if (t.id != TypeId::Float64) throw Unsupported("parquet DOUBLE -> " + t.str()); conv = PQ_COPY64; out_w = 8; col.phys = Phys::F64; break;
+        case pq::FIXED_LEN_BYTE_ARRAY:
+            if (!t.is_decimal() || se.type_length > 16) throw Unsupported("parquet FIXED_LEN_BYTE_ARRAY -> " + t.str());
+            if (t.precision <= 18) { conv = PQ_FLBA_TO_I64; out_w = 8; col.phys = Phys::I64; }
+            else { conv = PQ_FLBA_TO_I128; out_w = 16; col.phys = Phys::I128; }
+            break;
+        case pq::BYTE_ARRAY:
+            if (!t.is_string()) throw Unsupported("parquet BYTE_ARRAY -> " + t.str());
+            conv = -1; out_w = 4; col.phys = Phys::I32; col.is_dict = true;
+            if (!dicts[c]) dicts[c] = std::make_shared<Dictionary>();
+            col.dict = dicts[c];
+            break;
+        default: throw Unsupported("parquet physical type " + std::to_string(se.type));
+        }
+        if (t.is_decimal() && (se.scale != t.scale)) throw Unsupported("parquet decimal scale differs from the requested type (schema adapter casts are out of scope)");
+        col.data = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(total, 1) * out_w);
+        const bool optional = se.repetition == 1;
+        for (size_t u = 0; u < units.size(); u++) {
+            const pq::ColumnChunkMeta& cc = meta.row_groups[units[u].rg].columns[(size_t)leaf_of[c]];
+            if (cc.codec != pq::UNCOMPRESSED) throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (device decompression is pending; write UNCOMPRESSED)");
+            if (cc.num_values != units[u].rows) throw Unsupported("parquet: repeated column (num_values != num_rows)");
+            const size_t clen = (size_t)cc.total_compressed;
+            const uint8_t* host;
+            if (mem) {
+                if ((size_t)cc.start() + clen > mem_len) throw PlanError("parquet: column chunk beyond the end of the file image");
+                host = mem + cc.start();
+            } else {
+                uint8_t* dst = staging + soff[u];
+                if (fseeko(fh, (off_t)cc.start(), SEEK_SET) != 0 || fread(dst, 1, clen, fh) != clen) throw ExecError(3, "", "parquet: short read");
+                host = dst;
+            }
+            auto dchunk = std::make_shared<DeviceBuf>(clen + 64);
+            keep.push_back(dchunk);
+            cuda_check(cudaMemcpyAsync(dchunk->ptr, host, clen, cudaMemcpyHostToDevice, st), "H2D parquet chunk");
+            ctx->h2d_bytes += (int64_t)clen;
+            std::vector<pq::PageInfo> pages = pq::walk_pages(host, clen, cc.num_values);
+            // dictionary page
+            DeviceBufP ddict;
+            int dict_size = 0;
+            std::vector<PqPage> dpages;
+            int64_t row = units[u].row0, run_base = 0;
+            for (auto& pg : pages) {
+                if (pg.type == pq::DICTIONARY_PAGE) {
+                    dict_size = (int)pg.num_values;
+                    if (se.type == pq::BYTE_ARRAY) {
+                        // strings: parse on the host, unify with the plan-global dictionary, ship the code remap table
+                        std::vector<int32_t> remap((size_t)dict_size);
+                        const uint8_t* p = host + pg.data_offset;
+                        const uint8_t* e = p + pg.compressed_size;
+                        Dictionary& gd = *dicts[c];
+                        for (int k = 0; k < dict_size; k++) {
+                            if (p + 4 > e) throw PlanError("parquet: truncated dictionary page");
+                            uint32_t len;
+                            memcpy(&len, p, 4);
+                            p += 4;
+                            if (p + len > e) throw PlanError("parquet: truncated dictionary page");
+                            std::string v((const char*)p, len);
+                            p += len;
+                            auto it = std::find(gd.values.begin(), gd.values.end(), v);
+                            if (it == gd.values.end()) { remap[(size_t)k] = (int32_t)gd.values.size(); gd.values.push_back(v); }
+                            else remap[(size_t)k] = (int32_t)(it - gd.values.begin());
+                        }
+                        ddict = std::make_shared<DeviceBuf>(remap.size() * 4 + 16);
+                        cuda_check(cudaMemcpyAsync(ddict->ptr, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, st), "H2D dictionary remap");
+                        cuda_check(cudaStreamSynchronize(st), "dictionary remap"); // `remap` is a stack temporary
+                    } else {
+                        ddict = std::make_shared<DeviceBuf>((size_t)dict_size * out_w + 16);
+                        PqPage dp;
+                        memset(&dp, 0, sizeof(dp));
+                        dp.values_off = pg.data_offset;
+                        dp.values_bytes = pg.compressed_size;
+                        dp.num_values = dict_size;
+                        auto dpd = std::make_shared<DeviceBuf>(sizeof(PqPage));
+                        keep.push_back(dpd);
+                        cuda_check(cudaMemcpyAsync(dpd->ptr, &dp, sizeof(dp), cudaMemcpyHostToDevice, st), "H2D dict page");
+                        cuda_check(cudaStreamSynchronize(st), "dict page desc");
+                        launch_pq_plain((const unsigned char*)dchunk->ptr, (const PqPage*)dpd->ptr, 1, conv, se.type_length, ddict->ptr, st);
+                        ctx->kernel_launches++;
+                    }
+                    keep.push_back(ddict);
+                    continue;
+                }
+                if (pg.type != pq::DATA_PAGE && pg.type != pq::DATA_PAGE_V2) continue;
+                PqPage d;
+                memset(&d, 0, sizeof(d));
+                d.dst_row = row;
+                d.num_values = (int)pg.num_values;
+                int64_t off = pg.data_offset, left = pg.compressed_size;
+                if (pg.type == pq::DATA_PAGE) {
+                    if (optional) {
+                        uint32_t dl;
+                        memcpy(&dl, host + off, 4);
+                        d.def_off = off + 4;
+                        d.def_bytes = (int)dl;
+                        off += 4 + dl;
+                        left -= 4 + dl;
+                    }
+                } else {
+                    off += pg.rep_levels_bytes;
+                    d.def_off = off;
+                    d.def_bytes = pg.def_levels_bytes;
+                    off += pg.def_levels_bytes;
+                    left -= pg.rep_levels_bytes + pg.def_levels_bytes;
+                }
+                d.values_off = off;
+                d.values_bytes = (int)left;
+                if (pg.encoding == pq::PLAIN) {
+                    if (se.type == pq::BYTE_ARRAY) throw Unsupported("parquet: PLAIN-encoded string page (dictionary fallback); only dictionary-encoded strings are decoded");
+                    d.encoding = 0;
+                } else if (pg.encoding == pq::RLE_DICTIONARY || pg.encoding == pq::PLAIN_DICTIONARY) {
+                    d.encoding = 8;
+                    d.run_base = run_base;
+                    d.max_runs = (int)(pg.num_values / 8 + 64);
+                    run_base += d.max_runs;
+                } else throw Unsupported("parquet value encoding " + std::to_string(pg.encoding) + " (DELTA_* / BYTE_STREAM_SPLIT are next-row work)");
+                row += pg.num_values;
+                dpages.push_back(d);
+            }
+            if (dpages.empty()) continue;
+            auto dpd = std::make_shared<DeviceBuf>(dpages.size() * sizeof(PqPage));
+            keep.push_back(dpd);
+            cuda_check(cudaMemcpyAsync(dpd->ptr, dpages.data(), dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, st), "H2D page table");
+            cuda_check(cudaStreamSynchronize(st), "page table"); // dpages is a stack temporary
+            const unsigned char* dc = (const unsigned char*)dchunk->ptr;
+            if (optional) { launch_pq_check_def_levels(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), derr, st); ctx->kernel_launches++; }
+            if (conv >= 0) { launch_pq_plain(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), conv, se.type_length, col.data->ptr, st); ctx->kernel_launches++; }
+            if (run_base > 0) {
+                if (!ddict) throw PlanError("parquet: dictionary-encoded page without a dictionary page");
+                auto runs = std::make_shared<DeviceBuf>((size_t)run_base * sizeof(PqRun));
+                auto counts = std::make_shared<DeviceBuf>(dpages.size() * 4 + 16);
+                keep.push_back(runs);
+                keep.push_back(counts);
+                launch_pq_rle_scan(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), (PqRun*)runs->ptr, (int*)counts->ptr, derr, st);
+                launch_pq_rle_decode(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, dict_size,
+                                     col.data->ptr, derr, st);
+                ctx->kernel_launches += 2;
+            }
+        }
     }
 };
 
@@ -1404,7 +1690,19 @@ static ExecNodeP build_source(const OperatorP& op, ExecContext* ctx, PlanInputs*
         if (!st) throw PlanError("No input for scan");
         return std::make_shared<StreamSource>(ctx, st, op->schema);
     }
-    if (op->kind == OpKind::NativeScan) throw Unsupported("NativeScan (device Parquet decode) is wired in a later milestone");
+    if (op->kind == OpKind::NativeScan) {
+        if (build_only) {
+            auto s = std::make_shared<SchemaOnlySource>();
+            s->schema = op->schema;
+            return s;
+        }
+        auto s = std::make_shared<NativeScanSource>();
+        s->ctx = ctx;
+        s->schema = op->schema;
+        s->files = op->files;
+        s->fields = op->required_schema;
+        return s;
+    }
     return build_node(op, ctx, inputs, build_only);
 }
 
@@ -1646,4 +1944,13 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
     }
 }
 
+} // namespace cb200
+
+namespace cb200 {
+std::string describe_parquet(const std::string& path) {
+    const uint8_t* mem;
+    size_t len;
+    pq::FileMeta m = open_parquet(path, &mem, &len);
+    return pq::describe(m);
+}
 } // namespace cb200

@@ -123,6 +123,9 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
 
 // Debug / build-time: generate (and NVRTC-compile, no device needed) the kernels a plan would use,
 // assuming inputs without nulls and dictionary-encoded string keys.
+void register_memory_file(const std::string& name, const uint8_t* p, size_t n); // p == nullptr unregisters
+std::string describe_parquet(const std::string& path);
+
 std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const std::vector<int>& assume_bits = {});
 
 } // namespace cb200

@@ -120,6 +120,15 @@ int32_t cb200_plan_partition_starts(cb200_plan* plan, int64_t* starts, int32_t c
 /* kernels launched so far by this plan (bench.py reports it as gpu_launches) */
 int64_t cb200_plan_kernel_launches(cb200_plan* plan);
 
+/* ---- native Parquet scan --------------------------------------------------------------------------------------
+ * NativeScan plans (operator.proto:141-185) name files; besides plain paths / file:// URLs the library accepts
+ * "memory://<name>" for a Parquet file image the caller holds in (ideally pinned) host memory -- what a Spark
+ * executor has after fetching an object-store range.  Encoded pages are copied H2D as they are and decoded on
+ * the device.  `data` = NULL unregisters. */
+int cb200_register_memory_file(const char* name, const void* data, size_t len);
+/* JSON description of a Parquet file's footer as this library parsed it (tests compare it with pyarrow). */
+int cb200_parquet_describe(const char* path, char* out, size_t cap, cb200_error* err);
+
 /* Measurement: the library times every fused pipeline kernel with CUDA events on its own stream. */
 typedef struct cb200_stats {
     int64_t kernel_launches;   /* all kernels (pipelines, fold/finalize, helpers) */
