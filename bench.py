@@ -177,7 +177,7 @@ DEVICE = 0  # CUDA ordinal of this rank (set in main)
 
 
 def run_partial(native, plan_bytes, inp, chunk_rows):
-    with native.Plan(plan_bytes, [inp], config={"spark.comet.b200.chunkRows": str(chunk_rows)}, device=DEVICE) as p:
+    with native.Plan(plan_bytes, [inp] if inp is not None else [], config={"spark.comet.b200.chunkRows": str(chunk_rows)}, device=DEVICE) as p:
         state = p.collect()
         st = p.stats()
     return state, st
@@ -234,6 +234,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 22)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-input", default="parquet", choices=["parquet", "arrow", "both"])
+    ap.add_argument("--parquet-files", type=int, default=16)
+    ap.add_argument("--parquet-dictionary", default="all", choices=["all", "flags"],
+                    help="all = writer default of Spark/parquet-mr and pyarrow (dictionary-encode every column, PLAIN fallback); flags = PLAIN numerics")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -320,36 +324,80 @@ def main():
             checked &= g["col_9"] == cnt[k]
         del keep, gid
 
-    # ---- end-to-end leg: host Arrow buffers -> C ABI -> result (per rank; rank 0 merges) -------------
+    # ---- end-to-end leg: HOST buffers -> C ABI -> result (per rank; rank 0 merges) -----------------------------
+    # "parquet": the config's own input -- Parquet file images in pinned host memory, read through NativeScan;
+    #            encoded pages cross PCIe and are decoded on the device.
+    # "arrow"  : host Arrow RecordBatches through an ArrowArrayStream (the JVM-fed ScanExec path).
     e2e = None
+    e2e_extra = {}
     host = None
     if not args.no_e2e:
         batches, host = host_arrow_batches(torch, pa, tpch, variant, money, cols, args.e2e_batch_rows)
         e2e_chunk = 1 << 26
 
-        def step_e2e():
-            state, st = run_partial(native, partial_plan, batches, e2e_chunk)
-            states = gather_states(state)
-            r, st2 = (run_final(native, pa, final_plan, states) if rank == 0 else (None, None))
-            return st, st2
+        def timed(step_fn, steps):
+            step_fn()  # warm-up (JIT variants, pinned-page faults)
+            barrier()
+            t1 = time.perf_counter()
+            h2d = d2h = 0
+            for _ in range(steps):
+                st, st2 = step_fn()
+                h2d += st["h2d_bytes"] + (st2["h2d_bytes"] if st2 else 0)
+                d2h += st["d2h_bytes"] + (st2["d2h_bytes"] if st2 else 0)
+            barrier()
+            el = time.perf_counter() - t1
+            if world > 1:
+                t = torch.tensor([el], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                el = float(t.item())
+            return {"value": world * n * steps / el, "unit": "rows/s", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": max(d2h // steps, 1),
+                    "steps": steps, "ms_per_step": 1e3 * el / steps}
 
-        step_e2e()  # warm-up (JIT variants, pinned-page faults)
-        barrier()
-        t1 = time.perf_counter()
-        h2d = d2h = 0
-        for _ in range(args.e2e_steps):
-            st, st2 = step_e2e()
-            h2d += st["h2d_bytes"] + (st2["h2d_bytes"] if st2 else 0)
-            d2h += st["d2h_bytes"] + (st2["d2h_bytes"] if st2 else 0)
-        barrier()
-        e2e_elapsed = time.perf_counter() - t1
-        if world > 1:
-            t = torch.tensor([e2e_elapsed], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_elapsed = float(t.item())
-        e2e = {"value": world * n * args.e2e_steps / e2e_elapsed, "unit": "rows/s", "h2d_bytes_per_step": h2d // args.e2e_steps,
-               "d2h_bytes_per_step": max(d2h // args.e2e_steps, 1), "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / args.e2e_steps,
-               "input": f"pinned host Arrow batches of {args.e2e_batch_rows} rows via ArrowArrayStream, 64 Mi-row device chunks"}
+        def finish(state):
+            states = gather_states(state)
+            return run_final(native, pa, final_plan, states) if rank == 0 else (None, None)
+
+        if args.e2e_input in ("arrow", "both"):
+            def step_arrow():
+                state, st = run_partial(native, partial_plan, batches, e2e_chunk)
+                return st, finish(state)[1]
+            r = timed(step_arrow, args.e2e_steps)
+            r["input"] = f"pinned host Arrow batches of {args.e2e_batch_rows} rows via ArrowArrayStream, 64 Mi-row device chunks"
+            e2e_extra["e2e_arrow"] = r
+            e2e = r
+        if args.e2e_input in ("parquet", "both"):
+            import concurrent.futures as cf
+            import pyarrow.parquet as pq
+            tbl = pa.Table.from_batches(batches)
+            nf = max(1, min(args.parquet_files, n // (1 << 20) or 1))
+            per = (n + nf - 1) // nf
+
+            def write_slice(i):
+                sink = pa.BufferOutputStream()
+                pq.write_table(tbl.slice(i * per, per), sink, row_group_size=1 << 20, compression="NONE", use_dictionary=args.parquet_dictionary == "all" or ["l_returnflag", "l_linestatus"],
+                               data_page_version="1.0", store_decimal_as_integer=True)
+                return sink.getvalue()
+            t_w = time.perf_counter()
+            with cf.ThreadPoolExecutor(max_workers=nf) as ex:
+                bufs = list(ex.map(write_slice, range(nf)))
+            files, pinned = [], []
+            for i, b in enumerate(bufs):
+                h = torch.empty(b.size, dtype=torch.uint8, pin_memory=True)
+                h.numpy()[:] = np.frombuffer(b, dtype=np.uint8)
+                pinned.append(h)
+                files.append(native.register_memory_file(f"lineitem-r{rank}-{i}", h))
+            del bufs, tbl
+            pq_bytes = sum(h.numel() for h in pinned)
+            pq_plan = tpch.q1_partial_plan(variant, scan=tpch.q1_native_scan(variant, files))
+
+            def step_parquet():
+                state, st = run_partial(native, pq_plan, None, e2e_chunk)
+                return st, finish(state)[1]
+            r = timed(step_parquet, args.e2e_steps)
+            r["input"] = (f"{nf} Parquet file images in pinned host memory ({pq_bytes / 1e9:.2f} GB: uncompressed, 1 Mi-row row groups, INT64 decimals, "
+                          f"dictionary={args.parquet_dictionary}; written in {time.perf_counter() - t_w:.1f} s, not timed) through NativeScan; pages decoded on the device")
+            e2e_extra["e2e_parquet"] = r
+            e2e = r
 
     # ---- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded sample -----------------------
     cpu = None
@@ -395,6 +443,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+            if len(e2e_extra) > 1:
+                line.update({k: v for k, v in e2e_extra.items()})
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -470,93 +470,115 @@ struct NativeScanSource : ExecNode {
     ExecContext* ctx;
     std::vector<std::string> files;
     std::vector<StructField> fields;
-    size_t file_idx = 0, rg_idx = 0;
+
+    struct OpenFile {
+        pq::FileMeta meta;
+        const uint8_t* mem = nullptr;
+        size_t mem_len = 0;
+        FILE* fh = nullptr;
+        std::vector<int> leaf_of; // per output column: leaf index in this file
+    };
+    struct Unit { size_t file, rg; int64_t rows, row0; };
+    std::vector<OpenFile> open_files;
+    std::vector<Unit> all_units;
+    size_t next_unit = 0;
     bool opened = false;
-    pq::FileMeta meta;
-    const uint8_t* mem = nullptr;
-    size_t mem_len = 0;
-    FILE* fh = nullptr;
-    std::vector<int> leaf_of; // per output column: leaf index in the current file
     std::vector<DictionaryP> dicts;
     uint8_t* staging = nullptr;
     size_t staging_cap = 0;
+    cudaStream_t copy_stream = nullptr;
 
     ~NativeScanSource() override {
-        if (fh) fclose(fh);
+        for (auto& f : open_files) if (f.fh) fclose(f.fh);
         if (staging) cudaFreeHost(staging);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 
-    void open_next_file() {
-        if (fh) { fclose(fh); fh = nullptr; }
-        const std::string& path = files[file_idx];
-        meta = open_parquet(path, &mem, &mem_len);
-        if (!mem) {
-            fh = fopen(strip_file_scheme(path).c_str(), "rb");
-            if (!fh) throw ExecError(3, "", "parquet: cannot open " + path);
+    void open_all() { // footers are tiny: parse them all up front (the reference's ParquetSource does the same per file group)
+        for (auto& path : files) {
+            OpenFile of;
+            of.meta = open_parquet(path, &of.mem, &of.mem_len);
+            if (!of.mem) {
+                of.fh = fopen(strip_file_scheme(path).c_str(), "rb");
+                if (!of.fh) throw ExecError(3, "", "parquet: cannot open " + path);
+            }
+            for (auto& f : fields) {
+                int li = of.meta.leaf_index(f.name);
+                if (li < 0) throw Unsupported("parquet: column '" + f.name + "' missing from " + path + " (schema evolution / default values are out of scope)");
+                of.leaf_of.push_back(li);
+            }
+            for (size_t g = 0; g < of.meta.row_groups.size(); g++)
+                if (of.meta.row_groups[g].num_rows > 0) all_units.push_back({open_files.size(), g, of.meta.row_groups[g].num_rows, 0});
+            open_files.push_back(std::move(of));
         }
-        leaf_of.clear();
-        for (auto& f : fields) {
-            int li = meta.leaf_index(f.name);
-            if (li < 0) throw Unsupported("parquet: column '" + f.name + "' missing from " + path + " (schema evolution / default values are out of scope)");
-            leaf_of.push_back(li);
-        }
-        rg_idx = 0;
+        dicts.assign(fields.size(), nullptr);
+        cuda_check(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "copy stream");
         opened = true;
     }
+    const pq::ColumnChunkMeta& chunk_meta(const Unit& u, size_t c) const {
+        const OpenFile& f = open_files[u.file];
+        return f.meta.row_groups[u.rg].columns[(size_t)f.leaf_of[c]];
+    }
 
-    struct Unit { size_t rg; int64_t rows, row0; };
+    // host-side temporaries that must outlive the asynchronous uploads of one next() call
+    struct Arena {
+        std::vector<std::shared_ptr<std::vector<PqPage>>> pages;
+        std::vector<std::shared_ptr<std::vector<int32_t>>> remaps;
+        std::vector<DeviceBufP> dev;
+        std::vector<cudaEvent_t> events;
+        ~Arena() { for (auto e : events) cudaEventDestroy(e); }
+    };
 
     bool next(Batch& out) override {
         TraceSpan ts("parquet.next");
-        if (dicts.empty()) dicts.assign(fields.size(), nullptr);
-        // find the next file with row groups left
-        while (true) {
-            if (file_idx >= files.size()) return false;
-            if (!opened) open_next_file();
-            if (rg_idx < meta.row_groups.size()) break;
-            file_idx++;
-            opened = false;
-        }
+        if (!opened) open_all();
+        if (next_unit >= all_units.size()) return false;
         std::vector<Unit> units;
         int64_t total = 0;
-        while (rg_idx < meta.row_groups.size() && (units.empty() || total + meta.row_groups[rg_idx].num_rows <= ctx->chunk_rows)) {
-            units.push_back({rg_idx, meta.row_groups[rg_idx].num_rows, total});
-            total += meta.row_groups[rg_idx].num_rows;
-            rg_idx++;
+        while (next_unit < all_units.size() && (units.empty() || total + all_units[next_unit].rows <= ctx->chunk_rows)) {
+            Unit u = all_units[next_unit++];
+            u.row0 = total;
+            total += u.rows;
+            units.push_back(u);
         }
         out.n_rows = total;
         out.cols.clear();
         out.cols.resize(fields.size());
-        // staging: one pinned region for every chunk of this call (file-backed inputs only)
+        // file-backed inputs are staged through one pinned region (memory files are read in place)
         size_t need = 0;
         std::vector<std::vector<size_t>> stage_off(fields.size(), std::vector<size_t>(units.size(), 0));
+        bool any_file = false;
         for (size_t c = 0; c < fields.size(); c++)
             for (size_t u = 0; u < units.size(); u++) {
                 stage_off[c][u] = need;
-                need += ((size_t)meta.row_groups[units[u].rg].columns[(size_t)leaf_of[c]].total_compressed + 63) / 64 * 64;
+                if (!open_files[units[u].file].mem) { any_file = true; need += ((size_t)chunk_meta(units[u], c).total_compressed + 63) / 64 * 64; }
             }
-        if (!mem && need > staging_cap) {
+        if (any_file && need > staging_cap) {
             if (staging) cudaFreeHost(staging);
             cuda_check(cudaMallocHost((void**)&staging, need), "cudaMallocHost staging");
             staging_cap = need;
         }
-        std::vector<DeviceBufP> keep;
+        Arena arena;
         auto derr = std::make_shared<DeviceBuf>(64);
         cuda_check(cudaMemsetAsync(derr->ptr, 0, 64, ctx->stream), "memset parquet err");
-        for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, stage_off[c], out.cols[c], keep, (int*)derr->ptr);
+        // the copy stream must not run ahead of allocations made on the main stream
+        cudaEvent_t ready;
+        cuda_check(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming), "event");
+        arena.events.push_back(ready);
+        for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, stage_off[c], out.cols[c], arena, (int*)derr->ptr);
         int perr = 0;
         cuda_check(cudaMemcpyAsync(&perr, derr->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream), "parquet err");
         cuda_check(cudaStreamSynchronize(ctx->stream), "parquet decode sync");
+        cuda_check(cudaStreamSynchronize(copy_stream), "parquet copy sync");
         if (perr & 2) throw Unsupported("parquet: NULL values in data pages (definition-level scatter is pending)");
         if (perr & 4) throw ExecError(3, "", "parquet: dictionary index out of range (corrupt page)");
         if (perr & 1) throw Unsupported("parquet: RLE stream with pathological run structure");
         return true;
     }
 
-    void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<size_t>& soff, Column& col, std::vector<DeviceBufP>& keep,
-                       int* derr) {
+    void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<size_t>& soff, Column& col, Arena& arena, int* derr) {
         const DType& t = fields[c].type;
-        const pq::SchemaElement& se = meta.leaf(leaf_of[c]);
+        const pq::SchemaElement& se = open_files[units[0].file].meta.leaf(open_files[units[0].file].leaf_of[c]);
         cudaStream_t st = ctx->stream;
         // pick the device representation
         int conv, out_w;
@@ -590,41 +612,66 @@ struct NativeScanSource : ExecNode {
         }
         if (t.is_decimal() && (se.scale != t.scale)) throw Unsupported("parquet decimal scale differs from the requested type (schema adapter casts are out of scope)");
         col.data = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(total, 1) * out_w);
-        const bool optional = se.repetition == 1;
+        // All row groups of this column are decoded by ONE launch per kernel: their chunks sit back to back in one
+        // device buffer, page descriptors carry absolute offsets, dictionaries are concatenated.
+        size_t col_bytes = 0;
+        std::vector<size_t> chunk_off(units.size());
         for (size_t u = 0; u < units.size(); u++) {
-            const pq::ColumnChunkMeta& cc = meta.row_groups[units[u].rg].columns[(size_t)leaf_of[c]];
+            chunk_off[u] = col_bytes;
+            col_bytes += ((size_t)chunk_meta(units[u], c).total_compressed + 63) / 64 * 64;
+        }
+        auto dchunk = std::make_shared<DeviceBuf>(col_bytes + 64);
+        arena.dev.push_back(dchunk);
+        // allocation happened in main-stream order; let the copy stream see it
+        cudaEvent_t alloc_ev;
+        cuda_check(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming), "event");
+        arena.events.push_back(alloc_ev);
+        cuda_check(cudaEventRecord(alloc_ev, st), "event record");
+        cuda_check(cudaStreamWaitEvent(copy_stream, alloc_ev, 0), "stream wait");
+        auto dpages_p = std::make_shared<std::vector<PqPage>>();
+        auto remap_p = std::make_shared<std::vector<int32_t>>();
+        arena.pages.push_back(dpages_p);
+        arena.remaps.push_back(remap_p);
+        std::vector<PqPage>& dpages = *dpages_p;
+        std::vector<PqPage> dict_pages;                // fixed-width dictionary pages (decoded into the combined dictionary)
+        std::vector<int32_t>& remap_all = *remap_p;    // string columns: combined code remap tables
+        int64_t run_base = 0, dict_elems = 0;
+        bool optional = false;
+        for (size_t u = 0; u < units.size(); u++) {
+            const OpenFile& of = open_files[units[u].file];
+            const pq::SchemaElement& use = of.meta.leaf(of.leaf_of[c]);
+            if (use.type != se.type || use.type_length != se.type_length) throw Unsupported("parquet: column '" + fields[c].name + "' changes physical type between files");
+            const bool opt_u = use.repetition == 1;
+            optional = optional || opt_u;
+            const pq::ColumnChunkMeta& cc = chunk_meta(units[u], c);
             if (cc.codec != pq::UNCOMPRESSED) throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (device decompression is pending; write UNCOMPRESSED)");
             if (cc.num_values != units[u].rows) throw Unsupported("parquet: repeated column (num_values != num_rows)");
             const size_t clen = (size_t)cc.total_compressed;
             const uint8_t* host;
-            if (mem) {
-                if ((size_t)cc.start() + clen > mem_len) throw PlanError("parquet: column chunk beyond the end of the file image");
-                host = mem + cc.start();
+            if (of.mem) {
+                if ((size_t)cc.start() + clen > of.mem_len) throw PlanError("parquet: column chunk beyond the end of the file image");
+                host = of.mem + cc.start();
             } else {
                 uint8_t* dst = staging + soff[u];
-                if (fseeko(fh, (off_t)cc.start(), SEEK_SET) != 0 || fread(dst, 1, clen, fh) != clen) throw ExecError(3, "", "parquet: short read");
+                if (fseeko(of.fh, (off_t)cc.start(), SEEK_SET) != 0 || fread(dst, 1, clen, of.fh) != clen) throw ExecError(3, "", "parquet: short read");
                 host = dst;
             }
-            auto dchunk = std::make_shared<DeviceBuf>(clen + 64);
-            keep.push_back(dchunk);
-            cuda_check(cudaMemcpyAsync(dchunk->ptr, host, clen, cudaMemcpyHostToDevice, st), "H2D parquet chunk");
+            const int64_t base = (int64_t)chunk_off[u];
+            cuda_check(cudaMemcpyAsync((char*)dchunk->ptr + base, host, clen, cudaMemcpyHostToDevice, copy_stream), "H2D parquet chunk");
             ctx->h2d_bytes += (int64_t)clen;
             std::vector<pq::PageInfo> pages = pq::walk_pages(host, clen, cc.num_values);
-            // dictionary page
-            DeviceBufP ddict;
-            int dict_size = 0;
-            std::vector<PqPage> dpages;
-            int64_t row = units[u].row0, run_base = 0;
+            int64_t row = units[u].row0, this_dict_off = -1;
+            int this_dict_size = 0;
             for (auto& pg : pages) {
                 if (pg.type == pq::DICTIONARY_PAGE) {
-                    dict_size = (int)pg.num_values;
+                    this_dict_size = (int)pg.num_values;
+                    this_dict_off = dict_elems;
                     if (se.type == pq::BYTE_ARRAY) {
                         // strings: parse on the host, unify with the plan-global dictionary, ship the code remap table
-                        std::vector<int32_t> remap((size_t)dict_size);
                         const uint8_t* p = host + pg.data_offset;
                         const uint8_t* e = p + pg.compressed_size;
                         Dictionary& gd = *dicts[c];
-                        for (int k = 0; k < dict_size; k++) {
+                        for (int k = 0; k < this_dict_size; k++) {
                             if (p + 4 > e) throw PlanError("parquet: truncated dictionary page");
                             uint32_t len;
                             memcpy(&len, p, 4);
@@ -633,27 +680,19 @@ struct NativeScanSource : ExecNode {
                             std::string v((const char*)p, len);
                             p += len;
                             auto it = std::find(gd.values.begin(), gd.values.end(), v);
-                            if (it == gd.values.end()) { remap[(size_t)k] = (int32_t)gd.values.size(); gd.values.push_back(v); }
-                            else remap[(size_t)k] = (int32_t)(it - gd.values.begin());
+                            if (it == gd.values.end()) { remap_all.push_back((int32_t)gd.values.size()); gd.values.push_back(v); }
+                            else remap_all.push_back((int32_t)(it - gd.values.begin()));
                         }
-                        ddict = std::make_shared<DeviceBuf>(remap.size() * 4 + 16);
-                        cuda_check(cudaMemcpyAsync(ddict->ptr, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, st), "H2D dictionary remap");
-                        cuda_check(cudaStreamSynchronize(st), "dictionary remap"); // `remap` is a stack temporary
                     } else {
-                        ddict = std::make_shared<DeviceBuf>((size_t)dict_size * out_w + 16);
                         PqPage dp;
                         memset(&dp, 0, sizeof(dp));
-                        dp.values_off = pg.data_offset;
+                        dp.values_off = base + pg.data_offset;
                         dp.values_bytes = pg.compressed_size;
-                        dp.num_values = dict_size;
-                        auto dpd = std::make_shared<DeviceBuf>(sizeof(PqPage));
-                        keep.push_back(dpd);
-                        cuda_check(cudaMemcpyAsync(dpd->ptr, &dp, sizeof(dp), cudaMemcpyHostToDevice, st), "H2D dict page");
-                        cuda_check(cudaStreamSynchronize(st), "dict page desc");
-                        launch_pq_plain((const unsigned char*)dchunk->ptr, (const PqPage*)dpd->ptr, 1, conv, se.type_length, ddict->ptr, st);
-                        ctx->kernel_launches++;
+                        dp.num_values = this_dict_size;
+                        dp.dst_row = dict_elems; // decoded into the combined dictionary at this element offset
+                        dict_pages.push_back(dp);
                     }
-                    keep.push_back(ddict);
+                    dict_elems += this_dict_size;
                     continue;
                 }
                 if (pg.type != pq::DATA_PAGE && pg.type != pq::DATA_PAGE_V2) continue;
@@ -663,54 +702,71 @@ struct NativeScanSource : ExecNode {
                 d.num_values = (int)pg.num_values;
                 int64_t off = pg.data_offset, left = pg.compressed_size;
                 if (pg.type == pq::DATA_PAGE) {
-                    if (optional) {
+                    if (opt_u) {
                         uint32_t dl;
                         memcpy(&dl, host + off, 4);
-                        d.def_off = off + 4;
+                        d.def_off = base + off + 4;
                         d.def_bytes = (int)dl;
                         off += 4 + dl;
                         left -= 4 + dl;
                     }
                 } else {
                     off += pg.rep_levels_bytes;
-                    d.def_off = off;
+                    d.def_off = base + off;
                     d.def_bytes = pg.def_levels_bytes;
                     off += pg.def_levels_bytes;
                     left -= pg.rep_levels_bytes + pg.def_levels_bytes;
                 }
-                d.values_off = off;
+                d.values_off = base + off;
                 d.values_bytes = (int)left;
                 if (pg.encoding == pq::PLAIN) {
                     if (se.type == pq::BYTE_ARRAY) throw Unsupported("parquet: PLAIN-encoded string page (dictionary fallback); only dictionary-encoded strings are decoded");
                     d.encoding = 0;
                 } else if (pg.encoding == pq::RLE_DICTIONARY || pg.encoding == pq::PLAIN_DICTIONARY) {
+                    if (this_dict_off < 0) throw PlanError("parquet: dictionary-encoded page without a dictionary page");
                     d.encoding = 8;
                     d.run_base = run_base;
                     d.max_runs = (int)(pg.num_values / 8 + 64);
+                    d.dict_off = this_dict_off;
+                    d.dict_size = this_dict_size;
                     run_base += d.max_runs;
                 } else throw Unsupported("parquet value encoding " + std::to_string(pg.encoding) + " (DELTA_* / BYTE_STREAM_SPLIT are next-row work)");
                 row += pg.num_values;
                 dpages.push_back(d);
             }
-            if (dpages.empty()) continue;
-            auto dpd = std::make_shared<DeviceBuf>(dpages.size() * sizeof(PqPage));
-            keep.push_back(dpd);
-            cuda_check(cudaMemcpyAsync(dpd->ptr, dpages.data(), dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, st), "H2D page table");
-            cuda_check(cudaStreamSynchronize(st), "page table"); // dpages is a stack temporary
-            const unsigned char* dc = (const unsigned char*)dchunk->ptr;
-            if (optional) { launch_pq_check_def_levels(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), derr, st); ctx->kernel_launches++; }
-            if (conv >= 0) { launch_pq_plain(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), conv, se.type_length, col.data->ptr, st); ctx->kernel_launches++; }
-            if (run_base > 0) {
-                if (!ddict) throw PlanError("parquet: dictionary-encoded page without a dictionary page");
-                auto runs = std::make_shared<DeviceBuf>((size_t)run_base * sizeof(PqRun));
-                auto counts = std::make_shared<DeviceBuf>(dpages.size() * 4 + 16);
-                keep.push_back(runs);
-                keep.push_back(counts);
-                launch_pq_rle_scan(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), (PqRun*)runs->ptr, (int*)counts->ptr, derr, st);
-                launch_pq_rle_decode(dc, (const PqPage*)dpd->ptr, (int)dpages.size(), (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, dict_size,
-                                     col.data->ptr, derr, st);
-                ctx->kernel_launches += 2;
-            }
+        }
+        if (dpages.empty()) return;
+        const size_t n_data = dpages.size();
+        dpages.insert(dpages.end(), dict_pages.begin(), dict_pages.end()); // one upload for every descriptor of this column
+        // decode kernels (main stream) start when this column's pages have landed (copy stream)
+        cudaEvent_t copied;
+        cuda_check(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming), "event");
+        arena.events.push_back(copied);
+        cuda_check(cudaEventRecord(copied, copy_stream), "event record");
+        const unsigned char* dc = (const unsigned char*)dchunk->ptr;
+        auto dpd = std::make_shared<DeviceBuf>(dpages.size() * sizeof(PqPage));
+        arena.dev.push_back(dpd);
+        cuda_check(cudaMemcpyAsync(dpd->ptr, dpages.data(), dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, st), "H2D page table");
+        DeviceBufP ddict;
+        if (dict_elems > 0) {
+            ddict = std::make_shared<DeviceBuf>((size_t)dict_elems * out_w + 16);
+            arena.dev.push_back(ddict);
+            if (!remap_all.empty()) cuda_check(cudaMemcpyAsync(ddict->ptr, remap_all.data(), remap_all.size() * 4, cudaMemcpyHostToDevice, st), "H2D dictionary remap");
+        }
+        cuda_check(cudaStreamWaitEvent(st, copied, 0), "stream wait");
+        const PqPage* data_pages = (const PqPage*)dpd->ptr;
+        const PqPage* dpages_dev = data_pages + n_data;
+        if (!dict_pages.empty()) { launch_pq_plain(dc, dpages_dev, (int)dict_pages.size(), conv, se.type_length, ddict->ptr, st); ctx->kernel_launches++; }
+        if (optional) { launch_pq_check_def_levels(dc, data_pages, (int)n_data, derr, st); ctx->kernel_launches++; }
+        if (conv >= 0) { launch_pq_plain(dc, data_pages, (int)n_data, conv, se.type_length, col.data->ptr, st); ctx->kernel_launches++; }
+        if (run_base > 0) {
+            auto runs = std::make_shared<DeviceBuf>((size_t)run_base * sizeof(PqRun));
+            auto counts = std::make_shared<DeviceBuf>(n_data * 4 + 16);
+            arena.dev.push_back(runs);
+            arena.dev.push_back(counts);
+            launch_pq_rle_scan(dc, data_pages, (int)n_data, (PqRun*)runs->ptr, (int*)counts->ptr, derr, st);
+            launch_pq_rle_decode(dc, data_pages, (int)n_data, (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, col.data->ptr, derr, st);
+            ctx->kernel_launches += 2;
         }
     }
 };

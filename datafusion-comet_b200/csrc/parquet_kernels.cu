@@ -141,10 +141,12 @@ template <int DW> __device__ __forceinline__ void store_dict(const void* dict, i
     else ((ulonglong2*)out)[row] = ((const ulonglong2*)dict)[idx];
 }
 // one warp per run; blockIdx.y = page
-template <int DW> __global__ void k_pq_rle_decode(const u8* chunk, const PqPage* pages, const PqRun* runs, const int* run_counts, const void* dict, int dict_size,
+template <int DW> __global__ void k_pq_rle_decode(const u8* chunk, const PqPage* pages, const PqRun* runs, const int* run_counts, const void* dict_all,
                                                  void* out, int* err) {
     const PqPage pg = pages[blockIdx.y];
     if (pg.encoding == 0) return;
+    const void* dict = (const u8*)dict_all + (size_t)pg.dict_off * DW;
+    const int dict_size = pg.dict_size;
     const int n_runs = run_counts[blockIdx.y];
     const int lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
     for (int ri = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ri < n_runs; ri += gridDim.x * warps_per_block) {
@@ -167,12 +169,12 @@ template <int DW> __global__ void k_pq_rle_decode(const u8* chunk, const PqPage*
     }
 }
 void launch_pq_rle_decode(const unsigned char* chunk, const PqPage* pages, int n_pages, const PqRun* runs, const int* run_counts, const void* dict, int dict_width,
-                          int dict_size, void* out, int* err, cudaStream_t st) {
+                          void* out, int* err, cudaStream_t st) {
     if (n_pages <= 0) return;
     dim3 grid(32, (unsigned)n_pages), block(256);
-    if (dict_width == 4) k_pq_rle_decode<4><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, dict_size, out, err);
-    else if (dict_width == 8) k_pq_rle_decode<8><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, dict_size, out, err);
-    else k_pq_rle_decode<16><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, dict_size, out, err);
+    if (dict_width == 4) k_pq_rle_decode<4><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, out, err);
+    else if (dict_width == 8) k_pq_rle_decode<8><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, out, err);
+    else k_pq_rle_decode<16><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, out, err);
 }
 
 // definition levels (bit width 1): all levels must be 1 until NULL scatter lands

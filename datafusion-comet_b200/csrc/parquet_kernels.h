@@ -15,6 +15,8 @@ struct PqPage { // one data page of a column chunk already resident on the devic
     int encoding;           // 0 PLAIN, 8 RLE_DICTIONARY (2 PLAIN_DICTIONARY is the same on the wire)
     long long run_base;     // first entry of this page in the run table (RLE pages)
     int max_runs;           // capacity reserved for it
+    long long dict_off;     // element offset of this page's dictionary inside the column's combined dictionary buffer
+    int dict_size;
 };
 
 struct PqRun {              // one run of the RLE / bit-packed hybrid
@@ -34,7 +36,7 @@ void launch_pq_plain(const unsigned char* chunk, const PqPage* pages_dev, int n_
 void launch_pq_rle_scan(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st);
 // (2) decode runs (warp per run) and gather through the dictionary: dict_width 4/8/16 bytes per entry
 void launch_pq_rle_decode(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, const PqRun* runs, const int* run_counts, const void* dict,
-                          int dict_width, int dict_size, void* out, int* err, cudaStream_t st);
+                          int dict_width, void* out, int* err, cudaStream_t st);
 // definition levels of flat optional columns (max level 1): verify "no NULLs" (sets err bit 1 if a 0 level appears)
 void launch_pq_check_def_levels(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, int* err, cudaStream_t st);
 
