@@ -350,7 +350,7 @@ def main():
                 t = torch.tensor([el], device=device, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 el = float(t.item())
-            return {"value": world * n * steps / el, "unit": "rows/s", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": max(d2h // steps, 1),
+            return {"value": world * n * steps / el, "unit": "rows/s", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
                     "steps": steps, "ms_per_step": 1e3 * el / steps}
 
         def finish(state):

@@ -226,6 +226,13 @@ def if_(c, t, f):
     return _expr("if", f_len(1, c) + f_len(2, t) + f_len(3, f))
 
 
+def case_when(whens, thens, else_expr=None):  # CaseWhen expr.proto:473
+    body = b"".join(f_len(2, w) for w in whens) + b"".join(f_len(3, t) for t in thens)
+    if else_expr is not None:
+        body += f_len(4, else_expr)
+    return _expr("caseWhen", body)
+
+
 def in_(value, lst, negated=False):
     return _expr("in", f_len(1, value) + b"".join(f_len(2, x) for x in lst) + f_bool(3, negated))
 

@@ -143,8 +143,12 @@ struct Emitter {
         return name;
     }
 
+    // Branch guard: inside IF / CASE branches the reference evaluates the branch only on the rows that take it
+    // (CaseExpr evaluates `then` under the selection), so ANSI / arrow overflow errors of rows that do not take
+    // the branch must not fire.  Values are still computed (and ignored) for every row.
+    std::string guard;
     Val emit(const Expr& e) {
-        std::string k = key_of(e);
+        std::string k = guard.empty() ? key_of(e) : guard + "|" + key_of(e);
         auto it = cse.find(k);
         if (it != cse.end()) return it->second;
         Val r = emit_uncached(e);
@@ -223,10 +227,16 @@ struct Emitter {
         case ExprKind::CheckOverflow: return emit_check_overflow(e);
         case ExprKind::UnaryMinus: return emit_neg(e);
         case ExprKind::If: {
-            Val c = emit(*e.children[0]), a = emit(*e.children[1]), b = emit(*e.children[2]);
+            Val c = emit(*e.children[0]);
+            std::string ct = c.n.empty() ? c.v : declb("!" + c.n + " && " + c.v); // NULL condition -> else branch
+            const std::string outer = guard;
+            guard = outer.empty() ? ct : declb(outer + " && " + ct);
+            Val a = emit(*e.children[1]);
+            guard = outer.empty() ? "!(" + ct + ")" : declb(outer + " && !(" + ct + ")");
+            Val b = emit(*e.children[2]);
+            guard = outer;
             Val r;
             r.type = e.type;
-            std::string ct = c.n.empty() ? c.v : declb("!" + c.n + " && " + c.v); // NULL condition -> else branch
             if (e.type.is_decimal()) {
                 if (a.narrow && b.narrow) { r.v = decln(ct + " ? " + a.v + " : " + b.v); r.narrow = true; }
                 else r.v = declw(ct + " ? " + W(a) + " : " + W(b));
@@ -273,7 +283,7 @@ struct Emitter {
 
     void raise(const std::string& cond, int bit) {
         uses_err = true;
-        body << "    if (" << cond << ") cb::set_err(p, " << bit << ");\n";
+        body << "    if (" << (guard.empty() ? "" : guard + " && ") << cond << ") cb::set_err(p, " << bit << ");\n";
     }
 
     // ---- arithmetic --------------------------------------------------------------------------------
@@ -525,7 +535,9 @@ struct Emitter {
             if (c.narrow) { r.v = decln("-" + c.v); r.narrow = true; } // |v| < 2^63: cannot overflow
             else r.v = declw("cb::i128_neg(" + c.v + ")");
         }
-        else if (t.is_float()) r.v = decl(t, "-" + c.v);
+        else if (t.is_float()) // sign-bit flip on the raw bits: exact for NaN payloads / -0.0 like Rust's fneg (PTX neg.f64 leaves NaN results unspecified)
+            r.v = decl(t, t.id == TypeId::Float64 ? "__longlong_as_double(__double_as_longlong(" + c.v + ") ^ (long long)0x8000000000000000ull)"
+                                                  : "__int_as_float(__float_as_int(" + c.v + ") ^ (int)0x80000000u)");
         else if (t.id == TypeId::Int64) r.v = decl(t, "(cb::i64)(0ull - (cb::u64)" + c.v + ")");
         else {
             int bits = t.id == TypeId::Int8 ? 8 : t.id == TypeId::Int16 ? 16 : 32;

@@ -912,7 +912,7 @@ struct SelectNode : FusedBase {
         launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(0), &p);
         ctx->pipeline_rows += in.n_rows;
         int64_t kept = 0;
-        cuda_check(cudaMemcpyAsync(&kept, p.out_count, 8, cudaMemcpyDeviceToHost, st), "read kept count");
+        cuda_check(cudaMemcpyAsync(&kept, p.out_count, 8, cudaMemcpyDeviceToHost, st), "read kept count"); ctx->d2h_bytes += (int64_t)(8);
         ctx->check_device_errors(); // also synchronises
         out.n_rows = kept;
         // boolean outputs were written one byte per row; repack lazily at export
@@ -1185,7 +1185,7 @@ struct AggNode : FusedBase {
         cudaStream_t st = ctx->stream;
         int flags[8] = {0};
         if (hflags) {
-            cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "hash flags");
+            cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "hash flags"); ctx->d2h_bytes += (int64_t)(sizeof(flags));
             cuda_check(cudaStreamSynchronize(st), "hash flags sync");
         } else {
             hflags = std::make_shared<DeviceBuf>(64);
@@ -1255,8 +1255,8 @@ struct AggNode : FusedBase {
         ctx->pipeline_rows += b.n_rows;
         uint64_t masks[CB_MAX_COLS * 2];
         int flags[8];
-        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, ctx->stream), "read value masks");
-        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags");
+        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, ctx->stream), "read value masks"); ctx->d2h_bytes += (int64_t)(sizeof(masks));
+        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags"); ctx->d2h_bytes += (int64_t)(sizeof(flags));
         ctx->check_device_errors();
         if (flags[0] & 2) throw ExecError(15, "", "internal: hash table full");
         if (flags[0] & 4) throw Unsupported("decimal group key does not fit 64 bits (multi-word hash keys are pending)");
@@ -1278,7 +1278,7 @@ struct AggNode : FusedBase {
         const GeneratedKernel& g = last_gen;
         cudaStream_t st = ctx->stream;
         int flags[8];
-        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "read hash flags");
+        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "read hash flags"); ctx->d2h_bytes += (int64_t)(sizeof(flags));
         cuda_check(cudaStreamSynchronize(st), "flags sync");
         const int64_t ng = flags[4];
         const int64_t n_out = ng + ((flags[0] & 1) ? 1 : 0) + ((flags[0] & 8) ? 1 : 0);
@@ -1384,7 +1384,7 @@ struct AggNode : FusedBase {
         launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(n_groups), &p); // + producer warp
         ctx->pipeline_rows += r1 - r0;
         uint64_t masks[CB_MAX_COLS * 2];
-        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, st), "read value masks");
+        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, st), "read value masks"); ctx->d2h_bytes += (int64_t)(sizeof(masks));
         ctx->check_device_errors(); // synchronises
         // validate the assumptions this kernel was specialised for
         std::vector<int> seen(spec.cols.size(), -1);
@@ -1502,7 +1502,7 @@ struct AggNode : FusedBase {
         cuda_check(cudaLaunchKernel((const void*)last_mod->kernel(g.finalize_entry), dim3((ng + 127) / 128), dim3(128), args, 0, ctx->stream), "finalize launch");
         ctx->kernel_launches++;
         std::vector<uint8_t> hbuf(total_bytes);
-        cuda_check(cudaMemcpyAsync(hbuf.data(), dbuf->ptr, total_bytes, cudaMemcpyDeviceToHost, ctx->stream), "agg results D2H");
+        cuda_check(cudaMemcpyAsync(hbuf.data(), dbuf->ptr, total_bytes, cudaMemcpyDeviceToHost, ctx->stream), "agg results D2H"); ctx->d2h_bytes += (int64_t)(total_bytes);
         ctx->check_device_errors(); // synchronises
         const uint8_t* pres = hbuf.data() + off_present;
         std::vector<int> rows;
@@ -1669,7 +1669,7 @@ struct PartitionNode : ExecNode {
             out.cols.push_back(o);
         }
         ctx->partition_starts.assign((size_t)n_parts + 1, 0);
-        cuda_check(cudaMemcpyAsync(ctx->partition_starts.data(), starts->ptr, (size_t)(n_parts + 1) * 8, cudaMemcpyDeviceToHost, st), "starts D2H");
+        cuda_check(cudaMemcpyAsync(ctx->partition_starts.data(), starts->ptr, (size_t)(n_parts + 1) * 8, cudaMemcpyDeviceToHost, st), "starts D2H"); ctx->d2h_bytes += (int64_t)((size_t)(n_parts + 1) * 8);
         ctx->check_device_errors();
         return true;
     }
@@ -1939,7 +1939,7 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
             std::vector<int32_t> codes(n + 1);
             if (n) cuda_check(cudaMemcpyAsync(codes.data(), c.data->ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H key codes");
             std::vector<uint8_t> vb((n + 7) / 8 + 8, 0xff);
-            if (c.validity && n) cuda_check(cudaMemcpyAsync(vb.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity");
+            if (c.validity && n) { cuda_check(cudaMemcpyAsync(vb.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity"); ctx->d2h_bytes += (int64_t)((n + 7) / 8); }
             cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
             ctx->d2h_bytes += (int64_t)n * 4;
             offs.resize((n + 1) * 4);
@@ -1961,7 +1961,7 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
             ctx->d2h_bytes += (int64_t)(n * (size_t)w);
             if (c.validity) {
                 validity.resize((n + 7) / 8 + 8);
-                if (n) cuda_check(cudaMemcpyAsync(validity.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity");
+                if (n) { cuda_check(cudaMemcpyAsync(validity.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity"); ctx->d2h_bytes += (int64_t)((n + 7) / 8); }
             }
             cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
             if (c.validity) {

@@ -230,6 +230,27 @@ static ExprP decode_expr(PbReader r) {
             out->children = {a, b, d};
             break;
         }
+        case 38: { // CaseWhen expr.proto:473 -> nested IF chain (planner.rs:677-703 builds a CaseExpr with expr = None)
+            PbReader c = r.sub();
+            std::vector<ExprP> whens, thens;
+            ExprP els;
+            while (c.next()) {
+                if (c.field == 2) whens.push_back(decode_expr(c.sub()));
+                else if (c.field == 3) thens.push_back(decode_expr(c.sub()));
+                else if (c.field == 4) els = decode_expr(c.sub());
+                else c.skip();
+            }
+            if (whens.empty() || whens.size() != thens.size()) throw PlanError("CASE WHEN needs matching when/then lists");
+            ExprP tail = els; // may be null: ELSE NULL, typed when types are resolved
+            for (size_t i = whens.size(); i-- > 0;) {
+                ExprP n = mk(ExprKind::If);
+                n->children = {whens[i], thens[i]};
+                if (tail) n->children.push_back(tail);
+                tail = n;
+            }
+            out = tail;
+            break;
+        }
         case 90: r.skip(); break; // query_context
         default:
             throw Unsupported("expression field " + std::to_string(r.field) + " is outside the GPU hot path");
@@ -331,6 +352,13 @@ static void resolve(Expr& e, const std::vector<DType>& in) {
         e.type = ct(0);
         break;
     case ExprKind::If:
+        if (e.children.size() == 2) { // CASE without ELSE: NULL of the THEN type
+            auto nul = std::make_shared<Expr>();
+            nul->kind = ExprKind::Literal;
+            nul->lit_null = true;
+            nul->type = ct(1);
+            e.children.push_back(nul);
+        }
         if (ct(0).id != TypeId::Bool || ct(1) != ct(2)) throw Unsupported("IF with mismatched branch types");
         e.type = ct(1);
         break;
