@@ -233,11 +233,13 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=1 << 30)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 22)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 24, help="rows per device batch of the Parquet e2e leg (upload of batch k+1 overlaps decode+aggregate of batch k)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-input", default="parquet", choices=["parquet", "arrow", "both"])
     ap.add_argument("--parquet-files", type=int, default=16)
     ap.add_argument("--parquet-dictionary", default="all", choices=["all", "flags"],
                     help="all = writer default of Spark/parquet-mr and pyarrow (dictionary-encode every column, PLAIN fallback); flags = PLAIN numerics")
+    ap.add_argument("--parquet-compression", default="NONE", choices=["NONE", "SNAPPY"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -374,7 +376,7 @@ def main():
 
             def write_slice(i):
                 sink = pa.BufferOutputStream()
-                pq.write_table(tbl.slice(i * per, per), sink, row_group_size=1 << 20, compression="NONE", use_dictionary=args.parquet_dictionary == "all" or ["l_returnflag", "l_linestatus"],
+                pq.write_table(tbl.slice(i * per, per), sink, row_group_size=1 << 20, compression=args.parquet_compression, use_dictionary=args.parquet_dictionary == "all" or ["l_returnflag", "l_linestatus"],
                                data_page_version="1.0", store_decimal_as_integer=True)
                 return sink.getvalue()
             t_w = time.perf_counter()
@@ -391,11 +393,11 @@ def main():
             pq_plan = tpch.q1_partial_plan(variant, scan=tpch.q1_native_scan(variant, files))
 
             def step_parquet():
-                state, st = run_partial(native, pq_plan, None, e2e_chunk)
+                state, st = run_partial(native, pq_plan, None, args.e2e_chunk_rows)
                 return st, finish(state)[1]
             r = timed(step_parquet, args.e2e_steps)
-            r["input"] = (f"{nf} Parquet file images in pinned host memory ({pq_bytes / 1e9:.2f} GB: uncompressed, 1 Mi-row row groups, INT64 decimals, "
-                          f"dictionary={args.parquet_dictionary}; written in {time.perf_counter() - t_w:.1f} s, not timed) through NativeScan; pages decoded on the device")
+            r["input"] = (f"{nf} Parquet file images in pinned host memory ({pq_bytes / 1e9:.2f} GB: compression {args.parquet_compression}, 1 Mi-row row groups, INT64 decimals, "
+                          f"dictionary={args.parquet_dictionary}; written in {time.perf_counter() - t_w:.1f} s, not timed) through NativeScan in {args.e2e_chunk_rows}-row device batches (double-buffered upload); pages decoded on the device")
             e2e_extra["e2e_parquet"] = r
             e2e = r
 

@@ -535,9 +535,7 @@ struct Emitter {
             if (c.narrow) { r.v = decln("-" + c.v); r.narrow = true; } // |v| < 2^63: cannot overflow
             else r.v = declw("cb::i128_neg(" + c.v + ")");
         }
-        else if (t.is_float()) // sign-bit flip on the raw bits: exact for NaN payloads / -0.0 like Rust's fneg (PTX neg.f64 leaves NaN results unspecified)
-            r.v = decl(t, t.id == TypeId::Float64 ? "__longlong_as_double(__double_as_longlong(" + c.v + ") ^ (long long)0x8000000000000000ull)"
-                                                  : "__int_as_float(__float_as_int(" + c.v + ") ^ (int)0x80000000u)");
+        else if (t.is_float()) r.v = decl(t, (t.id == TypeId::Float64 ? "cb::f64_neg(" : "cb::f32_neg(") + c.v + ")"); // exact sign flip, see cb_math.h
         else if (t.id == TypeId::Int64) r.v = decl(t, "(cb::i64)(0ull - (cb::u64)" + c.v + ")");
         else {
             int bits = t.id == TypeId::Int8 ? 8 : t.id == TypeId::Int16 ? 16 : 32;

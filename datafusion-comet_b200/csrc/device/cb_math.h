@@ -405,6 +405,29 @@ CB_HD u32 pmod_u32(u32 hash, u32 n) { // shuffle/src/comet_partitioning.rs:51-57
 CB_HD i64 f64_total_key(u64 bits) { i64 b = (i64)bits; return b ^ (i64)(((u64)(b >> 63)) >> 1); }
 CB_HD i32 f32_total_key(u32 bits) { i32 b = (i32)bits; return b ^ (i32)(((u32)(b >> 31)) >> 1); }
 
+// Float negation = sign-bit flip, exact for NaN (sign and payload) like Rust's `-x` / arrow-arith `neg`.
+// On the device a plain `-x` (and any xor the optimiser can recognise as fneg) becomes neg.f64, which the
+// hardware executes as an add that returns the canonical +qNaN for NaN inputs (measured on sm_100a) -- so the
+// flip is done in opaque integer PTX.
+CB_HD double f64_neg(double x) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long b = (unsigned long long)__double_as_longlong(x), r;
+    asm("xor.b64 %0, %1, 0x8000000000000000;" : "=l"(r) : "l"(b));
+    return __longlong_as_double((long long)r);
+#else
+    u64 b; __builtin_memcpy(&b, &x, 8); b ^= 0x8000000000000000ull; __builtin_memcpy(&x, &b, 8); return x;
+#endif
+}
+CB_HD float f32_neg(float x) {
+#if defined(__CUDA_ARCH__)
+    unsigned int b = (unsigned int)__float_as_int(x), r;
+    asm("xor.b32 %0, %1, 0x80000000;" : "=r"(r) : "r"(b));
+    return __int_as_float((int)r);
+#else
+    u32 b; __builtin_memcpy(&b, &x, 4); b ^= 0x80000000u; __builtin_memcpy(&x, &b, 4); return x;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // double-double accumulation (float aggregates: result within 1 ULP of the exact sum)
 // ------------------------------------------------------------------------------------------------

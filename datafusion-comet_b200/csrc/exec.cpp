@@ -5,6 +5,7 @@
 #include "device/cb_params.h"
 #include "parquet.h"
 #include "parquet_kernels.h"
+#include "device/cb_snappy.h"
 #include "ranges.h"
 
 #include <algorithm>
@@ -484,13 +485,31 @@ struct NativeScanSource : ExecNode {
     size_t next_unit = 0;
     bool opened = false;
     std::vector<DictionaryP> dicts;
-    uint8_t* staging = nullptr;
-    size_t staging_cap = 0;
+    // Two "slots" alternate between consecutive batches so that batch k+1's encoded bytes cross PCIe (copy stream)
+    // while batch k is decoded and consumed (plan stream): per slot a pinned staging region (file-backed inputs),
+    // one device chunk buffer per column, and the events that order their reuse.
+    struct Slot {
+        uint8_t* staging = nullptr;
+        size_t staging_cap = 0;
+        std::vector<DeviceBufP> chunk;      // per column: encoded bytes of every row group of the batch, back to back
+        cudaEvent_t decoded = nullptr;      // plan stream: the decode kernels reading `chunk` have run
+        cudaEvent_t uploaded = nullptr;     // copy stream: the last H2D out of `staging` has run
+        bool used = false;
+    };
+    Slot slots[2];
     cudaStream_t copy_stream = nullptr;
+    int* h_flags = nullptr;                 // pinned: per-slot decode error flags
 
     ~NativeScanSource() override {
+        pending.reset();
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
         for (auto& f : open_files) if (f.fh) fclose(f.fh);
-        if (staging) cudaFreeHost(staging);
+        for (auto& sl : slots) {
+            if (sl.staging) cudaFreeHost(sl.staging);
+            if (sl.decoded) cudaEventDestroy(sl.decoded);
+            if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+        }
+        if (h_flags) cudaFreeHost(h_flags);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 
@@ -513,6 +532,12 @@ struct NativeScanSource : ExecNode {
         }
         dicts.assign(fields.size(), nullptr);
         cuda_check(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "copy stream");
+        cuda_check(cudaMallocHost((void**)&h_flags, 2 * sizeof(int)), "cudaMallocHost flags");
+        for (auto& sl : slots) {
+            sl.chunk.assign(fields.size(), nullptr);
+            cuda_check(cudaEventCreateWithFlags(&sl.decoded, cudaEventDisableTiming), "event");
+            cuda_check(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming), "event");
+        }
         opened = true;
     }
     const pq::ColumnChunkMeta& chunk_meta(const Unit& u, size_t c) const {
@@ -529,10 +554,24 @@ struct NativeScanSource : ExecNode {
         ~Arena() { for (auto e : events) cudaEventDestroy(e); }
     };
 
-    bool next(Batch& out) override {
-        TraceSpan ts("parquet.next");
-        if (!opened) open_all();
-        if (next_unit >= all_units.size()) return false;
+    // a batch whose uploads and decode kernels are queued but not yet waited for
+    struct Prepared {
+        Batch batch;
+        Arena arena;
+        DeviceBufP derr;
+        cudaEvent_t done = nullptr;
+        int slot = 0;
+        ~Prepared() { if (done) cudaEventDestroy(done); }
+    };
+    std::unique_ptr<Prepared> pending;
+    int64_t n_issued = 0;
+
+    std::unique_ptr<Prepared> issue() {
+        if (next_unit >= all_units.size()) return nullptr;
+        TraceSpan ts("parquet.issue");
+        auto pr = std::make_unique<Prepared>();
+        pr->slot = (int)(n_issued++ & 1);
+        Slot& sl = slots[pr->slot];
         std::vector<Unit> units;
         int64_t total = 0;
         while (next_unit < all_units.size() && (units.empty() || total + all_units[next_unit].rows <= ctx->chunk_rows)) {
@@ -541,10 +580,11 @@ struct NativeScanSource : ExecNode {
             total += u.rows;
             units.push_back(u);
         }
+        Batch& out = pr->batch;
         out.n_rows = total;
         out.cols.clear();
         out.cols.resize(fields.size());
-        // file-backed inputs are staged through one pinned region (memory files are read in place)
+        // file-backed inputs are staged through the slot's pinned region (memory files are read in place)
         size_t need = 0;
         std::vector<std::vector<size_t>> stage_off(fields.size(), std::vector<size_t>(units.size(), 0));
         bool any_file = false;
@@ -553,30 +593,46 @@ struct NativeScanSource : ExecNode {
                 stage_off[c][u] = need;
                 if (!open_files[units[u].file].mem) { any_file = true; need += ((size_t)chunk_meta(units[u], c).total_compressed + 63) / 64 * 64; }
             }
-        if (any_file && need > staging_cap) {
-            if (staging) cudaFreeHost(staging);
-            cuda_check(cudaMallocHost((void**)&staging, need), "cudaMallocHost staging");
-            staging_cap = need;
+        if (any_file) {
+            if (sl.used) cuda_check(cudaEventSynchronize(sl.uploaded), "staging reuse"); // the previous batch of this slot has left the staging region
+            if (need > sl.staging_cap) {
+                if (sl.staging) cudaFreeHost(sl.staging);
+                sl.staging = nullptr;
+                cuda_check(cudaMallocHost((void**)&sl.staging, need), "cudaMallocHost staging");
+                sl.staging_cap = need;
+            }
         }
-        Arena arena;
-        auto derr = std::make_shared<DeviceBuf>(64);
-        cuda_check(cudaMemsetAsync(derr->ptr, 0, 64, ctx->stream), "memset parquet err");
-        // the copy stream must not run ahead of allocations made on the main stream
-        cudaEvent_t ready;
-        cuda_check(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming), "event");
-        arena.events.push_back(ready);
-        for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, stage_off[c], out.cols[c], arena, (int*)derr->ptr);
-        int perr = 0;
-        cuda_check(cudaMemcpyAsync(&perr, derr->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream), "parquet err");
-        cuda_check(cudaStreamSynchronize(ctx->stream), "parquet decode sync");
-        cuda_check(cudaStreamSynchronize(copy_stream), "parquet copy sync");
-        if (perr & 2) throw Unsupported("parquet: NULL values in data pages (definition-level scatter is pending)");
-        if (perr & 4) throw ExecError(3, "", "parquet: dictionary index out of range (corrupt page)");
-        if (perr & 1) throw Unsupported("parquet: RLE stream with pathological run structure");
-        return true;
+        // the copy stream may overwrite the slot's chunk buffers only after the decode kernels of their previous batch
+        if (sl.used) cuda_check(cudaStreamWaitEvent(copy_stream, sl.decoded, 0), "stream wait");
+        pr->derr = std::make_shared<DeviceBuf>(64);
+        cuda_check(cudaMemsetAsync(pr->derr->ptr, 0, 64, ctx->stream), "memset parquet err");
+        for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, stage_off[c], out.cols[c], pr->arena, (int*)pr->derr->ptr, sl);
+        cuda_check(cudaEventRecord(sl.uploaded, copy_stream), "event record");
+        cuda_check(cudaEventRecord(sl.decoded, ctx->stream), "event record");
+        sl.used = true;
+        cuda_check(cudaMemcpyAsync(&h_flags[pr->slot], pr->derr->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream), "parquet err");
+        cuda_check(cudaEventCreateWithFlags(&pr->done, cudaEventDisableTiming), "event");
+        cuda_check(cudaEventRecord(pr->done, ctx->stream), "event record");
+        return pr;
     }
 
-    void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<size_t>& soff, Column& col, Arena& arena, int* derr) {
+    bool next(Batch& out) override {
+        TraceSpan ts("parquet.next");
+        if (!opened) open_all();
+        std::unique_ptr<Prepared> cur = pending ? std::move(pending) : issue();
+        if (!cur) return false;
+        pending = issue(); // prefetch: its H2D overlaps this batch's decode + the consumer's kernels
+        cuda_check(cudaEventSynchronize(cur->done), "parquet decode sync");
+        const int perr = h_flags[cur->slot];
+        if (perr & 2) throw PlanError("parquet: a column chunk whose statistics say null_count = 0 contains NULLs (corrupt statistics)");
+        if (perr & 8) throw PlanError("parquet: malformed Snappy page");
+        if (perr & 4) throw ExecError(3, "", "parquet: dictionary index out of range (corrupt page)");
+        if (perr & 1) throw Unsupported("parquet: malformed RLE stream, or one with more than n/8 + 64 runs per page");
+        out = std::move(cur->batch);
+        return true; // cur's arena is released here: device temporaries are freed in plan-stream order
+    }
+
+    void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<size_t>& soff, Column& col, Arena& arena, int* derr, Slot& sl) {
         const DType& t = fields[c].type;
         const pq::SchemaElement& se = open_files[units[0].file].meta.leaf(open_files[units[0].file].leaf_of[c]);
         cudaStream_t st = ctx->stream;
@@ -620,14 +676,18 @@ struct NativeScanSource : ExecNode {
             chunk_off[u] = col_bytes;
             col_bytes += ((size_t)chunk_meta(units[u], c).total_compressed + 63) / 64 * 64;
         }
-        auto dchunk = std::make_shared<DeviceBuf>(col_bytes + 64);
+        if (!sl.chunk[c] || sl.chunk[c]->bytes < col_bytes + 64) {
+            // (re)allocation happens in plan-stream order; let the copy stream see it.  The old buffer is freed in
+            // plan-stream order too, i.e. after every decode kernel that read it.
+            sl.chunk[c] = std::make_shared<DeviceBuf>(col_bytes + col_bytes / 8 + 64);
+            cudaEvent_t alloc_ev;
+            cuda_check(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming), "event");
+            arena.events.push_back(alloc_ev);
+            cuda_check(cudaEventRecord(alloc_ev, st), "event record");
+            cuda_check(cudaStreamWaitEvent(copy_stream, alloc_ev, 0), "stream wait");
+        }
+        DeviceBufP dchunk = sl.chunk[c];
         arena.dev.push_back(dchunk);
-        // allocation happened in main-stream order; let the copy stream see it
-        cudaEvent_t alloc_ev;
-        cuda_check(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming), "event");
-        arena.events.push_back(alloc_ev);
-        cuda_check(cudaEventRecord(alloc_ev, st), "event record");
-        cuda_check(cudaStreamWaitEvent(copy_stream, alloc_ev, 0), "stream wait");
         auto dpages_p = std::make_shared<std::vector<PqPage>>();
         auto remap_p = std::make_shared<std::vector<int32_t>>();
         arena.pages.push_back(dpages_p);
@@ -635,8 +695,27 @@ struct NativeScanSource : ExecNode {
         std::vector<PqPage>& dpages = *dpages_p;
         std::vector<PqPage> dict_pages;                // fixed-width dictionary pages (decoded into the combined dictionary)
         std::vector<int32_t>& remap_all = *remap_p;    // string columns: combined code remap tables
-        int64_t run_base = 0, dict_elems = 0;
-        bool optional = false;
+        int64_t run_base = 0, def_run_base = 0, dict_elems = 0;
+        size_t unc_bytes = 0;                          // device scratch for the bodies of Snappy pages
+        bool optional = false, nulls_possible = false, any_compressed = false;
+        unsigned char* const dc = (unsigned char*)dchunk->ptr;
+        std::vector<uint8_t> host_scratch;
+        // Snappy page bodies are decompressed into `dunc`; its offsets are assigned here and turned into pointers below
+        auto place_body = [&](PqPage& d, const unsigned char* src, int comp_bytes, int unc, bool compressed) {
+            if (compressed) {
+                d.comp = src;
+                d.comp_bytes = comp_bytes;
+                d.body = (unsigned char*)(uintptr_t)unc_bytes; // offset for now
+                d.body_bytes = unc;
+                unc_bytes += ((size_t)unc + 31) / 16 * 16;     // 16-byte aligned, >= 8 spare bytes for the unaligned-word loads
+                any_compressed = true;
+            } else {
+                d.comp = nullptr;
+                d.comp_bytes = 0;
+                d.body = (unsigned char*)src;
+                d.body_bytes = comp_bytes;
+            }
+        };
         for (size_t u = 0; u < units.size(); u++) {
             const OpenFile& of = open_files[units[u].file];
             const pq::SchemaElement& use = of.meta.leaf(of.leaf_of[c]);
@@ -644,7 +723,10 @@ struct NativeScanSource : ExecNode {
             const bool opt_u = use.repetition == 1;
             optional = optional || opt_u;
             const pq::ColumnChunkMeta& cc = chunk_meta(units[u], c);
-            if (cc.codec != pq::UNCOMPRESSED) throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (device decompression is pending; write UNCOMPRESSED)");
+            if (opt_u && cc.null_count != 0) nulls_possible = true; // unknown (-1) counts as possible
+            if (cc.codec != pq::UNCOMPRESSED && cc.codec != pq::SNAPPY)
+                throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (device decompression covers UNCOMPRESSED and SNAPPY; ZSTD / LZ4 / GZIP are next-row work)");
+            const bool snappy = cc.codec == pq::SNAPPY;
             if (cc.num_values != units[u].rows) throw Unsupported("parquet: repeated column (num_values != num_rows)");
             const size_t clen = (size_t)cc.total_compressed;
             const uint8_t* host;
@@ -652,7 +734,7 @@ struct NativeScanSource : ExecNode {
                 if ((size_t)cc.start() + clen > of.mem_len) throw PlanError("parquet: column chunk beyond the end of the file image");
                 host = of.mem + cc.start();
             } else {
-                uint8_t* dst = staging + soff[u];
+                uint8_t* dst = sl.staging + soff[u];
                 if (fseeko(of.fh, (off_t)cc.start(), SEEK_SET) != 0 || fread(dst, 1, clen, of.fh) != clen) throw ExecError(3, "", "parquet: short read");
                 host = dst;
             }
@@ -670,13 +752,20 @@ struct NativeScanSource : ExecNode {
                         // strings: parse on the host, unify with the plan-global dictionary, ship the code remap table
                         const uint8_t* p = host + pg.data_offset;
                         const uint8_t* e = p + pg.compressed_size;
+                        if (snappy) {
+                            host_scratch.assign((size_t)pg.uncompressed_size + 16, 0);
+                            if (cb::snappy_decode_serial(p, pg.compressed_size, host_scratch.data(), pg.uncompressed_size) != pg.uncompressed_size)
+                                throw PlanError("parquet: malformed Snappy dictionary page");
+                            p = host_scratch.data();
+                            e = p + pg.uncompressed_size;
+                        }
                         Dictionary& gd = *dicts[c];
                         for (int k = 0; k < this_dict_size; k++) {
                             if (p + 4 > e) throw PlanError("parquet: truncated dictionary page");
                             uint32_t len;
                             memcpy(&len, p, 4);
                             p += 4;
-                            if (p + len > e) throw PlanError("parquet: truncated dictionary page");
+                            if (len > (size_t)(e - p)) throw PlanError("parquet: truncated dictionary page");
                             std::string v((const char*)p, len);
                             p += len;
                             auto it = std::find(gd.values.begin(), gd.values.end(), v);
@@ -686,8 +775,7 @@ struct NativeScanSource : ExecNode {
                     } else {
                         PqPage dp;
                         memset(&dp, 0, sizeof(dp));
-                        dp.values_off = base + pg.data_offset;
-                        dp.values_bytes = pg.compressed_size;
+                        place_body(dp, dc + base + pg.data_offset, pg.compressed_size, pg.uncompressed_size, snappy);
                         dp.num_values = this_dict_size;
                         dp.dst_row = dict_elems; // decoded into the combined dictionary at this element offset
                         dict_pages.push_back(dp);
@@ -700,25 +788,19 @@ struct NativeScanSource : ExecNode {
                 memset(&d, 0, sizeof(d));
                 d.dst_row = row;
                 d.num_values = (int)pg.num_values;
-                int64_t off = pg.data_offset, left = pg.compressed_size;
+                const unsigned char* body = dc + base + pg.data_offset;
                 if (pg.type == pq::DATA_PAGE) {
-                    if (opt_u) {
-                        uint32_t dl;
-                        memcpy(&dl, host + off, 4);
-                        d.def_off = base + off + 4;
-                        d.def_bytes = (int)dl;
-                        off += 4 + dl;
-                        left -= 4 + dl;
-                    }
+                    // v1: [u32 length + definition levels (optional columns)] [values], compressed as one block
+                    if (opt_u) d.flags |= PQ_PAGE_V1_LEVELS;
+                    place_body(d, body, pg.compressed_size, pg.uncompressed_size, snappy);
                 } else {
-                    off += pg.rep_levels_bytes;
-                    d.def_off = base + off;
+                    // v2: repetition + definition levels sit uncompressed in front of the (optionally compressed) values
+                    const int lv = pg.rep_levels_bytes + pg.def_levels_bytes;
+                    if (lv > pg.compressed_size || lv > pg.uncompressed_size) throw PlanError("parquet: data page v2 level sizes exceed the page");
+                    d.def_ptr = body + pg.rep_levels_bytes;
                     d.def_bytes = pg.def_levels_bytes;
-                    off += pg.def_levels_bytes;
-                    left -= pg.rep_levels_bytes + pg.def_levels_bytes;
+                    place_body(d, body + lv, pg.compressed_size - lv, pg.uncompressed_size - lv, snappy && pg.v2_compressed);
                 }
-                d.values_off = base + off;
-                d.values_bytes = (int)left;
                 if (pg.encoding == pq::PLAIN) {
                     if (se.type == pq::BYTE_ARRAY) throw Unsupported("parquet: PLAIN-encoded string page (dictionary fallback); only dictionary-encoded strings are decoded");
                     d.encoding = 0;
@@ -731,19 +813,30 @@ struct NativeScanSource : ExecNode {
                     d.dict_size = this_dict_size;
                     run_base += d.max_runs;
                 } else throw Unsupported("parquet value encoding " + std::to_string(pg.encoding) + " (DELTA_* / BYTE_STREAM_SPLIT are next-row work)");
+                if (opt_u) {
+                    d.def_run_base = def_run_base;
+                    d.def_max_runs = (int)(pg.num_values / 8 + 64);
+                    def_run_base += d.def_max_runs;
+                }
                 row += pg.num_values;
                 dpages.push_back(d);
             }
+            if (row != units[u].row0 + units[u].rows) throw PlanError("parquet: data pages of column '" + fields[c].name + "' do not add up to the row group's row count");
         }
         if (dpages.empty()) return;
         const size_t n_data = dpages.size();
         dpages.insert(dpages.end(), dict_pages.begin(), dict_pages.end()); // one upload for every descriptor of this column
-        // decode kernels (main stream) start when this column's pages have landed (copy stream)
+        const int n_all = (int)dpages.size();
+        if (any_compressed) {
+            auto dunc = std::make_shared<DeviceBuf>(unc_bytes + 64);
+            arena.dev.push_back(dunc);
+            for (auto& d : dpages) if (d.comp) d.body = (unsigned char*)dunc->ptr + (size_t)(uintptr_t)d.body;
+        }
+        // decode kernels (plan stream) start when this column's pages have landed (copy stream)
         cudaEvent_t copied;
         cuda_check(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming), "event");
         arena.events.push_back(copied);
         cuda_check(cudaEventRecord(copied, copy_stream), "event record");
-        const unsigned char* dc = (const unsigned char*)dchunk->ptr;
         auto dpd = std::make_shared<DeviceBuf>(dpages.size() * sizeof(PqPage));
         arena.dev.push_back(dpd);
         cuda_check(cudaMemcpyAsync(dpd->ptr, dpages.data(), dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, st), "H2D page table");
@@ -754,19 +847,44 @@ struct NativeScanSource : ExecNode {
             if (!remap_all.empty()) cuda_check(cudaMemcpyAsync(ddict->ptr, remap_all.data(), remap_all.size() * 4, cudaMemcpyHostToDevice, st), "H2D dictionary remap");
         }
         cuda_check(cudaStreamWaitEvent(st, copied, 0), "stream wait");
-        const PqPage* data_pages = (const PqPage*)dpd->ptr;
+        PqPage* all_pages = (PqPage*)dpd->ptr;
+        PqPage* data_pages = all_pages;
         const PqPage* dpages_dev = data_pages + n_data;
-        if (!dict_pages.empty()) { launch_pq_plain(dc, dpages_dev, (int)dict_pages.size(), conv, se.type_length, ddict->ptr, st); ctx->kernel_launches++; }
-        if (optional) { launch_pq_check_def_levels(dc, data_pages, (int)n_data, derr, st); ctx->kernel_launches++; }
-        if (conv >= 0) { launch_pq_plain(dc, data_pages, (int)n_data, conv, se.type_length, col.data->ptr, st); ctx->kernel_launches++; }
+        if (any_compressed) { launch_pq_snappy(all_pages, n_all, derr, st); ctx->kernel_launches++; }
+        launch_pq_resolve(all_pages, n_all, st);
+        ctx->kernel_launches++;
+        if (!dict_pages.empty()) { launch_pq_plain(dpages_dev, (int)dict_pages.size(), conv, se.type_length, ddict->ptr, st); ctx->kernel_launches++; }
+        // definition levels: the statistics' null_count == 0 selects the verify-only fast path; otherwise values are decoded
+        // densely and scattered to their rows
+        const bool null_aware = optional && nulls_possible;
+        DeviceBufP dense = col.data, dvalid, didx;
+        if (optional && !null_aware) { launch_pq_check_def_levels(data_pages, (int)n_data, derr, st); ctx->kernel_launches++; }
+        if (null_aware) {
+            if (total >= (int64_t)1 << 32) throw Unsupported("parquet: NULL-aware decode of more than 2^32 rows per batch (lower spark.comet.b200.chunkRows)");
+            dense = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(total, 1) * out_w);
+            dvalid = std::make_shared<DeviceBuf>((size_t)total + 64);
+            didx = std::make_shared<DeviceBuf>((size_t)total * 4 + 64);
+            auto druns = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(def_run_base, 1) * sizeof(PqRun));
+            auto dcounts = std::make_shared<DeviceBuf>(n_data * 4 + 16);
+            for (auto& b : {dense, dvalid, didx, druns, dcounts}) arena.dev.push_back(b);
+            launch_pq_def_levels(data_pages, (int)n_data, (PqRun*)druns->ptr, (int*)dcounts->ptr, (unsigned char*)dvalid->ptr, (unsigned*)didx->ptr, derr, st);
+            ctx->kernel_launches += 3;
+        }
+        if (conv >= 0) { launch_pq_plain(data_pages, (int)n_data, conv, se.type_length, dense->ptr, st); ctx->kernel_launches++; }
         if (run_base > 0) {
             auto runs = std::make_shared<DeviceBuf>((size_t)run_base * sizeof(PqRun));
             auto counts = std::make_shared<DeviceBuf>(n_data * 4 + 16);
             arena.dev.push_back(runs);
             arena.dev.push_back(counts);
-            launch_pq_rle_scan(dc, data_pages, (int)n_data, (PqRun*)runs->ptr, (int*)counts->ptr, derr, st);
-            launch_pq_rle_decode(dc, data_pages, (int)n_data, (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, col.data->ptr, derr, st);
+            launch_pq_rle_scan(data_pages, (int)n_data, (PqRun*)runs->ptr, (int*)counts->ptr, derr, st);
+            launch_pq_rle_decode(data_pages, (int)n_data, (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, dense->ptr, derr, st);
             ctx->kernel_launches += 2;
+        }
+        if (null_aware) {
+            col.validity = std::make_shared<DeviceBuf>((size_t)(total + 31) / 32 * 4 + 16);
+            col.null_count = -1;
+            launch_pq_scatter((const unsigned char*)dvalid->ptr, (const unsigned*)didx->ptr, dense->ptr, col.data->ptr, (unsigned*)col.validity->ptr, total, out_w, st);
+            ctx->kernel_launches++;
         }
     }
 };

@@ -2,6 +2,7 @@
 // check every arithmetic routine against the oracle on CPU.  Test-only; not part of libcomet_b200.so.
 #define CB_HOST_TEST 1
 #include "device/cb_math.h"
+#include "device/cb_snappy.h"
 #include <cstdint>
 using namespace cb;
 extern "C" {
@@ -79,4 +80,5 @@ void hm_dd_sum_tree(int64_t n, const double* v, int lanes, double* out) { // lan
     for (int k = 0; k < lanes; k++) dd_add_dd(t, acc[k]);
     *out = t.hi;
 }
+long long hm_snappy(const uint8_t* in, long long n, uint8_t* out, long long cap) { return snappy_decode_serial(in, n, out, cap); }
 }

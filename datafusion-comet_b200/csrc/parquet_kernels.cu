@@ -7,6 +7,8 @@
 // decoders follow the format specification and are checked against pyarrow-written files.
 #include "parquet_kernels.h"
 #include "device/cb_math.h"
+#include "device/cb_snappy.h"
+#include <algorithm>
 
 namespace cb200 {
 using namespace cb;
@@ -31,12 +33,91 @@ __device__ __forceinline__ u32 load_u32_unaligned(const u8* p) {
     return (lo >> sh) | (hi << (32 - sh));
 }
 
+// ---- Snappy --------------------------------------------------------------------------------------------------
+// One warp per page.  Elements are inherently sequential (each tag's position depends on the previous one), so
+// lane 0 parses the tag (device/cb_snappy.h) and broadcasts it; the bytes are moved by the whole warp.  A copy
+// whose distance is shorter than its length repeats a pattern that already lies before the write position, so
+// every lane can compute its source independently; longer distances are plain forward copies in 32-byte steps.
+__global__ void k_pq_snappy(PqPage* pages, int n_pages, int* err) {
+    const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= n_pages) return;
+    const PqPage pg = pages[warp];
+    if (!pg.comp) return;
+    const u8* in = pg.comp;
+    const long long n = pg.comp_bytes;
+    u8* out = pg.body;
+    u64 ulen = 0;
+    long long pos = 0;
+    if (lane == 0) pos = snappy_preamble(in, n, ulen);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    ulen = __shfl_sync(0xffffffffu, ulen, 0);
+    if (pos < 0 || ulen != (u64)pg.body_bytes) { if (lane == 0) atomicOr(err, 8); return; }
+    long long o = 0;
+    bool bad = false;
+    while (pos < n) {
+        SnappyElem e;
+        if (lane == 0) {
+            e = snappy_next(in, n, pos);
+            if (e.kind < 0 || o + e.len > (long long)ulen || (e.kind == 1 && (e.src <= 0 || e.src > o))) e.kind = -1;
+        }
+        e.kind = __shfl_sync(0xffffffffu, e.kind, 0);
+        e.len = __shfl_sync(0xffffffffu, e.len, 0);
+        e.src = __shfl_sync(0xffffffffu, e.src, 0);
+        e.next = __shfl_sync(0xffffffffu, e.next, 0);
+        if (e.kind < 0) { bad = true; break; }
+        if (e.kind == 0) {
+            const u8* s = in + e.src;
+            for (int i = lane; i < e.len; i += 32) out[o + i] = s[i];
+        } else if (e.src >= e.len) {
+            const u8* s = out + o - e.src;  // no overlap with the bytes being written
+            for (int i = lane; i < e.len; i += 32) out[o + i] = s[i];
+        } else {
+            const u8* s = out + o - e.src;  // pattern of period e.src, entirely before the write position
+            const int period = (int)e.src;
+            for (int i = lane; i < e.len; i += 32) out[o + i] = s[i % period];
+        }
+        __syncwarp(); // the next element may read what this one wrote
+        o += e.len;
+        pos = e.next;
+    }
+    if ((bad || o != (long long)ulen) && lane == 0) atomicOr(err, 8);
+}
+void launch_pq_snappy(PqPage* pages, int n_pages, int* err, cudaStream_t st) {
+    if (n_pages > 0) k_pq_snappy<<<(n_pages + 3) / 4, 128, 0, st>>>(pages, n_pages, err);
+}
+
+// ---- locate levels / values inside the page body ------------------------------------------------------------------------
+__global__ void k_pq_resolve(PqPage* pages, int n_pages) {
+    int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= n_pages) return;
+    PqPage pg = pages[pi];
+    const u8* v = pg.body;
+    int left = pg.body_bytes;
+    if (pg.flags & PQ_PAGE_V1_LEVELS) {
+        u32 dl = left >= 4 ? ((u32)v[0] | ((u32)v[1] << 8) | ((u32)v[2] << 16) | ((u32)v[3] << 24)) : 0u;
+        if (left < 4 || dl > (u32)(left - 4)) dl = 0; // malformed: the level decoders will report the row-count mismatch
+        pages[pi].def_ptr = v + 4;
+        pages[pi].def_bytes = (int)dl;
+        v += 4 + dl;
+        left -= 4 + (int)dl;
+    }
+    pages[pi].values = v;
+    pages[pi].values_bytes = left;
+    pages[pi].nonnull = pg.num_values;
+}
+void launch_pq_resolve(PqPage* pages, int n_pages, cudaStream_t st) {
+    if (n_pages > 0) k_pq_resolve<<<(n_pages + 127) / 128, 128, 0, st>>>(pages, n_pages);
+}
+
 // ---- PLAIN ---------------------------------------------------------------------------------------------------
-template <int CONV> __global__ void k_pq_plain(const u8* chunk, const PqPage* pages, int flba_len, u8* out) {
+template <int CONV> __global__ void k_pq_plain(const PqPage* pages, int flba_len, u8* out) {
     const PqPage pg = pages[blockIdx.y];
     if (pg.encoding != 0) return; // dictionary-encoded page: decoded by k_pq_rle_decode
-    const u8* src = chunk + pg.values_off;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pg.num_values; i += gridDim.x * blockDim.x) {
+    const u8* src = pg.values;
+    const int w = CONV == PQ_COPY32 || CONV == PQ_I32_TO_I64 || CONV == PQ_I32_TO_I128 ? 4 : CONV == PQ_COPY64 || CONV == PQ_I64_TO_I128 ? 8 : flba_len;
+    const int have = w > 0 ? pg.values_bytes / w : 0;   // never read beyond the page, whatever the header claims
+    const int count = pg.nonnull < have ? pg.nonnull : have;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         long long row = pg.dst_row + i;
         if (CONV == PQ_COPY32) ((u32*)out)[row] = load_u32_unaligned(src + (size_t)i * 4);
         else if (CONV == PQ_COPY64) ((u64*)out)[row] = load_u64_unaligned(src + (size_t)i * 8);
@@ -55,17 +136,17 @@ template <int CONV> __global__ void k_pq_plain(const u8* chunk, const PqPage* pa
         }
     }
 }
-void launch_pq_plain(const unsigned char* chunk, const PqPage* pages, int n_pages, int conv, int flba_len, void* out, cudaStream_t st) {
+void launch_pq_plain(const PqPage* pages, int n_pages, int conv, int flba_len, void* out, cudaStream_t st) {
     if (n_pages <= 0) return;
     dim3 grid(64, (unsigned)n_pages), block(256);
     switch (conv) {
-    case PQ_COPY32: k_pq_plain<PQ_COPY32><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
-    case PQ_COPY64: k_pq_plain<PQ_COPY64><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
-    case PQ_I32_TO_I64: k_pq_plain<PQ_I32_TO_I64><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
-    case PQ_I64_TO_I128: k_pq_plain<PQ_I64_TO_I128><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
-    case PQ_I32_TO_I128: k_pq_plain<PQ_I32_TO_I128><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
-    case PQ_FLBA_TO_I64: k_pq_plain<PQ_FLBA_TO_I64><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
-    default: k_pq_plain<PQ_FLBA_TO_I128><<<grid, block, 0, st>>>(chunk, pages, flba_len, (u8*)out); break;
+    case PQ_COPY32: k_pq_plain<PQ_COPY32><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    case PQ_COPY64: k_pq_plain<PQ_COPY64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    case PQ_I32_TO_I64: k_pq_plain<PQ_I32_TO_I64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    case PQ_I64_TO_I128: k_pq_plain<PQ_I64_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    case PQ_I32_TO_I128: k_pq_plain<PQ_I32_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    case PQ_FLBA_TO_I64: k_pq_plain<PQ_FLBA_TO_I64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    default: k_pq_plain<PQ_FLBA_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
     }
 }
 
@@ -102,36 +183,41 @@ template <typename F> __device__ long long walk_hybrid(const u8* p, const u8* en
     return seen;
 }
 
-__global__ void k_pq_rle_scan(const u8* chunk, const PqPage* pages, int n_pages, PqRun* runs, int* run_counts, int* err) {
+// LEVELS = false: the dictionary indices of the page (first byte = bit width);  true: its definition levels (bit width 1)
+template <bool LEVELS> __global__ void k_pq_rle_scan(const PqPage* pages, int n_pages, PqRun* runs, int* run_counts, int* err) {
     int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= n_pages) return;
     const PqPage pg = pages[pi];
-    if (pg.encoding == 0) { run_counts[pi] = 0; return; }
-    const u8* p = chunk + pg.values_off;
-    const u8* end = p + pg.values_bytes;
-    int bw = *p++; // RLE_DICTIONARY: the first byte is the index bit width
-    PqRun* out = runs + pg.run_base;
+    if (LEVELS ? pg.def_bytes <= 0 : pg.encoding == 0) { run_counts[pi] = 0; return; }
+    const u8* p = LEVELS ? pg.def_ptr : pg.values;
+    const u8* end = p + (LEVELS ? pg.def_bytes : pg.values_bytes);
+    int bw = 1;
+    if (!LEVELS) bw = p < end ? *p++ : 0; // RLE_DICTIONARY: the first byte is the index bit width
+    const long long want = LEVELS ? pg.num_values : pg.nonnull;
+    const int cap = LEVELS ? pg.def_max_runs : pg.max_runs;
+    PqRun* out = runs + (LEVELS ? pg.def_run_base : pg.run_base);
     int n = 0;
     long long row = pg.dst_row;
-    long long seen = walk_hybrid(p, end, bw, pg.num_values, [&](int packed, int count, u32 value, const u8* data) {
-        if (n < pg.max_runs) {
+    long long seen = bw > 32 ? -1 : walk_hybrid(p, end, bw, want, [&](int packed, int count, u32 value, const u8* data) {
+        if (n < cap) {
             PqRun r;
             r.out_row = row;
-            r.src_off = (long long)(data - chunk);
+            r.src = data;
             r.count = count;
             r.value = value;
             r.bit_packed = packed;
             r.bit_width = bw;
+            if (packed && data + ((long long)count * bw + 7) / 8 > end) r.count = 0; // truncated page: never read beyond it (reported below)
             out[n] = r;
         }
         n++;
         row += count;
     });
-    if (n > pg.max_runs || seen != pg.num_values) atomicOr(err, 1);
-    run_counts[pi] = n < pg.max_runs ? n : pg.max_runs;
+    if (n > cap || seen != want) atomicOr(err, 1);
+    run_counts[pi] = n < cap ? n : cap;
 }
-void launch_pq_rle_scan(const unsigned char* chunk, const PqPage* pages, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st) {
-    if (n_pages > 0) k_pq_rle_scan<<<(n_pages + 63) / 64, 64, 0, st>>>(chunk, pages, n_pages, runs, run_counts, err);
+void launch_pq_rle_scan(const PqPage* pages, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st) {
+    if (n_pages > 0) k_pq_rle_scan<false><<<(n_pages + 63) / 64, 64, 0, st>>>(pages, n_pages, runs, run_counts, err);
 }
 
 template <int DW> __device__ __forceinline__ void store_dict(const void* dict, int dict_size, u32 idx, void* out, long long row, int* err) {
@@ -141,8 +227,7 @@ template <int DW> __device__ __forceinline__ void store_dict(const void* dict, i
     else ((ulonglong2*)out)[row] = ((const ulonglong2*)dict)[idx];
 }
 // one warp per run; blockIdx.y = page
-template <int DW> __global__ void k_pq_rle_decode(const u8* chunk, const PqPage* pages, const PqRun* runs, const int* run_counts, const void* dict_all,
-                                                 void* out, int* err) {
+template <int DW> __global__ void k_pq_rle_decode(const PqPage* pages, const PqRun* runs, const int* run_counts, const void* dict_all, void* out, int* err) {
     const PqPage pg = pages[blockIdx.y];
     if (pg.encoding == 0) return;
     const void* dict = (const u8*)dict_all + (size_t)pg.dict_off * DW;
@@ -154,46 +239,124 @@ template <int DW> __global__ void k_pq_rle_decode(const u8* chunk, const PqPage*
         if (!r.bit_packed) {
             for (int i = lane; i < r.count; i += 32) store_dict<DW>(dict, dict_size, r.value, out, r.out_row + i, err);
         } else {
-            const u8* src = chunk + r.src_off;
+            const u8* src = r.src;
             const int bw = r.bit_width;
+            const long long nbytes = ((long long)r.count * bw + 7) / 8;
             const u32 mask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
             for (int i = lane; i < r.count; i += 32) {
                 long long bit = (long long)i * bw;
                 const u8* q = src + (bit >> 3);
                 u64 w = 0;
-                for (int k = 0; k < 5; k++) w |= (u64)q[k] << (8 * k); // bw <= 32: value spans at most 5 bytes
+                for (int k = 0; k < 5; k++) if ((bit >> 3) + k < nbytes) w |= (u64)q[k] << (8 * k); // bw <= 32: value spans at most 5 bytes
                 u32 idx = (u32)(w >> (bit & 7)) & mask;
                 store_dict<DW>(dict, dict_size, idx, out, r.out_row + i, err);
             }
         }
     }
 }
-void launch_pq_rle_decode(const unsigned char* chunk, const PqPage* pages, int n_pages, const PqRun* runs, const int* run_counts, const void* dict, int dict_width,
-                          void* out, int* err, cudaStream_t st) {
+void launch_pq_rle_decode(const PqPage* pages, int n_pages, const PqRun* runs, const int* run_counts, const void* dict, int dict_width, void* out, int* err,
+                          cudaStream_t st) {
     if (n_pages <= 0) return;
     dim3 grid(32, (unsigned)n_pages), block(256);
-    if (dict_width == 4) k_pq_rle_decode<4><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, out, err);
-    else if (dict_width == 8) k_pq_rle_decode<8><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, out, err);
-    else k_pq_rle_decode<16><<<grid, block, 0, st>>>(chunk, pages, runs, run_counts, dict, out, err);
+    if (dict_width == 4) k_pq_rle_decode<4><<<grid, block, 0, st>>>(pages, runs, run_counts, dict, out, err);
+    else if (dict_width == 8) k_pq_rle_decode<8><<<grid, block, 0, st>>>(pages, runs, run_counts, dict, out, err);
+    else k_pq_rle_decode<16><<<grid, block, 0, st>>>(pages, runs, run_counts, dict, out, err);
 }
 
-// definition levels (bit width 1): all levels must be 1 until NULL scatter lands
-__global__ void k_pq_check_def(const u8* chunk, const PqPage* pages, int n_pages, int* err) {
+// ---- definition levels (flat optional columns: bit width 1) ---------------------------------------------------------------
+// fast path: the chunk statistics promise null_count == 0 -- verify it, one thread per page (run headers only for RLE runs)
+__global__ void k_pq_check_def(const PqPage* pages, int n_pages, int* err) {
     int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= n_pages) return;
     const PqPage pg = pages[pi];
     if (pg.def_bytes <= 0) return;
-    const u8* p = chunk + pg.def_off;
+    const u8* p = pg.def_ptr;
+    const u8* end = p + pg.def_bytes;
     bool bad = false;
-    long long seen = walk_hybrid(p, p + pg.def_bytes, 1, pg.num_values, [&](int packed, int count, u32 value, const u8* data) {
+    long long seen = walk_hybrid(p, end, 1, pg.num_values, [&](int packed, int count, u32 value, const u8* data) {
         if (!packed) { if (value != 1u) bad = true; }
-        else for (int i = 0; i < count; i++) if (!((data[i >> 3] >> (i & 7)) & 1)) { bad = true; break; }
+        else for (int i = 0; i < count && data + (i >> 3) < end; i++) if (!((data[i >> 3] >> (i & 7)) & 1)) { bad = true; break; }
     });
     if (bad) atomicOr(err, 2);
     if (seen != pg.num_values) atomicOr(err, 1);
 }
-void launch_pq_check_def_levels(const unsigned char* chunk, const PqPage* pages, int n_pages, int* err, cudaStream_t st) {
-    if (n_pages > 0) k_pq_check_def<<<(n_pages + 63) / 64, 64, 0, st>>>(chunk, pages, n_pages, err);
+void launch_pq_check_def_levels(const PqPage* pages, int n_pages, int* err, cudaStream_t st) {
+    if (n_pages > 0) k_pq_check_def<<<(n_pages + 63) / 64, 64, 0, st>>>(pages, n_pages, err);
+}
+
+// NULL-aware path, step 2: expand the level runs to one validity byte per row (warp per run; blockIdx.y = page)
+__global__ void k_pq_def_expand(const PqPage* pages, const PqRun* runs, const int* run_counts, u8* valid) {
+    const PqPage pg = pages[blockIdx.y];
+    const int n_runs = run_counts[blockIdx.y];
+    const int lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
+    for (int ri = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ri < n_runs; ri += gridDim.x * warps_per_block) {
+        const PqRun r = runs[pg.def_run_base + ri];
+        if (!r.bit_packed) for (int i = lane; i < r.count; i += 32) valid[r.out_row + i] = (u8)(r.value & 1u);
+        else for (int i = lane; i < r.count; i += 32) valid[r.out_row + i] = (u8)((r.src[i >> 3] >> (i & 7)) & 1);
+    }
+}
+// step 3: per page, idx[row] = dst_row + (non-null rows of the page before `row`): where the row's value sits in the
+// densely decoded value stream.  One block per page, running carry across 2048-row tiles.
+__global__ void k_pq_def_index(PqPage* pages, u8* valid, u32* idx) {
+    const PqPage pg = pages[blockIdx.x];
+    __shared__ u32 warp_sums[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 carry = 0;
+    const bool all_valid = pg.def_bytes <= 0; // required column mixed into an optional one across files: no levels, everything present
+    for (long long base = 0; base < pg.num_values; base += 2048) {
+        const long long r0 = pg.dst_row + base + (long long)threadIdx.x * 8;
+        u32 v[8], local = 0;
+        for (int k = 0; k < 8; k++) {
+            const bool in = base + threadIdx.x * 8 + k < pg.num_values;
+            v[k] = in ? (all_valid ? 1u : (u32)valid[r0 + k]) : 0u;
+            local += v[k];
+        }
+        u32 incl = local;
+        for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        u32 wbase = 0, total = 0;
+        for (int w = 0; w < 8; w++) { if (w < warp) wbase += warp_sums[w]; total += warp_sums[w]; }
+        u32 excl = carry + wbase + incl - local;
+        for (int k = 0; k < 8; k++) {
+            if (base + threadIdx.x * 8 + k < pg.num_values) {
+                idx[r0 + k] = (u32)pg.dst_row + excl;
+                if (all_valid) valid[r0 + k] = 1;
+            }
+            excl += v[k];
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pages[blockIdx.x].nonnull = (int)carry;
+}
+void launch_pq_def_levels(PqPage* pages, int n_pages, PqRun* runs, int* run_counts, unsigned char* valid, unsigned* idx, int* err, cudaStream_t st) {
+    if (n_pages <= 0) return;
+    k_pq_rle_scan<true><<<(n_pages + 63) / 64, 64, 0, st>>>(pages, n_pages, runs, run_counts, err);
+    k_pq_def_expand<<<dim3(32, (unsigned)n_pages), 256, 0, st>>>(pages, runs, run_counts, valid);
+    k_pq_def_index<<<n_pages, 256, 0, st>>>(pages, valid, idx);
+}
+
+// step 4 (after the values were decoded densely): scatter to row positions, zero the NULL slots, build the Arrow bitmap
+template <int W> __global__ void k_pq_scatter(const u8* valid, const u32* idx, const u8* dense, u8* out, u32* bitmap, long long total) {
+    const long long n32 = (total + 31) / 32 * 32;
+    for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < n32; row += (long long)gridDim.x * blockDim.x) {
+        const bool ok = row < total && valid[row] != 0;
+        if (row < total) {
+            if (W == 4) ((u32*)out)[row] = ok ? ((const u32*)dense)[idx[row]] : 0u;
+            else if (W == 8) ((u64*)out)[row] = ok ? ((const u64*)dense)[idx[row]] : 0ull;
+            else ((ulonglong2*)out)[row] = ok ? ((const ulonglong2*)dense)[idx[row]] : make_ulonglong2(0ull, 0ull);
+        }
+        const u32 word = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) bitmap[row >> 5] = word;
+    }
+}
+void launch_pq_scatter(const unsigned char* valid, const unsigned* idx, const void* dense, void* out, unsigned* bitmap, long long total, int width, cudaStream_t st) {
+    if (total <= 0) return;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    if (width == 4) k_pq_scatter<4><<<blocks, 256, 0, st>>>(valid, idx, (const u8*)dense, (u8*)out, bitmap, total);
+    else if (width == 8) k_pq_scatter<8><<<blocks, 256, 0, st>>>(valid, idx, (const u8*)dense, (u8*)out, bitmap, total);
+    else k_pq_scatter<16><<<blocks, 256, 0, st>>>(valid, idx, (const u8*)dense, (u8*)out, bitmap, total);
 }
 
 } // namespace cb200

@@ -1,27 +1,40 @@
-// parquet_kernels.h -- device-side Parquet page decode (PLAIN, RLE_DICTIONARY, definition levels).
+// parquet_kernels.h -- device-side Parquet page decode: Snappy decompression, PLAIN, RLE_DICTIONARY, definition
+// levels (validity + NULL scatter).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
 
 namespace cb200 {
 
-struct PqPage { // one data page of a column chunk already resident on the device
-    long long values_off;   // byte offset of the encoded VALUES (after the levels) inside the chunk buffer
-    int values_bytes;
-    long long def_off;      // byte offset of the RLE-encoded definition levels (0 length: column is required)
+enum { PQ_PAGE_V1_LEVELS = 1 }; // body starts with [u32 byte length][RLE definition levels] (DataPage v1 of an optional column)
+
+// One page of a column chunk resident on the device.  The host fills what the page HEADER tells it; everything
+// that lives inside the (possibly compressed) page body is resolved on the device by k_pq_resolve.
+struct PqPage {
+    unsigned char* body;          // v1: page body (levels + values); v2: the values section.  Snappy pages: where the decompressor writes
+    int body_bytes;               // uncompressed size of `body`
+    const unsigned char* comp;    // Snappy-compressed source, nullptr when `body` already holds the bytes
+    int comp_bytes;
+    int flags;
+    const unsigned char* def_ptr; // definition levels (RLE/bit-packed hybrid, bit width 1); v2: set by the host
     int def_bytes;
-    long long dst_row;      // first output row of this page
-    int num_values;
-    int encoding;           // 0 PLAIN, 8 RLE_DICTIONARY (2 PLAIN_DICTIONARY is the same on the wire)
-    long long run_base;     // first entry of this page in the run table (RLE pages)
-    int max_runs;           // capacity reserved for it
-    long long dict_off;     // element offset of this page's dictionary inside the column's combined dictionary buffer
+    const unsigned char* values;  // resolved: encoded values (non-null values only)
+    int values_bytes;
+    long long dst_row;            // first output row of this page
+    int num_values;               // rows of the page (incl. NULLs)
+    int nonnull;                  // resolved: encoded values present
+    int encoding;                 // 0 PLAIN, 8 RLE_DICTIONARY (2 PLAIN_DICTIONARY is the same on the wire)
+    long long run_base;           // value runs: first entry of this page in the run table, capacity
+    int max_runs;
+    long long def_run_base;       // definition-level runs (NULL-aware path)
+    int def_max_runs;
+    long long dict_off;           // element offset of this page's dictionary inside the column's combined dictionary buffer
     int dict_size;
 };
 
 struct PqRun {              // one run of the RLE / bit-packed hybrid
     long long out_row;      // absolute output row of the run's first value
-    long long src_off;      // byte offset (chunk buffer) of the packed data (bit-packed) -- unused for RLE runs
+    const unsigned char* src; // packed data (bit-packed runs)
     int count;              // values in the run
     unsigned value;         // RLE runs: the repeated value
     int bit_packed;
@@ -29,15 +42,25 @@ struct PqRun {              // one run of the RLE / bit-packed hybrid
 };
 
 enum PqConv { PQ_COPY32, PQ_COPY64, PQ_I32_TO_I64, PQ_FLBA_TO_I64, PQ_FLBA_TO_I128, PQ_I64_TO_I128, PQ_I32_TO_I128 };
+// err bits: 1 malformed / pathological RLE stream, 2 NULL found on the no-NULL fast path, 4 dictionary index out of range, 8 malformed Snappy page
 
-// PLAIN fixed-width pages -> output column (element width given by the conversion)
-void launch_pq_plain(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, int conv, int flba_len, void* out, cudaStream_t st);
+// Snappy: one warp per compressed page (pages with comp == nullptr are skipped)
+void launch_pq_snappy(PqPage* pages_dev, int n_pages, int* err, cudaStream_t st);
+// locate levels / values inside every page body; nonnull = num_values
+void launch_pq_resolve(PqPage* pages_dev, int n_pages, cudaStream_t st);
+// PLAIN fixed-width pages -> out[dst_row + k] for the page's k-th encoded value (element width given by the conversion)
+void launch_pq_plain(const PqPage* pages_dev, int n_pages, int conv, int flba_len, void* out, cudaStream_t st);
 // RLE_DICTIONARY pages: (1) scan run headers, one thread per page
-void launch_pq_rle_scan(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st);
+void launch_pq_rle_scan(const PqPage* pages_dev, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st);
 // (2) decode runs (warp per run) and gather through the dictionary: dict_width 4/8/16 bytes per entry
-void launch_pq_rle_decode(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, const PqRun* runs, const int* run_counts, const void* dict,
-                          int dict_width, void* out, int* err, cudaStream_t st);
-// definition levels of flat optional columns (max level 1): verify "no NULLs" (sets err bit 1 if a 0 level appears)
-void launch_pq_check_def_levels(const unsigned char* chunk, const PqPage* pages_dev, int n_pages, int* err, cudaStream_t st);
+void launch_pq_rle_decode(const PqPage* pages_dev, int n_pages, const PqRun* runs, const int* run_counts, const void* dict, int dict_width, void* out, int* err,
+                          cudaStream_t st);
+// definition levels of flat optional columns (max level 1)
+//   fast path (statistics promise no NULLs): verify it (err bit 2 otherwise)
+void launch_pq_check_def_levels(const PqPage* pages_dev, int n_pages, int* err, cudaStream_t st);
+//   NULL-aware path: valid[row] = level, idx[row] = dst_row(page) + number of non-null rows before `row` in its page, pages[].nonnull
+void launch_pq_def_levels(PqPage* pages_dev, int n_pages, PqRun* runs, int* run_counts, unsigned char* valid, unsigned* idx, int* err, cudaStream_t st);
+//   out[row] = valid[row] ? dense[idx[row]] : 0 ; bitmap = Arrow validity (total rows, width 4/8/16 bytes)
+void launch_pq_scatter(const unsigned char* valid, const unsigned* idx, const void* dense, void* out, unsigned* bitmap, long long total, int width, cudaStream_t st);
 
 } // namespace cb200

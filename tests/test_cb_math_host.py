@@ -13,12 +13,13 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 @pytest.fixture(scope="module")
 def hm():
     so = os.path.join(CSRC, "libcb200_hostmath.so")
-    src = [os.path.join(CSRC, "host_math_test.cpp"), os.path.join(CSRC, "device", "cb_math.h")]
+    src = [os.path.join(CSRC, "host_math_test.cpp"), os.path.join(CSRC, "device", "cb_math.h"), os.path.join(CSRC, "device", "cb_snappy.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in src):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
     lib = C.CDLL(so)
     lib.hm_mm3_bytes.restype = C.c_uint32
     lib.hm_pmod.restype = C.c_uint32
+    lib.hm_snappy.restype = C.c_longlong
     return lib
 
 
@@ -188,3 +189,28 @@ def test_wrapping_products(hm, oracle):
     assert oracle.dec_to_ints(out) == [wrap(x * y) for x, y in zip(a, b64)]
     hm.hm_mul_i128_wrap(C.c_int64(2000), _p(A), _p(B), _p(out))
     assert oracle.dec_to_ints(out) == [wrap(x * y) for x, y in zip(a, b)]
+
+
+def test_snappy_decoder_vs_pyarrow(hm):
+    """device/cb_snappy.h (the element parser the warp decompressor shares) against pyarrow's Snappy on page-like payloads"""
+    import pyarrow as pa
+    rng = np.random.default_rng(7)
+    payloads = [b"", b"a", b"abcd" * 1000, bytes(rng.integers(0, 256, 100_000, dtype=np.uint8)),                    # empty, tiny, overlapping copies, incompressible
+                rng.integers(0, 50, 200_000).astype(np.int64).tobytes(), (rng.integers(90000, 210000, 150_000) * 7).astype(np.int64).tobytes(),
+                np.repeat(rng.integers(0, 3, 5000).astype(np.int32), 40).tobytes(), b"x" * 70 + b"y" * 3 + b"x" * 100_000]
+    for raw in payloads:
+        comp = pa.compress(raw, codec="snappy", asbytes=True)
+        out = np.zeros(len(raw) + 8, dtype=np.uint8)
+        src = np.frombuffer(comp, dtype=np.uint8).copy()
+        n = hm.hm_snappy(_p(src), C.c_longlong(len(comp)), _p(out), C.c_longlong(len(raw)))
+        assert n == len(raw)
+        assert out[:n].tobytes() == raw
+    # malformed inputs are rejected, never over-read / over-written
+    comp = np.frombuffer(pa.compress(b"abcd" * 1000, codec="snappy", asbytes=True), dtype=np.uint8).copy()
+    out = np.zeros(4008, dtype=np.uint8)
+    assert hm.hm_snappy(_p(comp), C.c_longlong(len(comp) - 3), _p(out), C.c_longlong(4000)) == -1      # truncated
+    assert hm.hm_snappy(_p(comp), C.c_longlong(len(comp)), _p(out), C.c_longlong(100)) == -1            # declared length exceeds the page size
+    bad = comp.copy()
+    bad[2] = 0x01 | (7 << 2)   # a copy with offset beyond the start of the output
+    bad[3] = 0xff
+    assert hm.hm_snappy(_p(bad), C.c_longlong(len(bad)), _p(out), C.c_longlong(4000)) == -1

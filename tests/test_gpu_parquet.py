@@ -91,3 +91,96 @@ def test_dictionary_encoded_numeric_column(cb, tmp_path):
     res, _ = run(cb, plan)
     r = res.to_pylist()[0]
     assert r["col_0"] == int(a.sum()) and r["col_1"] == int(b.sum()) and r["col_2"] == n
+
+
+def _nullable_table(n, seed, null_frac=0.15):
+    import decimal
+    import pyarrow as pa
+    rng = np.random.default_rng(seed)
+    ctx = decimal.Context(prec=60)
+
+    def mask():
+        m = rng.random(n) < null_frac
+        m[: n // 50] = True                      # a long NULL stretch -> RLE level runs, pages with few / no values
+        m[n // 2: n // 2 + n // 40] = False      # and a long all-valid one
+        return m
+    i32 = rng.integers(-2**31, 2**31, n).astype(np.int32)
+    i64 = rng.integers(-2**62, 2**62, n)
+    f64 = rng.standard_normal(n)
+    d12 = rng.integers(-10**11, 10**11, n)
+    d30 = [int(a) * 10**12 + int(b) for a, b in zip(rng.integers(-10**17, 10**17, n), rng.integers(0, 10**12, n))]
+    lowcard = rng.integers(0, 40, n).astype(np.int64) * 1000
+    words = np.array(["AIR", "MAIL", "SHIP", "TRUCK", "RAIL", "REG AIR", "FOB", ""])[rng.integers(0, 8, n)]
+    ms = [mask() for _ in range(7)]
+    dec = lambda vals, p, s, m: pa.array([None if mm else decimal.Decimal(int(v)).scaleb(-s, context=ctx) for v, mm in zip(vals, m)], type=pa.decimal128(p, s))
+    return pa.table({
+        "i32": pa.array(i32, mask=ms[0]), "i64": pa.array(i64, mask=ms[1]), "f64": pa.array(f64, mask=ms[2]), "d12": dec(d12, 12, 2, ms[3]),
+        "d30": dec(d30, 30, 4, ms[4]), "low": pa.array(lowcard, mask=ms[5]), "word": pa.array(words.tolist(), mask=ms[6]).cast(pa.string()),
+        "req": pa.array(i64),                    # no NULLs: statistics say so -> verify-only fast path in the same file
+    })
+
+
+def _scan_all(cb, tbl, paths):
+    P = cb.proto
+    dts = {"i32": P.INT32, "i64": P.INT64, "f64": P.DOUBLE, "d12": P.DECIMAL(12, 2), "d30": P.DECIMAL(30, 4), "low": P.INT64, "word": P.STRING, "req": P.INT64}
+    fields = [(name, dts[name], True) for name in tbl.column_names]
+    sc = P.native_scan(fields, fields, paths)
+    return P.projection(sc, [P.bound(i, dts[name]) for i, name in enumerate(tbl.column_names)])
+
+
+@pytest.mark.parametrize("compression,version,dictionary,dec_as_int", [("NONE", "1.0", False, True), ("SNAPPY", "1.0", True, True), ("SNAPPY", "2.0", False, False),
+                                                                       ("NONE", "2.0", True, False), ("SNAPPY", "1.0", ["word", "low"], False)])
+def test_nulls_and_snappy_roundtrip(cb, tmp_path, compression, version, dictionary, dec_as_int):
+    """Every value and every NULL of a pyarrow-written file comes back: definition levels -> validity + scatter, Snappy pages
+    decompressed on the device, data page v1 / v2, PLAIN and dictionary encodings, INT64- and FLBA-backed decimals."""
+    import pyarrow.parquet as pq
+    n = 70_000
+    tbl = _nullable_table(n, seed=5)
+    path = str(tmp_path / "nulls.parquet")
+    use_dict = dictionary if dictionary is not False else ["word"]    # strings are only decoded from dictionary pages
+    pq.write_table(tbl, path, row_group_size=20_000, compression=compression, use_dictionary=use_dict, data_page_version=version, data_page_size=8192,
+                   store_decimal_as_integer=dec_as_int)
+    res, st = run(cb, _scan_all(cb, tbl, [path]), chunk_rows=45_000)
+    assert res.num_rows == n
+    for j, name in enumerate(tbl.column_names):
+        got, want = res.column(j).combine_chunks(), tbl.column(name).combine_chunks()
+        assert got.null_count == want.null_count, name
+        if name == "f64":
+            gv, wv = got.to_numpy(zero_copy_only=False), want.to_numpy(zero_copy_only=False)
+            ok = ~np.isnan(wv)
+            assert (np.isnan(gv) == np.isnan(wv)).all() and (gv[ok].view(np.uint64) == wv[ok].view(np.uint64)).all(), name
+        else:
+            assert got.cast(want.type).equals(want), name
+
+
+def test_aggregate_over_nullable_parquet_columns(cb, tmp_path):
+    import pyarrow.compute as pc
+    import pyarrow.parquet as pq
+    P = cb.proto
+    n = 120_000
+    tbl = _nullable_table(n, seed=9, null_frac=0.3)
+    path = str(tmp_path / "agg.parquet")
+    pq.write_table(tbl, path, row_group_size=50_000, compression="SNAPPY", use_dictionary=["word", "low"], data_page_version="1.0", store_decimal_as_integer=True)
+    fields = [("word", P.STRING, True), ("d12", P.DECIMAL(12, 2), True), ("i32", P.INT32, True)]
+    sc = P.native_scan(fields, fields, [path])
+    d = P.bound(1, P.DECIMAL(12, 2))
+    part = P.hash_agg(sc, [P.bound(0, P.STRING)], [P.agg_sum(d, P.DECIMAL(22, 2)), P.agg_count([d]), P.agg_count([P.literal(1, P.INT32)]),
+                                                    P.agg_sum(P.bound(2, P.INT32), P.INT64)], P.PARTIAL)
+    res, _ = run(cb, part)
+    got = {r["col_0"]: r for r in res.to_pylist()}
+    words = tbl.column("word").to_pylist()
+    d12 = tbl.column("d12").to_pylist()
+    i32 = tbl.column("i32").to_pylist()
+    exp = {}
+    for w, dv, iv in zip(words, d12, i32):
+        e = exp.setdefault(w, [None, 0, 0, None])
+        if dv is not None:
+            e[0] = dv if e[0] is None else e[0] + dv
+            e[1] += 1
+        e[2] += 1
+        if iv is not None:
+            e[3] = iv if e[3] is None else e[3] + iv
+    assert set(got) == set(exp)                       # includes the NULL group
+    for w, e in exp.items():
+        g = got[w]
+        assert g["col_1"] == e[0] and g["col_3"] == e[1] and g["col_4"] == e[2] and g["col_5"] == e[3], w
