@@ -685,7 +685,8 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
         std::vector<Val> outs;
         for (size_t i = 0; i < spec.outputs.size(); i++) {
             Val v = em.emit(*spec.outputs[i]);
-            if (v.type.is_string()) throw Unsupported("string columns in a fused projection");
+            // strings travel as dictionary codes: only a plain column reference can be projected (the node re-attaches the dictionary)
+            if (v.type.is_string() && spec.outputs[i]->kind != ExprKind::Bound) throw Unsupported("string expressions in a fused projection");
             outs.push_back(v);
             em.body << "    " << to_slot(v, "o.v[" + std::to_string(i) + "]") << " o.valid[" << i << "] = "
                     << (v.n.empty() ? "true" : "!" + v.n) << ";\n";
@@ -693,7 +694,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
             oc.type = v.type;
             oc.nullable = v.nullable();
             g.out_cols.push_back(oc);
-            g.out_bytes.push_back(out_width(v.type));
+            g.out_bytes.push_back(v.type.is_string() ? 4 : out_width(v.type));
         }
         em.body << "    return true;\n";
         tu << header(spec, defs.str());

@@ -35,55 +35,125 @@ __device__ __forceinline__ u32 load_u32_unaligned(const u8* p) {
 
 // ---- Snappy --------------------------------------------------------------------------------------------------
 // One warp per page.  Elements are inherently sequential (each tag's position depends on the previous one), so
-// lane 0 parses the tag (device/cb_snappy.h) and broadcasts it; the bytes are moved by the whole warp.  A copy
-// whose distance is shorter than its length repeats a pattern that already lies before the write position, so
-// every lane can compute its source independently; longer distances are plain forward copies in 32-byte steps.
-__global__ void k_pq_snappy(PqPage* pages, int n_pages, int* err) {
-    const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (warp >= n_pages) return;
+// lane 0 parses the tag and broadcasts it in two registers; the bytes are moved by the whole warp.  What makes a
+// serial decoder slow on a GPU is the latency of every dependent access, so both ends are kept in shared memory:
+//   * a 512-byte window of the compressed input, refilled with one coalesced 16-byte load per lane;
+//   * a 16 KB ring of the most recent output: a back-reference within it (almost all of them -- the reference
+//     compressor never looks back more than 64 KB, typical matches are far closer) is served without the
+//     store -> L2 -> load round trip.  Older references fall back to L2 loads of the page's own output.
+// A copy whose distance is shorter than its length repeats a pattern that lies entirely before the write position,
+// so every lane computes its source independently; element semantics are those of device/cb_snappy.h (host-tested).
+constexpr int SN_RING = 16384, SN_WIN = 512, SN_WARPS = 4;
+// A lone warp issues one dependent instruction every ~4.5 cycles, so the cost of a page is (elements x instructions
+// per element): positions are 32-bit offsets (a page is < 2 GiB), the common shapes -- a literal or a copy of at
+// most 32 bytes -- take one predicated step without a loop, and validation is a handful of compares.
+__global__ void __launch_bounds__(SN_WARPS * 32) k_pq_snappy(PqPage* pages, int n_pages, int* err) {
+    extern __shared__ __align__(16) u8 sn_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * SN_WARPS + wib;
+    if (warp >= n_pages) return; // warps are independent: no block-wide barrier below
     const PqPage pg = pages[warp];
     if (!pg.comp) return;
+    u8* ring = sn_smem + wib * (SN_RING + SN_WIN);
+    u8* win = ring + SN_RING;
     const u8* in = pg.comp;
-    const long long n = pg.comp_bytes;
+    const u32 n = (u32)pg.comp_bytes;
     u8* out = pg.body;
-    u64 ulen = 0;
-    long long pos = 0;
-    if (lane == 0) pos = snappy_preamble(in, n, ulen);
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    ulen = __shfl_sync(0xffffffffu, ulen, 0);
-    if (pos < 0 || ulen != (u64)pg.body_bytes) { if (lane == 0) atomicOr(err, 8); return; }
-    long long o = 0;
+    u64 ulen64 = 0;
+    long long pre = 0;
+    if (lane == 0) pre = snappy_preamble(in, n, ulen64);
+    pre = __shfl_sync(0xffffffffu, pre, 0);
+    ulen64 = __shfl_sync(0xffffffffu, ulen64, 0);
+    if (pre < 0 || ulen64 != (u64)pg.body_bytes) { if (lane == 0) atomicOr(err, 8); return; }
+    const u32 ulen = (u32)ulen64;
+    // the window holds input bytes [wbase, wbase + SN_WIN) where wbase is `in`-relative and 16-byte aligned in memory
+    const u32 misalign = (u32)((size_t)in & 15);
+    u32 pos = (u32)pre, o = 0;
+    int wbase = -SN_WIN - 16; // nothing loaded yet
     bool bad = false;
     while (pos < n) {
-        SnappyElem e;
-        if (lane == 0) {
-            e = snappy_next(in, n, pos);
-            if (e.kind < 0 || o + e.len > (long long)ulen || (e.kind == 1 && (e.src <= 0 || e.src > o))) e.kind = -1;
+        u32 wp = pos - (u32)wbase; // offset of the element inside the window
+        if (wp + 5 > (u32)SN_WIN) { // an element header is at most 5 bytes
+            wbase = (int)((pos + misalign) & ~15u) - (int)misalign;
+            const int lo = wbase + lane * 16;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (lo < (int)n) v = *(const uint4*)(in + lo); // reads < 16 bytes outside the page: inside the padded chunk buffer
+            __syncwarp();
+            ((uint4*)win)[lane] = v;
+            __syncwarp();
+            wp = pos - (u32)wbase;
         }
-        e.kind = __shfl_sync(0xffffffffu, e.kind, 0);
-        e.len = __shfl_sync(0xffffffffu, e.len, 0);
-        e.src = __shfl_sync(0xffffffffu, e.src, 0);
-        e.next = __shfl_sync(0xffffffffu, e.next, 0);
-        if (e.kind < 0) { bad = true; break; }
-        if (e.kind == 0) {
-            const u8* s = in + e.src;
-            for (int i = lane; i < e.len; i += 32) out[o + i] = s[i];
-        } else if (e.src >= e.len) {
-            const u8* s = out + o - e.src;  // no overlap with the bytes being written
-            for (int i = lane; i < e.len; i += 32) out[o + i] = s[i];
+        u32 w0 = 0xffffffffu, w1 = 0;
+        if (lane == 0) {
+            const u8* p = win + wp;
+            const u32 tag = p[0], t = tag & 3u;
+            u32 len, src = 0, hdr;
+            if (t == 0) {
+                hdr = 1; len = tag >> 2;
+                if (len >= 60) {
+                    const u32 extra = len - 59;
+                    const u32 raw = (u32)p[1] | ((u32)p[2] << 8) | ((u32)p[3] << 16) | ((u32)p[4] << 24);
+                    len = extra == 4 ? raw : raw & ((1u << (8 * extra)) - 1u);
+                    hdr += extra;
+                }
+                len += 1;
+                if (len < (1u << 27) && len <= ulen - o && hdr + len <= n - pos) w0 = len | (hdr << 27);
+            } else {
+                if (t == 1) { hdr = 2; len = ((tag >> 2) & 7u) + 4; src = ((tag >> 5) << 8) | p[1]; }
+                else if (t == 2) { hdr = 3; len = (tag >> 2) + 1; src = (u32)p[1] | ((u32)p[2] << 8); }
+                else { hdr = 5; len = (tag >> 2) + 1; src = (u32)p[1] | ((u32)p[2] << 8) | ((u32)p[3] << 16) | ((u32)p[4] << 24); }
+                if (src - 1u < o && len <= ulen - o && hdr <= n - pos) { w0 = len | (hdr << 27) | (1u << 30); w1 = src; }
+            }
+        }
+        w0 = __shfl_sync(0xffffffffu, w0, 0);
+        if (w0 == 0xffffffffu) { bad = true; break; }
+        const u32 len = w0 & ((1u << 27) - 1), hdr = (w0 >> 27) & 7u;
+        if (!(w0 & (1u << 30))) {
+            if (wp + hdr + len <= (u32)SN_WIN) { // short literal: already in the window
+                for (u32 i = lane; i < len; i += 32) {
+                    const u8 b = win[wp + hdr + i];
+                    out[o + i] = b;
+                    ring[(o + i) & (SN_RING - 1)] = b;
+                }
+            } else {
+                const u8* s = in + pos + hdr;
+                for (u32 i = lane; i < len; i += 32) {
+                    const u8 b = s[i];
+                    out[o + i] = b;
+                    ring[(o + i) & (SN_RING - 1)] = b;
+                }
+            }
+            pos += hdr + len;
         } else {
-            const u8* s = out + o - e.src;  // pattern of period e.src, entirely before the write position
-            const int period = (int)e.src;
-            for (int i = lane; i < e.len; i += 32) out[o + i] = s[i % period];
+            const u32 d = __shfl_sync(0xffffffffu, w1, 0);
+            const bool near = d + 64 <= (u32)SN_RING; // the source still sits in the ring and this copy (<= 64 bytes) does not overwrite it
+            if (d >= len) { // no overlap with the bytes being written
+                for (u32 i = lane; i < len; i += 32) {
+                    const u32 sp = o - d + i;
+                    const u8 b = near ? ring[sp & (SN_RING - 1)] : __ldcg(out + sp);
+                    out[o + i] = b;
+                    ring[(o + i) & (SN_RING - 1)] = b;
+                }
+            } else { // pattern of period d, entirely before the write position
+                for (u32 i = lane; i < len; i += 32) {
+                    const u32 sp = o - d + i % d;
+                    const u8 b = near ? ring[sp & (SN_RING - 1)] : __ldcg(out + sp);
+                    out[o + i] = b;
+                    ring[(o + i) & (SN_RING - 1)] = b;
+                }
+            }
+            pos += hdr;
         }
         __syncwarp(); // the next element may read what this one wrote
-        o += e.len;
-        pos = e.next;
+        o += len;
     }
-    if ((bad || o != (long long)ulen) && lane == 0) atomicOr(err, 8);
+    if ((bad || o != ulen) && lane == 0) atomicOr(err, 8);
 }
 void launch_pq_snappy(PqPage* pages, int n_pages, int* err, cudaStream_t st) {
-    if (n_pages > 0) k_pq_snappy<<<(n_pages + 3) / 4, 128, 0, st>>>(pages, n_pages, err);
+    if (n_pages <= 0) return;
+    const int smem = SN_WARPS * (SN_RING + SN_WIN);
+    cudaFuncSetAttribute(k_pq_snappy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); // per device, idempotent
+    k_pq_snappy<<<(n_pages + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem, st>>>(pages, n_pages, err);
 }
 
 // ---- locate levels / values inside the page body ------------------------------------------------------------------------
