@@ -347,4 +347,58 @@ void launch_gather_bits(const void* in_bits, const i64* row_idx, i64 n, void* ou
     if (n > 0) k_gather_bits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u8*)in_bits, row_idx, n, (u8*)out_bytes);
 }
 
+// ---- chunked exclusive scan (select pipelines: per-(tile, warp) kept-row counts -> output offsets) ------------------------
+// one block per chunk of 4096 entries: 256 threads x 16 consecutive entries, warp shuffles + one shared-memory hop
+__global__ void __launch_bounds__(256) k_scan_chunks(u32* data, long long m, u32* chunk_tot) {
+    __shared__ u32 wsum[8];
+    const long long base = (long long)blockIdx.x * 4096 + threadIdx.x * 16;
+    u32 v[16], local = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { v[k] = base + k < m ? data[base + k] : 0u; local += v[k]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+    u32 excl = wbase + incl - local;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { if (base + k < m) data[base + k] = excl; excl += v[k]; }
+    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = total;
+}
+// single block: exclusive scan of the chunk totals (any count, running carry), grand total
+__global__ void __launch_bounds__(1024) k_scan_totals(u32* chunk_tot, int n_chunks, long long* total_out) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n_chunks ? chunk_tot[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long wbase = 0, total = 0;
+        for (int w = 0; w < 32; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+        const unsigned long long carry = carry_s;
+        if (i < n_chunks) chunk_tot[i] = (u32)(carry + wbase + incl - v); // < 2^32: the caller bounds the row count
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = (long long)carry_s;
+}
+void launch_scan_u32(unsigned* data, long long m, int chunk, unsigned* chunk_off, long long* total, cudaStream_t st) {
+    (void)chunk; // fixed at 4096 (CB_SCAN_CHUNK in device/cb_params.h)
+    const int n_chunks = (int)((m + 4095) / 4096);
+    if (n_chunks > 0) k_scan_chunks<<<n_chunks, 256, 0, st>>>(data, m, chunk_off);
+    k_scan_totals<<<1, 1024, 0, st>>>(chunk_off, n_chunks, total);
+}
+
 } // namespace cb200

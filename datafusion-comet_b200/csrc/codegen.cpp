@@ -25,7 +25,7 @@ int phys_bytes(Phys p) {
 }
 
 size_t GeneratedKernel::dyn_smem(int n_groups) const {
-    size_t s = 128 + (size_t)stages * stage_bytes;
+    size_t s = (entry == "cb_pipeline_agg" ? 128 : 256) + (size_t)stages * stage_bytes; // barrier area: CB_BAR_BYTES of the select kernels
     if (hash) return s;
     if (!word_kinds.empty() && n_groups > 1) s += (size_t)n_groups * n_words * threads * 8;
     else if (!word_kinds.empty() && n_groups == 1 && n_words > 0) s += 0;
@@ -677,7 +677,13 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
     }
     std::ostringstream tu;
 
-    if (spec.sink == SinkKind::Select) {
+    if (spec.sink == SinkKind::Count) {
+        em.body << "    return " << keep << ";\n";
+        tu << header(spec, "#define CB_KERNEL_SELECT 1\n#define CB_SELECT_COUNT 1\n#define CB_NOUT 0\n");
+        tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
+        tu << "CB_D bool cb_row_keep(const Tile& t, int r, i64 grow, const PipeParams& p) {\n    (void)grow; (void)p;\n" << em.body.str() << "}\n} // namespace cb\n";
+        g.entry = "cb_select_count";
+    } else if (spec.sink == SinkKind::Select) {
         if (spec.outputs.size() > 16) throw Unsupported("more than 16 output columns");
         em.body << "    if (!(" << keep << ")) return false;\n";
         std::ostringstream defs;

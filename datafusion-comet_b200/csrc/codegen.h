@@ -25,7 +25,7 @@ struct SourceCol {
 // thread-private 64-bit partial sums are exact while rows/thread <= 2^CB_RPT_LOG2 (host enforces it per launch)
 #define CB_RPT_LOG2 14
 
-enum class SinkKind { Select, Agg };
+enum class SinkKind { Select, Agg, Count }; // Count: pass 1 of a select pipeline (predicates only, see cb_kernels.cuh)
 
 // accumulator word kinds (must match cb_kernels.cuh)
 enum WordKind { W_SUM128 = 0, W_DD_HI = 1, W_DD_LO = 2, W_WRAP64 = 3, W_MIN = 4, W_MAX = 5 };

@@ -51,6 +51,9 @@ CB_D void mbar_wait(u64* bar, u32 parity) {
         "r"(parity)
         : "memory");
 }
+CB_D void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 CB_D u64 l2_evict_first_policy() {
     u64 pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -308,9 +311,6 @@ CB_D Pair128 shfl_xor_pair(Pair128 v, int m) {
     return r;
 }
 
-CB_D void mbar_arrive(u64* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 CB_D void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CB_THREADS) : "memory"); }
 
 // CB_THREADS consumer threads + one producer warp.  The producer's elected lane keeps the CB_STAGES-deep
@@ -578,15 +578,86 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
 #endif // CB_KERNEL_AGG (fold/finalize)
 
 // =================================================================================================
-// SELECT kernel: filter + project + stable compaction (single pass, decoupled look-back)
+// SELECT kernels: filter + project + stable compaction in two streaming passes
+//
+//   pass 1  cb_select_count   stages only the columns the predicates read; every warp owns a contiguous span of each
+//                             tile and writes how many of its rows pass to sel_off[tile * NW + warp]
+//   (scan)  k_scan_chunks / k_scan_totals (aot_kernels.cu): exclusive prefix sum of those counts
+//   pass 2  cb_pipeline_select re-evaluates the predicate, evaluates the projections and writes every kept row at
+//                             its final position (stable row order, like FilterExec)
+//
+// A single-pass compaction needs a tile's predecessors' totals before it can write (decoupled look-back); with one
+// resident CTA per SM that wait sits on every tile's critical path and the first version ran at 10% of HBM peak.  Two
+// passes cost a second read of the predicate columns (4 of 20..36 bytes per row in Config 1) and in exchange both are
+// barrier-free streams with the same TMA ring / producer warp as the aggregate kernel.
 // =================================================================================================
 #ifdef CB_KERNEL_SELECT
 namespace cb {
 
-// tile descriptor: bits 63..62 status (0 invalid, 1 aggregate-only, 2 inclusive prefix), low 62 bits count
-#define CB_ST_AGG (1ull << 62)
-#define CB_ST_PREFIX (2ull << 62)
-#define CB_ST_MASK (3ull << 62)
+#define CB_BAR_BYTES 256                     // up to 16 stages: narrow pipelines (pass 1 reads 4 bytes per row) need depth to keep enough bytes in flight
+constexpr int SEL_NW = CB_THREADS / 32;      // consumer warps
+constexpr int SEL_RPW = CB_TILE / SEL_NW;    // contiguous rows of a tile owned by one warp
+constexpr int SEL_ROUNDS = SEL_RPW / 32;
+static_assert(CB_TILE % (SEL_NW * 32) == 0, "tile must be a multiple of 32 rows per warp");
+
+// barriers + producer warp shared by both passes; returns false for the producer warp (which is done)
+#define CB_SELECT_PROLOGUE()                                                                                          \
+    extern __shared__ __align__(128) u8 smem[];                                                                       \
+    constexpr int SB = stage_bytes();                                                                                 \
+    u64* full = reinterpret_cast<u64*>(smem);                                                                         \
+    u64* empty = full + CB_STAGES;                                                                                    \
+    u8* stages = smem + CB_BAR_BYTES;                                                                                 \
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;                                                     \
+    static_assert(2 * CB_STAGES * 8 <= CB_BAR_BYTES, "barrier area");                                                 \
+    if (tid == 0) {                                                                                                   \
+        for (int s = 0; s < CB_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], SEL_NW); }                 \
+        mbar_fence_init();                                                                                            \
+    }                                                                                                                 \
+    __syncthreads();                                                                                                  \
+    const int first = blockIdx.x, step = gridDim.x;                                                                   \
+    const int my_tiles = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;                               \
+    if (tid >= CB_THREADS) {                                                                                          \
+        if (tid == CB_THREADS) {                                                                                      \
+            const u64 policy = l2_evict_first_policy();                                                               \
+            for (int k = 0; k < my_tiles; k++) {                                                                      \
+                const int s = k % CB_STAGES, u = k / CB_STAGES;                                                       \
+                if (u > 0) mbar_wait(&empty[s], (u32)((u - 1) & 1));                                                  \
+                issue_tile(p, first + k * step, stages + (size_t)s * SB, &full[s], policy);                           \
+            }                                                                                                         \
+        }                                                                                                             \
+        return;                                                                                                       \
+    }
+
+#ifdef CB_SELECT_COUNT
+CB_D bool cb_row_keep(const Tile& t, int r, i64 grow, const PipeParams& p);
+
+extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_select_count(const __grid_constant__ PipeParams p) {
+    CB_SELECT_PROLOGUE()
+    for (int k = 0; k < my_tiles; k++) {
+        const int s = k % CB_STAGES;
+        mbar_wait(&full[s], (u32)((k / CB_STAGES) & 1));
+        Tile t;
+        tile_view(stages + (size_t)s * SB, t);
+        const int tile = first + k * step;
+        const i64 row0 = (i64)tile * CB_TILE;
+        const i64 rem = p.n_rows - row0;
+        const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < SEL_ROUNDS; q++) {
+            const int r = wid * SEL_RPW + q * 32 + lane;
+            const bool keep = r < rows ? cb_row_keep(t, r, row0 + r, p) : false;
+            cnt += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]); // this warp is done with stage s
+            p.sel_off[(size_t)tile * SEL_NW + wid] = (u32)cnt;
+        }
+    }
+}
+
+#else // ---- pass 2 --------------------------------------------------------------------------------------------
 
 struct SelOut {
     // filled by the generated program for one row: CB_NOUT values (raw 16-byte slots) + validity
@@ -597,146 +668,68 @@ struct SelOut {
 CB_D bool cb_row_select(const Tile& t, int r, i64 grow, const PipeParams& p, SelOut& o);
 
 CB_D void store_out(u8* base, int bytes, i64 idx, const u64* v) {
-    if (bytes == 16) { ulonglong2 x; x.x = v[0]; x.y = v[1]; reinterpret_cast<ulonglong2*>(base)[idx] = x; }
+    if (bytes == 16) { reinterpret_cast<ulonglong2*>(base)[idx] = make_ulonglong2(v[0], v[1]); }
     else if (bytes == 8) reinterpret_cast<u64*>(base)[idx] = v[0];
     else if (bytes == 4) reinterpret_cast<u32*>(base)[idx] = (u32)v[0];
     else if (bytes == 2) reinterpret_cast<u16*>(base)[idx] = (u16)v[0];
     else base[idx] = (u8)v[0];
 }
 
-extern "C" __global__ void __launch_bounds__(CB_THREADS, 1) cb_pipeline_select(const __grid_constant__ PipeParams p) {
-    extern __shared__ __align__(128) u8 smem[];
-    constexpr int SB = stage_bytes();
-    constexpr int NW = CB_THREADS / 32;
-    constexpr int ROUNDS = CB_TILE / CB_THREADS;
-    static_assert(CB_TILE % CB_THREADS == 0, "tile must be a multiple of the CTA size");
-    u64* bars = reinterpret_cast<u64*>(smem);
-    u8* stages = smem + 128;
-    __shared__ i32 s_tile[CB_STAGES];
-    __shared__ i32 s_wcount[ROUNDS][NW];
-    __shared__ i64 s_tile_base;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-    if (tid == 0) {
-        for (int s = 0; s < CB_STAGES; s++) mbar_init(&bars[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    u64 policy = 0;
-    // tiles are handed out in increasing order by a global ticket so that every predecessor of a
-    // tile is already owned by a resident CTA (forward progress of the look-back).
-    if (tid == 0) {
-        policy = l2_evict_first_policy();
-        for (int k = 0; k < CB_STAGES - 1; k++) {
-            int t = atomicAdd(p.tile_counter, 1);
-            s_tile[k] = t;
-            if (t < p.n_tiles) issue_tile(p, t, stages + (size_t)k * SB, &bars[k], policy);
-        }
-    }
-    __syncthreads();
-    for (int k = 0;; k++) {
+extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_select(const __grid_constant__ PipeParams p) {
+    CB_SELECT_PROLOGUE()
+    // where a warp's kept rows go: scanned pass-1 counts, or the row itself when nothing is filtered.  The two loads are
+    // issued one tile ahead so their latency (longer than a tile's share of HBM time) overlaps the previous tile.
+    auto warp_base = [&](int tile) -> i64 {
+        if (!p.sel_off) return (i64)tile * CB_TILE + (i64)wid * SEL_RPW;
+        const size_t e = (size_t)tile * SEL_NW + wid;
+        return (i64)p.sel_chunk[e / CB_SCAN_CHUNK] + (i64)p.sel_off[e];
+    };
+    i64 next_base = my_tiles > 0 ? warp_base(first) : 0;
+    for (int k = 0; k < my_tiles; k++) {
         const int s = k % CB_STAGES;
-        if (tid == 0) {
-            int kn = k + CB_STAGES - 1, sn = kn % CB_STAGES;
-            int t = atomicAdd(p.tile_counter, 1);
-            s_tile[sn] = t;
-            if (t < p.n_tiles) issue_tile(p, t, stages + (size_t)sn * SB, &bars[sn], policy);
-        }
-        const int tile = s_tile[s]; // written >= one __syncthreads ago
-        if (tile >= p.n_tiles) break;
-        mbar_wait(&bars[s], (u32)((k / CB_STAGES) & 1));
+        i64 wbase = next_base;
+        if (k + 1 < my_tiles) next_base = warp_base(first + (k + 1) * step);
+        mbar_wait(&full[s], (u32)((k / CB_STAGES) & 1));
         Tile t;
         tile_view(stages + (size_t)s * SB, t);
+        const int tile = first + k * step;
         const i64 row0 = (i64)tile * CB_TILE;
         const i64 rem = p.n_rows - row0;
         const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
-
-        // evaluate: row = round*CB_THREADS + tid keeps (round, warp, lane) order == row order
-        SelOut o[ROUNDS];
-        bool keep[ROUNDS];
-        u32 bal[ROUNDS];
+#if CB_NOUT <= 4
 #pragma unroll
-        for (int q = 0; q < ROUNDS; q++) {
-            int r = q * CB_THREADS + tid;
-            keep[q] = (r < rows) ? cb_row_select(t, r, row0 + r, p, o[q]) : false;
-            bal[q] = __ballot_sync(0xffffffffu, keep[q]);
-            if (lane == 0) s_wcount[q][wid] = __popc(bal[q]);
-        }
-        __syncthreads(); // also: stage s fully consumed
-        // exclusive prefix over (round, warp) -- tiny, every thread recomputes what it needs
-        int tile_total = 0, my_base[ROUNDS];
+#else
+#pragma unroll 1
+#endif
+        for (int q = 0; q < SEL_ROUNDS; q++) {
+            const int r = wid * SEL_RPW + q * 32 + lane;
+            SelOut o;
+            const bool keep = r < rows ? cb_row_select(t, r, row0 + r, p, o) : false;
+            const u32 bal = __ballot_sync(0xffffffffu, keep);
+            const int rank = __popc(bal & ((1u << lane) - 1u));
+            if (keep) {
 #pragma unroll
-        for (int q = 0; q < ROUNDS; q++) {
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                if (w == wid) my_base[q] = tile_total;
-                tile_total += s_wcount[q][w];
-            }
-        }
-        // decoupled look-back (one warp)
-        if (wid == 0) {
-            i64 excl = 0;
-            if (tile == 0) {
-                if (lane == 0) { __threadfence(); atomicExch((unsigned long long*)&p.tile_state[0], CB_ST_PREFIX | (u64)tile_total); }
-            } else {
-                if (lane == 0) { atomicExch((unsigned long long*)&p.tile_state[tile], CB_ST_AGG | (u64)tile_total); }
-                int look = tile - 1;
-                while (true) {
-                    int idx = look - lane;
-                    u64 d = idx >= 0 ? *((volatile u64*)&p.tile_state[idx]) : CB_ST_PREFIX; // before tile 0: prefix 0
-                    u32 invalid = __ballot_sync(0xffffffffu, (d & CB_ST_MASK) == 0);
-                    if (invalid) continue; // spin until the 32-window is published
-                    u32 isprefix = __ballot_sync(0xffffffffu, (d & CB_ST_MASK) == CB_ST_PREFIX);
-                    int firstp = isprefix ? __ffs(isprefix) - 1 : 32;
-                    i64 c = (lane <= firstp) ? (i64)(d & ~CB_ST_MASK) : 0;
-#pragma unroll
-                    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
-                    excl += c;
-                    if (isprefix) break;
-                    look -= 32;
-                }
-                if (lane == 0) { __threadfence(); atomicExch((unsigned long long*)&p.tile_state[tile], CB_ST_PREFIX | (u64)(excl + tile_total)); }
-            }
-            if (lane == 0) {
-                s_tile_base = excl;
-                if (tile == p.n_tiles - 1) *p.out_count = excl + tile_total;
-            }
-        }
-        __syncthreads();
-        const i64 base = s_tile_base;
-#pragma unroll
-        for (int q = 0; q < ROUNDS; q++) {
-            i64 wbase = base + my_base[q];
-            if (keep[q]) {
-                i64 idx = wbase + __popc(bal[q] & ((1u << lane) - 1u));
-#pragma unroll
-                for (int c = 0; c < CB_NOUT; c++) store_out(p.out[c], cb_out_bytes(c), idx, o[q].v[c]);
+                for (int c = 0; c < CB_NOUT; c++) store_out(p.out[c], cb_out_bytes(c), wbase + rank, o.v[c]);
             }
 #pragma unroll
             for (int c = 0; c < CB_NOUT; c++) {
                 if (!cb_out_nullable(c)) continue;
-                // this warp's kept rows occupy output bits [wbase, wbase + popc): scatter their validity
-                // compress vb by the keep mask (order-preserving) -- lane j owns kept-rank j
-                u32 packed = 0;
-                {
-                    u32 km = bal[q];
-                    int rank = __popc(km & ((1u << lane) - 1u));
-                    u32 bit = (keep[q] && o[q].valid[c]) ? (1u << rank) : 0u;
-#pragma unroll
-                    for (int m = 16; m >= 1; m >>= 1) bit |= __shfl_xor_sync(0xffffffffu, bit, m);
-                    packed = bit;
-                }
-                int cnt = __popc(bal[q]);
-                if (lane == 0 && cnt > 0) {
-                    u64 bits = (u64)packed << (wbase & 31);
-                    atomicOr(&p.out_valid[c][wbase >> 5], (u32)bits);
+                // the warp's kept rows occupy output bits [wbase, wbase + popc(bal)): compress the validity bits in
+                // keep order (lane j's bit lands at its rank) and OR them into the zeroed bitmap
+                u32 packed = __reduce_or_sync(0xffffffffu, (keep && o.valid[c]) ? (1u << rank) : 0u);
+                if (lane == 0 && bal != 0) {
+                    const u64 bits = (u64)packed << (wbase & 31);
+                    if ((u32)bits) atomicOr(&p.out_valid[c][wbase >> 5], (u32)bits);
                     if ((bits >> 32) != 0) atomicOr(&p.out_valid[c][(wbase >> 5) + 1], (u32)(bits >> 32));
                 }
             }
+            wbase += __popc(bal);
         }
-        __syncthreads(); // s_wcount / s_tile_base reuse
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]); // this warp is done with stage s
     }
 }
+#endif // CB_SELECT_COUNT
 
 } // namespace cb
 #endif // CB_KERNEL_SELECT

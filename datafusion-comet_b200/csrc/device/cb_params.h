@@ -10,6 +10,8 @@ namespace cb {
 #define CB_MAX_OUT 24
 #define CB_MAX_KEYS 4
 
+#define CB_SCAN_CHUNK 4096
+
 struct PipeParams {
     const u8* col[CB_MAX_COLS];      // input column value buffers (16-byte aligned, padded)
     const u8* val[CB_MAX_COLS];      // validity bitmaps (LSB order) or nullptr
@@ -19,8 +21,11 @@ struct PipeParams {
     i32 key_card[CB_MAX_KEYS];       // dense aggregate: cardinality of each key (incl. null slot)
     u8* out[CB_MAX_OUT];             // select: output value buffers
     u32* out_valid[CB_MAX_OUT];      // select: output validity bitmap words (zeroed) or nullptr
-    u64* tile_state;                 // select: look-back descriptors [n_tiles]
-    i32* tile_counter;               // select: dynamic tile ticket
+    // select (two passes): pass 1 writes the rows each (tile, warp) keeps into sel_off[tile * NW + warp]; an exclusive
+    // scan over chunks of CB_SCAN_CHUNK entries turns it into output offsets (sel_off: within the chunk, sel_chunk:
+    // of the chunk); pass 2 writes the kept rows at sel_chunk[e / CB_SCAN_CHUNK] + sel_off[e].  nullptr = keep all.
+    u32* sel_off;
+    u32* sel_chunk;
     i64* out_count;                  // select: total rows kept
     u8* partials;                    // agg: per-CTA partial slots [grid][n_groups][CB_WORDS] x 16 B
     u64* spill;                      // agg: exact 128-bit escape accumulators [n_groups][CB_WORDS][2]

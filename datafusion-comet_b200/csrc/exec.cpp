@@ -992,9 +992,10 @@ struct FusedBase : ExecNode {
     std::map<int, int> slot_of;
 
     // build the staged-column list for one batch signature
-    std::vector<SourceCol> stage_cols(const Batch* b) const {
+    std::vector<SourceCol> stage_cols(const Batch* b) const { return stage_cols_of(b, used_cols); }
+    std::vector<SourceCol> stage_cols_of(const Batch* b, const std::vector<int>& which) const {
         std::vector<SourceCol> cols;
-        for (int ci : used_cols) {
+        for (int ci : which) {
             SourceCol sc;
             sc.src_index = ci;
             sc.type = child->schema[ci];
@@ -1025,13 +1026,14 @@ struct FusedBase : ExecNode {
         }
         return out;
     }
-    void fill_inputs(cb::PipeParams& p, const Batch& b, int tile, int64_t row0 = 0, int64_t row1 = -1) const {
+    void fill_inputs(cb::PipeParams& p, const Batch& b, int tile, int64_t row0 = 0, int64_t row1 = -1) const { fill_inputs_of(p, b, used_cols, tile, row0, row1); }
+    void fill_inputs_of(cb::PipeParams& p, const Batch& b, const std::vector<int>& which, int tile, int64_t row0 = 0, int64_t row1 = -1) const {
         memset(&p, 0, sizeof(p));
         if (row1 < 0) row1 = b.n_rows;
         if (row0 & 1023) throw ExecError(15, "", "internal: launch range must start on a 1024-row boundary");
-        for (size_t i = 0; i < used_cols.size(); i++) {
-            const Column& c = b.cols[used_cols[i]];
-            if (!c.data) throw Unsupported("column " + std::to_string(used_cols[i]) + " (" + c.type.str() + ") has no fixed-width device representation");
+        for (size_t i = 0; i < which.size(); i++) {
+            const Column& c = b.cols[which[i]];
+            if (!c.data) throw Unsupported("column " + std::to_string(which[i]) + " (" + c.type.str() + ") has no fixed-width device representation");
             int w = phys_bytes(c.is_dict && c.phys == Phys::I32 ? Phys::Dict32 : c.phys);
             p.col[i] = (const cb::u8*)c.data->ptr + (w == 0 ? row0 / 8 : row0 * w);
             p.val[i] = c.validity ? (const cb::u8*)c.validity->ptr + row0 / 8 : nullptr;
@@ -1057,8 +1059,24 @@ static const size_t SMEM_BUDGET = 220 * 1024;
 // ---- filter + project -> compacted batch ----------------------------------------------------------------
 struct SelectNode : FusedBase {
     std::vector<ExprP> outputs;
-    DeviceBufP tile_state, counters; // reused across batches
+    DeviceBufP sel_off, sel_chunk, counters; // reused across batches
+    std::vector<int> pred_cols;              // child columns the predicates read (pass 1 stages only these)
+    std::map<int, int> pred_slot_of;
 
+    void assign_pred_slots() {
+        std::set<int> seen;
+        for (auto& e : predicates) collect_bound(e, pred_cols, seen);
+        for (size_t i = 0; i < pred_cols.size(); i++) pred_slot_of[pred_cols[i]] = (int)i;
+    }
+    static int stages_for(const PipelineSpec& s) {
+        int sb = 0;
+        for (auto& c : s.cols) {
+            int w = phys_bytes(c.phys);
+            sb += ((w == 0 ? s.tile / 8 : s.tile * w) + 127) / 128 * 128;
+            if (c.has_validity) sb += (s.tile / 8 + 127) / 128 * 128;
+        }
+        return (int)std::max<size_t>(2, std::min<size_t>(16, (SMEM_BUDGET - 1024) / (size_t)std::max(sb, 1)));
+    }
     PipelineSpec make_spec(const Batch* b) const {
         PipelineSpec s;
         s.cols = stage_cols(b);
@@ -1067,13 +1085,18 @@ struct SelectNode : FusedBase {
         s.sink = SinkKind::Select;
         s.threads = 256;
         s.tile = 1024;
-        int sb = 0;
-        for (auto& c : s.cols) {
-            int w = phys_bytes(c.phys);
-            sb += ((w == 0 ? s.tile / 8 : s.tile * w) + 127) / 128 * 128;
-            if (c.has_validity) sb += (s.tile / 8 + 127) / 128 * 128;
-        }
-        s.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (SMEM_BUDGET - 1024) / (size_t)sb));
+        s.stages = stages_for(s);
+        return s;
+    }
+    // pass 1: the predicates alone over the columns they read; same tile / warp geometry as pass 2
+    PipelineSpec make_count_spec(const Batch* b) const {
+        PipelineSpec s;
+        s.cols = stage_cols_of(b, pred_cols);
+        s.predicates = to_slots(predicates, pred_slot_of);
+        s.sink = SinkKind::Count;
+        s.threads = 256;
+        s.tile = 1024;
+        s.stages = stages_for(s);
         return s;
     }
 
@@ -1088,6 +1111,7 @@ struct SelectNode : FusedBase {
     }
 
     void run(const Batch& in, Batch& out) {
+        if (in.n_rows >= ((int64_t)1 << 32) - 8192) throw Unsupported("filter/projection over more than 2^32 rows per batch (lower spark.comet.b200.chunkRows)");
         PipelineSpec spec = make_spec(&in);
         GeneratedKernel g = generate_pipeline(spec);
         auto mod = jit_get(g, true);
@@ -1117,20 +1141,33 @@ struct SelectNode : FusedBase {
                 c.null_count = -1;
             }
         }
-        size_t need = (size_t)p.n_tiles * 8;
-        if (!tile_state || tile_state->bytes < need) tile_state = std::make_shared<DeviceBuf>(need);
-        if (!counters) counters = std::make_shared<DeviceBuf>(64);
-        cuda_check(cudaMemsetAsync(tile_state->ptr, 0, need, st), "memset tile state");
-        cuda_check(cudaMemsetAsync(counters->ptr, 0, 64, st), "memset counters");
-        p.tile_state = (cb::u64*)tile_state->ptr;
-        p.tile_counter = (cb::i32*)counters->ptr;
-        p.out_count = (cb::i64*)((char*)counters->ptr + 16);
-        int grid = std::min(ctx->num_sms, p.n_tiles);
-        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads), g.dyn_smem(0), &p);
+        const int grid = std::min(ctx->num_sms, p.n_tiles);
+        int64_t kept = in.n_rows;
+        int64_t* h_kept = nullptr;
+        if (!predicates.empty()) {
+            // pass 1: kept rows per (tile, warp), then their exclusive prefix sum = where pass 2 writes
+            GeneratedKernel cg = generate_pipeline(make_count_spec(&in));
+            auto cmod = jit_get(cg, true);
+            cb::PipeParams cp;
+            fill_inputs_of(cp, in, pred_cols, cg.tile);
+            const size_t m = (size_t)p.n_tiles * (size_t)(g.threads / 32);
+            const size_t n_chunks = (m + CB_SCAN_CHUNK - 1) / CB_SCAN_CHUNK;
+            if (!sel_off || sel_off->bytes < m * 4) sel_off = std::make_shared<DeviceBuf>(m * 4 + m / 2);
+            if (!sel_chunk || sel_chunk->bytes < (n_chunks + 1) * 4) sel_chunk = std::make_shared<DeviceBuf>((n_chunks + 1) * 4 + n_chunks * 2);
+            if (!counters) counters = std::make_shared<DeviceBuf>(64);
+            cp.sel_off = (cb::u32*)sel_off->ptr;
+            launch(cmod->kernel(cg.entry), dim3(grid), dim3(cg.threads + 32), cg.dyn_smem(0), &cp);
+            launch_scan_u32((unsigned*)sel_off->ptr, (long long)m, CB_SCAN_CHUNK, (unsigned*)sel_chunk->ptr, (long long*)counters->ptr, st);
+            ctx->kernel_launches += 2;
+            p.sel_off = (cb::u32*)sel_off->ptr;
+            p.sel_chunk = (cb::u32*)sel_chunk->ptr;
+            h_kept = (int64_t*)ctx->h_err + 1; // pinned scratch next to the error flag
+            cuda_check(cudaMemcpyAsync(h_kept, counters->ptr, 8, cudaMemcpyDeviceToHost, st), "read kept count"); ctx->d2h_bytes += (int64_t)(8);
+        }
+        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(0), &p);
         ctx->pipeline_rows += in.n_rows;
-        int64_t kept = 0;
-        cuda_check(cudaMemcpyAsync(&kept, p.out_count, 8, cudaMemcpyDeviceToHost, st), "read kept count"); ctx->d2h_bytes += (int64_t)(8);
         ctx->check_device_errors(); // also synchronises
+        if (h_kept) kept = *h_kept;
         out.n_rows = kept;
         // boolean outputs were written one byte per row; repack lazily at export
     }
@@ -2060,6 +2097,7 @@ static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* i
     std::vector<ExprP> roots = preds;
     for (auto& e : cols) roots.push_back(e);
     n->assign_slots(roots);
+    n->assign_pred_slots();
     if (n->used_cols.empty()) throw Unsupported("projection of constants only");
     return n;
 }
@@ -2073,6 +2111,7 @@ std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const s
     std::function<void(const ExecNodeP&)> walk = [&](const ExecNodeP& n) {
         if (auto s = std::dynamic_pointer_cast<SelectNode>(n)) {
             out.push_back(generate_pipeline(s->make_spec(nullptr)));
+            if (!s->predicates.empty()) out.push_back(generate_pipeline(s->make_count_spec(nullptr)));
             walk(s->child);
         } else if (auto pn = std::dynamic_pointer_cast<PartitionNode>(n)) {
             walk(pn->child);
