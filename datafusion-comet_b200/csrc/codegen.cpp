@@ -679,7 +679,8 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
 
     if (spec.sink == SinkKind::Count) {
         em.body << "    return " << keep << ";\n";
-        tu << header(spec, "#define CB_KERNEL_SELECT 1\n#define CB_SELECT_COUNT 1\n#define CB_NOUT 0\n");
+        if (spec.ltile <= 0 || spec.tile % spec.ltile) throw PlanError("count pass: stage tile must be a multiple of the logical tile");
+        tu << header(spec, "#define CB_KERNEL_SELECT 1\n#define CB_SELECT_COUNT 1\n#define CB_NOUT 0\n#define CB_LTILE " + std::to_string(spec.ltile) + "\n");
         tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
         tu << "CB_D bool cb_row_keep(const Tile& t, int r, i64 grow, const PipeParams& p) {\n    (void)grow; (void)p;\n" << em.body.str() << "}\n} // namespace cb\n";
         g.entry = "cb_select_count";

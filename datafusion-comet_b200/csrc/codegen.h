@@ -51,6 +51,7 @@ struct PipelineSpec {
     bool hash = false;                    // high-cardinality: global open-addressing table keyed by the packed key columns
     // tuning
     int tile = 512, stages = 3, threads = 256;
+    int ltile = 0;                        // Count sink: rows of one logical tile of the select pass (tile is a multiple of it)
 };
 
 struct GeneratedKernel {

@@ -595,10 +595,17 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
 namespace cb {
 
 #define CB_BAR_BYTES 256                     // up to 16 stages: narrow pipelines (pass 1 reads 4 bytes per row) need depth to keep enough bytes in flight
+// Pass 1 stages CB_TILE rows at a time but counts per LOGICAL tile of CB_LTILE rows (= pass 2's CB_TILE): its rows are
+// 4 bytes wide, and a 1024-row stage would leave each warp ~170 cycles per tile at HBM speed -- less than one
+// barrier wait + release costs.
+#ifndef CB_LTILE
+#define CB_LTILE CB_TILE
+#endif
 constexpr int SEL_NW = CB_THREADS / 32;      // consumer warps
-constexpr int SEL_RPW = CB_TILE / SEL_NW;    // contiguous rows of a tile owned by one warp
+constexpr int SEL_RPW = CB_LTILE / SEL_NW;   // contiguous rows of a logical tile owned by one warp
 constexpr int SEL_ROUNDS = SEL_RPW / 32;
-static_assert(CB_TILE % (SEL_NW * 32) == 0, "tile must be a multiple of 32 rows per warp");
+constexpr int SEL_SUB = CB_TILE / CB_LTILE;  // logical tiles per stage
+static_assert(CB_LTILE % (SEL_NW * 32) == 0 && CB_TILE % CB_LTILE == 0, "tile must be a multiple of 32 rows per warp");
 
 // barriers + producer warp shared by both passes; returns false for the producer warp (which is done)
 #define CB_SELECT_PROLOGUE()                                                                                          \
@@ -642,17 +649,26 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_select_count
         const i64 row0 = (i64)tile * CB_TILE;
         const i64 rem = p.n_rows - row0;
         const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
-        int cnt = 0;
+        int cnt[SEL_SUB];
 #pragma unroll
-        for (int q = 0; q < SEL_ROUNDS; q++) {
-            const int r = wid * SEL_RPW + q * 32 + lane;
-            const bool keep = r < rows ? cb_row_keep(t, r, row0 + r, p) : false;
-            cnt += __popc(__ballot_sync(0xffffffffu, keep));
+        for (int sub = 0; sub < SEL_SUB; sub++) {
+            cnt[sub] = 0;
+#pragma unroll
+            for (int q = 0; q < SEL_ROUNDS; q++) {
+                const int r = sub * CB_LTILE + wid * SEL_RPW + q * 32 + lane;
+                const bool keep = r < rows ? cb_row_keep(t, r, row0 + r, p) : false;
+                cnt[sub] += __popc(__ballot_sync(0xffffffffu, keep));
+            }
         }
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[s]); // this warp is done with stage s
-            p.sel_off[(size_t)tile * SEL_NW + wid] = (u32)cnt;
+            const i64 n_ltiles = (p.n_rows + CB_LTILE - 1) / CB_LTILE;
+#pragma unroll
+            for (int sub = 0; sub < SEL_SUB; sub++) {
+                const i64 lt = (i64)tile * SEL_SUB + sub;
+                if (lt < n_ltiles) p.sel_off[(size_t)lt * SEL_NW + wid] = (u32)cnt[sub];
+            }
         }
     }
 }
@@ -679,16 +695,19 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_sel
     CB_SELECT_PROLOGUE()
     // where a warp's kept rows go: scanned pass-1 counts, or the row itself when nothing is filtered.  The two loads are
     // issued one tile ahead so their latency (longer than a tile's share of HBM time) overlaps the previous tile.
-    auto warp_base = [&](int tile) -> i64 {
-        if (!p.sel_off) return (i64)tile * CB_TILE + (i64)wid * SEL_RPW;
+    // (the two halves stay separate registers until the tile is processed: adding them at load time would wait for them)
+    u32 nx_chunk = 0, nx_off = 0;
+    auto load_base = [&](int tile) {
         const size_t e = (size_t)tile * SEL_NW + wid;
-        return (i64)p.sel_chunk[e / CB_SCAN_CHUNK] + (i64)p.sel_off[e];
+        nx_chunk = p.sel_chunk[e / CB_SCAN_CHUNK];
+        nx_off = p.sel_off[e];
     };
-    i64 next_base = my_tiles > 0 ? warp_base(first) : 0;
+    const bool filtered = p.sel_off != nullptr;
+    if (filtered && my_tiles > 0) load_base(first);
     for (int k = 0; k < my_tiles; k++) {
         const int s = k % CB_STAGES;
-        i64 wbase = next_base;
-        if (k + 1 < my_tiles) next_base = warp_base(first + (k + 1) * step);
+        const u32 cur_chunk = nx_chunk, cur_off = nx_off;
+        if (filtered && k + 1 < my_tiles) load_base(first + (k + 1) * step);
         mbar_wait(&full[s], (u32)((k / CB_STAGES) & 1));
         Tile t;
         tile_view(stages + (size_t)s * SB, t);
@@ -696,6 +715,7 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_sel
         const i64 row0 = (i64)tile * CB_TILE;
         const i64 rem = p.n_rows - row0;
         const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
+        i64 wbase = filtered ? (i64)cur_chunk + (i64)cur_off : row0 + (i64)wid * SEL_RPW;
 #if CB_NOUT <= 4
 #pragma unroll
 #else

@@ -1068,13 +1068,17 @@ struct SelectNode : FusedBase {
         for (auto& e : predicates) collect_bound(e, pred_cols, seen);
         for (size_t i = 0; i < pred_cols.size(); i++) pred_slot_of[pred_cols[i]] = (int)i;
     }
-    static int stages_for(const PipelineSpec& s) {
+    static int stage_bytes_for(const PipelineSpec& s) {
         int sb = 0;
         for (auto& c : s.cols) {
             int w = phys_bytes(c.phys);
             sb += ((w == 0 ? s.tile / 8 : s.tile * w) + 127) / 128 * 128;
             if (c.has_validity) sb += (s.tile / 8 + 127) / 128 * 128;
         }
+        return sb;
+    }
+    static int stages_for(const PipelineSpec& s) {
+        const int sb = stage_bytes_for(s);
         return (int)std::max<size_t>(2, std::min<size_t>(16, (SMEM_BUDGET - 1024) / (size_t)std::max(sb, 1)));
     }
     PipelineSpec make_spec(const Batch* b) const {
@@ -1095,7 +1099,11 @@ struct SelectNode : FusedBase {
         s.predicates = to_slots(predicates, pred_slot_of);
         s.sink = SinkKind::Count;
         s.threads = 256;
-        s.tile = 1024;
+        s.ltile = 1024;
+        for (int tile : {4096, 2048, 1024}) { // the widest stage that still leaves a 3-deep ring (wide predicate columns: decimals)
+            s.tile = tile;
+            if (stage_bytes_for(s) * 3 + 1024 <= (int)SMEM_BUDGET) break;
+        }
         s.stages = stages_for(s);
         return s;
     }
@@ -1156,7 +1164,7 @@ struct SelectNode : FusedBase {
             if (!sel_chunk || sel_chunk->bytes < (n_chunks + 1) * 4) sel_chunk = std::make_shared<DeviceBuf>((n_chunks + 1) * 4 + n_chunks * 2);
             if (!counters) counters = std::make_shared<DeviceBuf>(64);
             cp.sel_off = (cb::u32*)sel_off->ptr;
-            launch(cmod->kernel(cg.entry), dim3(grid), dim3(cg.threads + 32), cg.dyn_smem(0), &cp);
+            launch(cmod->kernel(cg.entry), dim3(std::min(ctx->num_sms, cp.n_tiles)), dim3(cg.threads + 32), cg.dyn_smem(0), &cp);
             launch_scan_u32((unsigned*)sel_off->ptr, (long long)m, CB_SCAN_CHUNK, (unsigned*)sel_chunk->ptr, (long long*)counters->ptr, st);
             ctx->kernel_launches += 2;
             p.sel_off = (cb::u32*)sel_off->ptr;
