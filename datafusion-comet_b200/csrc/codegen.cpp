@@ -587,7 +587,7 @@ struct SlotPlan {
 };
 
 struct AggLayout { // where each aggregate finds its totals at finalize time
-    int w_sum = -1, w_cnt = -1, w_bits = -1, w_bad = -1, w_minmax = -1;
+    int w_sum = -1, w_cnt = -1, w_bits = -1, w_bad = -1, w_minmax = -1, w_abs = -1;
     bool is_f64_sum = false;
 };
 
@@ -846,6 +846,18 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                         bool first = slots.dedup.count(std::to_string((int)W_DD_HI) + "|dd|" + dv + "|" + condkey) == 0;
                         L.w_sum = slots.add(W_DD_HI, "dd|" + dv + "|" + condkey, 2);
                         if (first) em.body << "    if (" << use << ") acc.add_f64(g, " << L.w_sum << ", " << dv << ");\n";
+                    } else if (a.eval_mode != EvalMode::Legacy) {
+                        // SumInt ANSI / TRY (sum_int.rs:176-390): the reference adds row by row with add_checked, so whether it
+                        // overflows depends on the row order.  The exact 128-bit sum and the exact sum of magnitudes decide it for
+                        // EVERY order: sum|v| <= i64::MAX => no prefix of any order can overflow; total out of range => every
+                        // order overflows (the last prefix is the total); anything else is order-dependent (finalize raises it).
+                        std::string iv = "(cb::i64)" + v.v;
+                        bool first = slots.dedup.count(std::to_string((int)W_SUM128) + "|csum|" + v.v + "|" + condkey) == 0;
+                        L.w_sum = slots.add(W_SUM128, "csum|" + v.v + "|" + condkey);
+                        L.w_abs = slots.add(W_SUM128, "cabs|" + v.v + "|" + condkey);
+                        if (first)
+                            em.body << "    if (" << use << ") { acc.add_i64_wide(g, " << L.w_sum << ", " << iv << "); cb::i128 m_ = cb::i128_from_i64(" << iv
+                                    << "); acc.add_i128(g, " << L.w_abs << ", m_.hi < 0 ? cb::i128_neg(m_) : m_); }\n";
                     } else { // SumInt Legacy: wrapping i64 (sum_int.rs:432)
                         bool first = slots.dedup.count(std::to_string((int)W_WRAP64) + "|isum|" + v.v + "|" + condkey) == 0;
                         L.w_sum = slots.add(W_WRAP64, "isum|" + v.v + "|" + condkey);
@@ -888,6 +900,21 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                         em.body << "    if (!" << e.v << " && " << snull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
                         em.body << "    else if (!" << e.v << ") { acc.add_i128(g, " << L.w_sum << ", " << Emitter::W(s) << "); acc.add_i64_wrap(g, " << L.w_cnt
                                 << ", 1); }\n";
+                    } else if (a.datatype.is_integer() && a.eval_mode != EvalMode::Legacy) { // sum_int.rs:236-243 (ANSI), :331-389 (TRY)
+                        Val s = col(0);
+                        std::string snull = s.n.empty() ? "false" : s.n;
+                        L.w_sum = slots.add(W_SUM128, tag + "sum");
+                        L.w_abs = slots.add(W_SUM128, tag + "abs");
+                        L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
+                        std::string add = "{ acc.add_i64_wide(g, " + std::to_string(L.w_sum) + ", " + s.v + "); cb::i128 m_ = cb::i128_from_i64(" + s.v +
+                                          "); acc.add_i128(g, " + std::to_string(L.w_abs) + ", m_.hi < 0 ? cb::i128_neg(m_) : m_); acc.add_i64_wrap(g, " +
+                                          std::to_string(L.w_cnt) + ", 1); }";
+                        if (a.eval_mode == EvalMode::Try) { // state (sum, has_all_nulls): overflowed = !has_all_nulls && sum IS NULL
+                            Val e = col(1);
+                            L.w_bad = slots.add(W_WRAP64, tag + "bad");
+                            em.body << "    if (!" << e.v << " && " << snull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
+                            em.body << "    else if (!" << e.v << ") " << add << "\n";
+                        } else em.body << "    if (!" << snull << ") " << add << "\n";
                     } else if (a.datatype.is_integer()) { // sum_int.rs:497-528
                         Val s = col(0);
                         L.w_sum = slots.add(W_WRAP64, tag + "sum");
@@ -968,7 +995,7 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
         for (size_t ai = 0; ai < spec.aggs.size(); ai++) {
             const AggExpr& a = spec.aggs[ai];
             const AggLayout& L = layout[ai];
-            bool partial = spec.mode == AggMode::Partial;
+            bool partial = spec.mode != AggMode::Final; // Partial and PartialMerge emit state columns
             std::string A = "a" + std::to_string(ai);
             fin << "    { // aggregate " << ai << "\n";
             switch (a.kind) {
@@ -995,6 +1022,26 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
                         int c0 = add_out(a.datatype, true);
                         fin << "      bool ok = !ovf && n > 0;\n";
                         fin << "      cb::fin_store_i128(fp, " << c0 << ", g, ok ? s : cb::mk128(0, 0), ok);\n";
+                    }
+                } else if (a.datatype.is_integer() && a.eval_mode != EvalMode::Legacy) {
+                    fin << "      cb::i128 s = " << T128(L.w_sum) << ", ab = " << T128(L.w_abs) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
+                    fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
+                    fin << "      bool fits = s.hi == ((cb::i64)s.lo >> 63), absfits = ab.hi == 0 && (cb::i64)ab.lo >= 0;\n";
+                    fin << "      int cert = absfits ? 0 : !fits ? 1 : 2; // 0 no order overflows, 1 every order overflows, 2 order-dependent\n";
+                    fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
+                    fin << "      bool ovf = bad || (n > 0 && cert != 0);\n";
+                    if (a.eval_mode == EvalMode::Ansi) {
+                        fin << "      if (ovf) cb::set_err_raw(fp.err, 1);\n";
+                        int c0 = add_out(mk_type(TypeId::Int64), true);
+                        fin << "      cb::fin_store_i64(fp, " << c0 << ", g, (n > 0 && !ovf) ? (cb::i64)s.lo : 0, n > 0 && !ovf);\n";
+                    } else if (partial) { // TRY state(): sum = Some(0) while all-null, None after overflow; has_all_nulls (sum_int.rs:322-329)
+                        int c0 = add_out(mk_type(TypeId::Int64), true), c1 = add_out(mk_type(TypeId::Bool), false);
+                        fin << "      cb::fin_store_i64(fp, " << c0 << ", g, (n > 0 && !ovf) ? (cb::i64)s.lo : 0, !ovf);\n";
+                        fin << "      cb::fin_store_u8(fp, " << c1 << ", g, (n == 0 && !bad) ? 1 : 0, true);\n";
+                    } else { // TRY evaluate(): NULL when all inputs were NULL or the sum overflowed (sum_int.rs:310-316)
+                        int c0 = add_out(mk_type(TypeId::Int64), true);
+                        fin << "      bool ok = n > 0 && !ovf;\n";
+                        fin << "      cb::fin_store_i64(fp, " << c0 << ", g, ok ? (cb::i64)s.lo : 0, ok);\n";
                     }
                 } else if (a.datatype.is_integer()) {
                     int c0 = add_out(mk_type(TypeId::Int64), true);

@@ -75,7 +75,8 @@ void ExecContext::check_device_errors() {
     if (e & (1 << ERR_I128_OVERFLOW))
         throw ExecError(11, "", "Arrow error: Arithmetic overflow: Overflow happened on decimal arithmetic"); // arrow-arith checked ops
     if (e & (1 << ERR_ORDER_DEPENDENT))
-        throw ExecError(12, "", "decimal SUM/AVG may overflow depending on row order; the row-ordered fallback is not built yet");
+        throw ExecError(12, "", "SUM/AVG overflow here depends on the row order (some orderings of these rows overflow, others do not); "
+                                "the reference adds in row order -- the row-ordered fallback is not built yet, so the plan is refused rather than guessed");
     throw ExecError(13, "", "device error flags " + std::to_string(e));
 }
 

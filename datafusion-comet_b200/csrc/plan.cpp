@@ -445,8 +445,6 @@ static void resolve_agg(AggExpr& a, const std::vector<DType>& in, AggMode mode) 
     case AggKind::Sum:
         if (!(dt.is_decimal() || dt.is_integer() || dt.id == TypeId::Float64 || dt.id == TypeId::Float32))
             throw Unsupported("SUM over " + dt.str());
-        if (dt.is_integer() && a.eval_mode != EvalMode::Legacy)
-            throw Unsupported("SUM(int) in ANSI/TRY mode needs row-ordered overflow detection (sum_int.rs:107-390)");
         break;
     case AggKind::Avg:
         if (dt.is_decimal() && !a.sum_datatype.is_decimal()) throw PlanError("AVG(decimal) without a decimal sum type");
@@ -586,20 +584,23 @@ static OperatorP decode_operator(PbReader r) { // Operator operator.proto:32-86
                 else expr_modes.push_back(b.i64());
             } else b.skip();
         }
-        if (op->mode == AggMode::PartialMerge || std::find(expr_modes.begin(), expr_modes.end(), 2) != expr_modes.end())
-            throw Unsupported("PartialMerge aggregation (distinct rewrite, merge_as_partial.rs) is outside the GPU hot path");
+        // Operator-level PartialMerge (merge state columns, emit state columns) is the Final input path with the Partial
+        // output path.  Per-expression modes that DIFFER from the operator's (the distinct rewrite: MergeAsPartialUDF,
+        // merge_as_partial.rs:54-110) are not fused.
+        for (int64_t m : expr_modes)
+            if (m != (int64_t)op->mode) throw Unsupported("aggregate expressions whose mode differs from the operator's (distinct rewrite, merge_as_partial.rs) are outside the GPU hot path");
         const auto& cs = child_schema();
         for (auto& g : op->grouping) { resolve(*g, cs); op->schema.push_back(g->type); }
         for (auto& a : op->aggs) {
             resolve_agg(a, cs, op->mode);
-            if (op->mode == AggMode::Partial) for (auto& t : agg_state_types(a)) op->schema.push_back(t);
+            if (op->mode != AggMode::Final) for (auto& t : agg_state_types(a)) op->schema.push_back(t);
             else op->schema.push_back(agg_result_type(a));
         }
-        if (op->mode == AggMode::Final) {
+        if (op->mode != AggMode::Partial) {
             // DataFusion Final mode reads state columns positionally after the group columns
             size_t need = op->grouping.size();
             for (auto& a : op->aggs) need += agg_state_types(a).size();
-            if (cs.size() < need) throw PlanError("final aggregate: child has fewer columns than group + state columns");
+            if (cs.size() < need) throw PlanError("final / partial-merge aggregate: child has fewer columns than group + state columns");
             size_t at = op->grouping.size();
             for (auto& a : op->aggs)
                 for (auto& t : agg_state_types(a)) {

@@ -228,3 +228,32 @@ def test_nullable_inputs_q1(cb, oracle):
         q, r = divmod(s * 10**4, c)
         exp_avg = q + (1 if 2 * r >= c else 0)
         assert unscaled(g["col_6"]) == exp_avg
+
+
+@pytest.mark.parametrize("variant", ["dec", "f64"])
+def test_partial_merge_is_transparent(cb, variant):
+    """AggregateMode PartialMerge (operator.proto: merge state columns, emit state columns): Partial -> PartialMerge -> Final
+    over several partitions gives exactly what Partial -> Final gives."""
+    t = cb.tpch
+    P = cb.proto
+    n = 120_000
+    cols = t.gen_lineitem(n, seed=77)
+    parts = []
+    for lo, hi in [(0, 50_000), (50_000, 90_000), (90_000, n)]:
+        tbl = t.lineitem_table({k: v[lo:hi] for k, v in cols.items()}, variant)
+        parts.append(run(cb, t.q1_partial_plan(variant), [tbl.to_batches(max_chunksize=8192)]))
+    states = pa.concat_tables(parts)
+    direct = run(cb, t.q1_final_plan(variant), [states])
+    sc = P.scan(t.q1_state_fields(variant), source="shuffle")
+    merge_plan = P.hash_agg(sc, [P.bound(0, P.STRING), P.bound(1, P.STRING)], t.q1_aggs(variant, bound=False), P.PARTIAL_MERGE)
+    merged = run(cb, merge_plan, [pa.concat_tables(parts[:2])])            # two partitions pre-merged ...
+    assert merged.schema.types == parts[0].schema.types
+    via_merge = run(cb, t.q1_final_plan(variant), [pa.concat_tables([merged, parts[2]])])   # ... then finalised with the third
+    a, b = q1_groups(direct), q1_groups(via_merge)
+    assert a.keys() == b.keys()
+    for k in a:
+        for c in a[k]:
+            if variant == "f64" and isinstance(a[k][c], float):
+                assert math.isclose(a[k][c], b[k][c], rel_tol=1e-15), (k, c)    # double-double partial sums re-rounded once more
+            else:
+                assert a[k][c] == b[k][c], (k, c)
