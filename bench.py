@@ -47,52 +47,80 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic(rows, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE bulk launch of the fused kernel, from the committed `ncu --set full`
+    capture of this same workload (profiles/r1_traffic.json, written by tools/summarize_ncu.py); None when the capture was taken
+    at another size / variant."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["cb_pipeline_agg"]
+        return int(t["dram_bytes"]) if int(t["rows"]) == int(rows) and t["variant"] == variant else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started BEFORE the warm-up
+    (nvidia-smi's own start-up takes a second and its NVML initialisation can stall CUDA calls of other processes); only
+    samples whose timestamp falls inside [mark_begin, mark_end] are reported."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         self.path = tempfile.mktemp(prefix="cb200_clocks_", suffix=".csv")
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
+        time.sleep(0.05)  # let the sample that covers the end of the region land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[0]))
-                    mx.append(float(f[1]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= (self.t1 or r[0]) + 0.02]
+        if not inside and rows and self.t0 is not None:  # region shorter than the sampling period: the sample nearest to it
+            inside = [min(rows, key=lambda r: abs(r[0] - self.t0))]
+        if inside:
+            reasons = set()
+            for r in inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside), "reasons": sorted(reasons), "samples": len(inside)}
         return out
 
 
@@ -224,7 +252,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", default="dec", choices=["dec", "f64"])
@@ -286,12 +314,13 @@ def main():
         return res, st, st2
 
     # ---- device-resident leg -----------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     pipe_ms, pipe_launches, launches = 0.0, 0, 0
     res = None
@@ -302,6 +331,7 @@ def main():
         launches += st["kernel_launches"] + (st2["kernel_launches"] if st2 else 0)
     barrier()
     elapsed = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed], device=device, dtype=torch.float64)
@@ -438,7 +468,7 @@ def main():
                        "rows_per_gpu": n, "variant": variant, "parallelism": f"round-robin partitions x{world}, partial state gathered to rank 0",
                        "l2": f"inputs ({BYTES_PER_ROW[variant] * n / 1e9:.1f} GB per GPU) exceed L2; no flush needed",
                        "checked_against_torch_int64": checked},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(n, variant),
                          "kernel": "cb_pipeline_agg (fused scan+filter+project+partial aggregate)", "ms_per_launch": ms_per_launch,
                          "algorithmic_bytes_per_row": BYTES_PER_ROW[variant], "peak_source": peak_src},
             "gpu_launches": launches, "clocks": clocks,

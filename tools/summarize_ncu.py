@@ -55,6 +55,10 @@ else:
                 v = float(r[h.index(name)].replace(',', '')); u = units[h.index(name)]
                 return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}.get(u, 1)
             rd, wr = by('dram__bytes_read.sum'), by('dram__bytes_write.sum')
+            if len(sys.argv) > 3:  # also record it for bench.py's roofline.traffic:  full <rep> <json-out> <rows> <variant>
+                import json
+                json.dump({"cb_pipeline_agg": {"dram_bytes": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr), "rows": int(sys.argv[4]), "variant": sys.argv[5],
+                                               "duration_ms_under_ncu": t_s * 1e3, "source": path}}, open(sys.argv[3], "w"), indent=1)
             print(f"  => dram traffic {rd + wr:.0f} B per launch ({(rd + wr) / 1e9:.3f} GB; read {rd / 1e9:.3f} + write {wr / 1e9:.3f}), {(rd + wr) / t_s / 1e9:.1f} GB/s under the profiler")
         except Exception as e:
             print("  (no dram summary:", e, ")")
