@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=1 << 30)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 22)
-    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 24, help="rows per device batch of the Parquet e2e leg (upload of batch k+1 overlaps decode+aggregate of batch k)")
+    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 26, help="rows per device batch of the Parquet e2e leg (upload of batch k+1 overlaps decode+aggregate of batch k)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-input", default="parquet", choices=["parquet", "arrow", "both"])
     ap.add_argument("--parquet-files", type=int, default=16)
@@ -319,6 +319,9 @@ def main():
         sampler.start()
     for _ in range(args.warmup):
         step_resident()
+    import gc
+    gc.collect()
+    gc.disable()  # a collector pause in the middle of a 10 ms step is measurement noise, not engine time
     barrier()
     sampler.mark_begin()
     t0 = time.perf_counter()
@@ -332,6 +335,7 @@ def main():
     barrier()
     elapsed = time.perf_counter() - t0
     sampler.mark_end()
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed], device=device, dtype=torch.float64)

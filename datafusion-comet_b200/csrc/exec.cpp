@@ -528,11 +528,15 @@ struct NativeScanSource : ExecNode {
     };
     Slot slots[2];
     cudaStream_t copy_stream = nullptr;
+    // Decode kernels run on their own stream, not the plan's: the consumer synchronises the plan stream after every
+    // batch, and the prefetched batch's decode (which waits for its upload) must not be inside that wait.
+    cudaStream_t decode_stream = nullptr;
     int* h_flags = nullptr;                 // pinned: per-slot decode error flags
 
     ~NativeScanSource() override {
-        pending.reset();
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (decode_stream) cudaStreamSynchronize(decode_stream);
+        pending.reset();
         for (auto& f : open_files) if (f.fh) fclose(f.fh);
         for (auto& sl : slots) {
             if (sl.staging) cudaFreeHost(sl.staging);
@@ -542,6 +546,7 @@ struct NativeScanSource : ExecNode {
         }
         if (h_flags) cudaFreeHost(h_flags);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (decode_stream) cudaStreamDestroy(decode_stream);
     }
 
     void open_all() { // footers are tiny: parse them all up front (the reference's ParquetSource does the same per file group)
@@ -563,6 +568,7 @@ struct NativeScanSource : ExecNode {
         }
         dicts.assign(fields.size(), nullptr);
         cuda_check(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "copy stream");
+        cuda_check(cudaStreamCreateWithFlags(&decode_stream, cudaStreamNonBlocking), "decode stream");
         cuda_check(cudaMallocHost((void**)&h_flags, 2 * sizeof(int)), "cudaMallocHost flags");
         for (auto& sl : slots) {
             cuda_check(cudaEventCreateWithFlags(&sl.decoded, cudaEventDisableTiming), "event");
@@ -600,6 +606,15 @@ struct NativeScanSource : ExecNode {
     std::unique_ptr<Prepared> pending;
     int64_t n_issued = 0;
     double t_alloc = 0, t_pages = 0, t_h2d = 0, t_launch = 0; // CB200_TRACE: host milliseconds per issue()
+
+    // buffers come from the plan stream's pool order (DeviceBuf); the decode stream may touch them after this point
+    void allocations_visible(Arena& arena) {
+        cudaEvent_t ev;
+        cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+        arena.events.push_back(ev);
+        cuda_check(cudaEventRecord(ev, ctx->stream), "event record");
+        cuda_check(cudaStreamWaitEvent(decode_stream, ev, 0), "stream wait");
+    }
 
     std::unique_ptr<Prepared> issue() {
         if (next_unit >= all_units.size()) return nullptr;
@@ -663,12 +678,13 @@ struct NativeScanSource : ExecNode {
         if (sl.used) cuda_check(cudaEventSynchronize(sl.decoded), "page table reuse"); // two batches back: long done
         sl.meta_reset();
         pr->derr = std::make_shared<DeviceBuf>(64);
-        cuda_check(cudaMemsetAsync(pr->derr->ptr, 0, 64, ctx->stream), "memset parquet err");
+        allocations_visible(pr->arena);
+        cuda_check(cudaMemsetAsync(pr->derr->ptr, 0, 64, decode_stream), "memset parquet err");
         t_alloc = t_pages = t_h2d = t_launch = 0;
         if (trace_on()) {
             for (auto& e : pr->tr) cuda_check(cudaEventCreate(&e), "event");
             cuda_check(cudaEventRecord(pr->tr[0], copy_stream), "event record");
-            cuda_check(cudaEventRecord(pr->tr[2], ctx->stream), "event record");
+            cuda_check(cudaEventRecord(pr->tr[2], decode_stream), "event record");
         }
         double tt = now_ms();
         if (!sl.chunk || sl.chunk->bytes < dev_total + 64) {
@@ -706,19 +722,19 @@ struct NativeScanSource : ExecNode {
                 loc[c][u].dev = (unsigned char*)sl.chunk->ptr + r.dev_off + off;
             }
         cuda_check(cudaEventRecord(sl.uploaded, copy_stream), "event record");
-        cuda_check(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0), "stream wait"); // decode kernels start when the batch has landed
+        cuda_check(cudaStreamWaitEvent(decode_stream, sl.uploaded, 0), "stream wait"); // decode kernels start when the batch has landed
         t_h2d += now_ms() - tt;
         for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, loc[c], out.cols[c], pr->arena, (int*)pr->derr->ptr, sl);
         if (trace_on()) fprintf(stderr, "[cb200 trace]   issue breakdown: alloc %.3f  page tables %.3f  h2d enqueue (%zu ranges) %.3f  launches %.3f ms\n", t_alloc, t_pages, ranges.size(), t_h2d, t_launch);
-        cuda_check(cudaEventRecord(sl.decoded, ctx->stream), "event record");
+        cuda_check(cudaEventRecord(sl.decoded, decode_stream), "event record");
         if (trace_on()) {
             cuda_check(cudaEventRecord(pr->tr[1], copy_stream), "event record");
-            cuda_check(cudaEventRecord(pr->tr[3], ctx->stream), "event record");
+            cuda_check(cudaEventRecord(pr->tr[3], decode_stream), "event record");
         }
         sl.used = true;
-        cuda_check(cudaMemcpyAsync(&h_flags[pr->slot], pr->derr->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream), "parquet err");
+        cuda_check(cudaMemcpyAsync(&h_flags[pr->slot], pr->derr->ptr, 4, cudaMemcpyDeviceToHost, decode_stream), "parquet err");
         cuda_check(cudaEventCreateWithFlags(&pr->done, cudaEventDisableTiming), "event");
-        cuda_check(cudaEventRecord(pr->done, ctx->stream), "event record");
+        cuda_check(cudaEventRecord(pr->done, decode_stream), "event record");
         return pr;
     }
 
@@ -750,7 +766,6 @@ struct NativeScanSource : ExecNode {
     void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<ChunkLoc>& loc, Column& col, Arena& arena, int* derr, Slot& sl) {
         const DType& t = fields[c].type;
         const pq::SchemaElement& se = open_files[units[0].file].meta.leaf(open_files[units[0].file].leaf_of[c]);
-        cudaStream_t st = ctx->stream;
         // pick the device representation
         int conv, out_w;
         col.type = t;
@@ -919,63 +934,60 @@ struct NativeScanSource : ExecNode {
         const size_t n_data = dpages.size();
         dpages.insert(dpages.end(), dict_pages.begin(), dict_pages.end()); // one upload for every descriptor of this column
         const int n_all = (int)dpages.size();
-        if (any_compressed) {
-            auto dunc = std::make_shared<DeviceBuf>(unc_bytes + 64);
-            arena.dev.push_back(dunc);
-            for (auto& d : dpages) if (d.comp) d.body = (unsigned char*)dunc->ptr + (size_t)(uintptr_t)d.body;
+        // definition levels: the statistics' null_count == 0 selects the verify-only fast path; otherwise values are decoded
+        // densely and scattered to their rows
+        const bool null_aware = optional && nulls_possible;
+        if (null_aware && total >= (int64_t)1 << 32) throw Unsupported("parquet: NULL-aware decode of more than 2^32 rows per batch (lower spark.comet.b200.chunkRows)");
+        // ---- every device buffer of this column first (plan-stream pool order), then one hand-over to the decode stream ----
+        DeviceBufP dunc, ddict, dvalid, didx, druns, dcounts, runs, counts, dense = col.data;
+        auto keep = [&](size_t bytes) { auto b = std::make_shared<DeviceBuf>(bytes); arena.dev.push_back(b); return b; };
+        if (any_compressed) dunc = keep(unc_bytes + 64);
+        DeviceBufP dpd = keep(dpages.size() * sizeof(PqPage));
+        if (dict_elems > 0) ddict = keep((size_t)dict_elems * out_w + 16);
+        if (null_aware) {
+            dense = keep((size_t)std::max<int64_t>(total, 1) * out_w);
+            dvalid = keep((size_t)total + 64);
+            didx = keep((size_t)total * 4 + 64);
+            druns = keep((size_t)std::max<int64_t>(def_run_base, 1) * sizeof(PqRun));
+            dcounts = keep(n_data * 4 + 16);
+            col.validity = std::make_shared<DeviceBuf>((size_t)(total + 31) / 32 * 4 + 16);
+            col.null_count = -1;
         }
-        auto dpd = std::make_shared<DeviceBuf>(dpages.size() * sizeof(PqPage));
-        arena.dev.push_back(dpd);
+        if (run_base > 0) {
+            runs = keep((size_t)run_base * sizeof(PqRun));
+            counts = keep(n_data * 4 + 16);
+        }
+        allocations_visible(arena);
+        const cudaStream_t ds = decode_stream;
+        if (any_compressed) for (auto& d : dpages) if (d.comp) d.body = (unsigned char*)dunc->ptr + (size_t)(uintptr_t)d.body;
         void* pin_pages = sl.meta_alloc(dpages.size() * sizeof(PqPage));
         memcpy(pin_pages, dpages.data(), dpages.size() * sizeof(PqPage));
-        cuda_check(cudaMemcpyAsync(dpd->ptr, pin_pages, dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, st), "H2D page table");
-        DeviceBufP ddict;
-        if (dict_elems > 0) {
-            ddict = std::make_shared<DeviceBuf>((size_t)dict_elems * out_w + 16);
-            arena.dev.push_back(ddict);
-            if (!remap_all.empty()) {
-                void* pin_remap = sl.meta_alloc(remap_all.size() * 4);
-                memcpy(pin_remap, remap_all.data(), remap_all.size() * 4);
-                cuda_check(cudaMemcpyAsync(ddict->ptr, pin_remap, remap_all.size() * 4, cudaMemcpyHostToDevice, st), "H2D dictionary remap");
-            }
+        cuda_check(cudaMemcpyAsync(dpd->ptr, pin_pages, dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, ds), "H2D page table");
+        if (ddict && !remap_all.empty()) {
+            void* pin_remap = sl.meta_alloc(remap_all.size() * 4);
+            memcpy(pin_remap, remap_all.data(), remap_all.size() * 4);
+            cuda_check(cudaMemcpyAsync(ddict->ptr, pin_remap, remap_all.size() * 4, cudaMemcpyHostToDevice, ds), "H2D dictionary remap");
         }
         PqPage* all_pages = (PqPage*)dpd->ptr;
         PqPage* data_pages = all_pages;
         const PqPage* dpages_dev = data_pages + n_data;
-        if (any_compressed) { launch_pq_snappy(all_pages, n_all, derr, st); ctx->kernel_launches++; }
-        launch_pq_resolve(all_pages, n_all, st);
+        if (any_compressed) { launch_pq_snappy(all_pages, n_all, derr, ds); ctx->kernel_launches++; }
+        launch_pq_resolve(all_pages, n_all, ds);
         ctx->kernel_launches++;
-        if (!dict_pages.empty()) { launch_pq_plain(dpages_dev, (int)dict_pages.size(), conv, se.type_length, ddict->ptr, st); ctx->kernel_launches++; }
-        // definition levels: the statistics' null_count == 0 selects the verify-only fast path; otherwise values are decoded
-        // densely and scattered to their rows
-        const bool null_aware = optional && nulls_possible;
-        DeviceBufP dense = col.data, dvalid, didx;
-        if (optional && !null_aware) { launch_pq_check_def_levels(data_pages, (int)n_data, derr, st); ctx->kernel_launches++; }
+        if (!dict_pages.empty()) { launch_pq_plain(dpages_dev, (int)dict_pages.size(), conv, se.type_length, ddict->ptr, ds); ctx->kernel_launches++; }
+        if (optional && !null_aware) { launch_pq_check_def_levels(data_pages, (int)n_data, derr, ds); ctx->kernel_launches++; }
         if (null_aware) {
-            if (total >= (int64_t)1 << 32) throw Unsupported("parquet: NULL-aware decode of more than 2^32 rows per batch (lower spark.comet.b200.chunkRows)");
-            dense = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(total, 1) * out_w);
-            dvalid = std::make_shared<DeviceBuf>((size_t)total + 64);
-            didx = std::make_shared<DeviceBuf>((size_t)total * 4 + 64);
-            auto druns = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(def_run_base, 1) * sizeof(PqRun));
-            auto dcounts = std::make_shared<DeviceBuf>(n_data * 4 + 16);
-            for (auto& b : {dense, dvalid, didx, druns, dcounts}) arena.dev.push_back(b);
-            launch_pq_def_levels(data_pages, (int)n_data, (PqRun*)druns->ptr, (int*)dcounts->ptr, (unsigned char*)dvalid->ptr, (unsigned*)didx->ptr, derr, st);
+            launch_pq_def_levels(data_pages, (int)n_data, (PqRun*)druns->ptr, (int*)dcounts->ptr, (unsigned char*)dvalid->ptr, (unsigned*)didx->ptr, derr, ds);
             ctx->kernel_launches += 3;
         }
-        if (conv >= 0) { launch_pq_plain(data_pages, (int)n_data, conv, se.type_length, dense->ptr, st); ctx->kernel_launches++; }
+        if (conv >= 0) { launch_pq_plain(data_pages, (int)n_data, conv, se.type_length, dense->ptr, ds); ctx->kernel_launches++; }
         if (run_base > 0) {
-            auto runs = std::make_shared<DeviceBuf>((size_t)run_base * sizeof(PqRun));
-            auto counts = std::make_shared<DeviceBuf>(n_data * 4 + 16);
-            arena.dev.push_back(runs);
-            arena.dev.push_back(counts);
-            launch_pq_rle_scan(data_pages, (int)n_data, (PqRun*)runs->ptr, (int*)counts->ptr, derr, st);
-            launch_pq_rle_decode(data_pages, (int)n_data, (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, dense->ptr, derr, st);
+            launch_pq_rle_scan(data_pages, (int)n_data, (PqRun*)runs->ptr, (int*)counts->ptr, derr, ds);
+            launch_pq_rle_decode(data_pages, (int)n_data, (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, dense->ptr, derr, ds);
             ctx->kernel_launches += 2;
         }
         if (null_aware) {
-            col.validity = std::make_shared<DeviceBuf>((size_t)(total + 31) / 32 * 4 + 16);
-            col.null_count = -1;
-            launch_pq_scatter((const unsigned char*)dvalid->ptr, (const unsigned*)didx->ptr, dense->ptr, col.data->ptr, (unsigned*)col.validity->ptr, total, out_w, st);
+            launch_pq_scatter((const unsigned char*)dvalid->ptr, (const unsigned*)didx->ptr, dense->ptr, col.data->ptr, (unsigned*)col.validity->ptr, total, out_w, ds);
             ctx->kernel_launches++;
         }
         t_launch += now_ms() - tt;
