@@ -2104,7 +2104,19 @@ static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* i
             n->aggs.push_back(c);
         }
         n->assign_slots(roots);
-        if (n->used_cols.empty()) throw Unsupported("aggregate that reads no input column (COUNT(*) only) -- pending");
+        if (n->used_cols.empty()) {
+            // COUNT(*) / COUNT(1) alone reads no column: stage the narrowest fixed-width one just to drive the row loop
+            int best = -1, best_w = 1 << 30;
+            for (size_t c = 0; c < src->schema.size(); c++) {
+                const DType& t = src->schema[c];
+                if (t.is_string()) continue;
+                int w = std::max(1, phys_bytes(phys_of(t)));
+                if (w < best_w) { best = (int)c; best_w = w; }
+            }
+            if (best < 0) throw Unsupported("COUNT(*) over a child with only string columns");
+            n->used_cols.push_back(best);
+            n->slot_of[best] = 0;
+        }
         return n;
     }
     auto n = std::make_shared<SelectNode>();

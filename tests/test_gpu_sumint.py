@@ -122,3 +122,19 @@ def test_small_int_inputs_widen(cb, oracle):
     got = {r["col_0"]: r["col_1"] for r in res.to_pylist()}
     for i, name in enumerate(["x", "y", "z"]):
         assert got[name] == int(vals[keys == i].astype(np.int64).sum())
+
+
+def test_count_star_alone(cb):
+    """COUNT(*) reads no column; with and without a filter, ungrouped and through Partial -> Final."""
+    P = cb.proto
+    n = 70_001
+    rng = np.random.default_rng(1)
+    d = rng.integers(8000, 10000, n).astype(np.int32)
+    tbl = pa.table({"s": pa.array(["x"] * n), "k": pa.array(rng.integers(0, 9, n)), "d": pa.array(d, type=pa.date32())})
+    sc = P.scan([P.STRING, P.INT64, P.DATE])
+    partial = P.hash_agg(sc, [], [P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    final = P.hash_agg(P.scan([P.INT64], source="shuffle"), [], [P.agg_count([P.unbound("c", P.INT32)])], P.FINAL)
+    st = run(cb, partial, [tbl.to_batches(max_chunksize=8192)], 30_000)
+    assert run(cb, final, [st]).column(0).to_pylist() == [n]
+    filtered = P.hash_agg(P.filter_(sc, P.lt(P.bound(2, P.DATE), P.literal(9000, P.DATE))), [], [P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    assert run(cb, filtered, [tbl.to_batches(max_chunksize=8192)]).column(0).to_pylist() == [int((d < 9000).sum())]
