@@ -90,10 +90,24 @@ void start(cb200_plan* p) {
     TraceSpan ts("plan.start");
     ExecContext& ctx = p->ctx;
     cuda_check(cudaSetDevice(ctx.device), "cudaSetDevice");
-    cudaDeviceProp prop;
-    cuda_check(cudaGetDeviceProperties(&prop, ctx.device), "cudaGetDeviceProperties");
-    if (prop.major < 10) throw ExecError(CB200_ERR_CUDA, "", "comet_b200 kernels are built for sm_100a; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
-    ctx.num_sms = prop.multiProcessorCount;
+    {
+        // cudaGetDeviceProperties costs 2-6 ms per call (it walks the whole property table, PCI topology included): two
+        // attributes, queried once per device, are all a plan needs
+        struct DevInfo { int major = 0, minor = 0, sms = 0; bool known = false; };
+        static DevInfo info[64];
+        static std::mutex info_mu;
+        std::lock_guard<std::mutex> lk(info_mu);
+        if (ctx.device < 0 || ctx.device >= 64) throw ExecError(CB200_ERR_CUDA, "", "device ordinal out of range");
+        DevInfo& di = info[ctx.device];
+        if (!di.known) {
+            cuda_check(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, ctx.device), "cudaDeviceGetAttribute");
+            cuda_check(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, ctx.device), "cudaDeviceGetAttribute");
+            cuda_check(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, ctx.device), "cudaDeviceGetAttribute");
+            di.known = true;
+        }
+        if (di.major < 10) throw ExecError(CB200_ERR_CUDA, "", "comet_b200 kernels are built for sm_100a; device is sm_" + std::to_string(di.major * 10 + di.minor));
+        ctx.num_sms = di.sms;
+    }
     {
         // per-plan CUDA resources come from a per-device free list: creating a stream, events and pinned /
         // device scratch costs ~2 ms per plan, which matters when a plan runs for 10 ms

@@ -3,6 +3,7 @@
 // Every emitted operation names the reference rule it implements; the arithmetic itself is the
 // hand-written device library device/cb_math.h (host-tested against the oracle).
 #include "codegen.h"
+#include <mutex>
 #include "ranges.h"
 
 #include <climits>
@@ -658,8 +659,61 @@ std::string to_slot(const Val& v, const std::string& dst) {
 
 } // namespace
 
-// =================================================================================================
+// ---- memo: the same plan shape is generated again for every batch / every short-lived plan handle ------------------
+namespace {
+void sig_expr(std::ostringstream& o, const Expr& e) {
+    uint64_t fb;
+    memcpy(&fb, &e.lit_f64, 8);
+    o << (int)e.kind << '|' << e.type.str() << '|' << e.index << '|' << e.lit_null << '|' << e.lit_i64 << '|' << fb << '|' << (uint64_t)e.lit_dec << ','
+      << (uint64_t)(e.lit_dec >> 64) << '|' << e.lit_str << '|' << (int)e.eval_mode << '|' << e.fail_on_error << '|' << e.negated << '|' << e.wide_decimal << '|'
+      << e.return_type.str() << '(';
+    for (auto& c : e.children) { sig_expr(o, *c); o << ','; }
+    o << ')';
+}
+std::string spec_signature(const PipelineSpec& s) {
+    std::ostringstream o;
+    o << (int)s.sink << ';' << (int)s.mode << ';' << s.ungrouped << ';' << s.hash << ';' << s.tile << ';' << s.stages << ';' << s.threads << ';' << s.ltile << ";C";
+    for (auto& c : s.cols) o << c.src_index << ':' << c.type.str() << ':' << (int)c.phys << ':' << c.has_validity << ':' << c.assume_bits << ',';
+    o << ";P";
+    for (auto& e : s.predicates) { sig_expr(o, *e); o << ';'; }
+    o << ";O";
+    for (auto& e : s.outputs) { sig_expr(o, *e); o << ';'; }
+    o << ";K";
+    for (size_t i = 0; i < s.keys.size(); i++) { sig_expr(o, *s.keys[i]); o << (i < s.key_nullable.size() && s.key_nullable[i]) << ';'; }
+    o << ";A";
+    for (auto& a : s.aggs) {
+        o << (int)a.kind << ':' << a.datatype.str() << ':' << a.sum_datatype.str() << ':' << (int)a.eval_mode << '[';
+        for (auto& c : a.children) { sig_expr(o, *c); o << ','; }
+        o << "]F";
+        if (a.filter) sig_expr(o, *a.filter);
+        o << ';';
+    }
+    o << ";S";
+    for (auto& v : s.state_slots) { for (int x : v) o << x << ','; o << ';'; }
+    return o.str();
+}
+std::mutex g_memo_mu;
+std::map<std::string, GeneratedKernel> g_memo;
+GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec);
+} // namespace
+
 GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
+    const std::string sig = spec_signature(spec);
+    {
+        std::lock_guard<std::mutex> lk(g_memo_mu);
+        auto it = g_memo.find(sig);
+        if (it != g_memo.end()) return it->second;
+    }
+    GeneratedKernel g = generate_pipeline_uncached(spec);
+    std::lock_guard<std::mutex> lk(g_memo_mu);
+    if (g_memo.size() > 4096) g_memo.clear(); // plan shapes are few; this only bounds a pathological caller
+    g_memo[sig] = g;
+    return g;
+}
+
+// =================================================================================================
+namespace {
+GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
     GeneratedKernel g;
     g.threads = spec.threads;
     g.tile = spec.tile;
@@ -1121,5 +1175,6 @@ GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
     g.key = k.str();
     return g;
 }
+} // namespace
 
 } // namespace cb200
