@@ -780,21 +780,57 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         std::string null_group_cond;
         std::ostringstream unpack; // hash: cb_unpack_key body (reverse of the packing)
         if (spec.hash) {
-            int total_bits = 0;
-            std::string packed = em.fresh("pk");
-            em.body << "    cb::u64 " << packed << " = 0;\n";
-            std::vector<std::string> unpack_steps;
+            // Key columns are packed, in order, into 64-bit words: [value bits][null bit if nullable]; a key never straddles
+            // words.  One word: the packed word IS the table key (single 128-bit probe).  More: see find_slot_multi.
+            struct KeyPlan { Val v; int bits; bool nullable; int word; };
+            std::vector<KeyPlan> kp;
+            int n_words_k = 1, used = 0;
             for (size_t k = 0; k < spec.keys.size(); k++) {
-                Val kv = em.emit(*spec.keys[k]);
+                KeyPlan q;
+                q.v = em.emit(*spec.keys[k]);
                 const DType& kt = spec.keys[k]->type;
-                int bits = key_bits(kt);
-                bool nullable = kv.nullable();
-                if (nullable && bits == 64 && spec.keys.size() == 1) { // no spare bit: NULL rows go to the reserved NULL-key slot
-                    null_group_cond = kv.n;
-                    nullable = false;
+                q.bits = key_bits(kt);
+                // The packing must not depend on whether THIS batch carries a validity buffer (a later batch may): every key
+                // reserves its null flag.  Exception: a single 64-bit key sends NULL rows to the reserved NULL-key group, which
+                // leaves the packing of non-NULL keys untouched.
+                q.nullable = true;
+                if (q.bits == 0) throw Unsupported("group key of type " + kt.str() + " cannot be packed into 64-bit hash key words");
+                if (q.bits == 64 && spec.keys.size() == 1) {
+                    null_group_cond = q.v.n;
+                    q.nullable = false;
                 }
-                if (bits == 0) throw Unsupported("group key of type " + kt.str() + " cannot be packed into the 64-bit hash key");
-                total_bits += bits + (nullable ? 1 : 0);
+                int need = q.bits + (q.nullable ? 1 : 0);
+                if (need > 64) { // a nullable 64-bit key among several: its null flag opens the next word
+                    if (used > 0) { n_words_k++; used = 0; }
+                    q.word = n_words_k - 1;
+                    used = 64;
+                    kp.push_back(q);
+                    continue;
+                }
+                if (used + need > 64) { n_words_k++; used = 0; }
+                q.word = n_words_k - 1;
+                used += need;
+                kp.push_back(q);
+            }
+            // nullable 64-bit keys in multi-key groups: value fills a word, the null flag travels in an extra flags word
+            std::vector<size_t> wide_nullable;
+            for (size_t k = 0; k < kp.size(); k++) if (kp[k].nullable && kp[k].bits == 64) wide_nullable.push_back(k);
+            int flags_word = -1;
+            if (!wide_nullable.empty()) flags_word = n_words_k++;
+            if (n_words_k > 4) throw Unsupported("group keys need more than 256 packed bits");
+            g.key_words = n_words_k;
+            std::vector<std::string> pk(n_words_k);
+            for (int w = 0; w < n_words_k; w++) { pk[w] = em.fresh("pk"); em.body << "    cb::u64 " << pk[w] << " = 0;\n"; }
+            std::vector<std::string> unpack_steps;
+            for (size_t k = 0; k < kp.size(); k++) {
+                const KeyPlan& q = kp[k];
+                const Val& kv = q.v;
+                const DType& kt = spec.keys[k]->type;
+                const int bits = q.bits;
+                const bool wide_null = q.nullable && bits == 64;
+                const bool inline_null = q.nullable && !wide_null;
+                const std::string& packed = pk[q.word];
+                const std::string isn = kv.n.empty() ? "false" : kv.n;
                 std::string raw;
                 if (kt.is_decimal()) {
                     if (kv.narrow) raw = "(cb::u64)" + kv.v;
@@ -805,18 +841,20 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                 } else if (kt.id == TypeId::Bool) raw = "(" + kv.v + " ? 1ull : 0ull)";
                 else raw = "(cb::u64)(cb::i64)" + kv.v;
                 std::string mask = bits == 64 ? "0xffffffffffffffffull" : u64lit((1ull << bits) - 1);
-                if (nullable) raw = "(" + kv.n + " ? 0ull : " + raw + ")";
+                if (q.nullable && !kv.n.empty()) raw = "(" + kv.n + " ? 0ull : " + raw + ")";
                 if (bits == 64) em.body << "    " << packed << " = " << raw << ";\n";
                 else em.body << "    " << packed << " = (" << packed << " << " << bits << ") | (" << raw << " & " << mask << ");\n";
-                if (nullable) em.body << "    " << packed << " = (" << packed << " << 1) | (" << kv.n << " ? 1ull : 0ull);\n";
-                // unpack (emitted in reverse order below)
+                if (inline_null) em.body << "    " << packed << " = (" << packed << " << 1) | (" << isn << " ? 1ull : 0ull);\n";
+                if (wide_null) em.body << "    " << pk[flags_word] << " = (" << pk[flags_word] << " << 1) | (" << isn << " ? 1ull : 0ull);\n";
+                // unpack (emitted in reverse order below): consumes the same bits from k<word>
                 std::ostringstream u;
-                std::string kc = std::to_string(k);
+                std::string kc = std::to_string(k), kwv = "k" + std::to_string(q.word);
                 u << "    {\n";
-                if (nullable) u << "      bool isnull = (key & 1ull) != 0; key >>= 1;\n";
+                if (inline_null) u << "      bool isnull = (" << kwv << " & 1ull) != 0; " << kwv << " >>= 1;\n";
+                else if (wide_null) u << "      bool isnull = (k" << flags_word << " & 1ull) != 0; k" << flags_word << " >>= 1;\n";
                 else u << "      bool isnull = null_group;\n";
-                if (bits == 64) u << "      cb::u64 raw = key; key = 0;\n";
-                else u << "      cb::u64 raw = key & " << mask << "; key >>= " << bits << ";\n";
+                if (bits == 64) u << "      cb::u64 raw = " << kwv << "; " << kwv << " = 0;\n";
+                else u << "      cb::u64 raw = " << kwv << " & " << mask << "; " << kwv << " >>= " << bits << ";\n";
                 if (kt.is_decimal()) u << "      cb::fin_store_i128(fp, " << kc << ", g, cb::i128_from_i64((cb::i64)raw), !isnull);\n";
                 else if (kt.id == TypeId::Bool) u << "      cb::fin_store_u8(fp, " << kc << ", g, (int)raw, !isnull);\n";
                 else if (bits == 64) u << "      cb::fin_store_i64(fp, " << kc << ", g, (cb::i64)raw, !isnull);\n";
@@ -828,9 +866,16 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                 u << "    }\n";
                 unpack_steps.push_back(u.str());
             }
-            if (total_bits > 64) throw Unsupported("group keys need " + std::to_string(total_bits) + " bits; multi-word hash keys are pending");
+            for (int w = 0; w < n_words_k; w++) unpack << "    cb::u64 k" << w << " = kw[" << w << "]; (void)k" << w << ";\n";
             for (auto it = unpack_steps.rbegin(); it != unpack_steps.rend(); ++it) unpack << *it;
-            gid = "acc.find_slot(" + packed + ")";
+            if (n_words_k == 1) gid = "acc.find_slot(" + pk[0] + ")";
+            else {
+                std::string arr = em.fresh("kw");
+                em.body << "    cb::u64 " << arr << "[" << n_words_k << "] = {";
+                for (int w = 0; w < n_words_k; w++) em.body << (w ? ", " : "") << pk[w];
+                em.body << "};\n";
+                gid = "acc.find_slot_multi(" + arr + ")";
+            }
             if (!null_group_cond.empty()) {
                 em.body << "    if (" << null_group_cond << ") atomicOr(p.hflags, 8);\n";
                 gid = "(" + null_group_cond + " ? p.max_groups + 1 : " + gid + ")";
@@ -1156,7 +1201,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
 
         std::ostringstream defs;
         defs << "#define CB_KERNEL_AGG 1\n#define CB_WORDS " << g.n_words << "\n#define CB_G1 " << (spec.ungrouped ? 1 : 0) << "\n#define CB_W_ROWS " << w_rows
-             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n";
+             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n#define CB_KEY_WORDS " << (spec.hash ? g.key_words : 1) << "\n";
         tu << header(spec, defs.str());
         tu << "constexpr __host__ __device__ int cb_word_kind(int w) { return ";
         for (size_t i = 0; i < slots.kinds.size(); i++) tu << "w == " << i << " ? " << slots.kinds[i] << " : ";
@@ -1164,7 +1209,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
         tu << "CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc) {\n    (void)grow;\n" << em.body.str() << "}\n";
         tu << "CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T) {\n" << fin.str() << "}\n";
-        if (spec.hash) tu << "CB_D void cb_unpack_key(const FinParams& fp, int g, u64 key, bool null_group) {\n" << unpack.str() << "}\n";
+        if (spec.hash) tu << "CB_D void cb_unpack_key(const FinParams& fp, int g, const u64* kw, bool null_group) {\n" << unpack.str() << "}\n";
         tu << "} // namespace cb\n";
         g.entry = "cb_pipeline_agg";
         g.finalize_entry = "cb_finalize";

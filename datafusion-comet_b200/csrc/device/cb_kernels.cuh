@@ -158,6 +158,9 @@ CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& a
 // Thread-private accumulator file.  Word (g, w) of thread t lives at acc[(g*CB_WORDS + w)*CB_THREADS + t]
 // (8-byte words interleaved across threads => every warp access is bank-conflict-free no matter
 // which group each lane updates).  For the ungrouped case the words are registers.
+#ifndef CB_KEY_WORDS
+#define CB_KEY_WORDS 1
+#endif
 #ifndef CB_HASH
 #define CB_HASH 0
 #endif
@@ -206,6 +209,61 @@ struct Acc {
         atomicOr(p->hflags, 2);
         return p->max_groups;
     }
+#if CB_KEY_WORDS > 1
+    // Keys wider than 64 bits: the slot holds a 64-bit TAG (a hash of all key words, never the empty pattern) and the
+    // group id; the key itself lives in hkey_of_gid[gid * CB_KEY_WORDS ..], written by the claimer before it publishes
+    // the id.  A tag match is confirmed against the stored words; a mismatch is a tag collision and probing goes on.
+    CB_D static u64 key_tag(const u64* kw) {
+        u64 h = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+        for (int i = 0; i < CB_KEY_WORDS; i++) {
+            u64 x = kw[i] + h;
+            x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+            h = (h << 5 | h >> 59) ^ x;
+        }
+        return h == CB_EMPTY_KEY ? 0ull : h;
+    }
+    CB_D bool same_key(int g, const u64* kw) const {
+        const u64* k = p->hkey_of_gid + (size_t)g * CB_KEY_WORDS;
+        bool eq = true;
+#pragma unroll
+        for (int i = 0; i < CB_KEY_WORDS; i++) eq = eq && __ldcg(k + i) == kw[i];
+        return eq;
+    }
+    CB_D int find_slot_multi(const u64* kw) const {
+        const u32 mask = p->hmask;
+        const u64 tag = key_tag(kw);
+        u32 s = (u32)(tag ^ (tag >> 32)) & mask;
+        for (u32 probe = 0; probe <= mask; probe++) {
+            ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2*>(p->hkeys) + s);
+            if (slot.x == CB_EMPTY_KEY) {
+                u64 prev = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)tag);
+                if (prev == CB_EMPTY_KEY) {
+                    int g = atomicAdd(&p->hflags[4], 1);
+                    if (g >= p->max_groups) { atomicOr(p->hflags, 2); g = p->max_groups; } // cannot happen: host sizes max_groups >= rows
+                    else {
+#pragma unroll
+                        for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)g * CB_KEY_WORDS + i] = kw[i];
+                    }
+                    __threadfence();
+                    *((volatile i32*)&p->hkeys[2 * (size_t)s + 1]) = g;
+                    return g;
+                }
+                slot.x = prev;
+                slot.y = ~0ull;
+            }
+            if (slot.x == tag) {
+                int g = (i32)(u32)slot.y;
+                if (g < 0) g = wait_gid(s);
+                __threadfence(); // the claimer's key words are visible once its id is
+                if (g >= p->max_groups || same_key(g, kw)) return g;
+            }
+            s = (s + 1u) & mask;
+        }
+        atomicOr(p->hflags, 2);
+        return p->max_groups;
+    }
+#endif
     CB_D u64* W(int g, int w) const { return p->htotals + ((size_t)g * CB_WORDS + w) * 2; }
     CB_D void add_i64_wrap(int g, int w, i64 v) { atomicAdd((unsigned long long*)W(g, w), (unsigned long long)v); }
     CB_D void add_i128(int g, int w, i128 v) {
@@ -488,7 +546,7 @@ CB_D void fin_store_i32(const FinParams& fp, int c, int g, i32 v, bool valid, in
 
 CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T);
 #if CB_HASH
-CB_D void cb_unpack_key(const FinParams& fp, int g, u64 key, bool null_group);
+CB_D void cb_unpack_key(const FinParams& fp, int g, const u64* kw, bool null_group); // kw: CB_KEY_WORDS packed words
 
 // non-zero identities (MIN / MAX words) for a fresh range of group ids; all-zero layouts use a memset instead
 extern "C" __global__ void cb_hash_init(u64* totals, long long first, long long n) {
@@ -502,10 +560,18 @@ extern "C" __global__ void cb_hash_init(u64* totals, long long first, long long 
 extern "C" __global__ void cb_hash_rehash(const u64* key_of_gid, int n_groups, u64* hkeys, u32 mask) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
+#if CB_KEY_WORDS > 1
+    u64 kw[CB_KEY_WORDS];
+#pragma unroll
+    for (int i = 0; i < CB_KEY_WORDS; i++) kw[i] = key_of_gid[(size_t)g * CB_KEY_WORDS + i];
+    const u64 key = Acc::key_tag(kw); // distinct keys may share a tag: each takes its own slot
+    u32 s = (u32)(key ^ (key >> 32)) & mask;
+#else
     u64 key = key_of_gid[g];
     u64 h = key;
     h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
     u32 s = (u32)h & mask;
+#endif
     while (true) {
         u64 prev = atomicCAS((unsigned long long*)&hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);
         if (prev == CB_EMPTY_KEY) { *((i32*)&hkeys[2 * (size_t)s + 1]) = g; return; }
@@ -565,7 +631,10 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
     }
     const u64* TH = fp.totals + (size_t)gid * CB_WORDS * 2;
     fp.present[g] = 1;
-    cb_unpack_key(fp, g, is_sentinel ? CB_EMPTY_KEY : (is_null_group ? 0ull : fp.hkeys[gid]), is_null_group);
+    u64 kw[CB_KEY_WORDS];
+#pragma unroll
+    for (int i = 0; i < CB_KEY_WORDS; i++) kw[i] = (is_sentinel || is_null_group) ? (is_sentinel ? CB_EMPTY_KEY : 0ull) : fp.hkeys[(size_t)gid * CB_KEY_WORDS + i];
+    cb_unpack_key(fp, g, kw, is_null_group);
     cb_finalize_group(fp, g, TH);
     return;
 #else

@@ -1225,6 +1225,7 @@ struct AggNode : FusedBase {
     bool hash_mode = false, strategy_decided = false;
     DeviceBufP hkeys, hkey_of_gid, htotals, hflags;
     int64_t hcap = 0, max_groups = 0;
+    int key_words = 1;                 // 64-bit words per packed group key (hkey_of_gid stride)
     static constexpr int DENSE_MAX_GROUPS = 64;
 
     // ---- range assumptions (see ranges.h) ----------------------------------------------------------------
@@ -1472,11 +1473,11 @@ struct AggNode : FusedBase {
         if (need > max_groups) {
             int64_t nm = std::max<int64_t>(need, max_groups + max_groups / 4);
             auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
-            auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 + 16);
+            auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 * key_words + 16);
             cb::u64* tp = (cb::u64*)ntot->ptr;
             if (cur > 0) {
                 cuda_check(cudaMemcpyAsync(tp, htotals->ptr, (size_t)cur * n_words * 16, cudaMemcpyDeviceToDevice, st), "copy totals");
-                cuda_check(cudaMemcpyAsync(nkog->ptr, hkey_of_gid->ptr, (size_t)cur * 8, cudaMemcpyDeviceToDevice, st), "copy group keys");
+                cuda_check(cudaMemcpyAsync(nkog->ptr, hkey_of_gid->ptr, (size_t)cur * 8 * key_words, cudaMemcpyDeviceToDevice, st), "copy group keys");
             }
             init_totals(mod, tp, cur, nm + 2 - cur);
             if (htotals) // reserved groups move to the new tail
@@ -1514,6 +1515,8 @@ struct AggNode : FusedBase {
         if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds)) throw ExecError(15, "", "internal: accumulator layout changed between launches");
         n_words = g.n_words;
         word_kinds = g.word_kinds;
+        if (have_totals && g.key_words != key_words) throw ExecError(15, "", "internal: group key packing changed between launches");
+        key_words = g.key_words;
         {
             TraceSpan ts("hash.ensure_table");
             ensure_table(mod, b.n_rows);
@@ -1534,7 +1537,7 @@ struct AggNode : FusedBase {
         cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags"); ctx->d2h_bytes += (int64_t)(sizeof(flags));
         ctx->check_device_errors();
         if (flags[0] & 2) throw ExecError(15, "", "internal: hash table full");
-        if (flags[0] & 4) throw Unsupported("decimal group key does not fit 64 bits (multi-word hash keys are pending)");
+        if (flags[0] & 4) throw Unsupported("decimal(p > 18) group key whose value does not fit 64 bits");
         for (size_t i = 0; i < spec.cols.size(); i++) {
             if (!spec.cols[i].type.is_decimal()) continue;
             uint64_t lo = masks[2 * i], hi = masks[2 * i + 1];

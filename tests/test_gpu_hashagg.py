@@ -116,3 +116,51 @@ def test_table_growth_and_rehash(cb):
     out = run(cb, plan, [pa.table({"k": k, "v": v}).to_batches(max_chunksize=8192)], 16_384)
     assert out.num_rows == len(np.unique(k))
     assert sum(out.column(1).to_pylist()) == n
+
+
+def test_multi_word_keys_with_nulls(cb):
+    """(int64, int64, date32) needs 3 key words + a null-flag word: tag + stored-key probing, collisions resolved by the full key."""
+    P = cb.proto
+    import datetime
+    n = 80_000
+    rng = np.random.default_rng(21)
+    a = rng.integers(-3, 3, n) * (2**40)
+    b = rng.integers(0, 40, n) - 20
+    d = rng.integers(9000, 9010, n).astype(np.int32)
+    v = rng.integers(-1000, 1000, n)
+    ma, mb, md = rng.random(n) < 0.1, rng.random(n) < 0.1, rng.random(n) < 0.1
+    tbl = pa.table({"a": pa.array(a, mask=ma), "b": pa.array(b, mask=mb), "d": pa.array(d, type=pa.date32(), mask=md), "v": pa.array(v)})
+    plan = P.hash_agg(P.scan([P.INT64, P.INT64, P.DATE, P.INT64]), [P.bound(0, P.INT64), P.bound(1, P.INT64), P.bound(2, P.DATE)],
+                      [P.agg_sum(P.bound(3, P.INT64), P.INT64), P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    out = run(cb, plan, [tbl.to_batches(max_chunksize=8192)], 30_000)
+    exp = {}
+    for i in range(n):
+        k = (None if ma[i] else int(a[i]), None if mb[i] else int(b[i]), None if md[i] else int(d[i]))
+        e = exp.setdefault(k, [0, 0])
+        e[0] += int(v[i])
+        e[1] += 1
+    epoch = datetime.date(1970, 1, 1)
+    got = {(r["col_0"], r["col_1"], None if r["col_2"] is None else (r["col_2"] - epoch).days): [r["col_3"], r["col_4"]] for r in out.to_pylist()}
+    assert got == exp
+
+
+def test_key_nullability_may_change_between_batches(cb):
+    """The first chunk has no validity buffers, later chunks do: the key packing must not depend on that."""
+    P = cb.proto
+    n = 40_000
+    rng = np.random.default_rng(22)
+    k1 = rng.integers(0, 50, n).astype(np.int32)
+    k2 = rng.integers(0, 7, n).astype(np.int32)
+    v = rng.integers(0, 100, n)
+    m1 = np.zeros(n, dtype=bool)
+    m1[n // 2:] = rng.random(n - n // 2) < 0.2           # NULLs only in the second half
+    tbl = pa.table({"k1": pa.array(k1, mask=m1), "k2": pa.array(k2), "v": pa.array(v)})
+    plan = P.hash_agg(P.scan([P.INT32, P.INT32, P.INT64]), [P.bound(0, P.INT32), P.bound(1, P.INT32)],
+                      [P.agg_sum(P.bound(2, P.INT64), P.INT64)], P.PARTIAL)
+    for batches in (tbl.to_batches(max_chunksize=4096), [tbl.slice(0, n // 2).to_batches()[0]] + tbl.slice(n // 2).to_batches(max_chunksize=4096)):
+        out = run(cb, plan, [batches], 10_000)
+        exp = {}
+        for i in range(n):
+            k = (None if m1[i] else int(k1[i]), int(k2[i]))
+            exp[k] = exp.get(k, 0) + int(v[i])
+        assert {(r["col_0"], r["col_1"]): r["col_2"] for r in out.to_pylist()} == exp
