@@ -1206,6 +1206,8 @@ struct AggNode : FusedBase {
     AggMode mode = AggMode::Partial;
     bool ungrouped = false;
     bool emitted = false;
+    std::vector<Batch> outq;          // output batches (more than one only after a dense -> hash migration)
+    size_t outq_pos = 0;
 
     // running state
     std::vector<int> cards;                       // current cardinality per key (incl. null slot)
@@ -1397,7 +1399,19 @@ struct AggNode : FusedBase {
             hash_mode = !ungrouped && (!densifiable || n_groups > DENSE_MAX_GROUPS);
             strategy_decided = true;
         } else if (!hash_mode && (!densifiable || n_groups > DENSE_MAX_GROUPS)) {
-            throw Unsupported("group cardinality grew past the dense path mid-stream (dense -> hash migration pending)");
+            // The key cardinality outgrew the dense layout mid-stream.  A Partial / PartialMerge aggregate may emit a group more
+            // than once (the Final stage merges state rows, exactly as it does for Spark's own spilling partial aggregates): flush
+            // what the dense path has accumulated as one state batch and carry on with the hash table.
+            if (mode == AggMode::Final) throw Unsupported("group cardinality grew past the dense path mid-stream in a Final aggregate");
+            if (have_totals) {
+                Batch early;
+                finalize(early);
+                if (early.n_rows > 0) outq.push_back(std::move(early));
+            }
+            have_totals = false;
+            totals.reset(); spill.reset(); partials.reset();
+            totals_groups = 0; n_words = 0; word_kinds.clear(); cards.clear(); rows_scanned = 0;
+            hash_mode = true;
         }
         if (hash_mode) {
             key_has_null_prev = key_has_null;
@@ -1722,7 +1736,11 @@ struct AggNode : FusedBase {
     }
 
     bool next(Batch& out) override {
-        if (emitted) return false;
+        if (emitted) {
+            if (outq_pos >= outq.size()) return false;
+            out = std::move(outq[outq_pos++]);
+            return true;
+        }
         if (keys.size() > CB_MAX_KEYS) throw Unsupported("more than 4 group keys");
         key_has_null.assign(keys.size(), false);
         key_dicts.assign(keys.size(), nullptr);
@@ -1735,7 +1753,11 @@ struct AggNode : FusedBase {
         }
         emitted = true;
         if (!have_totals) {
-            if (!ungrouped) return false; // grouped aggregate over no rows: no output rows
+            if (!ungrouped) { // grouped aggregate over no (further) rows
+                if (outq_pos >= outq.size()) return false;
+                out = std::move(outq[outq_pos++]);
+                return true;
+            }
             // ungrouped aggregate over an empty input still emits one row: run finalize over identities
             PipelineSpec spec = make_spec(nullptr, 1);
             last_gen = generate_pipeline(spec);
@@ -1749,8 +1771,11 @@ struct AggNode : FusedBase {
             cuda_check(cudaStreamSynchronize(ctx->stream), "identity totals sync");
             totals_groups = 1;
         }
-        if (hash_mode) finalize_hash(out);
-        else finalize(out);
+        Batch last;
+        if (hash_mode) finalize_hash(last);
+        else finalize(last);
+        outq.push_back(std::move(last));
+        out = std::move(outq[outq_pos++]);
         return true;
     }
 

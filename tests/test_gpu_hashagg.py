@@ -164,3 +164,30 @@ def test_key_nullability_may_change_between_batches(cb):
             k = (None if m1[i] else int(k1[i]), int(k2[i]))
             exp[k] = exp.get(k, 0) + int(v[i])
         assert {(r["col_0"], r["col_1"]): r["col_2"] for r in out.to_pylist()} == exp
+
+
+def test_dense_to_hash_migration_mid_stream(cb):
+    """A dictionary key starts with 6 values (dense, thread-private accumulators) and grows to 300 in later batches: the dense
+    state is flushed as one partial-state batch, the rest goes through the hash table, and Final merges the duplicates."""
+    P = cb.proto
+    rng = np.random.default_rng(31)
+    names_small = [f"s{i}" for i in range(6)]
+    names_big = [f"b{i:03d}" for i in range(294)] + names_small          # overlaps the early groups
+    batches, exp = [], {}
+    for bi in range(12):
+        names = names_small if bi < 4 else names_big
+        n = 5000
+        codes = rng.integers(0, len(names), n).astype(np.int32)
+        vals = rng.integers(-10**6, 10**6, n)
+        for c, v in zip(codes.tolist(), vals.tolist()):
+            e = exp.setdefault(names[c], [0, 0])
+            e[0] += v
+            e[1] += 1
+        batches.append(pa.RecordBatch.from_arrays([pa.DictionaryArray.from_arrays(pa.array(codes), pa.array(names)), pa.array(vals)], names=["k", "v"]))
+    partial = P.hash_agg(P.scan([P.STRING, P.INT64]), [P.bound(0, P.STRING)], [P.agg_sum(P.bound(1, P.INT64), P.INT64), P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    final = P.hash_agg(P.scan([P.STRING, P.INT64, P.INT64], source="shuffle"), [P.bound(0, P.STRING)],
+                       [P.agg_sum(P.unbound("s", P.INT64), P.INT64), P.agg_count([P.unbound("c", P.INT32)])], P.FINAL)
+    state = run(cb, partial, [batches], 5000)                              # one device chunk per batch
+    assert state.num_rows > len(exp)                                       # the early groups appear twice: once per path
+    res = run(cb, final, [state])
+    assert {r["col_0"]: [r["col_1"], r["col_2"]] for r in res.to_pylist()} == exp
