@@ -80,6 +80,7 @@ struct ExecContext {
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     int64_t chunk_rows = 1ll << 26;
+    int hash_threads = 512;   // consumer threads per CTA of the hash-aggregate kernel (tuning knob)
     int batch_size = 8192;
     int* d_err = nullptr;   // device error flags
     int* h_err = nullptr;   // pinned host mirror

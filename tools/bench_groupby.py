@@ -57,7 +57,7 @@ def main():
         t.add(P.INT64, keys.data_ptr(), 8, keep=keys)
         t.add(m, val.data_ptr(), w, keep=val)
         t0 = time.perf_counter()
-        p = native.Plan(map_plan, [t], config={"spark.comet.b200.chunkRows": str(1 << 31)}, device=local)
+        p = native.Plan(map_plan, [t], config={"spark.comet.b200.chunkRows": str(1 << 31), "spark.comet.b200.hashThreads": os.environ.get("CB200_HASH_THREADS", "512")}, device=local)
         rows, cols = p.execute_device()
         starts = p.partition_starts()
         st = p.stats()
@@ -74,7 +74,7 @@ def main():
         rt = native.DeviceTable(n_recv)
         for i, (vt, vb) in enumerate(recvd):
             rt.add_bytes(state_types[i], vt.data_ptr(), widths[i], vb.data_ptr() if vb is not None else None, keep=(vt, vb))
-        p2 = native.Plan(final_plan, [rt], config={"spark.comet.b200.chunkRows": str(1 << 31)}, device=local)
+        p2 = native.Plan(final_plan, [rt], config={"spark.comet.b200.chunkRows": str(1 << 31), "spark.comet.b200.hashThreads": os.environ.get("CB200_HASH_THREADS", "512")}, device=local)
         out = p2.execute_device()
         n_groups = out[0] if out else 0
         st2 = p2.stats()
