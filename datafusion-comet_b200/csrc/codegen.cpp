@@ -778,7 +778,6 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         //           hash : key columns packed into one 64-bit word -> slot of the global table.
         std::string gid = "0";
         std::string null_group_cond;
-        bool warp_agg = false; // hash, single-word key: one lane per distinct key of the warp probes and counts
         std::ostringstream unpack; // hash: cb_unpack_key body (reverse of the packing)
         if (spec.hash) {
             // Key columns are packed, in order, into 64-bit words: [value bits][null bit if nullable]; a key never straddles
@@ -869,7 +868,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
             }
             for (int w = 0; w < n_words_k; w++) unpack << "    cb::u64 k" << w << " = kw[" << w << "]; (void)k" << w << ";\n";
             for (auto it = unpack_steps.rbegin(); it != unpack_steps.rend(); ++it) unpack << *it;
-            if (n_words_k == 1) { gid = "acc.find_slot_warp(" + pk[0] + ")"; warp_agg = null_group_cond.empty(); }
+            if (n_words_k == 1) gid = "acc.find_slot(" + pk[0] + ")";
             else {
                 std::string arr = em.fresh("kw");
                 em.body << "    cb::u64 " << arr << "[" << n_words_k << "] = {";
@@ -891,8 +890,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         }
         em.body << "    const int g = " << gid << ";\n";
         int w_rows = slots.add(W_WRAP64, "cnt|true"); // rows passing the filter == COUNT(*) == non-null count of never-null inputs
-        if (warp_agg) em.body << "    if (acc.leader) acc.add_i64_wrap(g, " << w_rows << ", (cb::i64)acc.npeers);\n"; // one atomic per key per warp
-        else em.body << "    acc.add_i64_wrap(g, " << w_rows << ", 1);\n";
+        em.body << "    acc.add_i64_wrap(g, " << w_rows << ", 1);\n";
 
         for (size_t ai = 0; ai < spec.aggs.size(); ai++) {
             const AggExpr& a = spec.aggs[ai];
