@@ -624,6 +624,8 @@ struct NativeScanSource : ExecNode {
         Slot& sl = slots[pr->slot];
         std::vector<Unit> units;
         int64_t total = 0;
+        // (Tried and removed: ramping the batch size up from 8 Mi rows so that the first upload -- which has nothing to overlap
+        // with -- is short.  Batches of different sizes defeat the stream-ordered pool's block reuse: 177 ms -> 486 ms per step.)
         while (next_unit < all_units.size() && (units.empty() || total + all_units[next_unit].rows <= ctx->chunk_rows)) {
             Unit u = all_units[next_unit++];
             u.row0 = total;
@@ -653,7 +655,12 @@ struct NativeScanSource : ExecNode {
                 items.push_back({cc.start(), c});
             }
             std::sort(items.begin(), items.end());
-            bool open_range = false;
+            // consecutive row groups of one file are adjacent in the file, so the range could stay open across units (a batch
+            // becomes a handful of copies of hundreds of MB).  Measured: no gain over one ~12 MB copy per row group (185 vs
+            // 177 ms per step), so it stays opt-in.
+            static const bool merge_units = getenv("CB200_MERGE_UNITS") ? atoi(getenv("CB200_MERGE_UNITS")) != 0 : false;
+            bool open_range = merge_units && !ranges.empty() && ranges.back().file == units[u].file && (size_t)u > 0 && units[u - 1].file == units[u].file &&
+                              ranges.back().end - ranges.back().start < ((int64_t)1 << 30);
             for (auto& it : items) {
                 const int64_t st0 = it.first, en0 = st0 + chunk_meta(units[u], it.second).total_compressed;
                 if (open_range && st0 >= ranges.back().end && st0 - ranges.back().end <= 65536) ranges.back().end = std::max(ranges.back().end, en0);
