@@ -174,11 +174,13 @@ def bind_table(native, P, tpch, variant, n, money, cols):
     return t
 
 
-def host_arrow_batches(torch, pa, tpch, variant, money, cols, batch_rows):
-    """Copy the device columns into PINNED host memory and wrap them as zero-copy Arrow batches."""
+def host_arrow_batches(torch, pa, tpch, variant, money, cols, batch_rows, pin=True):
+    """Copy the device columns into host memory (PINNED when they are uploaded from there: the Arrow e2e leg; pageable when they
+    only feed the Parquet writer or the CPU baseline -- 8 ranks x 42 GB of pinned memory is not something to ask of a box) and
+    wrap them as zero-copy Arrow batches."""
     host = {}
     for k, t in list(money.items()) + [(k, cols[k]) for k in ("l_returnflag", "l_linestatus", "l_shipdate")]:
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
         h.copy_(t)
         host[k] = h
     torch.cuda.synchronize()
@@ -368,7 +370,7 @@ def main():
     e2e_extra = {}
     host = None
     if not args.no_e2e:
-        batches, host = host_arrow_batches(torch, pa, tpch, variant, money, cols, args.e2e_batch_rows)
+        batches, host = host_arrow_batches(torch, pa, tpch, variant, money, cols, args.e2e_batch_rows, pin=args.e2e_input in ("arrow", "both"))
         e2e_chunk = 1 << 26
 
         def timed(step_fn, steps):
@@ -444,7 +446,7 @@ def main():
         cores = os.cpu_count() or 1
         m = min(n, 200_000_000)
         if host is None:
-            _, host = host_arrow_batches(torch, pa, tpch, variant, {k: v[:m] for k, v in money.items()}, {k: v[:m] for k, v in cols.items()}, m)
+            _, host = host_arrow_batches(torch, pa, tpch, variant, {k: v[:m] for k, v in money.items()}, {k: v[:m] for k, v in cols.items()}, m, pin=False)
         hv = lambda k: host[k].numpy()[:m]
         a = (hv("l_quantity").view(np.uint64), hv("l_extendedprice").view(np.uint64), hv("l_discount").view(np.uint64), hv("l_tax").view(np.uint64),
              hv("l_shipdate"), hv("l_returnflag").view(np.uint8), hv("l_linestatus").view(np.uint8), 3, 2, tpch.DATE_1998_09_02)
