@@ -1297,7 +1297,7 @@ struct AggNode : FusedBase {
             acc /= 2;
         }
         if (acc + 2 * (size_t)probe.stage_bytes + 1024 > SMEM_BUDGET)
-            throw Unsupported("too many groups x aggregates for the dense path (hash aggregation path pending)");
+            throw Unsupported("too many groups x aggregates for the thread-private accumulators of the dense path");
         s.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (SMEM_BUDGET - 1024 - acc) / (size_t)probe.stage_bytes));
         return s;
     }
@@ -1344,7 +1344,7 @@ struct AggNode : FusedBase {
         cuda_check(cudaMemcpyAsync(hdr, dd.d.n_codes, sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream), "dict header");
         cuda_check(cudaStreamSynchronize(ctx->stream), "dict encode");
         int n_codes = hdr[0], derr = hdr[8];
-        if (derr & CB_DICT_FULL) throw Unsupported("string key cardinality exceeds the dense dictionary (hash aggregation path pending)");
+        if (derr & CB_DICT_FULL) throw Unsupported("plain Utf8 group key with more distinct values than the device dictionary holds (dictionary-encode the column)");
         if (derr & CB_DICT_COLLISION) throw ExecError(14, "", "64-bit hash collision between distinct group key strings");
         // fetch newly added dictionary strings (metadata-sized)
         if (n_codes > dd.host_known) {
