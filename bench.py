@@ -477,6 +477,7 @@ def main():
                        "checked_against_torch_int64": checked},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(n, variant),
                          "kernel": "cb_pipeline_agg (fused scan+filter+project+partial aggregate)", "ms_per_launch": ms_per_launch,
+                         "spec_peak": 8000.0, "frac_of_spec_peak": achieved / 8000.0,
                          "algorithmic_bytes_per_row": BYTES_PER_ROW[variant], "peak_source": peak_src},
             "gpu_launches": launches, "clocks": clocks,
         }

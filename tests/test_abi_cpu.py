@@ -107,3 +107,59 @@ def test_create_plan_without_gpu_fails_loudly(cb):
     with pytest.raises(cb.native.CometB200Error):       # executing does: no CPU fallback
         p.execute()
     p.release()
+
+
+def test_case_when_decodes_to_guarded_branches(cb):
+    """CaseWhen (expr.proto:473) -> nested IF; ANSI errors inside a branch are raised only for rows that take it."""
+    P = cb.proto
+    i = P.bound(0, P.INT32)
+    cw = P.case_when([P.lt(i, P.literal(0, P.INT32))], [P.add(i, i, P.INT32, P.ANSI)])          # no ELSE -> typed NULL
+    src = cb.native.kernel_source(P.projection(P.scan([P.INT32]), [cw]))
+    body = src[src.index("cb_row_select"):]
+    assert "cb::set_err(p, 1)" in body
+    guard_line = [ln for ln in body.splitlines() if "cb::set_err(p, 1)" in ln][0]
+    assert "&&" in guard_line and "if (" in guard_line                                            # the overflow test is ANDed with the branch condition
+    ok, why = cb.native.supports(P.projection(P.scan([P.INT32]), [P.case_when([P.lt(i, P.literal(0, P.INT32))], [i, i])]))
+    assert not ok                                                                                 # mismatched when/then lists
+
+
+def test_filter_project_is_two_streaming_passes(cb):
+    """pass 1 stages only the predicate columns and counts per (tile, warp); pass 2 writes at scanned offsets; no look-back."""
+    plan = cb.tpch.config1_plan("f64")
+    keys = cb.native.compile_plan(plan)
+    assert len(keys) == 2
+    sel, cnt = cb.native.kernel_source(plan, 0), cb.native.kernel_source(plan, 1)
+    assert "#define CB_SELECT_COUNT 1" in cnt and "#define CB_NCOLS 1\n" in cnt and "#define CB_LTILE 1024" in cnt   # only l_shipdate is staged
+    assert "#define CB_NCOLS 3\n" in sel and "CB_SELECT_COUNT" not in sel
+    hdr = open(os.path.join(ROOT, "datafusion-comet_b200", "csrc", "device", "cb_kernels.cuh")).read()
+    assert "sel_chunk" in hdr and "tile_state" not in hdr
+
+
+def test_partial_merge_and_try_sum_state_layouts(cb):
+    P = cb.proto
+    t = cb.tpch
+    # operator-level PartialMerge: state in, state out
+    sc = P.scan(t.q1_state_fields("dec"), source="shuffle")
+    pm = P.hash_agg(sc, [P.bound(0, P.STRING), P.bound(1, P.STRING)], t.q1_aggs("dec", bound=False), P.PARTIAL_MERGE)
+    ok, why = cb.native.supports(pm)
+    assert ok, why
+    # TRY sum carries (sum, has_all_nulls): a Final plan whose child lacks the flag column is a plan error
+    bad = P.hash_agg(P.scan([P.INT64, P.INT64], source="shuffle"), [P.bound(0, P.INT64)], [P.agg_sum(P.unbound("s", P.INT64), P.INT64, P.TRY)], P.FINAL)
+    ok, why = cb.native.supports(bad)
+    assert not ok and "state" in why
+    good = P.hash_agg(P.scan([P.INT64, P.INT64, P.BOOL], source="shuffle"), [P.bound(0, P.INT64)], [P.agg_sum(P.unbound("s", P.INT64), P.INT64, P.TRY)], P.FINAL)
+    ok, why = cb.native.supports(good)
+    assert ok, why
+
+
+def test_wide_group_keys_use_tag_and_stored_key(cb):
+    P = cb.proto
+    one = P.hash_agg(P.scan([P.INT64, P.INT64]), [P.bound(0, P.INT64)], [P.agg_sum(P.bound(1, P.INT64), P.INT64)], P.PARTIAL)
+    three = P.hash_agg(P.scan([P.INT64, P.INT64, P.DATE, P.INT64]), [P.bound(0, P.INT64), P.bound(1, P.INT64), P.bound(2, P.DATE)],
+                       [P.agg_sum(P.bound(3, P.INT64), P.INT64)], P.PARTIAL)
+    s1, s3 = cb.native.kernel_source(one), cb.native.kernel_source(three)
+    assert "#define CB_KEY_WORDS 1" in s1 and "acc.find_slot(" in s1
+    assert "#define CB_KEY_WORDS 4" in s3 and "acc.find_slot_multi(" in s3       # 64 + 64 + 33 bits + the null-flag word of the 64-bit keys
+    too_wide = P.hash_agg(P.scan([P.INT64] * 6), [P.bound(k, P.INT64) for k in range(5)], [P.agg_sum(P.bound(5, P.INT64), P.INT64)], P.PARTIAL)
+    ok, why = cb.native.supports(too_wide)
+    assert not ok
