@@ -1,4 +1,6 @@
 """CPU-only: the hand-written Parquet footer / page-header parser (Thrift compact) agrees with pyarrow's reader."""
+import struct
+
 import numpy as np
 import pyarrow.parquet as pq
 import pytest
@@ -57,3 +59,51 @@ def test_native_scan_plan_supported(cb):
     plan = t.q1_partial_plan("dec", scan=t.q1_native_scan("dec", ["file:///tmp/none.parquet"]))
     ok, why = cb.native.supports(plan)
     assert ok, why
+
+
+@pytest.mark.parametrize("compression,version,dictionary", [("NONE", "1.0", False), ("SNAPPY", "1.0", True), ("SNAPPY", "2.0", False), ("NONE", "2.0", True)])
+def test_parquet_oracle_matches_pyarrow(tmp_path, compression, version, dictionary):
+    """oracle/parquet_oracle.py (page headers, Snappy, RLE hybrid levels, PLAIN / dictionary values) against pyarrow's reader."""
+    import decimal
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from oracle import parquet_oracle as po
+    rng = np.random.default_rng(3)
+    n = 12_000
+    ctx = decimal.Context(prec=60)
+    m = [rng.random(n) < 0.2 for _ in range(5)]
+    m[0][:700] = True
+    i64 = rng.integers(-2**60, 2**60, n)
+    low = rng.integers(0, 30, n).astype(np.int32)
+    f64 = rng.standard_normal(n)
+    d30 = [int(a) * 10**10 + int(b) for a, b in zip(rng.integers(-10**15, 10**15, n), rng.integers(0, 10**10, n))]
+    words = np.array(["AIR", "MAIL", "SHIP", "", "TRUCK"])[rng.integers(0, 5, n)]
+    tbl = pa.table({"i64": pa.array(i64, mask=m[0]), "low": pa.array(low, mask=m[1]), "f64": pa.array(f64, mask=m[2]),
+                    "d30": pa.array([None if mm else decimal.Decimal(v).scaleb(-4, context=ctx) for v, mm in zip(d30, m[3])], type=pa.decimal128(30, 4)),
+                    "word": pa.array(words.tolist(), mask=m[4]), "req": pa.array(i64)})
+    path = str(tmp_path / "o.parquet")
+    pq.write_table(tbl, path, row_group_size=5000, compression=compression, use_dictionary=True if dictionary else ["word"], data_page_version=version, data_page_size=4096)
+    raw = open(path, "rb").read()
+    md = pq.ParquetFile(path).metadata
+    for ci, name in enumerate(tbl.column_names):
+        got_v, got_ok = [], []
+        for rg in range(md.num_row_groups):
+            c = md.row_group(rg).column(ci)
+            start = c.dictionary_page_offset if c.has_dictionary_page and c.dictionary_page_offset else c.data_page_offset
+            start = min(start, c.data_page_offset)
+            tl = md.schema.column(ci).length if c.physical_type == "FIXED_LEN_BYTE_ARRAY" else 0
+            v, ok = po.decode_chunk(raw, start, c.total_compressed_size, c.num_values, c.physical_type, c.compression, True, tl)
+            got_v.append(v)
+            got_ok.append(ok)
+        v, ok = np.concatenate(got_v), np.concatenate(got_ok)
+        want = tbl.column(name).to_pylist()
+        assert [w is not None for w in want] == ok.tolist(), name
+        for g, w in zip(v[ok].tolist(), [w for w in want if w is not None]):
+            if name == "d30":
+                assert g == int(w.scaleb(4)), name
+            elif name == "word":
+                assert g.decode() == w, name
+            elif name == "f64":
+                assert struct.pack("<d", g) == struct.pack("<d", w), name
+            else:
+                assert g == w, name
