@@ -41,9 +41,9 @@ def elem_at(src, p):
     if t == 1:
         return (2, ((tag >> 2) & 7) + 4, ((tag >> 5) << 8) | src[p + 1]) if p + 1 < len(src) else None
     nb = 2 if t == 2 else 4
-    if p + nb >= len(src) + 0 and p + nb > len(src) - 0:
-        pass
-    return (1 + nb, (tag >> 2) + 1, int.from_bytes(src[p + 1:p + 1 + nb], "little")) if p + nb < len(src) + 0 or p + 1 + nb <= len(src) else None
+    if p + 1 + nb > len(src):
+        return None
+    return 1 + nb, (tag >> 2) + 1, int.from_bytes(src[p + 1:p + 1 + nb], "little")
 
 
 def preamble(src):
