@@ -265,6 +265,7 @@ def reference_arm(args, rank, world):
     d = oracle.dec_from_i64
     a = (d(cols["l_quantity"]), d(cols["l_extendedprice"]), d(cols["l_discount"]), d(cols["l_tax"]), cols["l_shipdate"],
          cols["l_returnflag"], cols["l_linestatus"], 3, 2, tpch.DATE_1998_09_02)
+    a = tuple(oracle.numa_spread(x, usable_cores()) if isinstance(x, np.ndarray) else x for x in a)
     cores = best_thread_count(lambda c: oracle.q1_dec(*a, c), usable_cores())
     for _ in range(args.warmup):
         oracle.q1_dec(*a, cores)
@@ -480,6 +481,7 @@ def main():
         hv = lambda k: host[k].numpy()[:m]
         a = (hv("l_quantity").view(np.uint64), hv("l_extendedprice").view(np.uint64), hv("l_discount").view(np.uint64), hv("l_tax").view(np.uint64),
              hv("l_shipdate"), hv("l_returnflag").view(np.uint8), hv("l_linestatus").view(np.uint8), 3, 2, tpch.DATE_1998_09_02)
+        a = tuple(oracle.numa_spread(x, usable_cores()) if isinstance(x, np.ndarray) else x for x in a)
         cores = best_thread_count(lambda c: oracle.q1_dec(*a, c), usable_cores())
         reps, tc = 0, time.perf_counter()
         while reps < 3 or time.perf_counter() - tc < 5.0:

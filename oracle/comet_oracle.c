@@ -882,3 +882,20 @@ int64_t co_filter_project_f64(int64_t n, const double *qty, const double *price,
     free(cnt);
     return total;
 }
+
+/* NUMA placement helper for the timed baseline (no reference equivalent: DataFusion reads each partition on the core that
+ * produced it).  Copies `n` elements with the SAME static partition co_q1_dec uses, so every page of `dst` is first touched --
+ * and therefore placed -- on the socket of the thread that will later scan it. */
+void co_parallel_copy(void *dst, const void *src, int64_t n, int elem_bytes, int n_threads) {
+    int T = nthreads_or_default(n_threads);
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        int t = omp_get_thread_num();
+#else
+        int t = 0;
+#endif
+        int64_t lo = n * t / T, hi = n * (t + 1) / T;
+        memcpy((char *)dst + lo * elem_bytes, (const char *)src + lo * elem_bytes, (size_t)(hi - lo) * (size_t)elem_bytes);
+    }
+}

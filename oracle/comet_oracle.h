@@ -188,4 +188,7 @@ int64_t co_filter_project_f64(int64_t n, const double *qty, const double *price,
 #ifdef __cplusplus
 }
 #endif
+/* first-touch placement of baseline inputs (see comet_oracle.c) */
+void co_parallel_copy(void *dst, const void *src, int64_t n, int elem_bytes, int n_threads);
+
 #endif

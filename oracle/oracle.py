@@ -473,3 +473,15 @@ def filter_project_f64(qty, price, shipdate, cutoff, n_threads=0):
     m = lib().co_filter_project_f64(C.c_int64(n), _p(qty), _p(price), _p(shipdate), C.c_int32(cutoff),
                                     C.c_int(n_threads), _p(out))
     return out[:m]
+
+
+def numa_spread(a, n_threads=0):
+    """A copy of `a` whose pages are first touched by the OpenMP threads that will scan them (co_parallel_copy): on a multi-socket
+    host a numpy array filled by one thread lives on one socket and every other socket reads it remotely."""
+    a = np.ascontiguousarray(a)
+    out = np.empty_like(a)
+    n = a.shape[0]
+    if n == 0:
+        return out
+    lib().co_parallel_copy(_p(out), _p(a), C.c_int64(n), C.c_int(a.nbytes // n), C.c_int(n_threads))
+    return out
