@@ -264,7 +264,7 @@ def reference_arm(args, rank, world):
     cols = tpch.gen_lineitem(n, seed=42)
     d = oracle.dec_from_i64
     a = (d(cols["l_quantity"]), d(cols["l_extendedprice"]), d(cols["l_discount"]), d(cols["l_tax"]), cols["l_shipdate"],
-         cols["l_returnflag"], cols["l_linestatus"], 3, 2, tpch.DATE_1998_09_02)
+         cols["l_returnflag"], cols["l_linestatus"], 3, 2, tpch.Q1_CUTOFF)
     a = tuple(oracle.numa_spread(x, usable_cores()) if isinstance(x, np.ndarray) else x for x in a)
     cores = best_thread_count(lambda c: oracle.q1_dec(*a, c), usable_cores())
     for _ in range(args.warmup):
@@ -379,7 +379,7 @@ def main():
     # cheap full-size check (rank 0's partition): count(*) per group and sum(l_quantity) are exact integers
     checked = None
     if rank == 0 and world == 1:
-        keep = cols["l_shipdate"] <= tpch.DATE_1998_09_02
+        keep = cols["l_shipdate"] <= tpch.Q1_CUTOFF
         gid = cols["l_returnflag"].to(torch.int64) * 2 + cols["l_linestatus"].to(torch.int64)
         cnt = torch.bincount(gid[keep], minlength=6).cpu().tolist()
         sq = torch.zeros(6, dtype=torch.int64, device=device).scatter_add_(0, gid[keep], cols["l_quantity"][keep]).cpu().tolist()
@@ -480,7 +480,7 @@ def main():
             _, host = host_arrow_batches(torch, pa, tpch, variant, {k: v[:m] for k, v in money.items()}, {k: v[:m] for k, v in cols.items()}, m, pin=False)
         hv = lambda k: host[k].numpy()[:m]
         a = (hv("l_quantity").view(np.uint64), hv("l_extendedprice").view(np.uint64), hv("l_discount").view(np.uint64), hv("l_tax").view(np.uint64),
-             hv("l_shipdate"), hv("l_returnflag").view(np.uint8), hv("l_linestatus").view(np.uint8), 3, 2, tpch.DATE_1998_09_02)
+             hv("l_shipdate"), hv("l_returnflag").view(np.uint8), hv("l_linestatus").view(np.uint8), 3, 2, tpch.Q1_CUTOFF)
         a = tuple(oracle.numa_spread(x, usable_cores()) if isinstance(x, np.ndarray) else x for x in a)
         cores = best_thread_count(lambda c: oracle.q1_dec(*a, c), usable_cores())
         reps, tc = 0, time.perf_counter()

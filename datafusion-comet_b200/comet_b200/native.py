@@ -62,7 +62,8 @@ class DeviceColumn(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pipeline_launches", C.c_int64), ("pipeline_ms", C.c_double),
-                ("pipeline_rows", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("pipeline_rows", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("scan_pruned_row_groups", C.c_int64), ("scan_pruned_rows", C.c_int64)]
 
 
 EXPORTED = ["cb200_plan_stats", "cb200_register_memory_file", "cb200_parquet_describe", "cb200_table_add_column_bytes", "cb200_plan_dict_value", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",

@@ -15,7 +15,8 @@ import pyarrow as pa
 from . import proto as P
 
 D12 = P.DECIMAL(12, 2)
-DATE_1998_09_02 = 10471  # Q1: date '1998-12-01' - interval '90' day ; Config 1 cutoff
+DATE_1998_09_02 = 10471  # Config 1 cutoff (BASELINE.json configs[0]: l_shipdate < '1998-09-02')
+Q1_CUTOFF = 10493        # Q1: date '1998-12-01' - interval '68 days' = 1998-09-24 (reference benchmarks/tpc/queries/tpch/q1.sql:17)
 DATE_1994_01_01 = 8766
 DATE_1995_01_01 = 9131
 DATE_1995_06_17 = 9298
@@ -146,7 +147,7 @@ def write_lineitem_parquet(cols, path, variant="dec", row_group_size=1 << 20, de
     return path
 
 
-def q1_partial_plan(variant="dec", cutoff=DATE_1998_09_02, scan=None):
+def q1_partial_plan(variant="dec", cutoff=Q1_CUTOFF, scan=None):
     """Map-stage plan of TPC-H Q1: Scan -> Filter -> Project -> HashAggregate(Partial)."""
     m = _money(variant)
     sc = scan if scan is not None else P.scan(q1_scan_fields(variant))
@@ -184,15 +185,29 @@ def q6_aggs(variant, bound=True):
     return [P.agg_sum(P.multiply(price, disc, P.DOUBLE), P.DOUBLE)]
 
 
-def q6_partial_plan(variant="dec"):
-    """TPC-H Q6: 3-predicate filter + ungrouped SUM(l_extendedprice * l_discount)."""
+Q6_COLUMNS = ["l_quantity", "l_extendedprice", "l_discount", "l_shipdate"]
+
+
+def q6_predicate(variant):
     m = _money(variant)
-    sc = P.scan(q6_scan_fields(variant))
     qty, disc, ship = P.bound(0, m), P.bound(2, m), P.bound(3, P.DATE)
-    pred = P.and_(P.and_(P.and_(P.and_(P.gt_eq(ship, P.literal(DATE_1994_01_01, P.DATE)), P.lt(ship, P.literal(DATE_1995_01_01, P.DATE))),
+    return P.and_(P.and_(P.and_(P.and_(P.gt_eq(ship, P.literal(DATE_1994_01_01, P.DATE)), P.lt(ship, P.literal(DATE_1995_01_01, P.DATE))),
                                 P.gt_eq(disc, _lit_money(5, variant))), P.lt_eq(disc, _lit_money(7, variant))),
                   P.lt(qty, _lit_money(2400, variant)))
-    flt = P.filter_(sc, pred)
+
+
+def q6_native_scan(variant, files, push_filters=True):
+    """NativeScan with the Q6 projection; `data_filters` carries the predicate the way Spark pushes it to the scan
+    (CometNativeScan.scala: exprToProto(filter, scan.output)) -- the reference prunes row groups with it."""
+    fields = list(zip(Q6_COLUMNS, q6_scan_fields(variant), [True] * 4))
+    return P.native_scan(fields, fields, files, data_filters=[q6_predicate(variant)] if push_filters else ())
+
+
+def q6_partial_plan(variant="dec", scan=None):
+    """TPC-H Q6: 3-predicate filter + ungrouped SUM(l_extendedprice * l_discount)."""
+    m = _money(variant)
+    sc = scan if scan is not None else P.scan(q6_scan_fields(variant))
+    flt = P.filter_(sc, q6_predicate(variant))
     proj = P.projection(flt, [P.bound(1, m), P.bound(2, m)])
     return P.hash_agg(proj, [], q6_aggs(variant), P.PARTIAL)
 

@@ -359,6 +359,8 @@ int cb200_plan_stats(cb200_plan* plan, cb200_stats* out) {
     out->pipeline_rows = c.pipeline_rows;
     out->h2d_bytes = c.h2d_bytes;
     out->d2h_bytes = c.d2h_bytes;
+    out->scan_pruned_row_groups = c.scan_pruned_row_groups;
+    out->scan_pruned_rows = c.scan_pruned_rows;
     return 0;
 }
 

@@ -148,6 +148,7 @@ struct Emitter {
     // (CaseExpr evaluates `then` under the selection), so ANSI / arrow overflow errors of rows that do not take
     // the branch must not fire.  Values are still computed (and ignored) for every row.
     std::string guard;
+    std::string base_guard; // hash pipelines evaluate every row slot (no early return for filtered rows): errors only from kept rows
     Val emit(const Expr& e) {
         std::string k = guard.empty() ? key_of(e) : guard + "|" + key_of(e);
         auto it = cse.find(k);
@@ -164,6 +165,7 @@ struct Emitter {
         std::string s = std::to_string(slot);
         if (c.has_validity) r.n = declb("!cb::ldv(t.val[" + s + "], r)");
         std::string notnull = r.n.empty() ? "" : "if (!" + r.n + ") ";
+        if (!base_guard.empty()) notnull = r.n.empty() ? "if (in_range) " : "if (in_range && !" + r.n + ") ";
         if (c.type.is_decimal()) {
             bool narrow = col_bounds[slot] < R63;
             if (c.phys == Phys::I128) {
@@ -284,7 +286,7 @@ struct Emitter {
 
     void raise(const std::string& cond, int bit) {
         uses_err = true;
-        body << "    if (" << (guard.empty() ? "" : guard + " && ") << cond << ") cb::set_err(p, " << bit << ");\n";
+        body << "    if (" << (base_guard.empty() ? "" : base_guard + " && ") << (guard.empty() ? "" : guard + " && ") << cond << ") cb::set_err(p, " << bit << ");\n";
     }
 
     // ---- arithmetic --------------------------------------------------------------------------------
@@ -697,6 +699,8 @@ std::map<std::string, GeneratedKernel> g_memo;
 GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec);
 } // namespace
 
+std::string pipeline_signature(const PipelineSpec& spec) { return spec_signature(spec); }
+
 GeneratedKernel generate_pipeline(const PipelineSpec& spec) {
     const std::string sig = spec_signature(spec);
     {
@@ -723,6 +727,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
     if (spec.cols.size() > 24) throw Unsupported("more than 24 staged input columns");
 
     Emitter em(spec);
+    if (spec.sink == SinkKind::Agg && spec.hash) em.base_guard = "in_range"; // hash pipelines also visit the row slots past the end of the tile
     // predicates first: `keep` = every predicate TRUE (FilterExec drops NULL and FALSE)
     std::string keep = "true";
     for (auto& p : spec.predicates) {
@@ -771,9 +776,41 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         g.entry = "cb_pipeline_select";
     } else {
         // ---------------- aggregate ----------------
-        em.body << "    if (!(" << keep << ")) return;\n";
+        if (spec.hash) {
+            // no early return: the table update is warp-cooperative, absent / filtered rows take part with keep_ = false.  Errors
+            // of expressions evaluated below must still come from kept rows only.
+            em.body << "    const bool keep_ = in_range && (" << keep << ");\n";
+            em.base_guard = "keep_";
+        } else em.body << "    (void)in_range;\n    if (!(" << keep << ")) return;\n";
         SlotPlan slots;
         std::vector<AggLayout> layout(spec.aggs.size());
+        // one accumulator update: `if (cond) acc.add_*(g, w, v)` on the dense paths, the warp-cooperative `acc.h_*(cond, w, v)`
+        // (every lane takes part, see cb_kernels.cuh) on the hash path
+        const bool H = spec.hash;
+        auto upd = [&](const std::string& op, const std::string& cond, int w, const std::string& val = "") {
+            std::ostringstream o;
+            const std::string ws = std::to_string(w);
+            if (H) {
+                if (op == "count") o << "acc.h_count(" << cond << ", " << ws << ");";
+                else if (op == "wrap") o << "acc.h_add_wrap(" << cond << ", " << ws << ", " << val << ");";
+                else if (op == "wide") o << "acc.h_add_i64_wide(" << cond << ", " << ws << ", " << val << ");";
+                else if (op == "i128") o << "acc.h_add_i128(" << cond << ", " << ws << ", " << val << ");";
+                else if (op == "f64") o << "acc.h_add_f64(" << cond << ", " << ws << ", " << val << ");";
+                else if (op == "min") o << "acc.h_min(" << cond << ", " << ws << ", " << val << ");";
+                else o << "acc.h_max(" << cond << ", " << ws << ", " << val << ");";
+            } else {
+                o << "if (" << cond << ") ";
+                if (op == "count") o << "acc.add_i64_wrap(g, " << ws << ", 1);";
+                else if (op == "wrap") o << "acc.add_i64_wrap(g, " << ws << ", " << val << ");";
+                else if (op == "wide") o << "acc.add_i64_wide(g, " << ws << ", " << val << ");";
+                else if (op == "i128") o << "acc.add_i128(g, " << ws << ", " << val << ");";
+                else if (op == "f64") o << "acc.add_f64(g, " << ws << ", " << val << ");";
+                else if (op == "min") o << "acc.min_i64(g, " << ws << ", " << val << ");";
+                else o << "acc.max_i64(g, " << ws << ", " << val << ");";
+            }
+            em.body << "    " << o.str() << "\n";
+        };
+        auto absval = [&](const std::string& iv) { return "cb::i128_abs_of_i64(" + iv + ")"; };
         // group id.  dense: mixed radix over key codes, NULL key -> last slot of that key.
         //           hash : key columns packed into one 64-bit word -> slot of the global table.
         std::string gid = "0";
@@ -835,7 +872,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                 if (kt.is_decimal()) {
                     if (kv.narrow) raw = "(cb::u64)" + kv.v;
                     else {
-                        em.body << "    if (!cb::i128_fits_i64(" << kv.v << ")) atomicOr(p.hflags, 4);\n";
+                        em.body << "    if (keep_ && !cb::i128_fits_i64(" << kv.v << ")) atomicOr(p.hflags, 4);\n";
                         raw = kv.v + ".lo";
                     }
                 } else if (kt.id == TypeId::Bool) raw = "(" + kv.v + " ? 1ull : 0ull)";
@@ -868,17 +905,13 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
             }
             for (int w = 0; w < n_words_k; w++) unpack << "    cb::u64 k" << w << " = kw[" << w << "]; (void)k" << w << ";\n";
             for (auto it = unpack_steps.rbegin(); it != unpack_steps.rend(); ++it) unpack << *it;
-            if (n_words_k == 1) gid = "acc.find_slot(" + pk[0] + ")";
-            else {
+            {
                 std::string arr = em.fresh("kw");
                 em.body << "    cb::u64 " << arr << "[" << n_words_k << "] = {";
                 for (int w = 0; w < n_words_k; w++) em.body << (w ? ", " : "") << pk[w];
                 em.body << "};\n";
-                gid = "acc.find_slot_multi(" + arr + ")";
-            }
-            if (!null_group_cond.empty()) {
-                em.body << "    if (" << null_group_cond << ") atomicOr(p.hflags, 8);\n";
-                gid = "(" + null_group_cond + " ? p.max_groups + 1 : " + gid + ")";
+                if (!null_group_cond.empty()) em.body << "    if (keep_ && " << null_group_cond << ") atomicOr(p.hflags, 8);\n";
+                em.body << "    acc.begin(keep_, " << arr << ", " << (null_group_cond.empty() ? "false" : null_group_cond) << ");\n";
             }
         } else if (!spec.ungrouped) {
             for (size_t k = 0; k < spec.keys.size(); k++) {
@@ -888,9 +921,9 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                 gid = "(" + gid + ") * p.key_card[" + std::to_string(k) + "] + " + code;
             }
         }
-        em.body << "    const int g = " << gid << ";\n";
+        if (!spec.hash) em.body << "    const int g = " << gid << ";\n";
         int w_rows = slots.add(W_WRAP64, "cnt|true"); // rows passing the filter == COUNT(*) == non-null count of never-null inputs
-        em.body << "    acc.add_i64_wrap(g, " << w_rows << ", 1);\n";
+        upd("count", "true", w_rows);
 
         for (size_t ai = 0; ai < spec.aggs.size(); ai++) {
             const AggExpr& a = spec.aggs[ai];
@@ -913,7 +946,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                     std::string k = "cnt|" + condkey;
                     bool first = slots.dedup.count(std::to_string((int)W_WRAP64) + "|" + k) == 0;
                     int w = slots.add(W_WRAP64, k);
-                    if (first) em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << w << ", 1);\n";
+                    if (first) upd("count", use, w);
                     return w;
                 };
                 switch (a.kind) {
@@ -930,21 +963,17 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                         if (first) {
                             // per-thread 64-bit partials are exact while rows/thread * |v| < 2^63 (host caps rows/thread at 2^CB_RPT_LOG2)
                             u128r vb = em.bound_of(*a.children[0]);
-                            if (spec.hash) // table words are full 128-bit totals: always sign-extend + carry
-                                em.body << "    if (" << use << ") acc." << (v.narrow ? "add_i64_wide" : "add_i128") << "(g, " << L.w_sum << ", " << v.v << ");\n";
-                            else if (v.narrow && vb < (R63 >> CB_RPT_LOG2))
-                                em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << L.w_sum << ", " << v.v << ");\n";
-                            else if (v.narrow)
-                                em.body << "    if (" << use << ") acc.add_i64_wide(g, " << L.w_sum << ", " << v.v << ");\n";
-                            else
-                                em.body << "    if (" << use << ") acc.add_i128(g, " << L.w_sum << ", " << v.v << ");\n";
+                            if (spec.hash) upd(v.narrow ? "wide" : "i128", use, L.w_sum, v.v); // table words are full 128-bit totals: always sign-extend + carry
+                            else if (v.narrow && vb < (R63 >> CB_RPT_LOG2)) upd("wrap", use, L.w_sum, v.v);
+                            else if (v.narrow) upd("wide", use, L.w_sum, v.v);
+                            else upd("i128", use, L.w_sum, v.v);
                         }
                     } else if (f64) {
                         L.is_f64_sum = true;
                         std::string dv = v.type.id == TypeId::Float64 ? v.v : "(double)" + v.v;
                         bool first = slots.dedup.count(std::to_string((int)W_DD_HI) + "|dd|" + dv + "|" + condkey) == 0;
                         L.w_sum = slots.add(W_DD_HI, "dd|" + dv + "|" + condkey, 2);
-                        if (first) em.body << "    if (" << use << ") acc.add_f64(g, " << L.w_sum << ", " << dv << ");\n";
+                        if (first) upd("f64", use, L.w_sum, dv);
                     } else if (a.eval_mode != EvalMode::Legacy) {
                         // SumInt ANSI / TRY (sum_int.rs:176-390): the reference adds row by row with add_checked, so whether it
                         // overflows depends on the row order.  The exact 128-bit sum and the exact sum of magnitudes decide it for
@@ -954,13 +983,11 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                         bool first = slots.dedup.count(std::to_string((int)W_SUM128) + "|csum|" + v.v + "|" + condkey) == 0;
                         L.w_sum = slots.add(W_SUM128, "csum|" + v.v + "|" + condkey);
                         L.w_abs = slots.add(W_SUM128, "cabs|" + v.v + "|" + condkey);
-                        if (first)
-                            em.body << "    if (" << use << ") { acc.add_i64_wide(g, " << L.w_sum << ", " << iv << "); cb::i128 m_ = cb::i128_from_i64(" << iv
-                                    << "); acc.add_i128(g, " << L.w_abs << ", m_.hi < 0 ? cb::i128_neg(m_) : m_); }\n";
+                        if (first) { upd("wide", use, L.w_sum, iv); upd("i128", use, L.w_abs, absval(iv)); }
                     } else { // SumInt Legacy: wrapping i64 (sum_int.rs:432)
                         bool first = slots.dedup.count(std::to_string((int)W_WRAP64) + "|isum|" + v.v + "|" + condkey) == 0;
                         L.w_sum = slots.add(W_WRAP64, "isum|" + v.v + "|" + condkey);
-                        if (first) em.body << "    if (" << use << ") acc.add_i64_wrap(g, " << L.w_sum << ", (cb::i64)" << v.v << ");\n";
+                        if (first) upd("wrap", use, L.w_sum, "(cb::i64)" + v.v);
                     }
                     break;
                 }
@@ -973,7 +1000,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                     std::string sk = std::string(mn ? "min|" : "max|") + v.v + "|" + condkey;
                     bool first = slots.dedup.count(std::to_string((int)(mn ? W_MIN : W_MAX)) + "|" + sk) == 0;
                     L.w_minmax = slots.add(mn ? W_MIN : W_MAX, sk);
-                    if (first) em.body << "    if (" << use << ") acc." << (mn ? "min_i64" : "max_i64") << "(g, " << L.w_minmax << ", " << key << ");\n";
+                    if (first) upd(mn ? "min" : "max", use, L.w_minmax, key);
                     break;
                 }
                 }
@@ -986,7 +1013,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                 case AggKind::Count: { // count merge = sum of partial counts
                     Val c = col(0);
                     L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
-                    em.body << "    if (" << (c.n.empty() ? "true" : "!" + c.n) << ") acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
+                    upd("wrap", c.n.empty() ? "true" : "!" + c.n, L.w_cnt, c.v);
                     break;
                 }
                 case AggKind::Sum:
@@ -996,37 +1023,41 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                         L.w_sum = slots.add(W_SUM128, tag + "sum");
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
                         L.w_bad = slots.add(W_WRAP64, tag + "bad");
-                        em.body << "    if (!" << e.v << " && " << snull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
-                        em.body << "    else if (!" << e.v << ") { acc.add_i128(g, " << L.w_sum << ", " << Emitter::W(s) << "); acc.add_i64_wrap(g, " << L.w_cnt
-                                << ", 1); }\n";
+                        std::string bad = em.declb("!" + e.v + " && " + snull), ok = em.declb("!" + e.v + " && !(" + snull + ")");
+                        upd("count", bad, L.w_bad);
+                        upd("i128", ok, L.w_sum, Emitter::W(s));
+                        upd("count", ok, L.w_cnt);
                     } else if (a.datatype.is_integer() && a.eval_mode != EvalMode::Legacy) { // sum_int.rs:236-243 (ANSI), :331-389 (TRY)
                         Val s = col(0);
                         std::string snull = s.n.empty() ? "false" : s.n;
                         L.w_sum = slots.add(W_SUM128, tag + "sum");
                         L.w_abs = slots.add(W_SUM128, tag + "abs");
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
-                        std::string add = "{ acc.add_i64_wide(g, " + std::to_string(L.w_sum) + ", " + s.v + "); cb::i128 m_ = cb::i128_from_i64(" + s.v +
-                                          "); acc.add_i128(g, " + std::to_string(L.w_abs) + ", m_.hi < 0 ? cb::i128_neg(m_) : m_); acc.add_i64_wrap(g, " +
-                                          std::to_string(L.w_cnt) + ", 1); }";
+                        std::string ok;
                         if (a.eval_mode == EvalMode::Try) { // state (sum, has_all_nulls): overflowed = !has_all_nulls && sum IS NULL
                             Val e = col(1);
                             L.w_bad = slots.add(W_WRAP64, tag + "bad");
-                            em.body << "    if (!" << e.v << " && " << snull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
-                            em.body << "    else if (!" << e.v << ") " << add << "\n";
-                        } else em.body << "    if (!" << snull << ") " << add << "\n";
+                            upd("count", em.declb("!" + e.v + " && " + snull), L.w_bad);
+                            ok = em.declb("!" + e.v + " && !(" + snull + ")");
+                        } else ok = em.declb("!(" + snull + ")");
+                        upd("wide", ok, L.w_sum, s.v);
+                        upd("i128", ok, L.w_abs, absval(s.v));
+                        upd("count", ok, L.w_cnt);
                     } else if (a.datatype.is_integer()) { // sum_int.rs:497-528
                         Val s = col(0);
                         L.w_sum = slots.add(W_WRAP64, tag + "sum");
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
-                        em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc.add_i64_wrap(g, " << L.w_sum << ", " << s.v
-                                << "); acc.add_i64_wrap(g, " << L.w_cnt << ", 1); }\n";
+                        const std::string ok = s.n.empty() ? "true" : "!" + s.n;
+                        upd("wrap", ok, L.w_sum, s.v);
+                        upd("count", ok, L.w_cnt);
                     } else {
                         Val s = col(0);
                         L.is_f64_sum = true;
                         L.w_sum = slots.add(W_DD_HI, tag + "sum", 2);
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
-                        em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc.add_f64(g, " << L.w_sum << ", (double)" << s.v
-                                << "); acc.add_i64_wrap(g, " << L.w_cnt << ", 1); }\n";
+                        const std::string ok = s.n.empty() ? "true" : "!" + s.n;
+                        upd("f64", ok, L.w_sum, "(double)" + s.v);
+                        upd("count", ok, L.w_cnt);
                     }
                     break;
                 case AggKind::Avg:
@@ -1036,15 +1067,16 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
                         L.w_bad = slots.add(W_WRAP64, tag + "bad");
                         std::string cnull = c.n.empty() ? "false" : c.n, snull = s.n.empty() ? "false" : s.n;
-                        em.body << "    if (!" << cnull << ") acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
-                        em.body << "    if (" << snull << " || " << cnull << ") acc.add_i64_wrap(g, " << L.w_bad << ", 1);\n";
-                        em.body << "    if (!" << snull << ") acc.add_i128(g, " << L.w_sum << ", " << Emitter::W(s) << ");\n";
+                        upd("wrap", "!" + cnull, L.w_cnt, c.v);
+                        upd("count", "(" + snull + " || " + cnull + ")", L.w_bad);
+                        upd("i128", "!" + snull, L.w_sum, Emitter::W(s));
                     } else { // avg.rs:279-309
                         Val s = col(0), c = col(1);
                         L.is_f64_sum = true;
                         L.w_sum = slots.add(W_DD_HI, tag + "sum", 2);
                         L.w_cnt = slots.add(W_WRAP64, tag + "cnt");
-                        em.body << "    acc.add_f64(g, " << L.w_sum << ", " << s.v << "); acc.add_i64_wrap(g, " << L.w_cnt << ", " << c.v << ");\n";
+                        upd("f64", "true", L.w_sum, s.v);
+                        upd("wrap", "true", L.w_cnt, c.v);
                     }
                     break;
                 case AggKind::Min: case AggKind::Max: {
@@ -1055,8 +1087,9 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                     std::string key = s.type.is_decimal() ? (s.narrow ? s.v : "(cb::i64)" + s.v + ".lo")
                                       : s.type.id == TypeId::Float64 ? "cb::f64_total_key((cb::u64)__double_as_longlong(" + s.v + "))"
                                                                      : "(cb::i64)" + s.v;
-                    em.body << "    if (" << (s.n.empty() ? "true" : "!" + s.n) << ") { acc." << (mn ? "min_i64" : "max_i64") << "(g, " << L.w_minmax << ", "
-                            << key << "); acc.add_i64_wrap(g, " << L.w_cnt << ", 1); }\n";
+                    const std::string ok = s.n.empty() ? "true" : "!" + s.n;
+                    upd(mn ? "min" : "max", ok, L.w_minmax, key);
+                    upd("count", ok, L.w_cnt);
                     break;
                 }
                 }
@@ -1108,10 +1141,11 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                     // exact total; overflow decided by the certificate (see DESIGN.md "decimal sums")
                     fin << "      cb::i128 s = " << T128(L.w_sum) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
                     fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
-                    fin << "      int cert = cb::sum_cert(fp.cert[" << ai << "], cb::dec_fits_p(s, " << a.datatype.precision << ")); // 0 fits, 1 overflow, 2 order-dependent\n";
+                    fin << "      int cert = cb::sum_cert(cb::cert_level(n, fp.cert_b[" << ai << "][0], fp.cert_b[" << ai << "][1], " << a.datatype.precision
+                        << "), cb::dec_fits_p(s, " << a.datatype.precision << ")); // 0 fits, 1 overflow, 2 order-dependent\n";
                     fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
                     fin << "      bool ovf = bad || (n > 0 && cert != 0);\n";
-                    if (a.eval_mode == EvalMode::Ansi) fin << "      if (ovf && !bad) cb::set_err_raw(fp.err, 1);\n";
+                    if (a.eval_mode == EvalMode::Ansi) fin << "      if (n > 0 && !bad && cert == 1) cb::set_err_raw(fp.err, 1); // certain overflow only: an order-dependent sum is reported as such\n";
                     if (partial) {
                         int c0 = add_out(a.datatype, true), c1 = add_out(mk_type(TypeId::Bool), false);
                         // state(): sum = Some(0) while empty, None after overflow (sum_decimal.rs:526-538)
@@ -1130,7 +1164,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                     fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
                     fin << "      bool ovf = bad || (n > 0 && cert != 0);\n";
                     if (a.eval_mode == EvalMode::Ansi) {
-                        fin << "      if (ovf) cb::set_err_raw(fp.err, 1);\n";
+                        fin << "      if (bad || (n > 0 && cert == 1)) cb::set_err_raw(fp.err, 1);\n";
                         int c0 = add_out(mk_type(TypeId::Int64), true);
                         fin << "      cb::fin_store_i64(fp, " << c0 << ", g, (n > 0 && !ovf) ? (cb::i64)s.lo : 0, n > 0 && !ovf);\n";
                     } else if (partial) { // TRY state(): sum = Some(0) while all-null, None after overflow; has_all_nulls (sum_int.rs:322-329)
@@ -1158,7 +1192,9 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                     int sp = a.sum_datatype.precision;
                     fin << "      cb::i128 s = " << T128(L.w_sum) << "; cb::i64 n = " << T64(L.w_cnt) << ";\n";
                     fin << "      bool bad = " << (L.w_bad >= 0 ? T64(L.w_bad) + " > 0" : "false") << ";\n";
-                    fin << "      int cert = cb::sum_cert(fp.cert[" << ai << "], cb::dec_fits_p(s, " << sp << "));\n";
+                    // addends: input rows (Partial) / merged state rows (Final, PartialMerge: `n` is the merged COUNT there)
+                    fin << "      int cert = cb::sum_cert(cb::cert_level(" << (spec.mode == AggMode::Partial ? "n" : "(cb::i64)T[CB_W_ROWS * 2]") << ", fp.cert_b[" << ai
+                        << "][0], fp.cert_b[" << ai << "][1], " << sp << "), cb::dec_fits_p(s, " << sp << "));\n";
                     fin << "      if (n > 0 && !bad && cert == 2) cb::set_err_raw(fp.err, 2);\n";
                     fin << "      bool notnull = !bad && !(n > 0 && cert != 0);\n";
                     if (partial) { // state(): sums and counts share is_not_null as validity (avg_decimal.rs:640-656)
@@ -1167,7 +1203,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
                         fin << "      cb::fin_store_i64(fp, " << c1 << ", g, n, notnull);\n";
                     } else {
                         int c0 = add_out(a.datatype, true);
-                        if (a.eval_mode == EvalMode::Ansi) fin << "      if (!notnull && n > 0) cb::set_err_raw(fp.err, 1);\n";
+                        if (a.eval_mode == EvalMode::Ansi) fin << "      if (n > 0 && (bad || cert == 1)) cb::set_err_raw(fp.err, 1);\n";
                         int d = a.datatype.scale - a.sum_datatype.scale;
                         if (d < 0) d = 0;
                         fin << "      cb::i128 r = cb::mk128(0, 0); bool ok = notnull && n > 0 && cb::avg_decimal_eval(s, n, " << d << ", "
@@ -1207,7 +1243,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         for (size_t i = 0; i < slots.kinds.size(); i++) tu << "w == " << i << " ? " << slots.kinds[i] << " : ";
         tu << "0; }\n";
         tu << "#include \"cb_kernels.cuh\"\nnamespace cb {\n";
-        tu << "CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc) {\n    (void)grow;\n" << em.body.str() << "}\n";
+        tu << "CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc, bool in_range) {\n    (void)grow;\n" << em.body.str() << "}\n";
         tu << "CB_D void cb_finalize_group(const FinParams& fp, int g, const u64* T) {\n" << fin.str() << "}\n";
         if (spec.hash) tu << "CB_D void cb_unpack_key(const FinParams& fp, int g, const u64* kw, bool null_group) {\n" << unpack.str() << "}\n";
         tu << "} // namespace cb\n";

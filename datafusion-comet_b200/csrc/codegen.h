@@ -72,5 +72,7 @@ struct GeneratedKernel {
 };
 
 GeneratedKernel generate_pipeline(const PipelineSpec& spec);
+// canonical text of a pipeline (expressions, column encodings, sink): equal specs give equal strings
+std::string pipeline_signature(const PipelineSpec& spec);
 
 } // namespace cb200

@@ -153,7 +153,9 @@ CB_D void tile_view(u8* stage_base, Tile& t) {
 #ifdef CB_KERNEL_AGG
 namespace cb {
 struct Acc;
-CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc);
+// dense / ungrouped: called for rows of the tile only.  hash: called by whole warps for every slot of the tile, `in_range` false
+// for the slots past the last row (the warp-cooperative table update needs convergent lanes).
+CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& acc, bool in_range);
 
 // Thread-private accumulator file.  Word (g, w) of thread t lives at acc[(g*CB_WORDS + w)*CB_THREADS + t]
 // (8-byte words interleaved across threads => every warp access is bank-conflict-free no matter
@@ -168,124 +170,184 @@ CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& a
 
 #if CB_HASH
 // ---- hash aggregation: accumulators live in a global open-addressing table, updated with atomics -------------
+// The table is fed WARP-COOPERATIVELY.  Lanes of a warp hold 32 consecutive rows; rows with equal keys that sit next to each
+// other (clustered inputs: ~4 lines per order in Config 4) form a RUN.  Per run, one lane -- its head -- probes the key table
+// once and issues one atomic per accumulator word with the run's combined value (segmented shuffle reduction); the other lanes
+// never touch the table.  Round 1 probed and issued 2-3 returning atomics per ROW and ran at < 5 % of the HBM roofline: the kernel
+// was bound by L2 atomic throughput, not by the 24 bytes per row it streams.
 struct Acc {
     const PipeParams* p;
     u64 vm[2 * CB_NCOLS];
+    // state of the current row iteration (begin() sets it)
+    int g;          // group id (valid on head lanes)
+    int run_end;    // last lane of this lane's run
+    bool head, keep;
     CB_D void vm_or(int c, i128 raw) { u64 s = (u64)(raw.hi >> 63); vm[2 * c] |= raw.lo ^ s; vm[2 * c + 1] |= (u64)raw.hi ^ s; }
     CB_D void vm_or64(int c, i64 raw) { vm[2 * c] |= (u64)raw ^ (u64)(raw >> 63); }
 
-    // dense group id of `key` (inserting it if new).  Linear probing; a plain L2 load first so that hits on
-    // existing keys (clustered inputs) need no CAS.  The claimer publishes the id it drew; concurrent finders of the
-    // same key wait for the publication (independent thread scheduling keeps the claimer running).
-    // slot s = 16 bytes {key, gid}: one 128-bit L2 load answers "is it my key, and which group"
+    // slot s = 16 bytes {key or tag, gid}: one 128-bit L2 load answers "is it my key, and which group"
     CB_D int wait_gid(u32 s) const {
-        int g;
-        while ((g = *((volatile i32*)&p->hkeys[2 * (size_t)s + 1])) < 0) {}
-        return g;
+        int g_;
+        while ((g_ = *((volatile i32*)&p->hkeys[2 * (size_t)s + 1])) < 0) {}
+        return g_;
     }
-    // (Tried and removed: electing one prober per distinct key of a warp with __match_any_sync.  On Config 4 -- ~4 adjacent
-    // rows per key -- it measured 17.0 ms against 15.6 ms for plain per-lane probing at 512 threads: the kernel is bound by the
-    // accumulator atomics, not by the probes, and hits on an existing key are one L2 load anyway.)
-    CB_D int find_slot(u64 key) const {
-        const u32 mask = p->hmask;
-        if (key == CB_EMPTY_KEY) { atomicOr(p->hflags, 1); return p->max_groups; }
-        u64 h = key;
-        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
-        u32 s = (u32)h & mask;
-        for (u32 probe = 0; probe <= mask; probe++) {
-            ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2*>(p->hkeys) + s);
-            if (slot.x == key) { int g = (i32)(u32)slot.y; return g >= 0 ? g : wait_gid(s); }
-            if (slot.x == CB_EMPTY_KEY) {
-                u64 prev = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);
-                if (prev == CB_EMPTY_KEY) {
-                    int g = atomicAdd(&p->hflags[4], 1);
-                    if (g >= p->max_groups) { atomicOr(p->hflags, 2); g = p->max_groups; } // cannot happen: host sizes max_groups >= rows
-                    else p->hkey_of_gid[g] = key;
-                    __threadfence();
-                    *((volatile i32*)&p->hkeys[2 * (size_t)s + 1]) = g;
-                    return g;
-                }
-                if (prev == key) return wait_gid(s);
-            }
-            s = (s + 1u) & mask;
-        }
-        atomicOr(p->hflags, 2);
-        return p->max_groups;
-    }
-#if CB_KEY_WORDS > 1
-    // Keys wider than 64 bits: the slot holds a 64-bit TAG (a hash of all key words, never the empty pattern) and the
-    // group id; the key itself lives in hkey_of_gid[gid * CB_KEY_WORDS ..], written by the claimer before it publishes
-    // the id.  A tag match is confirmed against the stored words; a mismatch is a tag collision and probing goes on.
-    CB_D static u64 key_tag(const u64* kw) {
+    CB_D static u64 mix64(u64 h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33; return h; }
+    CB_D static u64 key_tag(const u64* kw) { // CB_KEY_WORDS > 1: 64-bit tag of all key words, never the empty pattern
         u64 h = 0x9e3779b97f4a7c15ull;
 #pragma unroll
         for (int i = 0; i < CB_KEY_WORDS; i++) {
-            u64 x = kw[i] + h;
-            x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+            u64 x = mix64(kw[i] + h);
             h = (h << 5 | h >> 59) ^ x;
         }
         return h == CB_EMPTY_KEY ? 0ull : h;
     }
-    CB_D bool same_key(int g, const u64* kw) const {
-        const u64* k = p->hkey_of_gid + (size_t)g * CB_KEY_WORDS;
+    CB_D bool same_key(int g_, const u64* kw) const {
+        const u64* k = p->hkey_of_gid + (size_t)g_ * CB_KEY_WORDS;
         bool eq = true;
 #pragma unroll
         for (int i = 0; i < CB_KEY_WORDS; i++) eq = eq && __ldcg(k + i) == kw[i];
         return eq;
     }
-    CB_D int find_slot_multi(const u64* kw) const {
-        const u32 mask = p->hmask;
-        const u64 tag = key_tag(kw);
-        u32 s = (u32)(tag ^ (tag >> 32)) & mask;
-        for (u32 probe = 0; probe <= mask; probe++) {
-            ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2*>(p->hkeys) + s);
-            if (slot.x == CB_EMPTY_KEY) {
-                u64 prev = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)tag);
-                if (prev == CB_EMPTY_KEY) {
-                    int g = atomicAdd(&p->hflags[4], 1);
-                    if (g >= p->max_groups) { atomicOr(p->hflags, 2); g = p->max_groups; } // cannot happen: host sizes max_groups >= rows
+
+    // Group ids of the head lanes' keys, inserting new keys.  Called by the whole warp (convergent).
+    //   probe   : linear probing from the key's home slot; a hit on a published slot resolves the lane, an empty slot is claimed
+    //             with a CAS, a slot whose id is not published yet leaves the lane PENDING (no spinning here: the publisher may be
+    //             a lane of this very warp that is waiting at the next step)
+    //   claim   : the lanes that claimed a slot draw consecutive DENSE group ids with ONE atomic per warp, store the key words of
+    //             their group and publish the id into the slot
+    //   pending : now it is safe to wait for the other claimer's publication; wide keys compare the stored words and go on probing
+    //             after a tag collision
+    CB_D void resolve(const u64* kw, bool want, bool null_group) {
+        const u32 lane = threadIdx.x & 31u, mask = p->hmask;
+        g = 0;
+        bool unresolved = want;
+        if (want && null_group) { g = p->max_groups + 1; unresolved = false; }           // reserved group of the NULL key
+        if (CB_KEY_WORDS == 1 && unresolved && kw[0] == CB_EMPTY_KEY) { atomicOr(p->hflags, 1); g = p->max_groups; unresolved = false; } // the key equal to the empty pattern
+        const u64 tag = CB_KEY_WORDS == 1 ? kw[0] : key_tag(kw);
+        u32 s = (CB_KEY_WORDS == 1 ? (u32)mix64(tag) : (u32)(tag ^ (tag >> 32))) & mask;
+        u32 probes = 0;
+        while (__any_sync(0xffffffffu, unresolved)) {
+            bool claimed = false, pending = false;
+            if (unresolved) {
+                while (true) {
+                    if (probes++ > mask) { atomicOr(p->hflags, 2); g = p->max_groups; unresolved = false; break; } // table full: cannot happen (host sizes it)
+                    ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2*>(p->hkeys) + s);
+                    if (slot.x == CB_EMPTY_KEY) {
+                        const u64 prev = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)tag);
+                        if (prev == CB_EMPTY_KEY) { claimed = true; break; }
+                        slot.x = prev;
+                        slot.y = ~0ull; // somebody else just took it: its id may not be out yet
+                    }
+                    if (slot.x == tag) {
+                        const int gs = (i32)(u32)slot.y;
+                        if (gs < 0) { pending = true; break; }
+                        if (CB_KEY_WORDS == 1 || gs >= p->max_groups || same_key(gs, kw)) { g = gs; unresolved = false; break; }
+                    }
+                    s = (s + 1u) & mask;
+                }
+            }
+            const u32 cm = __ballot_sync(0xffffffffu, claimed);
+            if (cm) {
+                const int leader = __ffs(cm) - 1;
+                int base = 0;
+                if ((int)lane == leader) base = atomicAdd(&p->hflags[4], __popc(cm));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (claimed) {
+                    int gn = base + __popc(cm & ((1u << lane) - 1u));
+                    if (gn >= p->max_groups) { atomicOr(p->hflags, 2); gn = p->max_groups; } // cannot happen: host sizes max_groups >= rows
                     else {
 #pragma unroll
-                        for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)g * CB_KEY_WORDS + i] = kw[i];
+                        for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)gn * CB_KEY_WORDS + i] = kw[i];
                     }
                     __threadfence();
-                    *((volatile i32*)&p->hkeys[2 * (size_t)s + 1]) = g;
-                    return g;
+                    *((volatile i32*)&p->hkeys[2 * (size_t)s + 1]) = gn;
+                    g = gn;
+                    unresolved = false;
                 }
-                slot.x = prev;
-                slot.y = ~0ull;
             }
-            if (slot.x == tag) {
-                int g = (i32)(u32)slot.y;
-                if (g < 0) g = wait_gid(s);
+            if (pending) {
+                const int gs = wait_gid(s);
                 __threadfence(); // the claimer's key words are visible once its id is
-                if (g >= p->max_groups || same_key(g, kw)) return g;
+                if (CB_KEY_WORDS == 1 || gs >= p->max_groups || same_key(gs, kw)) { g = gs; unresolved = false; }
+                else s = (s + 1u) & mask; // tag collision: keep probing
             }
-            s = (s + 1u) & mask;
         }
-        atomicOr(p->hflags, 2);
-        return p->max_groups;
     }
-#endif
-    CB_D u64* W(int g, int w) const { return p->htotals + ((size_t)g * CB_WORDS + w) * 2; }
-    CB_D void add_i64_wrap(int g, int w, i64 v) { atomicAdd((unsigned long long*)W(g, w), (unsigned long long)v); }
-    CB_D void add_i128(int g, int w, i128 v) {
-        u64* s = W(g, w);
-        u64 old = atomicAdd((unsigned long long*)&s[0], (unsigned long long)v.lo);
-        u64 carry = (old + v.lo) < old ? 1ull : 0ull;
-        u64 hi = (u64)v.hi + carry;
-        if (hi) atomicAdd((unsigned long long*)&s[1], (unsigned long long)hi);
+
+    // start of a row iteration: run structure of the warp's 32 rows + group ids of the run heads
+    CB_D void begin(bool keep_, const u64* kw, bool null_group) {
+        const u32 lane = threadIdx.x & 31u;
+        keep = keep_;
+        bool same_prev = lane != 0;
+#pragma unroll
+        for (int i = 0; i < CB_KEY_WORDS; i++) same_prev = same_prev && (__shfl_up_sync(0xffffffffu, kw[i], 1) == kw[i]);
+        const bool prev_keep = __shfl_up_sync(0xffffffffu, (int)keep_, 1) != 0;
+        const bool prev_null = __shfl_up_sync(0xffffffffu, (int)null_group, 1) != 0;
+        head = keep_ && !(same_prev && prev_keep && prev_null == null_group);
+        const u32 stops = __ballot_sync(0xffffffffu, head) | ~__ballot_sync(0xffffffffu, keep_); // a run ends before the next head / absent row
+        const u32 above = lane == 31u ? 0u : (stops & ~((2u << lane) - 1u));
+        run_end = above ? __ffs(above) - 2 : 31;
+        resolve(kw, head, null_group);
     }
-    CB_D void add_i64_wide(int g, int w, i64 v) { add_i128(g, w, i128_from_i64(v)); }
-    CB_D void add_f64(int g, int w, double x) { // double-double in one 16-byte word pair, updated with a 128-bit CAS
-        u64* s = W(g, w);
+
+    CB_D u64* W(int w) const { return p->htotals + ((size_t)g * CB_WORDS + w) * 2; }
+    CB_D bool in_run(int off) const { return (int)(threadIdx.x & 31u) + off <= run_end; }
+    // count of rows of the run with `c`: no shuffles needed, the ballot has it
+    CB_D void h_count(bool c, int w) {
+        const u32 lane = threadIdx.x & 31u;
+        const u32 m = __ballot_sync(0xffffffffu, keep && c);
+        if (head) {
+            const u32 run = (run_end == 31 ? 0xffffffffu : ((2u << run_end) - 1u)) & ~((1u << lane) - 1u);
+            const int n = __popc(m & run);
+            if (n) atomicAdd((unsigned long long*)W(w), (unsigned long long)n);
+        }
+    }
+    CB_D void h_add_wrap(bool c, int w, i64 v) { // wrapping 64-bit sum (SumInt Legacy, merged counts)
+        u64 x = (keep && c) ? (u64)v : 0ull;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const u64 o = __shfl_down_sync(0xffffffffu, x, off); if (in_run(off)) x += o; }
+        if (head && x) atomicAdd((unsigned long long*)W(w), (unsigned long long)x);
+    }
+    CB_D void h_add_i128(bool c, int w, i128 v) { // exact 128-bit sum: (lo, hi) words with carry
+        u64 lo = (keep && c) ? v.lo : 0ull;
+        i64 hi = (keep && c) ? v.hi : 0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u64 olo = __shfl_down_sync(0xffffffffu, lo, off);
+            const i64 ohi = __shfl_down_sync(0xffffffffu, hi, off);
+            if (in_run(off)) { const u64 n = lo + olo; hi += ohi + (n < lo ? 1 : 0); lo = n; }
+        }
+        if (head && (lo | (u64)hi)) {
+            u64* s = W(w);
+            u64 carry = 0;
+            if (lo) { const u64 old = atomicAdd((unsigned long long*)&s[0], (unsigned long long)lo); carry = (old + lo) < old ? 1ull : 0ull; }
+            const u64 h2 = (u64)hi + carry;
+            if (h2) atomicAdd((unsigned long long*)&s[1], (unsigned long long)h2);
+        }
+    }
+    CB_D void h_add_i64_wide(bool c, int w, i64 v) { h_add_i128(c, w, i128_from_i64(v)); }
+    CB_D void h_add_f64(bool c, int w, double x) { // double-double: run partial in lane order, then one 128-bit CAS loop per run
+        dd a;
+        a.hi = (keep && c) ? x : 0.0;
+        a.lo = 0.0;
+        bool any = keep && c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            dd o;
+            o.hi = __shfl_down_sync(0xffffffffu, a.hi, off);
+            o.lo = __shfl_down_sync(0xffffffffu, a.lo, off);
+            const bool oany = __shfl_down_sync(0xffffffffu, (int)any, off) != 0;
+            if (in_run(off) && oany) { if (any) dd_add_dd(a, o); else a = o; any = true; }
+        }
+        if (!(head && any)) return;
+        u64* s = W(w);
         u64 o0 = __ldcg(&s[0]), o1 = __ldcg(&s[1]);
         while (true) {
-            dd a;
-            a.hi = __longlong_as_double((i64)o0);
-            a.lo = __longlong_as_double((i64)o1);
-            dd_add_double(a, x);
-            u64 n0 = (u64)__double_as_longlong(a.hi), n1 = (u64)__double_as_longlong(a.lo), r0, r1;
+            dd t;
+            t.hi = __longlong_as_double((i64)o0);
+            t.lo = __longlong_as_double((i64)o1);
+            dd_add_dd(t, a);
+            u64 n0 = (u64)__double_as_longlong(t.hi), n1 = (u64)__double_as_longlong(t.lo), r0, r1;
             asm volatile(
                 "{\n"
                 ".reg .b128 cmp, nv, res;\n"
@@ -301,8 +363,18 @@ struct Acc {
             o0 = r0; o1 = r1;
         }
     }
-    CB_D void min_i64(int g, int w, i64 key) { atomicMin((long long*)W(g, w), (long long)key); }
-    CB_D void max_i64(int g, int w, i64 key) { atomicMax((long long*)W(g, w), (long long)key); }
+    CB_D void h_min(bool c, int w, i64 key) {
+        i64 x = (keep && c) ? key : (i64)0x7fffffffffffffffll;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const i64 o = __shfl_down_sync(0xffffffffu, x, off); if (in_run(off) && o < x) x = o; }
+        if (head && x != (i64)0x7fffffffffffffffll) atomicMin((long long*)W(w), (long long)x);
+    }
+    CB_D void h_max(bool c, int w, i64 key) {
+        i64 x = (keep && c) ? key : (i64)0x8000000000000000ll;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const i64 o = __shfl_down_sync(0xffffffffu, x, off); if (in_run(off) && o > x) x = o; }
+        if (head && x != (i64)0x8000000000000000ll) atomicMax((long long*)W(w), (long long)x);
+    }
 };
 #else
 struct Acc {
@@ -433,8 +505,14 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_agg
         const i64 row0 = (i64)tile * CB_TILE;
         const i64 rem = p.n_rows - row0;
         const int rows = rem < CB_TILE ? (int)rem : CB_TILE;
+#if CB_HASH
+        static_assert(CB_TILE % CB_THREADS == 0, "hash tiles are whole warps");
 #pragma unroll 2
-        for (int r = tid; r < rows; r += CB_THREADS) cb_row_agg(t, r, row0 + r, p, acc);
+        for (int r = tid; r < CB_TILE; r += CB_THREADS) cb_row_agg(t, r, row0 + r, p, acc, r < rows);
+#else
+#pragma unroll 2
+        for (int r = tid; r < rows; r += CB_THREADS) cb_row_agg(t, r, row0 + r, p, acc, true);
+#endif
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[s]); // this warp is done with stage s
     }
@@ -571,9 +649,7 @@ extern "C" __global__ void cb_hash_rehash(const u64* key_of_gid, int n_groups, u
     u32 s = (u32)(key ^ (key >> 32)) & mask;
 #else
     u64 key = key_of_gid[g];
-    u64 h = key;
-    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
-    u32 s = (u32)h & mask;
+    u32 s = (u32)Acc::mix64(key) & mask;
 #endif
     while (true) {
         u64 prev = atomicCAS((unsigned long long*)&hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)key);

@@ -353,6 +353,19 @@ CB_HD bool i64_mul_overflow(i64 a, i64 b, i64& r) { i128 p = mul_i64_i64(a, b); 
 //                                         overflows (the last prefix is the total), otherwise order-dependent
 //   2: the 128-bit total may have wrapped
 // returns 0 fits, 1 overflows (NULL / ANSI error), 2 order-dependent (cannot be decided without row order)
+CB_HD i128 i128_abs_of_i64(i64 v) { i128 m = i128_from_i64(v); return m.hi < 0 ? i128_neg(m) : m; } // |v| as 128 bits (|i64::MIN| fits)
+// the host certificate, per GROUP: n = addends of this group, B = bound on the magnitude of any addend (lo, hi; hi = ~0: none)
+CB_HD int cert_level(i64 n, u64 blo, u64 bhi, int p) {
+    if (n <= 0) return 0;
+    if (bhi == ~0ull) return 2;
+    const u64 m = (u64)n;
+    const u64 p0 = blo * m, c0 = umulhi64(blo, m);
+    const u64 q = bhi * m, p1 = q + c0;
+    const u64 p2 = umulhi64(bhi, m) + (p1 < q ? 1ull : 0ull);
+    if (p2 != 0 || (p1 >> 63) != 0) return 2;                     // n * B >= 2^127: the 128-bit total may have wrapped
+    const u128 mx = pow10_u128(p);
+    return (p1 < mx.hi || (p1 == mx.hi && p0 < mx.lo)) ? 0 : 1;   // n * B <= 10^p - 1 ?
+}
 CB_HD int sum_cert(int h, bool total_fits) {
     if (h == 0) return total_fits ? 0 : 1;
     if (h == 1 && !total_fits) return 1;

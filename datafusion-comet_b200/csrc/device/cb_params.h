@@ -60,7 +60,8 @@ struct FinParams {
     i32 max_groups;
     i32 sentinel_used;     // hash aggregation: slot `cap` holds the key equal to the EMPTY sentinel
     i32 null_group_used;   // hash aggregation: slot `cap+1` holds the all-NULL key (single nullable 64-bit key)
-    i32 cert[CB_MAX_OUT];  // per aggregate: 0 = host certified that the decimal sum cannot overflow for any row order, 2 = not certified
+    u64 cert_b[CB_MAX_OUT][2]; // per aggregate: bound (lo, hi) on the magnitude of any single addend of a decimal SUM / AVG, from the observed value
+                               // masks through the range propagation (hi = ~0: unbounded); finalize turns it into a per-group certificate (cb::cert_level)
 };
 
 } // namespace cb

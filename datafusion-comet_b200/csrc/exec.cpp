@@ -3,9 +3,6 @@
 
 #include "aot_kernels.h"
 #include "device/cb_params.h"
-#include "parquet.h"
-#include "parquet_kernels.h"
-#include "device/cb_snappy.h"
 #include "ranges.h"
 
 #include <algorithm>
@@ -23,12 +20,12 @@ namespace cb200 {
 // error bits raised by kernels (device/cb_kernels.cuh set_err)
 enum { ERR_I128_OVERFLOW = 0, ERR_ANSI_OVERFLOW = 1, ERR_ORDER_DEPENDENT = 2 };
 
-static bool trace_on() {
+bool trace_on() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("CB200_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
     return on == 1;
 }
-static double now_ms() {
+double now_ms() {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
@@ -410,596 +407,57 @@ struct TableSource : ExecNode {
         schema = fields;
         if (table->cols.size() != fields.size()) throw PlanError("bound device table has " + std::to_string(table->cols.size()) + " columns, scan declares " + std::to_string(fields.size()));
     }
+    // The table is handed out in slices of spark.comet.b200.chunkRows rows (a multiple of 1024, so every slice starts on the byte /
+    // tile boundaries the kernels assume): a consumer's per-batch state -- hash-table headroom for "every row a new group" -- is
+    // bounded by the chunk, not by the table.
+    int64_t pos = 0;
+    bool packed = false;
+    int64_t rows_hint() const override { return table->n_rows - pos; }
     bool next(Batch& out) override {
         if (done) return false;
-        done = true;
-        out.n_rows = table->n_rows;
-        out.cols = table->cols;
-        if (table->needs_packing) { // byte-per-row validity / booleans (received from an exchange) -> Arrow bitmaps
-            size_t n = (size_t)out.n_rows;
-            for (auto& c : out.cols) {
+        if (table->needs_packing && !packed) { // byte-per-row validity / booleans (received from an exchange) -> Arrow bitmaps, once
+            size_t n = (size_t)table->n_rows;
+            for (auto& c : table->cols) {
                 if (c.valid_bytes && !c.validity) {
                     c.validity = std::make_shared<DeviceBuf>((n + 31) / 32 * 4 + 8);
-                    launch_bytes_to_bitmap((const unsigned char*)c.valid_bytes->ptr, out.n_rows, (uint32_t*)c.validity->ptr, ctx->stream);
+                    launch_bytes_to_bitmap((const unsigned char*)c.valid_bytes->ptr, table->n_rows, (uint32_t*)c.validity->ptr, ctx->stream);
                     ctx->kernel_launches++;
                 }
                 if (c.bool_bytes && !c.data) {
                     c.data = std::make_shared<DeviceBuf>((n + 31) / 32 * 4 + 8);
-                    launch_bytes_to_bitmap((const unsigned char*)c.bool_bytes->ptr, out.n_rows, (uint32_t*)c.data->ptr, ctx->stream);
+                    launch_bytes_to_bitmap((const unsigned char*)c.bool_bytes->ptr, table->n_rows, (uint32_t*)c.data->ptr, ctx->stream);
                     ctx->kernel_launches++;
                 }
+            }
+            packed = true;
+        }
+        const int64_t chunk = std::max<int64_t>(1024, ctx->chunk_rows / 1024 * 1024);
+        const int64_t r0 = pos, r1 = std::min(table->n_rows, pos + chunk);
+        pos = r1;
+        if (pos >= table->n_rows) done = true;
+        out.n_rows = r1 - r0;
+        out.cols = table->cols;
+        if (r0 > 0 || r1 < table->n_rows) {
+            for (auto& c : out.cols) {
+                auto slice = [&](DeviceBufP& b, size_t num, size_t den) { // element = num / den bytes
+                    if (!b) return;
+                    auto v = std::make_shared<DeviceBuf>((char*)b->ptr + (size_t)r0 * num / den, (size_t)(r1 - r0) * num / den + 1);
+                    v->owner = b;
+                    b = v;
+                };
+                const int w = phys_bytes(c.is_dict && c.phys == Phys::I32 ? Phys::Dict32 : c.phys);
+                if (w == 0) slice(c.data, 1, 8);
+                else slice(c.data, (size_t)w, 1);
+                slice(c.validity, 1, 8);
+                slice(c.valid_bytes, 1, 1);
+                slice(c.bool_bytes, 1, 1);
+                if (c.null_count > 0) c.null_count = -1;
             }
         }
         return out.n_rows > 0;
     }
 };
 
-
-// =================================================================================================
-// native Parquet scan (NativeScan -> DataSourceExec(ParquetSource), native/core/src/parquet/parquet_exec.rs:60-200)
-// =================================================================================================
-// Footer and page headers are parsed on the host (parquet.cpp); encoded pages cross PCIe as they sit in the
-// file and are decoded on the device (parquet_kernels.cu).  d(p<=18) / INT64 decimals stay 8 bytes wide in HBM
-// (the Parquet physical width) and the fused kernels read them as such.
-static std::mutex g_memfile_mu;
-static std::map<std::string, std::pair<const uint8_t*, size_t>> g_memfiles;
-void register_memory_file(const std::string& name, const uint8_t* p, size_t n) {
-    std::lock_guard<std::mutex> lk(g_memfile_mu);
-    if (p) g_memfiles[name] = {p, n};
-    else g_memfiles.erase(name);
-}
-static bool lookup_memory_file(const std::string& path, const uint8_t** p, size_t* n) {
-    const std::string pre = "memory://";
-    if (path.compare(0, pre.size(), pre) != 0) return false;
-    std::lock_guard<std::mutex> lk(g_memfile_mu);
-    auto it = g_memfiles.find(path.substr(pre.size()));
-    if (it == g_memfiles.end()) throw ExecError(3, "", "parquet: memory file '" + path + "' is not registered");
-    *p = it->second.first;
-    *n = it->second.second;
-    return true;
-}
-static std::string strip_file_scheme(const std::string& p) { return p.compare(0, 7, "file://") == 0 ? p.substr(7) : p; }
-
-pq::FileMeta open_parquet(const std::string& path, const uint8_t** mem, size_t* mem_len) {
-    *mem = nullptr;
-    *mem_len = 0;
-    if (lookup_memory_file(path, mem, mem_len)) return pq::parse_footer(*mem, *mem_len);
-    int64_t sz = 0;
-    return pq::read_footer(strip_file_scheme(path), &sz);
-}
-
-struct NativeScanSource : ExecNode {
-    ExecContext* ctx;
-    std::vector<std::string> files;
-    std::vector<StructField> fields;
-
-    struct OpenFile {
-        pq::FileMeta meta;
-        const uint8_t* mem = nullptr;
-        size_t mem_len = 0;
-        FILE* fh = nullptr;
-        std::vector<int> leaf_of; // per output column: leaf index in this file
-    };
-    struct Unit { size_t file, rg; int64_t rows, row0; };
-    struct ChunkLoc { const uint8_t* host; unsigned char* dev; }; // one column chunk of a batch: its bytes on the host and where they land on the device
-    std::vector<OpenFile> open_files;
-    std::vector<Unit> all_units;
-    size_t next_unit = 0;
-    bool opened = false;
-    std::vector<DictionaryP> dicts;
-    // Two "slots" alternate between consecutive batches so that batch k+1's encoded bytes cross PCIe (copy stream)
-    // while batch k is decoded and consumed (plan stream): per slot a pinned staging region (file-backed inputs),
-    // one device chunk buffer per column, and the events that order their reuse.
-    struct Slot {
-        uint8_t* staging = nullptr;
-        size_t staging_cap = 0;
-        DeviceBufP chunk;                   // encoded bytes of the batch: the needed byte ranges of every row group, back to back
-        cudaEvent_t decoded = nullptr;      // plan stream: the decode kernels reading `chunk` have run
-        cudaEvent_t uploaded = nullptr;     // copy stream: the last H2D out of `staging` has run
-        bool used = false;
-        // pinned bump arena for page tables / dictionary remaps: uploads from pageable memory would make every
-        // cudaMemcpyAsync wait for the stream (the driver copies synchronously), serialising host and copy engine
-        std::vector<std::pair<uint8_t*, size_t>> meta_blocks;
-        size_t meta_used = 0;
-        void* meta_alloc(size_t bytes) {
-            bytes = (bytes + 63) / 64 * 64;
-            if (meta_blocks.empty() || meta_used + bytes > meta_blocks.back().second) {
-                size_t cap = std::max<size_t>(bytes, (size_t)1 << 20);
-                uint8_t* p = nullptr;
-                cuda_check(cudaMallocHost((void**)&p, cap), "cudaMallocHost page tables");
-                meta_blocks.push_back({p, cap});
-                meta_used = 0;
-            }
-            void* r = meta_blocks.back().first + meta_used;
-            meta_used += bytes;
-            return r;
-        }
-        void meta_reset() { // caller made sure the uploads of the slot's previous batch have run
-            if (meta_blocks.size() > 1) {
-                size_t total = 0;
-                for (auto& b : meta_blocks) { total += b.second; cudaFreeHost(b.first); }
-                meta_blocks.clear();
-                uint8_t* p = nullptr;
-                cuda_check(cudaMallocHost((void**)&p, total), "cudaMallocHost page tables");
-                meta_blocks.push_back({p, total});
-            }
-            meta_used = 0;
-        }
-    };
-    Slot slots[2];
-    cudaStream_t copy_stream = nullptr;
-    // Decode kernels run on their own stream, not the plan's: the consumer synchronises the plan stream after every
-    // batch, and the prefetched batch's decode (which waits for its upload) must not be inside that wait.
-    cudaStream_t decode_stream = nullptr;
-    int* h_flags = nullptr;                 // pinned: per-slot decode error flags
-
-    ~NativeScanSource() override {
-        if (copy_stream) cudaStreamSynchronize(copy_stream);
-        if (decode_stream) cudaStreamSynchronize(decode_stream);
-        pending.reset();
-        for (auto& f : open_files) if (f.fh) fclose(f.fh);
-        for (auto& sl : slots) {
-            if (sl.staging) cudaFreeHost(sl.staging);
-            for (auto& b : sl.meta_blocks) cudaFreeHost(b.first);
-            if (sl.decoded) cudaEventDestroy(sl.decoded);
-            if (sl.uploaded) cudaEventDestroy(sl.uploaded);
-        }
-        if (h_flags) cudaFreeHost(h_flags);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
-        if (decode_stream) cudaStreamDestroy(decode_stream);
-    }
-
-    void open_all() { // footers are tiny: parse them all up front (the reference's ParquetSource does the same per file group)
-        for (auto& path : files) {
-            OpenFile of;
-            of.meta = open_parquet(path, &of.mem, &of.mem_len);
-            if (!of.mem) {
-                of.fh = fopen(strip_file_scheme(path).c_str(), "rb");
-                if (!of.fh) throw ExecError(3, "", "parquet: cannot open " + path);
-            }
-            for (auto& f : fields) {
-                int li = of.meta.leaf_index(f.name);
-                if (li < 0) throw Unsupported("parquet: column '" + f.name + "' missing from " + path + " (schema evolution / default values are out of scope)");
-                of.leaf_of.push_back(li);
-            }
-            for (size_t g = 0; g < of.meta.row_groups.size(); g++)
-                if (of.meta.row_groups[g].num_rows > 0) all_units.push_back({open_files.size(), g, of.meta.row_groups[g].num_rows, 0});
-            open_files.push_back(std::move(of));
-        }
-        dicts.assign(fields.size(), nullptr);
-        cuda_check(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "copy stream");
-        cuda_check(cudaStreamCreateWithFlags(&decode_stream, cudaStreamNonBlocking), "decode stream");
-        cuda_check(cudaMallocHost((void**)&h_flags, 2 * sizeof(int)), "cudaMallocHost flags");
-        for (auto& sl : slots) {
-            cuda_check(cudaEventCreateWithFlags(&sl.decoded, cudaEventDisableTiming), "event");
-            cuda_check(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming), "event");
-        }
-        opened = true;
-    }
-    const pq::ColumnChunkMeta& chunk_meta(const Unit& u, size_t c) const {
-        const OpenFile& f = open_files[u.file];
-        return f.meta.row_groups[u.rg].columns[(size_t)f.leaf_of[c]];
-    }
-
-    // host-side temporaries that must outlive the asynchronous uploads of one next() call
-    struct Arena {
-        std::vector<std::shared_ptr<std::vector<PqPage>>> pages;
-        std::vector<std::shared_ptr<std::vector<int32_t>>> remaps;
-        std::vector<DeviceBufP> dev;
-        std::vector<cudaEvent_t> events;
-        ~Arena() { for (auto e : events) cudaEventDestroy(e); }
-    };
-
-    // a batch whose uploads and decode kernels are queued but not yet waited for
-    struct Prepared {
-        Batch batch;
-        Arena arena;
-        DeviceBufP derr;
-        cudaEvent_t done = nullptr;
-        cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr}; // CB200_TRACE: copy-stream begin/end, plan-stream begin/end
-        int slot = 0;
-        ~Prepared() {
-            if (done) cudaEventDestroy(done);
-            for (auto e : tr) if (e) cudaEventDestroy(e);
-        }
-    };
-    std::unique_ptr<Prepared> pending;
-    int64_t n_issued = 0;
-    double t_alloc = 0, t_pages = 0, t_h2d = 0, t_launch = 0; // CB200_TRACE: host milliseconds per issue()
-
-    // buffers come from the plan stream's pool order (DeviceBuf); the decode stream may touch them after this point
-    void allocations_visible(Arena& arena) {
-        cudaEvent_t ev;
-        cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
-        arena.events.push_back(ev);
-        cuda_check(cudaEventRecord(ev, ctx->stream), "event record");
-        cuda_check(cudaStreamWaitEvent(decode_stream, ev, 0), "stream wait");
-    }
-
-    std::unique_ptr<Prepared> issue() {
-        if (next_unit >= all_units.size()) return nullptr;
-        TraceSpan ts("parquet.issue");
-        auto pr = std::make_unique<Prepared>();
-        pr->slot = (int)(n_issued++ & 1);
-        Slot& sl = slots[pr->slot];
-        std::vector<Unit> units;
-        int64_t total = 0;
-        // (Tried and removed: ramping the batch size up from 8 Mi rows so that the first upload -- which has nothing to overlap
-        // with -- is short.  Batches of different sizes defeat the stream-ordered pool's block reuse: 177 ms -> 486 ms per step.)
-        while (next_unit < all_units.size() && (units.empty() || total + all_units[next_unit].rows <= ctx->chunk_rows)) {
-            Unit u = all_units[next_unit++];
-            u.row0 = total;
-            total += u.rows;
-            units.push_back(u);
-        }
-        Batch& out = pr->batch;
-        out.n_rows = total;
-        out.cols.clear();
-        out.cols.resize(fields.size());
-        // Upload plan: per row group, the selected column chunks sorted by file offset and merged into byte ranges
-        // (gaps of unselected columns up to 64 KB ride along) -- PCIe moves few large copies faster than many
-        // chunk-sized ones (measured on this box: 49 GB/s at 1.8 MB per copy, 54 GB/s at 12 MB).
-        struct Range { size_t file; int64_t start, end; size_t dev_off; };
-        std::vector<Range> ranges;
-        std::vector<std::vector<ChunkLoc>> loc(fields.size(), std::vector<ChunkLoc>(units.size()));
-        std::vector<std::vector<size_t>> range_of(fields.size(), std::vector<size_t>(units.size(), 0));
-        bool any_file = false;
-        for (size_t u = 0; u < units.size(); u++) {
-            const OpenFile& of = open_files[units[u].file];
-            if (!of.mem) any_file = true;
-            std::vector<std::pair<int64_t, size_t>> items; // (file offset, column)
-            for (size_t c = 0; c < fields.size(); c++) {
-                const pq::ColumnChunkMeta& cc = chunk_meta(units[u], c);
-                if (cc.total_compressed < 0 || cc.start() < 0) throw PlanError("parquet: negative column chunk offset / size");
-                if (of.mem && (size_t)cc.start() + (size_t)cc.total_compressed > of.mem_len) throw PlanError("parquet: column chunk beyond the end of the file image");
-                items.push_back({cc.start(), c});
-            }
-            std::sort(items.begin(), items.end());
-            // consecutive row groups of one file are adjacent in the file, so the range could stay open across units (a batch
-            // becomes a handful of copies of hundreds of MB).  Measured: no gain over one ~12 MB copy per row group (185 vs
-            // 177 ms per step), so it stays opt-in.
-            static const bool merge_units = getenv("CB200_MERGE_UNITS") ? atoi(getenv("CB200_MERGE_UNITS")) != 0 : false;
-            bool open_range = merge_units && !ranges.empty() && ranges.back().file == units[u].file && (size_t)u > 0 && units[u - 1].file == units[u].file &&
-                              ranges.back().end - ranges.back().start < ((int64_t)1 << 30);
-            for (auto& it : items) {
-                const int64_t st0 = it.first, en0 = st0 + chunk_meta(units[u], it.second).total_compressed;
-                if (open_range && st0 >= ranges.back().end && st0 - ranges.back().end <= 65536) ranges.back().end = std::max(ranges.back().end, en0);
-                else if (open_range && st0 < ranges.back().end) ranges.back().end = std::max(ranges.back().end, en0); // overlapping chunks (same column projected twice)
-                else { ranges.push_back({units[u].file, st0, en0, 0}); open_range = true; }
-                range_of[it.second][u] = ranges.size() - 1;
-            }
-        }
-        size_t dev_total = 0;
-        for (auto& r : ranges) { r.dev_off = dev_total; dev_total += ((size_t)(r.end - r.start) + 255) / 256 * 256; }
-        if (any_file) { // file-backed inputs are staged through the slot's pinned region with the device layout (memory files are read in place)
-            if (sl.used) cuda_check(cudaEventSynchronize(sl.uploaded), "staging reuse"); // the previous batch of this slot has left the staging region
-            if (dev_total > sl.staging_cap) {
-                if (sl.staging) cudaFreeHost(sl.staging);
-                sl.staging = nullptr;
-                cuda_check(cudaMallocHost((void**)&sl.staging, dev_total), "cudaMallocHost staging");
-                sl.staging_cap = dev_total;
-            }
-        }
-        // the copy stream may overwrite the slot's chunk buffers only after the decode kernels of their previous batch
-        if (sl.used) cuda_check(cudaStreamWaitEvent(copy_stream, sl.decoded, 0), "stream wait");
-        if (sl.used) cuda_check(cudaEventSynchronize(sl.decoded), "page table reuse"); // two batches back: long done
-        sl.meta_reset();
-        pr->derr = std::make_shared<DeviceBuf>(64);
-        allocations_visible(pr->arena);
-        cuda_check(cudaMemsetAsync(pr->derr->ptr, 0, 64, decode_stream), "memset parquet err");
-        t_alloc = t_pages = t_h2d = t_launch = 0;
-        if (trace_on()) {
-            for (auto& e : pr->tr) cuda_check(cudaEventCreate(&e), "event");
-            cuda_check(cudaEventRecord(pr->tr[0], copy_stream), "event record");
-            cuda_check(cudaEventRecord(pr->tr[2], decode_stream), "event record");
-        }
-        double tt = now_ms();
-        if (!sl.chunk || sl.chunk->bytes < dev_total + 64) {
-            // (re)allocation happens in plan-stream order; let the copy stream see it.  The old buffer is freed in
-            // plan-stream order too, i.e. after every decode kernel that read it.
-            sl.chunk = std::make_shared<DeviceBuf>(dev_total + dev_total / 8 + 64);
-            cudaEvent_t alloc_ev;
-            cuda_check(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming), "event");
-            pr->arena.events.push_back(alloc_ev);
-            cuda_check(cudaEventRecord(alloc_ev, ctx->stream), "event record");
-            cuda_check(cudaStreamWaitEvent(copy_stream, alloc_ev, 0), "stream wait");
-        }
-        pr->arena.dev.push_back(sl.chunk);
-        t_alloc += now_ms() - tt;
-        tt = now_ms();
-        for (auto& r : ranges) {
-            const OpenFile& of = open_files[r.file];
-            const size_t len = (size_t)(r.end - r.start);
-            const uint8_t* host;
-            if (of.mem) host = of.mem + r.start;
-            else {
-                uint8_t* dst = sl.staging + r.dev_off;
-                if (fseeko(of.fh, (off_t)r.start, SEEK_SET) != 0 || fread(dst, 1, len, of.fh) != len) throw ExecError(3, "", "parquet: short read");
-                host = dst;
-            }
-            cuda_check(cudaMemcpyAsync((char*)sl.chunk->ptr + r.dev_off, host, len, cudaMemcpyHostToDevice, copy_stream), "H2D parquet range");
-            ctx->h2d_bytes += (int64_t)len;
-        }
-        for (size_t c = 0; c < fields.size(); c++)
-            for (size_t u = 0; u < units.size(); u++) {
-                const Range& r = ranges[range_of[c][u]];
-                const int64_t off = chunk_meta(units[u], c).start() - r.start;
-                const OpenFile& of = open_files[r.file];
-                loc[c][u].host = (of.mem ? of.mem + r.start : sl.staging + r.dev_off) + off;
-                loc[c][u].dev = (unsigned char*)sl.chunk->ptr + r.dev_off + off;
-            }
-        cuda_check(cudaEventRecord(sl.uploaded, copy_stream), "event record");
-        cuda_check(cudaStreamWaitEvent(decode_stream, sl.uploaded, 0), "stream wait"); // decode kernels start when the batch has landed
-        t_h2d += now_ms() - tt;
-        for (size_t c = 0; c < fields.size(); c++) decode_column(c, units, total, loc[c], out.cols[c], pr->arena, (int*)pr->derr->ptr, sl);
-        if (trace_on()) fprintf(stderr, "[cb200 trace]   issue breakdown: alloc %.3f  page tables %.3f  h2d enqueue (%zu ranges) %.3f  launches %.3f ms\n", t_alloc, t_pages, ranges.size(), t_h2d, t_launch);
-        cuda_check(cudaEventRecord(sl.decoded, decode_stream), "event record");
-        if (trace_on()) {
-            cuda_check(cudaEventRecord(pr->tr[1], copy_stream), "event record");
-            cuda_check(cudaEventRecord(pr->tr[3], decode_stream), "event record");
-        }
-        sl.used = true;
-        cuda_check(cudaMemcpyAsync(&h_flags[pr->slot], pr->derr->ptr, 4, cudaMemcpyDeviceToHost, decode_stream), "parquet err");
-        cuda_check(cudaEventCreateWithFlags(&pr->done, cudaEventDisableTiming), "event");
-        cuda_check(cudaEventRecord(pr->done, decode_stream), "event record");
-        return pr;
-    }
-
-    bool next(Batch& out) override {
-        TraceSpan ts("parquet.next");
-        if (!opened) open_all();
-        std::unique_ptr<Prepared> cur = pending ? std::move(pending) : issue();
-        if (!cur) return false;
-        pending = issue(); // prefetch: its H2D overlaps this batch's decode + the consumer's kernels
-        cuda_check(cudaEventSynchronize(cur->done), "parquet decode sync");
-        if (trace_on() && cur->tr[0]) {
-            cudaEventSynchronize(cur->tr[1]);
-            float h2d = 0, dec = 0, lag = 0;
-            cudaEventElapsedTime(&h2d, cur->tr[0], cur->tr[1]);
-            cudaEventElapsedTime(&dec, cur->tr[2], cur->tr[3]);
-            cudaEventElapsedTime(&lag, cur->tr[0], cur->tr[3]);
-            fprintf(stderr, "[cb200 trace]   batch of %lld rows: copy stream %.3f ms, plan stream (waits + decode) %.3f ms, first upload -> decoded %.3f ms\n",
-                    (long long)cur->batch.n_rows, h2d, dec, lag);
-        }
-        const int perr = h_flags[cur->slot];
-        if (perr & 2) throw PlanError("parquet: a column chunk whose statistics say null_count = 0 contains NULLs (corrupt statistics)");
-        if (perr & 8) throw PlanError("parquet: malformed Snappy page");
-        if (perr & 4) throw ExecError(3, "", "parquet: dictionary index out of range (corrupt page)");
-        if (perr & 1) throw Unsupported("parquet: malformed RLE stream, or one with more than n/8 + 64 runs per page");
-        out = std::move(cur->batch);
-        return true; // cur's arena is released here: device temporaries are freed in plan-stream order
-    }
-
-    void decode_column(size_t c, const std::vector<Unit>& units, int64_t total, const std::vector<ChunkLoc>& loc, Column& col, Arena& arena, int* derr, Slot& sl) {
-        const DType& t = fields[c].type;
-        const pq::SchemaElement& se = open_files[units[0].file].meta.leaf(open_files[units[0].file].leaf_of[c]);
-        // pick the device representation
-        int conv, out_w;
-        col.type = t;
-        col.null_count = 0;
-        switch (se.type) {
-        case pq::INT32:
-            if (!(t.is_integer() || t.id == TypeId::Date || (t.is_decimal() && t.precision <= 9))) throw Unsupported("parquet INT32 -> " + t.str());
-            if (t.id == TypeId::Int64) { conv = PQ_I32_TO_I64; out_w = 8; col.phys = Phys::I64; }
-            else { conv = PQ_COPY32; out_w = 4; col.phys = Phys::I32; }
-            break;
-        case pq::INT64:
-            if (!(t.id == TypeId::Int64 || t.id == TypeId::Timestamp || t.id == TypeId::TimestampNtz || (t.is_decimal() && t.precision <= 18)))
-                throw Unsupported("parquet INT64 -> " + t.str());
-            conv = PQ_COPY64; out_w = 8; col.phys = Phys::I64;
-            break;
-        case pq::FLOAT: if (t.id != TypeId::Float32) throw Unsupported("parquet FLOAT -> " + t.str()); conv = PQ_COPY32; out_w = 4; col.phys = Phys::F32; break;
-        case pq::DOUBLE: if (t.id != TypeId::Float64) throw Unsupported("parquet DOUBLE -> " + t.str()); conv = PQ_COPY64; out_w = 8; col.phys = Phys::F64; break;
-        case pq::FIXED_LEN_BYTE_ARRAY:
-            if (!t.is_decimal() || se.type_length > 16) throw Unsupported("parquet FIXED_LEN_BYTE_ARRAY -> " + t.str());
-            if (t.precision <= 18) { conv = PQ_FLBA_TO_I64; out_w = 8; col.phys = Phys::I64; }
-            else { conv = PQ_FLBA_TO_I128; out_w = 16; col.phys = Phys::I128; }
-            break;
-        case pq::BYTE_ARRAY:
-            if (!t.is_string()) throw Unsupported("parquet BYTE_ARRAY -> " + t.str());
-            conv = -1; out_w = 4; col.phys = Phys::I32; col.is_dict = true;
-            if (!dicts[c]) dicts[c] = std::make_shared<Dictionary>();
-            col.dict = dicts[c];
-            break;
-        default: throw Unsupported("parquet physical type " + std::to_string(se.type));
-        }
-        if (t.is_decimal() && (se.scale != t.scale)) throw Unsupported("parquet decimal scale differs from the requested type (schema adapter casts are out of scope)");
-        double tt = now_ms();
-        col.data = std::make_shared<DeviceBuf>((size_t)std::max<int64_t>(total, 1) * out_w);
-        // All row groups of this column are decoded by ONE launch per kernel: page descriptors carry absolute device
-        // addresses, dictionaries are concatenated.
-        t_alloc += now_ms() - tt;
-        tt = now_ms();
-        auto dpages_p = std::make_shared<std::vector<PqPage>>();
-        auto remap_p = std::make_shared<std::vector<int32_t>>();
-        arena.pages.push_back(dpages_p);
-        arena.remaps.push_back(remap_p);
-        std::vector<PqPage>& dpages = *dpages_p;
-        std::vector<PqPage> dict_pages;                // fixed-width dictionary pages (decoded into the combined dictionary)
-        std::vector<int32_t>& remap_all = *remap_p;    // string columns: combined code remap tables
-        int64_t run_base = 0, def_run_base = 0, dict_elems = 0;
-        size_t unc_bytes = 0;                          // device scratch for the bodies of Snappy pages
-        bool optional = false, nulls_possible = false, any_compressed = false;
-        std::vector<uint8_t> host_scratch;
-        // Snappy page bodies are decompressed into `dunc`; its offsets are assigned here and turned into pointers below
-        auto place_body = [&](PqPage& d, const unsigned char* src, int comp_bytes, int unc, bool compressed) {
-            if (compressed) {
-                d.comp = src;
-                d.comp_bytes = comp_bytes;
-                d.body = (unsigned char*)(uintptr_t)unc_bytes; // offset for now
-                d.body_bytes = unc;
-                unc_bytes += ((size_t)unc + 31) / 16 * 16;     // 16-byte aligned, >= 8 spare bytes for the unaligned-word loads
-                any_compressed = true;
-            } else {
-                d.comp = nullptr;
-                d.comp_bytes = 0;
-                d.body = (unsigned char*)src;
-                d.body_bytes = comp_bytes;
-            }
-        };
-        for (size_t u = 0; u < units.size(); u++) {
-            const OpenFile& of = open_files[units[u].file];
-            const pq::SchemaElement& use = of.meta.leaf(of.leaf_of[c]);
-            if (use.type != se.type || use.type_length != se.type_length) throw Unsupported("parquet: column '" + fields[c].name + "' changes physical type between files");
-            const bool opt_u = use.repetition == 1;
-            optional = optional || opt_u;
-            const pq::ColumnChunkMeta& cc = chunk_meta(units[u], c);
-            if (opt_u && cc.null_count != 0) nulls_possible = true; // unknown (-1) counts as possible
-            if (cc.codec != pq::UNCOMPRESSED && cc.codec != pq::SNAPPY)
-                throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (device decompression covers UNCOMPRESSED and SNAPPY; ZSTD / LZ4 / GZIP are next-row work)");
-            const bool snappy = cc.codec == pq::SNAPPY;
-            if (cc.num_values != units[u].rows) throw Unsupported("parquet: repeated column (num_values != num_rows)");
-            const size_t clen = (size_t)cc.total_compressed;
-            const uint8_t* host = loc[u].host;
-            unsigned char* const dc = loc[u].dev;
-            const int64_t base = 0;
-            std::vector<pq::PageInfo> pages = pq::walk_pages(host, clen, cc.num_values);
-            int64_t row = units[u].row0, this_dict_off = -1;
-            int this_dict_size = 0;
-            for (auto& pg : pages) {
-                if (pg.type == pq::DICTIONARY_PAGE) {
-                    this_dict_size = (int)pg.num_values;
-                    this_dict_off = dict_elems;
-                    if (se.type == pq::BYTE_ARRAY) {
-                        // strings: parse on the host, unify with the plan-global dictionary, ship the code remap table
-                        const uint8_t* p = host + pg.data_offset;
-                        const uint8_t* e = p + pg.compressed_size;
-                        if (snappy) {
-                            host_scratch.assign((size_t)pg.uncompressed_size + 16, 0);
-                            if (cb::snappy_decode_serial(p, pg.compressed_size, host_scratch.data(), pg.uncompressed_size) != pg.uncompressed_size)
-                                throw PlanError("parquet: malformed Snappy dictionary page");
-                            p = host_scratch.data();
-                            e = p + pg.uncompressed_size;
-                        }
-                        Dictionary& gd = *dicts[c];
-                        for (int k = 0; k < this_dict_size; k++) {
-                            if (p + 4 > e) throw PlanError("parquet: truncated dictionary page");
-                            uint32_t len;
-                            memcpy(&len, p, 4);
-                            p += 4;
-                            if (len > (size_t)(e - p)) throw PlanError("parquet: truncated dictionary page");
-                            std::string v((const char*)p, len);
-                            p += len;
-                            auto it = std::find(gd.values.begin(), gd.values.end(), v);
-                            if (it == gd.values.end()) { remap_all.push_back((int32_t)gd.values.size()); gd.values.push_back(v); }
-                            else remap_all.push_back((int32_t)(it - gd.values.begin()));
-                        }
-                    } else {
-                        PqPage dp;
-                        memset(&dp, 0, sizeof(dp));
-                        place_body(dp, dc + base + pg.data_offset, pg.compressed_size, pg.uncompressed_size, snappy);
-                        dp.num_values = this_dict_size;
-                        dp.dst_row = dict_elems; // decoded into the combined dictionary at this element offset
-                        dict_pages.push_back(dp);
-                    }
-                    dict_elems += this_dict_size;
-                    continue;
-                }
-                if (pg.type != pq::DATA_PAGE && pg.type != pq::DATA_PAGE_V2) continue;
-                PqPage d;
-                memset(&d, 0, sizeof(d));
-                d.dst_row = row;
-                d.num_values = (int)pg.num_values;
-                const unsigned char* body = dc + base + pg.data_offset;
-                if (pg.type == pq::DATA_PAGE) {
-                    // v1: [u32 length + definition levels (optional columns)] [values], compressed as one block
-                    if (opt_u) d.flags |= PQ_PAGE_V1_LEVELS;
-                    place_body(d, body, pg.compressed_size, pg.uncompressed_size, snappy);
-                } else {
-                    // v2: repetition + definition levels sit uncompressed in front of the (optionally compressed) values
-                    const int lv = pg.rep_levels_bytes + pg.def_levels_bytes;
-                    if (lv > pg.compressed_size || lv > pg.uncompressed_size) throw PlanError("parquet: data page v2 level sizes exceed the page");
-                    d.def_ptr = body + pg.rep_levels_bytes;
-                    d.def_bytes = pg.def_levels_bytes;
-                    place_body(d, body + lv, pg.compressed_size - lv, pg.uncompressed_size - lv, snappy && pg.v2_compressed);
-                }
-                if (pg.encoding == pq::PLAIN) {
-                    if (se.type == pq::BYTE_ARRAY) throw Unsupported("parquet: PLAIN-encoded string page (dictionary fallback); only dictionary-encoded strings are decoded");
-                    d.encoding = 0;
-                } else if (pg.encoding == pq::RLE_DICTIONARY || pg.encoding == pq::PLAIN_DICTIONARY) {
-                    if (this_dict_off < 0) throw PlanError("parquet: dictionary-encoded page without a dictionary page");
-                    d.encoding = 8;
-                    d.run_base = run_base;
-                    d.max_runs = (int)(pg.num_values / 8 + 64);
-                    d.dict_off = this_dict_off;
-                    d.dict_size = this_dict_size;
-                    run_base += d.max_runs;
-                } else throw Unsupported("parquet value encoding " + std::to_string(pg.encoding) + " (DELTA_* / BYTE_STREAM_SPLIT are next-row work)");
-                if (opt_u) {
-                    d.def_run_base = def_run_base;
-                    d.def_max_runs = (int)(pg.num_values / 8 + 64);
-                    def_run_base += d.def_max_runs;
-                }
-                row += pg.num_values;
-                dpages.push_back(d);
-            }
-            if (row != units[u].row0 + units[u].rows) throw PlanError("parquet: data pages of column '" + fields[c].name + "' do not add up to the row group's row count");
-        }
-        t_pages += now_ms() - tt;
-        if (dpages.empty()) return;
-        tt = now_ms();
-        const size_t n_data = dpages.size();
-        dpages.insert(dpages.end(), dict_pages.begin(), dict_pages.end()); // one upload for every descriptor of this column
-        const int n_all = (int)dpages.size();
-        // definition levels: the statistics' null_count == 0 selects the verify-only fast path; otherwise values are decoded
-        // densely and scattered to their rows
-        const bool null_aware = optional && nulls_possible;
-        if (null_aware && total >= (int64_t)1 << 32) throw Unsupported("parquet: NULL-aware decode of more than 2^32 rows per batch (lower spark.comet.b200.chunkRows)");
-        // ---- every device buffer of this column first (plan-stream pool order), then one hand-over to the decode stream ----
-        DeviceBufP dunc, ddict, dvalid, didx, druns, dcounts, runs, counts, dense = col.data;
-        auto keep = [&](size_t bytes) { auto b = std::make_shared<DeviceBuf>(bytes); arena.dev.push_back(b); return b; };
-        if (any_compressed) dunc = keep(unc_bytes + 64);
-        DeviceBufP dpd = keep(dpages.size() * sizeof(PqPage));
-        if (dict_elems > 0) ddict = keep((size_t)dict_elems * out_w + 16);
-        if (null_aware) {
-            dense = keep((size_t)std::max<int64_t>(total, 1) * out_w);
-            dvalid = keep((size_t)total + 64);
-            didx = keep((size_t)total * 4 + 64);
-            druns = keep((size_t)std::max<int64_t>(def_run_base, 1) * sizeof(PqRun));
-            dcounts = keep(n_data * 4 + 16);
-            col.validity = std::make_shared<DeviceBuf>((size_t)(total + 31) / 32 * 4 + 16);
-            col.null_count = -1;
-        }
-        if (run_base > 0) {
-            runs = keep((size_t)run_base * sizeof(PqRun));
-            counts = keep(n_data * 4 + 16);
-        }
-        allocations_visible(arena);
-        const cudaStream_t ds = decode_stream;
-        if (any_compressed) for (auto& d : dpages) if (d.comp) d.body = (unsigned char*)dunc->ptr + (size_t)(uintptr_t)d.body;
-        void* pin_pages = sl.meta_alloc(dpages.size() * sizeof(PqPage));
-        memcpy(pin_pages, dpages.data(), dpages.size() * sizeof(PqPage));
-        cuda_check(cudaMemcpyAsync(dpd->ptr, pin_pages, dpages.size() * sizeof(PqPage), cudaMemcpyHostToDevice, ds), "H2D page table");
-        if (ddict && !remap_all.empty()) {
-            void* pin_remap = sl.meta_alloc(remap_all.size() * 4);
-            memcpy(pin_remap, remap_all.data(), remap_all.size() * 4);
-            cuda_check(cudaMemcpyAsync(ddict->ptr, pin_remap, remap_all.size() * 4, cudaMemcpyHostToDevice, ds), "H2D dictionary remap");
-        }
-        PqPage* all_pages = (PqPage*)dpd->ptr;
-        PqPage* data_pages = all_pages;
-        const PqPage* dpages_dev = data_pages + n_data;
-        if (any_compressed) { launch_pq_snappy(all_pages, n_all, derr, ds); ctx->kernel_launches++; }
-        launch_pq_resolve(all_pages, n_all, ds);
-        ctx->kernel_launches++;
-        if (!dict_pages.empty()) { launch_pq_plain(dpages_dev, (int)dict_pages.size(), conv, se.type_length, ddict->ptr, ds); ctx->kernel_launches++; }
-        if (optional && !null_aware) { launch_pq_check_def_levels(data_pages, (int)n_data, derr, ds); ctx->kernel_launches++; }
-        if (null_aware) {
-            launch_pq_def_levels(data_pages, (int)n_data, (PqRun*)druns->ptr, (int*)dcounts->ptr, (unsigned char*)dvalid->ptr, (unsigned*)didx->ptr, derr, ds);
-            ctx->kernel_launches += 3;
-        }
-        if (conv >= 0) { launch_pq_plain(data_pages, (int)n_data, conv, se.type_length, dense->ptr, ds); ctx->kernel_launches++; }
-        if (run_base > 0) {
-            launch_pq_rle_scan(data_pages, (int)n_data, (PqRun*)runs->ptr, (int*)counts->ptr, derr, ds);
-            launch_pq_rle_decode(data_pages, (int)n_data, (const PqRun*)runs->ptr, (const int*)counts->ptr, ddict->ptr, out_w, dense->ptr, derr, ds);
-            ctx->kernel_launches += 2;
-        }
-        if (null_aware) {
-            launch_pq_scatter((const unsigned char*)dvalid->ptr, (const unsigned*)didx->ptr, dense->ptr, col.data->ptr, (unsigned*)col.validity->ptr, total, out_w, ds);
-            ctx->kernel_launches++;
-        }
-        t_launch += now_ms() - tt;
-    }
-};
 
 // =================================================================================================
 // fused pipeline nodes
@@ -1204,6 +662,10 @@ struct SelectNode : FusedBase {
 // build-time only (cb200_compile_plan_assume): value-range assumptions per source column, so the specialised
 // kernels of known workloads can be compiled ahead of time
 std::vector<int> g_build_assume;
+
+// value ranges seen by earlier plans, per pipeline signature (see AggNode::consume)
+static std::mutex g_profile_mu;
+static std::map<std::string, std::vector<int>> g_range_profile;
 
 // ---- dense / ungrouped aggregation --------------------------------------------------------------------
 struct AggNode : FusedBase {
@@ -1446,6 +908,17 @@ struct AggNode : FusedBase {
         const int64_t SAMPLE = 1 << 20;
         bool have_obs = false;
         for (int ci : used_cols) if (child->schema[(size_t)ci].is_decimal() && observed_bits[(size_t)ci] >= 0) have_obs = true;
+        if (mode == AggMode::Partial && !have_obs && b.n_rows > 2 * SAMPLE) {
+            // Range profile of the last plan with this very pipeline (the previous task of the same stage reads the same table):
+            // start at its ranges instead of sampling again.  A profile is only a guess -- every launch validates it.
+            profile_key = pipeline_signature(make_spec(&b, n_groups, SAFE));
+            std::lock_guard<std::mutex> lk(g_profile_mu);
+            auto it = g_range_profile.find(profile_key);
+            if (it != g_range_profile.end() && it->second.size() == observed_bits.size()) {
+                observed_bits = it->second;
+                for (int ci : used_cols) if (child->schema[(size_t)ci].is_decimal() && observed_bits[(size_t)ci] >= 0) have_obs = true;
+            }
+        }
         if (mode != AggMode::Partial) {
             run_range(b, 0, b.n_rows, n_groups, SAFE);
         } else if (!have_obs && b.n_rows > 2 * SAMPLE) {
@@ -1457,7 +930,13 @@ struct AggNode : FusedBase {
         } else {
             run_range(b, 0, b.n_rows, n_groups, have_obs ? TIGHT : TYPE);
         }
+        if (!profile_key.empty()) {
+            std::lock_guard<std::mutex> lk(g_profile_mu);
+            if (g_range_profile.size() > 256) g_range_profile.clear();
+            g_range_profile[profile_key] = observed_bits;
+        }
     }
+    std::string profile_key;
 
     // ---- hash aggregation: table sizing, launch, flags ------------------------------------------------------------
     void launch_named(const std::shared_ptr<CompiledModule>& mod, const char* name, dim3 grid, dim3 block, void** args) {
@@ -1502,6 +981,15 @@ struct AggNode : FusedBase {
         if (need + 2 >= INT32_MAX) throw ExecError(16, "", "more than 2^31 groups in one partition; lower spark.comet.b200.chunkRows");
         if (need > max_groups) {
             int64_t nm = std::max<int64_t>(need, max_groups + max_groups / 4);
+            // When the source knows how many rows are still to come, size for them at the distinct ratio seen so far (+30 %) in ONE
+            // step: growing means copying the totals and re-inserting every key.
+            const int64_t remaining = child->rows_hint();
+            if (remaining > 0 && rows_scanned > 0 && cur > 0) {
+                const double ratio = std::min(1.0, 1.3 * (double)cur / (double)rows_scanned);
+                const int64_t est = cur + incoming + (int64_t)(ratio * (double)remaining);
+                nm = std::max(nm, std::min<int64_t>(est, cur + incoming + remaining));
+                if (nm + 2 >= INT32_MAX) nm = INT32_MAX - 3;
+            }
             auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
             auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 * key_words + 16);
             cb::u64* tp = (cb::u64*)ntot->ptr;
@@ -1517,7 +1005,7 @@ struct AggNode : FusedBase {
             htotals = ntot; hkey_of_gid = nkog; max_groups = nm;
         }
         int64_t cap = std::max<int64_t>(hcap, 1 << 16);
-        while (cap < 2 * need) cap <<= 1;
+        while (cap < 2 * std::max(need, max_groups)) cap <<= 1; // load <= 0.5 even when every reserved group id gets used
         if (cap != hcap) {
             auto nkeys = std::make_shared<DeviceBuf>((size_t)cap * 16);
             cuda_check(cudaMemsetAsync(nkeys->ptr, 0xff, (size_t)cap * 16, st), "memset key slots");
@@ -1600,7 +1088,7 @@ struct AggNode : FusedBase {
         fp.max_groups = (int)max_groups;
         fp.n_groups = (int)n_out;
         fp.err = ctx->d_err;
-        for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) fp.cert[ai] = certificate(ai);
+        fill_certificates(fp);
         if (g.out_cols.size() > CB_MAX_OUT) throw Unsupported("too many output columns");
         out.n_rows = n_out;
         out.cols.clear();
@@ -1735,20 +1223,25 @@ struct AggNode : FusedBase {
         return true;
     }
 
-    // host certificate: can the decimal sum of aggregate `ai` overflow for ANY row order, given the observed input ranges?
-    int certificate(size_t ai) const {
+    // Host side of the overflow certificate: a bound on the magnitude of any single addend of decimal SUM / AVG `ai`, from the value
+    // masks observed on its input columns pushed through the same range propagation the code generator uses.  finalize multiplies
+    // it by the group's own addend count (cb::cert_level): n * B <= 10^p - 1 means no row order can overflow.
+    u128r certificate(size_t ai) const {
         const AggExpr& a = aggs[ai];
         if (!(a.kind == AggKind::Sum || a.kind == AggKind::Avg) || !a.datatype.is_decimal()) return 0;
         std::vector<u128r> bounds(child->schema.size(), RSAT);
         for (size_t c = 0; c < bounds.size(); c++)
             if (child->schema[c].is_decimal() && !observed_bits.empty())
                 bounds[c] = observed_bits[c] < 0 ? 0 : (observed_bits[c] >= 127 ? RSAT : (u128r)1 << observed_bits[c]);
-        u128r B;
-        if (mode == AggMode::Partial) B = expr_maxabs(*a.children[0], bounds);
-        else B = bounds[(size_t)state_cols[ai][0]];
-        int sp = a.kind == AggKind::Avg ? a.sum_datatype.precision : a.datatype.precision;
-        u128r total = r_mul((u128r)std::max<int64_t>(rows_scanned, 1), B);
-        return total <= r_prec_max(sp) ? 0 : total < RSAT ? 1 : 2; // see cb::sum_cert
+        if (mode == AggMode::Partial) return expr_maxabs(*a.children[0], bounds);
+        return bounds[(size_t)state_cols[ai][0]];
+    }
+    void fill_certificates(cb::FinParams& fp) const {
+        for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) {
+            const u128r b = certificate(ai);
+            fp.cert_b[ai][0] = b >= RSAT ? ~0ull : (uint64_t)b;
+            fp.cert_b[ai][1] = b >= RSAT ? ~0ull : (uint64_t)(b >> 64);
+        }
     }
 
     bool next(Batch& out) override {
@@ -1804,7 +1297,7 @@ struct AggNode : FusedBase {
         fp.totals = (cb::u64*)totals->ptr;
         fp.n_groups = ng;
         fp.err = ctx->d_err;
-        for (size_t ai = 0; ai < aggs.size() && ai < CB_MAX_OUT; ai++) fp.cert[ai] = certificate(ai);
+        fill_certificates(fp);
         // all finalize outputs live in ONE device buffer so the (tiny) result comes back in a single copy
         std::vector<size_t> off_v, off_n;
         size_t total_bytes = 0;
@@ -2071,12 +1564,7 @@ static ExecNodeP build_source(const OperatorP& op, ExecContext* ctx, PlanInputs*
             s->schema = op->schema;
             return s;
         }
-        auto s = std::make_shared<NativeScanSource>();
-        s->ctx = ctx;
-        s->schema = op->schema;
-        s->files = op->files;
-        s->fields = op->required_schema;
-        return s;
+        return make_native_scan(op, ctx);
     }
     return build_node(op, ctx, inputs, build_only);
 }
@@ -2114,6 +1602,7 @@ static ExecNodeP build_node(const OperatorP& op, ExecContext* ctx, PlanInputs* i
             cols = nc;
         }
     }
+    if (!preds.empty()) src->push_filters(preds); // the fused filter still runs on every row; the source may prune with it
     if (agg_op) {
         auto n = std::make_shared<AggNode>();
         n->ctx = ctx;
@@ -2334,13 +1823,4 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
     }
 }
 
-} // namespace cb200
-
-namespace cb200 {
-std::string describe_parquet(const std::string& path) {
-    const uint8_t* mem;
-    size_t len;
-    pq::FileMeta m = open_parquet(path, &mem, &len);
-    return pq::describe(m);
-}
 } // namespace cb200

@@ -32,6 +32,8 @@ struct TraceSpan {
     explicit TraceSpan(const char* n);
     ~TraceSpan();
 };
+bool trace_on();
+double now_ms();
 void set_alloc_stream(cudaStream_t s); // stream used by DeviceBuf allocations made on this thread
 
 struct DeviceBuf {
@@ -39,6 +41,7 @@ struct DeviceBuf {
     size_t bytes = 0;
     bool owned = true;
     cudaStream_t stream = nullptr;
+    std::shared_ptr<void> owner;               // non-owning views: the block this pointer lives in (kept alive with the view)
     DeviceBuf() {}
     DeviceBuf(size_t n);                       // cudaMalloc, padded
     DeviceBuf(void* p, size_t n) : ptr(p), bytes(n), owned(false) {}
@@ -94,6 +97,7 @@ struct ExecContext {
     int64_t pipeline_launches = 0;
     int64_t pipeline_rows = 0;    // rows those launches scanned
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int64_t scan_pruned_row_groups = 0, scan_pruned_rows = 0; // Parquet row groups skipped by statistics (parquet_exec.rs:143-196)
     std::vector<int64_t> partition_starts; // last ShuffleWriter batch: partition p = rows [starts[p], starts[p+1])
     void check_device_errors();
     void collect_timing();
@@ -103,6 +107,11 @@ struct ExecNode {
     std::vector<DType> schema;
     virtual ~ExecNode() {}
     virtual bool next(Batch& out) = 0; // false = end of stream
+    // predicates (over this node's output columns) that the consumer applies to every row anyway: a source may use them to skip
+    // data that cannot pass (Parquet row groups whose statistics rule them out)
+    virtual void push_filters(const std::vector<ExprP>&) {}
+    // rows this node will still produce, if it knows (-1: unknown): lets a hash aggregate size its table once instead of growing it
+    virtual int64_t rows_hint() const { return -1; }
 };
 using ExecNodeP = std::shared_ptr<ExecNode>;
 
@@ -118,6 +127,9 @@ struct PlanInputs {
     std::vector<std::shared_ptr<DeviceTable>> tables; // parallel to streams; non-null entry overrides
 };
 ExecNodeP build_exec(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs);
+
+// native Parquet scan (scan_parquet.cpp)
+ExecNodeP make_native_scan(const OperatorP& op, ExecContext* ctx);
 
 // Export helpers (host-visible Arrow C Data)
 void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols);

@@ -51,39 +51,50 @@ struct TReader { // Thrift compact protocol (THRIFT-110)
         *size = b >> 4;
         if (*size == 15) *size = (uint32_t)varint();
     }
-    void skip(int type) {
+    void need(size_t n) const { if ((size_t)(end - p) < n) throw PlanError("parquet: truncated thrift value"); }
+    void skip(int type, int depth = 0) {
+        if (depth > 64) throw PlanError("parquet: thrift structure nested too deeply");
         switch (type) {
         case 1: case 2: break;          // bool encoded in the field header
-        case 3: p++; break;             // byte
+        case 3: need(1); p++; break;    // byte
         case 4: case 5: case 6: zigzag(); break;
-        case 7: p += 8; break;          // double
+        case 7: need(8); p += 8; break; // double
         case 8: binary(); break;
         case 9: case 10: {
             int et; uint32_t n;
             list_header(&et, &n);
+            if (n > (uint64_t)(end - p)) throw PlanError("parquet: thrift list longer than its buffer"); // every element takes at least one byte
             for (uint32_t i = 0; i < n; i++) {
-                if (et == 1 || et == 2) p++; // bools in lists take one byte each
-                else skip(et);
+                if (et == 1 || et == 2) { need(1); p++; } // bools in lists take one byte each
+                else skip(et, depth + 1);
             }
             break;
         }
         case 11: {
             uint32_t n = (uint32_t)varint();
             if (n) {
+                need(1);
                 uint8_t kv = *p++;
-                for (uint32_t i = 0; i < n; i++) { skip(kv >> 4); skip(kv & 0x0f); }
+                if (n > (uint64_t)(end - p) + 1) throw PlanError("parquet: thrift map longer than its buffer");
+                for (uint32_t i = 0; i < n; i++) { skip(kv >> 4, depth + 1); skip(kv & 0x0f, depth + 1); }
             }
             break;
         }
         case 12: {
             int16_t fid = 0, last = 0;
             int t;
-            while ((t = field(&fid, last)) != 0) { skip(t); last = fid; }
+            while ((t = field(&fid, last)) != 0) { skip(t, depth + 1); last = fid; }
             break;
         }
         default: throw PlanError("parquet: unknown thrift type " + std::to_string(type));
         }
-        if (p > end) throw PlanError("parquet: truncated thrift value");
+    }
+    // element count of a list whose elements take at least one byte each
+    uint32_t list_of(int* elem_type) {
+        uint32_t n;
+        list_header(elem_type, &n);
+        if (n > (uint64_t)(end - p)) throw PlanError("parquet: thrift list longer than its buffer");
+        return n;
     }
 };
 
@@ -104,6 +115,32 @@ SchemaElement parse_schema_element(TReader& r) {
         case 6: e.converted_type = (int)r.zigzag(); break;
         case 7: e.scale = (int)r.zigzag(); break;
         case 8: e.precision = (int)r.zigzag(); break;
+        case 10: { // LogicalType union: 5 DECIMAL, 8 TIMESTAMP{2: unit{1 MILLIS, 2 MICROS, 3 NANOS}}, 10 INTEGER{1 bitWidth, 2 isSigned}
+            int16_t f2 = 0, l2 = 0; int t2;
+            while ((t2 = r.field(&f2, l2)) != 0) {
+                if (f2 == 5) { e.logical_decimal = true; r.skip(t2); }
+                else if (f2 == 8 && t2 == 12) {
+                    int16_t f3 = 0, l3 = 0; int t3;
+                    while ((t3 = r.field(&f3, l3)) != 0) {
+                        if (f3 == 2 && t3 == 12) {
+                            int16_t f4 = 0, l4 = 0; int t4;
+                            while ((t4 = r.field(&f4, l4)) != 0) { if (f4 >= 1 && f4 <= 3) e.ts_unit = f4; r.skip(t4); l4 = f4; }
+                        } else r.skip(t3);
+                        l3 = f3;
+                    }
+                } else if (f2 == 10 && t2 == 12) {
+                    int16_t f3 = 0, l3 = 0; int t3;
+                    while ((t3 = r.field(&f3, l3)) != 0) {
+                        if (f3 == 1 && t3 == 3) { r.need(1); e.int_bits = (int)(signed char)*r.p++; }
+                        else if (f3 == 2 && (t3 == 1 || t3 == 2)) e.int_signed = t3 == 1 ? 1 : 0;
+                        else r.skip(t3);
+                        l3 = f3;
+                    }
+                } else r.skip(t2);
+                l2 = f2;
+            }
+            break;
+        }
         default: r.skip(t);
         }
         last = fid;
@@ -111,14 +148,18 @@ SchemaElement parse_schema_element(TReader& r) {
     return e;
 }
 
-int64_t parse_statistics_null_count(TReader& r) {
-    int64_t nulls = -1;
+// Statistics (parquet.thrift): 1 max / 2 min are the deprecated signed-byte-order pair (ignored), 3 null_count,
+// 5 max_value / 6 min_value follow the column's own sort order
+void parse_statistics(TReader& r, ColumnChunkMeta& m) {
+    bool have_min = false, have_max = false;
     FOR_FIELDS(r) {
-        if (fid == 3) nulls = r.zigzag();
+        if (fid == 3) m.null_count = r.zigzag();
+        else if (fid == 5 && t == 8) { m.max_value = r.binary(); have_max = true; }
+        else if (fid == 6 && t == 8) { m.min_value = r.binary(); have_min = true; }
         else r.skip(t);
         last = fid;
     }
-    return nulls;
+    m.has_min_max = have_min && have_max;
 }
 
 ColumnChunkMeta parse_column_meta(TReader& r) {
@@ -126,15 +167,15 @@ ColumnChunkMeta parse_column_meta(TReader& r) {
     FOR_FIELDS(r) {
         switch (fid) {
         case 1: m.type = (int)r.zigzag(); break;
-        case 2: { int et; uint32_t n; r.list_header(&et, &n); for (uint32_t i = 0; i < n; i++) m.encodings.push_back((int)r.zigzag()); break; }
-        case 3: { int et; uint32_t n; r.list_header(&et, &n); for (uint32_t i = 0; i < n; i++) m.path.push_back(r.binary()); break; }
+        case 2: { int et; uint32_t n = r.list_of(&et); for (uint32_t i = 0; i < n; i++) m.encodings.push_back((int)r.zigzag()); break; }
+        case 3: { int et; uint32_t n = r.list_of(&et); for (uint32_t i = 0; i < n; i++) m.path.push_back(r.binary()); break; }
         case 4: m.codec = (int)r.zigzag(); break;
         case 5: m.num_values = r.zigzag(); break;
         case 6: m.total_uncompressed = r.zigzag(); break;
         case 7: m.total_compressed = r.zigzag(); break;
         case 9: m.data_page_offset = r.zigzag(); break;
         case 11: m.dictionary_page_offset = r.zigzag(); break;
-        case 12: m.null_count = parse_statistics_null_count(r); break;
+        case 12: parse_statistics(r, m); break;
         default: r.skip(t);
         }
         last = fid;
@@ -156,7 +197,7 @@ RowGroupMeta parse_row_group(TReader& r) {
     RowGroupMeta g;
     FOR_FIELDS(r) {
         switch (fid) {
-        case 1: { int et; uint32_t n; r.list_header(&et, &n); for (uint32_t i = 0; i < n; i++) g.columns.push_back(parse_column_chunk(r)); break; }
+        case 1: { int et; uint32_t n = r.list_of(&et); for (uint32_t i = 0; i < n; i++) g.columns.push_back(parse_column_chunk(r)); break; }
         case 3: g.num_rows = r.zigzag(); break;
         default: r.skip(t);
         }
@@ -181,9 +222,9 @@ FileMeta parse_footer(const uint8_t* file, size_t len) {
     FileMeta m;
     FOR_FIELDS(r) {
         switch (fid) {
-        case 2: { int et; uint32_t n; r.list_header(&et, &n); for (uint32_t i = 0; i < n; i++) m.schema.push_back(parse_schema_element(r)); break; }
+        case 2: { int et; uint32_t n = r.list_of(&et); for (uint32_t i = 0; i < n; i++) m.schema.push_back(parse_schema_element(r)); break; }
         case 3: m.num_rows = r.zigzag(); break;
-        case 4: { int et; uint32_t n; r.list_header(&et, &n); for (uint32_t i = 0; i < n; i++) m.row_groups.push_back(parse_row_group(r)); break; }
+        case 4: { int et; uint32_t n = r.list_of(&et); for (uint32_t i = 0; i < n; i++) m.row_groups.push_back(parse_row_group(r)); break; }
         default: r.skip(t);
         }
         last = fid;

@@ -23,6 +23,11 @@ enum PageType { DATA_PAGE = 0, INDEX_PAGE = 1, DICTIONARY_PAGE = 2, DATA_PAGE_V2
 
 struct SchemaElement {
     int type = -1, type_length = 0, repetition = 0, num_children = 0, converted_type = -1, scale = 0, precision = 0;
+    // LogicalType (field 10): what the physical bytes mean where converted_type is absent or too coarse
+    int ts_unit = 0;       // TIMESTAMP: 1 MILLIS, 2 MICROS, 3 NANOS (0 = not a logical timestamp)
+    int int_bits = 0;      // INTEGER: bit width (0 = not a logical integer)
+    int int_signed = 1;
+    bool logical_decimal = false;
     std::string name;
 };
 struct ColumnChunkMeta {
@@ -31,6 +36,8 @@ struct ColumnChunkMeta {
     std::vector<std::string> path;
     int64_t num_values = 0, total_uncompressed = 0, total_compressed = 0, data_page_offset = 0, dictionary_page_offset = -1;
     int64_t null_count = -1; // statistics, -1 unknown
+    bool has_min_max = false; // statistics min_value / max_value (fields 5, 6: the type's own sort order), PLAIN-encoded
+    std::string min_value, max_value;
     int64_t start() const { return dictionary_page_offset > 0 && dictionary_page_offset < data_page_offset ? dictionary_page_offset : data_page_offset; }
 };
 struct RowGroupMeta {

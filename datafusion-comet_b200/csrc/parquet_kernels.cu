@@ -33,6 +33,16 @@ __device__ __forceinline__ u32 load_u32_unaligned(const u8* p) {
     return (lo >> sh) | (hi << (32 - sh));
 }
 
+__global__ void k_pq_copy(uint4* dst, const uint4* src, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void launch_pq_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    const size_t n16 = bytes / 16;
+    if (n16 == 0) return;
+    const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, 296);
+    k_pq_copy<<<blocks, 256, 0, st>>>((uint4*)dst, (const uint4*)src, n16);
+}
+
 // ---- Snappy --------------------------------------------------------------------------------------------------
 // One warp per page.  Elements are inherently sequential (each tag's position depends on the previous one), so
 // lane 0 parses the tag and broadcasts it in two registers; the bytes are moved by the whole warp.  What makes a
@@ -180,13 +190,14 @@ void launch_pq_resolve(PqPage* pages, int n_pages, cudaStream_t st) {
 }
 
 // ---- PLAIN ---------------------------------------------------------------------------------------------------
-template <int CONV> __global__ void k_pq_plain(const PqPage* pages, int flba_len, u8* out) {
+template <int CONV> __global__ void k_pq_plain(const PqPage* pages, int flba_len, u8* out, int* err) {
     const PqPage pg = pages[blockIdx.y];
     if (pg.encoding != 0) return; // dictionary-encoded page: decoded by k_pq_rle_decode
     const u8* src = pg.values;
     const int w = CONV == PQ_COPY32 || CONV == PQ_I32_TO_I64 || CONV == PQ_I32_TO_I128 ? 4 : CONV == PQ_COPY64 || CONV == PQ_I64_TO_I128 ? 8 : flba_len;
     const int have = w > 0 ? pg.values_bytes / w : 0;   // never read beyond the page, whatever the header claims
     const int count = pg.nonnull < have ? pg.nonnull : have;
+    if (pg.nonnull > have && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 16); // short page: the rows it cannot fill must not pass silently
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         long long row = pg.dst_row + i;
         if (CONV == PQ_COPY32) ((u32*)out)[row] = load_u32_unaligned(src + (size_t)i * 4);
@@ -206,17 +217,17 @@ template <int CONV> __global__ void k_pq_plain(const PqPage* pages, int flba_len
         }
     }
 }
-void launch_pq_plain(const PqPage* pages, int n_pages, int conv, int flba_len, void* out, cudaStream_t st) {
+void launch_pq_plain(const PqPage* pages, int n_pages, int conv, int flba_len, void* out, int* err, cudaStream_t st) {
     if (n_pages <= 0) return;
     dim3 grid(64, (unsigned)n_pages), block(256);
     switch (conv) {
-    case PQ_COPY32: k_pq_plain<PQ_COPY32><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
-    case PQ_COPY64: k_pq_plain<PQ_COPY64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
-    case PQ_I32_TO_I64: k_pq_plain<PQ_I32_TO_I64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
-    case PQ_I64_TO_I128: k_pq_plain<PQ_I64_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
-    case PQ_I32_TO_I128: k_pq_plain<PQ_I32_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
-    case PQ_FLBA_TO_I64: k_pq_plain<PQ_FLBA_TO_I64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
-    default: k_pq_plain<PQ_FLBA_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out); break;
+    case PQ_COPY32: k_pq_plain<PQ_COPY32><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
+    case PQ_COPY64: k_pq_plain<PQ_COPY64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
+    case PQ_I32_TO_I64: k_pq_plain<PQ_I32_TO_I64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
+    case PQ_I64_TO_I128: k_pq_plain<PQ_I64_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
+    case PQ_I32_TO_I128: k_pq_plain<PQ_I32_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
+    case PQ_FLBA_TO_I64: k_pq_plain<PQ_FLBA_TO_I64><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
+    default: k_pq_plain<PQ_FLBA_TO_I128><<<grid, block, 0, st>>>(pages, flba_len, (u8*)out, err); break;
     }
 }
 
@@ -267,6 +278,7 @@ template <bool LEVELS> __global__ void k_pq_rle_scan(const PqPage* pages, int n_
     const int cap = LEVELS ? pg.def_max_runs : pg.max_runs;
     PqRun* out = runs + (LEVELS ? pg.def_run_base : pg.run_base);
     int n = 0;
+    bool truncated = false;
     long long row = pg.dst_row;
     long long seen = bw > 32 ? -1 : walk_hybrid(p, end, bw, want, [&](int packed, int count, u32 value, const u8* data) {
         if (n < cap) {
@@ -277,13 +289,14 @@ template <bool LEVELS> __global__ void k_pq_rle_scan(const PqPage* pages, int n_
             r.value = value;
             r.bit_packed = packed;
             r.bit_width = bw;
-            if (packed && data + ((long long)count * bw + 7) / 8 > end) r.count = 0; // truncated page: never read beyond it (reported below)
+            if (packed && data + ((long long)count * bw + 7) / 8 > end) { r.count = 0; truncated = true; } // truncated page: never read beyond it
             out[n] = r;
         }
         n++;
         row += count;
     });
     if (n > cap || seen != want) atomicOr(err, 1);
+    if (truncated) atomicOr(err, 16);
     run_counts[pi] = n < cap ? n : cap;
 }
 void launch_pq_rle_scan(const PqPage* pages, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st) {

@@ -42,14 +42,17 @@ struct PqRun {              // one run of the RLE / bit-packed hybrid
 };
 
 enum PqConv { PQ_COPY32, PQ_COPY64, PQ_I32_TO_I64, PQ_FLBA_TO_I64, PQ_FLBA_TO_I128, PQ_I64_TO_I128, PQ_I32_TO_I128 };
-// err bits: 1 malformed / pathological RLE stream, 2 NULL found on the no-NULL fast path, 4 dictionary index out of range, 8 malformed Snappy page
+// err bits: 1 malformed / pathological RLE stream, 2 NULL found on the no-NULL fast path, 4 dictionary index out of range, 8 malformed Snappy page, 16 truncated page (fewer encoded values than the header declares)
 
+// dst[0, bytes) = src[0, bytes) with SM loads/stores (bytes a multiple of 16, both 16-byte aligned).  `src` may be mapped pinned
+// host memory: small tables reach the device without queueing on a copy engine.
+void launch_pq_copy(void* dst, const void* src, size_t bytes, cudaStream_t st);
 // Snappy: one warp per compressed page (pages with comp == nullptr are skipped)
 void launch_pq_snappy(PqPage* pages_dev, int n_pages, int* err, cudaStream_t st);
 // locate levels / values inside every page body; nonnull = num_values
 void launch_pq_resolve(PqPage* pages_dev, int n_pages, cudaStream_t st);
 // PLAIN fixed-width pages -> out[dst_row + k] for the page's k-th encoded value (element width given by the conversion)
-void launch_pq_plain(const PqPage* pages_dev, int n_pages, int conv, int flba_len, void* out, cudaStream_t st);
+void launch_pq_plain(const PqPage* pages_dev, int n_pages, int conv, int flba_len, void* out, int* err, cudaStream_t st);
 // RLE_DICTIONARY pages: (1) scan run headers, one thread per page
 void launch_pq_rle_scan(const PqPage* pages_dev, int n_pages, PqRun* runs, int* run_counts, int* err, cudaStream_t st);
 // (2) decode runs (warp per run) and gather through the dictionary: dict_width 4/8/16 bytes per entry

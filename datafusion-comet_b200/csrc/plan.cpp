@@ -536,10 +536,16 @@ static OperatorP decode_operator(PbReader r) { // Operator operator.proto:32-86
                 while (fp.next()) {
                     if (fp.field == 1) {
                         PbReader pf = fp.sub();
+                        int64_t start = 0, length = 0;
                         while (pf.next()) {
                             if (pf.field == 1) op->files.push_back(pf.bytes());
+                            else if (pf.field == 2) start = pf.i64();
+                            else if (pf.field == 3) length = pf.i64();
+                            else if (pf.field == 5) throw Unsupported("partition values in NativeScan");
                             else pf.skip();
                         }
+                        op->file_start.push_back(start);
+                        op->file_length.push_back(length);
                     } else fp.skip();
                 }
             } else b.skip();

@@ -113,6 +113,7 @@ struct Operator {
     std::vector<int64_t> projection_vector;
     std::vector<ExprP> data_filters;
     std::vector<std::string> files;
+    std::vector<int64_t> file_start, file_length; // SparkPartitionedFile.start / length (operator.proto:103-109); 0 / 0 = the whole file
     // Projection
     std::vector<ExprP> project_list;
     // Filter

@@ -137,6 +137,8 @@ typedef struct cb200_stats {
     int64_t pipeline_rows;     /* input rows those launches scanned */
     int64_t h2d_bytes;         /* host->device bytes copied by Arrow-stream sources */
     int64_t d2h_bytes;         /* device->host bytes copied by cb200_execute */
+    int64_t scan_pruned_row_groups; /* Parquet row groups skipped because their statistics rule the pushed filters out */
+    int64_t scan_pruned_rows;
 } cb200_stats;
 int cb200_plan_stats(cb200_plan* plan, cb200_stats* out);
 

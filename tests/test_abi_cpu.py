@@ -45,7 +45,7 @@ def test_generated_q1_kernel_is_fused_and_uses_tma(cb):
     assert "#define CB_KERNEL_AGG 1" in src and "cb_row_agg" in src and "cb_finalize_group" in src
     # one kernel for scan+filter+project+aggregate: the filter literal and the aggregate updates are in the same row program
     body = src[src.index("CB_D void cb_row_agg"):]
-    assert "10471" in body and "acc.add_" in body
+    assert "10493" in body and "acc.add_" in body
     hdr = open(os.path.join(ROOT, "datafusion-comet_b200", "csrc", "device", "cb_kernels.cuh")).read()
     assert "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes" in hdr
 
@@ -158,8 +158,8 @@ def test_wide_group_keys_use_tag_and_stored_key(cb):
     three = P.hash_agg(P.scan([P.INT64, P.INT64, P.DATE, P.INT64]), [P.bound(0, P.INT64), P.bound(1, P.INT64), P.bound(2, P.DATE)],
                        [P.agg_sum(P.bound(3, P.INT64), P.INT64)], P.PARTIAL)
     s1, s3 = cb.native.kernel_source(one), cb.native.kernel_source(three)
-    assert "#define CB_KEY_WORDS 1" in s1 and "acc.find_slot(" in s1
-    assert "#define CB_KEY_WORDS 4" in s3 and "acc.find_slot_multi(" in s3       # 64 + 64 + 33 bits + the null-flag word of the 64-bit keys
+    assert "#define CB_KEY_WORDS 1" in s1 and "acc.begin(keep_" in s1 and "acc.h_add_wrap(" in s1   # warp-cooperative table update
+    assert "#define CB_KEY_WORDS 4" in s3 and "acc.begin(keep_" in s3            # 64 + 64 + 33 bits + the null-flag word of the 64-bit keys
     too_wide = P.hash_agg(P.scan([P.INT64] * 6), [P.bound(k, P.INT64) for k in range(5)], [P.agg_sum(P.bound(5, P.INT64), P.INT64)], P.PARTIAL)
     ok, why = cb.native.supports(too_wide)
     assert not ok

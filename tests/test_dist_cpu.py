@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
     n = 40_000
     cols = tpch.gen_lineitem(n, seed=77)
     lo, hi = partition_bounds(n, rank, world)
-    keep = cols["l_shipdate"][lo:hi] <= tpch.DATE_1998_09_02
+    keep = cols["l_shipdate"][lo:hi] <= tpch.Q1_CUTOFF
     gid = (cols["l_returnflag"][lo:hi].astype(np.int64) * 2 + cols["l_linestatus"][lo:hi])[keep]
     acc = oracle.SumDecimalGroups(6, 22)
     acc.update(oracle.dec_from_i64(cols["l_quantity"][lo:hi][keep]), None, gid)
@@ -36,7 +36,7 @@ def _worker(rank, world, port, q):
             ss = np.stack([t["sum_lo"].to_numpy(), t["sum_hi"].to_numpy()], axis=1).astype(np.uint64)
             fin.merge(ss, t["sum_valid"].to_numpy(), t["is_empty"].to_numpy(), t["gid"].to_numpy())
         out, outv = fin.evaluate()
-        keep_all = cols["l_shipdate"] <= tpch.DATE_1998_09_02
+        keep_all = cols["l_shipdate"] <= tpch.Q1_CUTOFF
         gid_all = cols["l_returnflag"].astype(np.int64) * 2 + cols["l_linestatus"]
         exp = [int(cols["l_quantity"][keep_all & (gid_all == k)].sum()) if (keep_all & (gid_all == k)).any() else None for k in range(6)]
         q.put(oracle.dec_to_ints(out, outv) == exp)

@@ -44,7 +44,7 @@ def test_q1_dec_from_parquet(cb, oracle, tmp_path, as_int, memory, chunk):
     res, _ = run(cb, t.q1_final_plan("dec"), [state])
     d = oracle.dec_from_i64
     exp = oracle.q1_dec(d(cols["l_quantity"]), d(cols["l_extendedprice"]), d(cols["l_discount"]), d(cols["l_tax"]), cols["l_shipdate"],
-                        cols["l_returnflag"], cols["l_linestatus"], 3, 2, t.DATE_1998_09_02, 1)
+                        cols["l_returnflag"], cols["l_linestatus"], 3, 2, t.Q1_CUTOFF, 1)
     got = {(r["col_0"], r["col_1"]): r for r in res.to_pylist()}
     for k, e in enumerate(exp):
         if e is None:
@@ -184,3 +184,134 @@ def test_aggregate_over_nullable_parquet_columns(cb, tmp_path):
     for w, e in exp.items():
         g = got[w]
         assert g["col_1"] == e[0] and g["col_3"] == e[1] and g["col_4"] == e[2] and g["col_5"] == e[3], w
+
+
+# ---- row-group pruning by statistics, file splits, annotations (round 2) ------------------------------------------------------
+def _sorted_q6_files(cb, tmp_path, n, seed, variant):
+    t = cb.tpch
+    cols = t.gen_lineitem(n, seed=seed)
+    order = np.argsort(cols["l_shipdate"], kind="stable")           # date-clustered, like a table written ORDER BY l_shipdate
+    cols = {k: v[order] for k, v in cols.items()}
+    path = t.write_lineitem_parquet(cols, str(tmp_path / f"q6_{variant}.parquet"), variant, row_group_size=16_384, columns=t.Q6_COLUMNS)
+    return cols, path
+
+
+@pytest.mark.parametrize("variant", ["dec", "f64"])
+def test_q6_row_groups_pruned_by_min_max(cb, oracle, tmp_path, variant, monkeypatch):
+    """parquet_exec.rs:143-196: row groups whose statistics rule the pushed predicate out are never read.  Q6 over a
+    date-clustered file touches one year in seven; the result is the unpruned result bit for bit."""
+    t = cb.tpch
+    n = 400_000
+    cols, path = _sorted_q6_files(cb, tmp_path, n, 41, variant)
+    plan = t.q6_partial_plan(variant, scan=t.q6_native_scan(variant, [path]))
+    state, st = run(cb, plan, chunk_rows=60_000)
+    n_rg = (n + 16_383) // 16_384
+    assert st["scan_pruned_row_groups"] >= n_rg * 0.8 and st["scan_pruned_rows"] >= n * 0.8
+    monkeypatch.setenv("CB200_NO_PRUNE", "1")
+    state_all, st_all = run(cb, plan, chunk_rows=60_000)
+    assert st_all["scan_pruned_row_groups"] == 0
+    assert st["h2d_bytes"] <= 0.2 * st_all["h2d_bytes"]              # <= 10-20 % of the file crosses PCIe
+    assert state.equals(state_all)
+    res, _ = run(cb, t.q6_final_plan(variant), [state])
+    if variant == "dec":
+        d = oracle.dec_from_i64
+        exp = oracle.q6_dec(d(cols["l_quantity"]), d(cols["l_extendedprice"]), d(cols["l_discount"]), cols["l_shipdate"], t.DATE_1994_01_01, t.DATE_1995_01_01, 5, 7, 2400, 1)
+        assert unscaled(res.column(0)[0].as_py()) == exp
+    # the filter above the scan is pushed even when the JVM sends no data_filters (the conjuncts are the same expressions)
+    plan2 = t.q6_partial_plan(variant, scan=t.q6_native_scan(variant, [path], push_filters=False))
+    monkeypatch.delenv("CB200_NO_PRUNE")
+    state2, st2 = run(cb, plan2, chunk_rows=60_000)
+    assert st2["scan_pruned_row_groups"] == st["scan_pruned_row_groups"] and state2.equals(state)
+
+
+def test_q1_prunes_nothing_it_should_not(cb, tmp_path):
+    """Q1 keeps 98 % of the rows: only the row groups entirely after the cut-off may go, and the result must not move."""
+    t = cb.tpch
+    n = 200_000
+    cols = t.gen_lineitem(n, seed=43)
+    order = np.argsort(cols["l_shipdate"], kind="stable")
+    cols = {k: v[order] for k, v in cols.items()}
+    path = t.write_lineitem_parquet(cols, str(tmp_path / "q1s.parquet"), "dec", row_group_size=8192)
+    plan = t.q1_partial_plan("dec", scan=t.q1_native_scan("dec", [path]))
+    state, st = run(cb, plan)
+    exp_pruned = sum(1 for g in range(0, n, 8192) if cols["l_shipdate"][g] > t.Q1_CUTOFF)
+    assert st["scan_pruned_row_groups"] == exp_pruned > 0
+    import os
+    os.environ["CB200_NO_PRUNE"] = "1"
+    try:
+        state_all, _ = run(cb, plan)
+    finally:
+        del os.environ["CB200_NO_PRUNE"]
+    key = lambda tb: sorted(tb.to_pylist(), key=lambda r: (r["col_0"], r["col_1"]))
+    assert key(state) == key(state_all)
+
+
+def test_file_splits_own_the_row_groups_that_start_inside_them(cb, tmp_path):
+    """SparkPartitionedFile.start / length (operator.proto:103-109): two tasks over the two halves of one file see every row
+    group exactly once."""
+    import pyarrow.parquet as pq
+    t = cb.tpch
+    P = cb.proto
+    n = 100_000
+    cols = t.gen_lineitem(n, seed=45)
+    path = t.write_lineitem_parquet(cols, str(tmp_path / "split.parquet"), "dec", row_group_size=10_000)
+    import os
+    size = os.path.getsize(path)
+    md = pq.ParquetFile(path).metadata
+    starts = [md.row_group(g).column(0).dictionary_page_offset or md.row_group(g).column(0).data_page_offset for g in range(md.num_row_groups)]
+    cut = starts[4] + 1                                              # split point in the middle of a row group
+    fields = list(zip(t.Q1_COLUMNS, t.q1_scan_fields("dec"), [True] * 7))
+    counts = []
+    for lo, ln in ((0, cut), (cut, size - cut)):
+        sc = P.native_scan(fields, fields, [(path, lo, ln, size)])
+        plan = P.hash_agg(sc, [], [P.agg_count([P.literal(1, P.INT32)]), P.agg_sum(P.bound(0, t.D12), P.DECIMAL(22, 2))], P.PARTIAL)
+        res, _ = run(cb, plan)
+        counts.append((res.column(0)[0].as_py(), unscaled(res.column(1)[0].as_py())))
+    exp_first = sum(md.row_group(g).num_rows for g in range(md.num_row_groups) if starts[g] < cut)
+    assert counts[0][0] == exp_first and counts[0][0] + counts[1][0] == n
+    assert counts[0][1] + counts[1][1] == int(cols["l_quantity"].sum())
+
+
+def test_annotations_that_change_the_meaning_of_the_bytes_are_refused(cb, tmp_path):
+    """TIMESTAMP_MILLIS / NANOS read as microseconds or UINT32 sign-extended would be silently wrong data: Unsupported (the caller
+    keeps its CPU path), never a guess.  Microsecond timestamps decode."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    P = cb.proto
+    n = 1000
+    ts = np.arange(n, dtype=np.int64) * 1_000_000 + 1_600_000_000_000_000
+    for unit, ok in (("us", True), ("ms", False), ("ns", False)):
+        path = str(tmp_path / f"ts_{unit}.parquet")
+        arr = pa.array(ts if unit == "us" else (ts // 1000 if unit == "ms" else ts * 1000), type=pa.timestamp(unit))
+        pq.write_table(pa.table({"t": arr}), path, compression="NONE", use_dictionary=False, coerce_timestamps=None, version="2.6")
+        fields = [("t", P.TIMESTAMP, True)]
+        plan = P.projection(P.native_scan(fields, fields, [path]), [P.bound(0, P.TIMESTAMP)])
+        if ok:
+            res, _ = run(cb, plan)
+            assert res.column(0).cast(pa.int64()).to_numpy().tolist() == ts.tolist()
+        else:
+            with pytest.raises(cb.native.Unsupported):
+                run(cb, plan)
+    path = str(tmp_path / "u32.parquet")
+    pq.write_table(pa.table({"u": pa.array([1, 2**31 + 5, 7], type=pa.uint32())}), path, compression="NONE", use_dictionary=False)
+    fields = [("u", P.INT64, True)]
+    with pytest.raises(cb.native.Unsupported):
+        run(cb, P.projection(P.native_scan(fields, fields, [path]), [P.bound(0, P.INT64)]))
+
+
+def test_scan_blocks_are_reused_across_plans(cb, tmp_path):
+    """Ten plans over the same files in a row, alternating batch sizes: results identical every time (the slot blocks come back
+    from the process-wide cache; a stale pointer or a missing stream dependency would show up as a wrong sum)."""
+    t = cb.tpch
+    P = cb.proto
+    n = 250_000
+    cols = t.gen_lineitem(n, seed=47)
+    path = t.write_lineitem_parquet(cols, str(tmp_path / "reuse.parquet"), "dec", row_group_size=8192)
+    fields = list(zip(t.Q1_COLUMNS, t.q1_scan_fields("dec"), [True] * 7))
+    sc = P.native_scan(fields, fields, [path])
+    plan = P.hash_agg(sc, [], [P.agg_sum(P.bound(1, t.D12), P.DECIMAL(22, 2)), P.agg_sum(P.bound(3, t.D12), P.DECIMAL(22, 2)), P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    exp = (int(cols["l_extendedprice"].sum()), int(cols["l_tax"].sum()), n)
+    for i in range(10):
+        res, _ = run(cb, plan, chunk_rows=[20_000, 64_000, 250_000][i % 3])
+        r = res.to_pylist()[0]
+        assert (unscaled(r["col_0"]), unscaled(r["col_2"]), r["col_4"]) == exp, i

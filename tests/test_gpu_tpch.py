@@ -55,7 +55,7 @@ def test_q1_dec_partial_and_final(cb, oracle, n, chunk, dictionary):
     res = run(cb, t.q1_final_plan("dec"), [state])
     exp = oracle.q1_dec(dec(oracle, cols["l_quantity"]), dec(oracle, cols["l_extendedprice"]), dec(oracle, cols["l_discount"]),
                         dec(oracle, cols["l_tax"]), cols["l_shipdate"], cols["l_returnflag"], cols["l_linestatus"], 3, 2,
-                        t.DATE_1998_09_02, 1)
+                        t.Q1_CUTOFF, 1)
     got = q1_groups(res)
     n_exp = 0
     for k, e in enumerate(exp):
@@ -80,7 +80,7 @@ def test_q1_dec_partial_state_matches_accumulators(cb, oracle):
     cols = t.gen_lineitem(n, seed=7)
     tbl = t.lineitem_table(cols, "dec", dictionary=True)
     state = run(cb, t.q1_partial_plan("dec"), [tbl.to_batches(max_chunksize=8192)])
-    keep = cols["l_shipdate"] <= t.DATE_1998_09_02
+    keep = cols["l_shipdate"] <= t.Q1_CUTOFF
     gid = (cols["l_returnflag"].astype(np.int64) * 2 + cols["l_linestatus"])[keep]
     acc = oracle.SumDecimalGroups(6, 22)
     acc.update(dec(oracle, cols["l_quantity"][keep]), None, gid)
@@ -102,7 +102,7 @@ def test_q1_f64(cb, oracle, n):
     res = run(cb, t.q1_final_plan("f64"), [state])
     got = q1_groups(res)
     f = {k: (cols[k].astype(np.float64) / 100.0) for k in ("l_quantity", "l_extendedprice", "l_discount", "l_tax")}
-    keep = cols["l_shipdate"] <= t.DATE_1998_09_02
+    keep = cols["l_shipdate"] <= t.Q1_CUTOFF
     gid = (cols["l_returnflag"].astype(np.int64) * 2 + cols["l_linestatus"])
     dp = f["l_extendedprice"] * (1.0 - f["l_discount"])
     ch = dp * (1.0 + f["l_tax"])
@@ -213,7 +213,7 @@ def test_nullable_inputs_q1(cb, oracle):
     state = run(cb, t.q1_partial_plan("dec"), [tbl.to_batches(max_chunksize=8192)], 20_000)
     res = run(cb, t.q1_final_plan("dec"), [state])
     got = q1_groups(res)
-    keep = vs & (cols["l_shipdate"] <= t.DATE_1998_09_02)
+    keep = vs & (cols["l_shipdate"] <= t.Q1_CUTOFF)
     gid = cols["l_returnflag"].astype(np.int64) * 2 + cols["l_linestatus"]
     for k in range(6):
         m = keep & (gid == k)

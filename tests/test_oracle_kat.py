@@ -419,9 +419,9 @@ def test_q1_dec_threads_agree(oracle):
     tpch, c = _lineitem(50000, 8)
     d = oracle.dec_from_i64
     args = (d(c["l_quantity"]), d(c["l_extendedprice"]), d(c["l_discount"]), d(c["l_tax"]), c["l_shipdate"], c["l_returnflag"],
-            c["l_linestatus"], 3, 2, tpch.DATE_1998_09_02)
+            c["l_linestatus"], 3, 2, tpch.Q1_CUTOFF)
     a, b = oracle.q1_dec(*args, 1), oracle.q1_dec(*args, 5)
     assert a == b
-    keep = c["l_shipdate"] <= tpch.DATE_1998_09_02
+    keep = c["l_shipdate"] <= tpch.Q1_CUTOFF
     k0 = keep & (c["l_returnflag"] == 0) & (c["l_linestatus"] == 0)
     assert a[0]["sum_qty"] == int(c["l_quantity"][k0].sum()) and a[0]["count"] == int(k0.sum())
