@@ -66,7 +66,8 @@ class Stats(C.Structure):
                 ("scan_pruned_row_groups", C.c_int64), ("scan_pruned_rows", C.c_int64)]
 
 
-EXPORTED = ["cb200_plan_stats", "cb200_register_memory_file", "cb200_parquet_describe", "cb200_table_add_column_bytes", "cb200_plan_dict_value", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
+EXPORTED = ["cb200_comm_unique_id", "cb200_comm_create", "cb200_comm_destroy", "cb200_comm_rank", "cb200_comm_world", "cb200_nccl_info", "cb200_exchange",
+            "cb200_exchange_layout", "cb200_comm_allgather_small", "cb200_plan_stats", "cb200_register_memory_file", "cb200_parquet_describe", "cb200_table_add_column_bytes", "cb200_plan_dict_value", "cb200_plan_partition_starts", "cb200_compile_plan_assume", "cb200_version", "cb200_supports", "cb200_create_plan", "cb200_plan_num_columns", "cb200_execute",
             "cb200_release", "cb200_table_create", "cb200_table_add_column", "cb200_plan_bind_table",
             "cb200_table_release", "cb200_execute_device", "cb200_plan_kernel_launches", "cb200_compile_plan",
             "cb200_plan_kernel_source"]
@@ -186,6 +187,88 @@ def kernel_source(op_bytes, index=0):
     if n < 0:
         _raise(err)
     return buf.value.decode()
+
+
+class ExchangeStats(C.Structure):
+    _fields_ = [("rows_sent", C.c_int64), ("rows_received", C.c_int64), ("bytes_sent", C.c_int64), ("bytes_received", C.c_int64),
+                ("payload_ms", C.c_double)]
+
+
+def exchange_layout(counts, world, me):
+    """(total, recv_counts, recv_offsets) of rank `me` from the row-major N x N count matrix (host arithmetic only)."""
+    f = lib().cb200_exchange_layout
+    f.restype = C.c_int64
+    f.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    m = (C.c_int64 * (world * world))(*[int(x) for x in counts])
+    rc, ro = (C.c_int64 * world)(), (C.c_int64 * world)()
+    total = f(m, world, me, rc, ro)
+    return total, list(rc), list(ro)
+
+
+class Comm:
+    """One NCCL communicator per process / GPU, owned by the library (cb200_comm_*).  `bcast(bytes_or_None) -> bytes` is the
+    caller's control channel for the 128-byte id (torch.distributed here; the Spark driver in the reference's world)."""
+
+    def __init__(self, rank, world, device, bcast=None):
+        l = lib()
+        l.cb200_comm_create.restype = C.c_void_p
+        l.cb200_comm_create.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_Error)]
+        l.cb200_comm_unique_id.argtypes = [C.c_char_p, C.POINTER(_Error)]
+        l.cb200_comm_destroy.argtypes = [C.c_void_p]
+        err = _Error()
+        idb = C.create_string_buffer(128)
+        if world > 1:
+            if rank == 0 and l.cb200_comm_unique_id(idb, C.byref(err)) != 0:
+                _raise(err)
+            got = bcast(bytes(idb.raw) if rank == 0 else None)
+            idb = C.create_string_buffer(got, 128)
+        self.rank, self.world, self.device = rank, world, device
+        self.handle = l.cb200_comm_create(idb, rank, world, device, C.byref(err))
+        if not self.handle:
+            _raise(err)
+
+    def exchange(self, map_plan):
+        """Collective: partition r of every rank's last ShuffleWriter batch -> rank r.  Returns (DeviceTable, stats dict)."""
+        l = lib()
+        l.cb200_exchange.restype = C.c_void_p
+        l.cb200_exchange.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(ExchangeStats), C.POINTER(_Error)]
+        err, n, st = _Error(), C.c_int64(0), ExchangeStats()
+        h = l.cb200_exchange(self.handle, map_plan.handle, C.byref(n), C.byref(st), C.byref(err))
+        if not h:
+            _raise(err)
+        t = DeviceTable.__new__(DeviceTable)
+        t.handle, t.n_rows, t._keep = h, n.value, []
+        return t, {k: getattr(st, k) for k, _ in ExchangeStats._fields_}
+
+    def allgather_small(self, payload, slot_bytes=1 << 16):
+        """Every rank's small bytes payload on every rank (list of bytes, rank order).  slot_bytes must be the same on all ranks."""
+        l = lib()
+        l.cb200_comm_allgather_small.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(_Error)]
+        if len(payload) + 8 > slot_bytes:
+            raise ValueError(f"payload of {len(payload)} bytes does not fit the {slot_bytes}-byte slot (pass a larger slot_bytes on every rank)")
+        out = C.create_string_buffer(slot_bytes * self.world)
+        sizes = (C.c_int64 * self.world)()
+        err = _Error()
+        if l.cb200_comm_allgather_small(self.handle, payload, len(payload), slot_bytes, out, sizes, C.byref(err)) != 0:
+            _raise(err)
+        return [out.raw[r * slot_bytes: r * slot_bytes + sizes[r]] for r in range(self.world)]
+
+    def destroy(self):
+        if self.handle:
+            lib().cb200_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def nccl_info():
+    f = lib().cb200_nccl_info
+    f.restype = C.c_char_p
+    return f().decode()
 
 
 class DeviceTable:

@@ -1,6 +1,7 @@
 // abi.cpp -- extern "C" surface of libcomet_b200.so (include/comet_b200.h).
 #include "../../include/comet_b200.h"
 
+#include "abi_internal.h"
 #include "exec.h"
 #include "jit.h"
 #include "plan.h"
@@ -13,20 +14,6 @@
 
 using namespace cb200;
 
-struct cb200_table {
-    std::shared_ptr<DeviceTable> t;
-};
-
-struct cb200_plan {
-    OperatorP op;
-    ExecContext ctx;
-    PlanInputs inputs;
-    ExecNodeP root;
-    Batch last; // keeps device results alive for cb200_execute_device
-    bool started = false, finished = false;
-    int partition = 0, partition_count = 1;
-};
-
 namespace {
 
 struct CtxRes {
@@ -37,36 +24,6 @@ struct CtxRes {
 };
 std::mutex g_pool_mu;
 std::map<int, std::vector<CtxRes>> g_pool;
-
-void set_error(cb200_error* e, int code, const std::string& cls, const std::string& msg) {
-    if (!e) return;
-    e->code = code;
-    snprintf(e->error_class, sizeof(e->error_class), "%s", cls.c_str());
-    snprintf(e->message, sizeof(e->message), "%s", msg.c_str());
-}
-void clear_error(cb200_error* e) {
-    if (e) { e->code = 0; e->error_class[0] = 0; e->message[0] = 0; }
-}
-
-template <typename F> auto guarded(cb200_error* err, F&& f, decltype(f()) on_error) -> decltype(f()) {
-    clear_error(err);
-    try {
-        return f();
-    } catch (const Unsupported& e) {
-        set_error(err, CB200_ERR_UNSUPPORTED, "", e.what());
-    } catch (const PlanError& e) {
-        set_error(err, CB200_ERR_PLAN, "", e.what());
-    } catch (const JitError& e) {
-        set_error(err, CB200_ERR_JIT, "", e.what());
-    } catch (const ExecError& e) {
-        set_error(err, e.code >= 10 ? CB200_ERR_SPARK : e.code, e.error_class, e.what());
-    } catch (const std::exception& e) { // the reference turns panics into a pending exception (errors.rs:832-850)
-        set_error(err, CB200_ERR_PLAN, "", std::string("native panic: ") + e.what());
-    } catch (...) {
-        set_error(err, CB200_ERR_PLAN, "", "native panic: unknown exception");
-    }
-    return on_error;
-}
 
 void parse_config(const uint8_t* cfg, size_t len, ExecContext& ctx) { // config.proto ConfigMap
     if (!cfg || !len) return;
@@ -154,7 +111,7 @@ extern "C" {
 const char* cb200_version(void) { return "comet_b200 0.1.0 (sm_100a; reference apache/datafusion-comet 1.1.0 @2699f59b)"; }
 
 int cb200_supports(const uint8_t* op_proto, size_t op_len, cb200_error* why) {
-    return guarded(why, [&]() -> int {
+    return cb200_guarded(why, [&]() -> int {
         OperatorP op = decode_plan(op_proto, op_len);
         plan_kernels_for_build(op); // exercises fusion + code generation rules
         return 1;
@@ -164,7 +121,7 @@ int cb200_supports(const uint8_t* op_proto, size_t op_len, cb200_error* why) {
 cb200_plan* cb200_create_plan(const uint8_t* op_proto, size_t op_len, const uint8_t* cfg_proto, size_t cfg_len, struct ArrowArrayStream** inputs,
                               int32_t n_inputs, int32_t partition, int32_t partition_count, int32_t batch_size, int32_t device_ordinal, cb200_error* err) {
     TraceSpan ts("create_plan");
-    return guarded(err, [&]() -> cb200_plan* {
+    return cb200_guarded(err, [&]() -> cb200_plan* {
         auto p = std::unique_ptr<cb200_plan>(new cb200_plan());
         p->op = decode_plan(op_proto, op_len);
         p->ctx.device = device_ordinal;
@@ -184,7 +141,7 @@ int32_t cb200_plan_num_columns(cb200_plan* plan) { return plan ? (int32_t)plan->
 
 static int64_t execute_common(cb200_plan* plan, cb200_error* err, const std::function<void(Batch&)>& sink) {
     TraceSpan ts("execute");
-    return guarded(err, [&]() -> int64_t {
+    return cb200_guarded(err, [&]() -> int64_t {
         if (!plan) throw PlanError("null plan handle");
         if (plan->finished) return -1;
         start(plan);
@@ -255,7 +212,7 @@ cb200_table* cb200_table_create(int64_t n_rows) {
 
 int cb200_table_add_column(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width, const void* dev_values,
                            const void* dev_validity, int64_t null_count, const char* const* dict_values, int32_t n_dict, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         if (!t) throw PlanError("null table handle");
         Column c;
         c.type = dtype_from_ids(type_id, precision, scale);
@@ -306,7 +263,7 @@ const char* cb200_plan_dict_value(cb200_plan* plan, int32_t col, int32_t i, int3
 
 int cb200_table_add_column_bytes(cb200_table* t, int32_t type_id, int32_t precision, int32_t scale, int32_t value_width, const void* dev_values,
                                  const void* dev_validity_bytes, const char* const* dict_values, int32_t n_dict, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         if (!t) throw PlanError("null table handle");
         size_t n = (size_t)t->t->n_rows;
         bool is_bool = type_id == (int)TypeId::Bool;
@@ -330,7 +287,7 @@ int cb200_table_add_column_bytes(cb200_table* t, int32_t type_id, int32_t precis
 }
 
 int cb200_plan_bind_table(cb200_plan* plan, int32_t input_index, cb200_table* t, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         if (!plan || !t) throw PlanError("null handle");
         if (plan->started) throw PlanError("tables must be bound before the first execute");
         if (input_index < 0 || input_index >= (int)plan->inputs.tables.size()) throw PlanError("input index out of range");
@@ -365,7 +322,7 @@ int cb200_plan_stats(cb200_plan* plan, cb200_stats* out) {
 }
 
 int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, size_t keys_cap, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         OperatorP op = decode_plan(op_proto, op_len);
         auto ks = plan_kernels_for_build(op);
         std::string keys;
@@ -380,7 +337,7 @@ int cb200_compile_plan(const uint8_t* op_proto, size_t op_len, char* keys_out, s
 
 int cb200_compile_plan_assume(const uint8_t* op_proto, size_t op_len, const int32_t* assume_bits, int32_t n_assume, int32_t source_index,
                               char* src_out, size_t src_cap, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         OperatorP op = decode_plan(op_proto, op_len);
         std::vector<int> as(assume_bits, assume_bits + n_assume);
         auto ks = plan_kernels_for_build(op, as);
@@ -397,7 +354,7 @@ int cb200_register_memory_file(const char* name, const void* data, size_t len) {
 }
 
 int cb200_parquet_describe(const char* path, char* out, size_t cap, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         std::string s = describe_parquet(path ? path : "");
         if (out && cap) snprintf(out, cap, "%s", s.c_str());
         return (int)s.size();
@@ -405,7 +362,7 @@ int cb200_parquet_describe(const char* path, char* out, size_t cap, cb200_error*
 }
 
 int cb200_plan_kernel_source(const uint8_t* op_proto, size_t op_len, int32_t index, char* out, size_t cap, cb200_error* err) {
-    return guarded(err, [&]() -> int {
+    return cb200_guarded(err, [&]() -> int {
         OperatorP op = decode_plan(op_proto, op_len);
         auto ks = plan_kernels_for_build(op);
         if (index < 0 || index >= (int)ks.size()) throw PlanError("kernel index out of range");

@@ -126,7 +126,7 @@ struct Emitter {
         uint64_t fb;
         memcpy(&fb, &e.lit_f64, 8);
         o << fb << "|" << (uint64_t)e.lit_dec << "," << (uint64_t)(e.lit_dec >> 64) << "|" << (int)e.eval_mode << "|"
-          << e.fail_on_error << "|" << e.negated << "|" << e.wide_decimal << "|" << e.return_type.str() << "(";
+          << e.fail_on_error << "|" << e.negated << "|" << e.wide_decimal << "|" << e.integral_div << e.check_divide_overflow << "|" << e.return_type.str() << "(";
         for (auto& c : e.children) o << key_of(*c) << ",";
         o << ")";
         return o.str();
@@ -297,6 +297,24 @@ struct Emitter {
         std::string nn = or_null(l.n, rr.n);
         std::string valid = nn.empty() ? "true" : "!" + nn;
         const DType &lt = l.type, &rt = rr.type;
+        if (lt.is_decimal() && e.kind == ExprKind::Div) {
+            // decimal_div / decimal_integral_div (spark-expr/src/math_funcs/div.rs:75-190): only rows where both sides are valid are
+            // evaluated (try_binary); a zero divisor is an error in ANSI mode and yields 0 otherwise (unreachable: the JVM serde wraps
+            // the divisor in nullIf(= 0) outside ANSI mode)
+            const int s1 = lt.scale, s2 = rt.scale, s3 = e.type.scale;
+            const int l_exp = std::max(0, s2 + s3 + 1 - s1), r_exp = std::max(0, s1 - (s2 + s3 + 1));
+            std::string ok = fresh("b"), fits = fresh("b");
+            r.v = fresh();
+            body << "    cb::i128 " << r.v << " = cb::mk128(0, 0); bool " << ok << " = true, " << fits << " = true;\n";
+            body << "    if (" << valid << ") " << ok << " = cb::dec_div(" << W(l) << ", " << W(rr) << ", " << l_exp << ", " << r_exp << ", "
+                 << (e.integral_div ? "true" : "false") << ", " << r.v << ", " << fits << ");\n";
+            if (e.eval_mode == EvalMode::Ansi) {
+                raise(valid + " && !" + ok, 3);
+                if (e.integral_div && e.check_divide_overflow) raise(valid + " && " + ok + " && !" + fits, 1);
+            }
+            r.n = nn;
+            return r;
+        }
         if (lt.is_decimal()) {
             int op = e.kind == ExprKind::Add ? 0 : e.kind == ExprKind::Sub ? 1 : 2;
             const u128r raw = r_binary_raw(e, bound_of(*e.children[0]), bound_of(*e.children[1]));
@@ -346,10 +364,32 @@ struct Emitter {
             (void)opc;
             r.v = decl(e.type, fn + "(" + l.v + ", " + rr.v + ")");
             r.n = nn;
+            if (e.kind == ExprKind::Div && e.eval_mode != EvalMode::Legacy) {
+                // checked_div (checked_arithmetic.rs:53-128; planner.rs:1094-1125 routes float Divide there under TRY / ANSI):
+                // a zero divisor is NULL in TRY mode and DIVIDE_BY_ZERO in ANSI mode; everything else is IEEE
+                std::string z = declb(rr.v + (lt.id == TypeId::Float64 ? " == 0.0" : " == 0.0f"));
+                if (e.eval_mode == EvalMode::Ansi) raise(valid + " && " + z, 3);
+                else r.n = or_null(nn, z);
+            }
             return r;
         }
         // integers: Legacy wraps (arrow-arith *_wrapping); Try -> NULL, Ansi -> error (checked_arithmetic.rs:53-128)
         int bits = lt.id == TypeId::Int8 ? 8 : lt.id == TypeId::Int16 ? 16 : lt.id == TypeId::Int32 ? 32 : 64;
+        if (e.kind == ExprKind::Div) {
+            // Legacy: arrow-arith `div` (checked: zero divisor / MIN / -1 fail the query); TRY -> NULL, ANSI -> Spark errors
+            // (checked_div, checked_arithmetic.rs:45,90-100)
+            std::string err = fresh("e"), q = fresh();
+            body << "    int " << err << " = 0; cb::i64 " << q << " = 0;\n";
+            body << "    if (" << valid << ") " << q << " = cb::i64_div_checked((cb::i64)" << l.v << ", (cb::i64)" << rr.v << ", " << bits << ", " << err << ");\n";
+            r.v = decl(e.type, "(" + ctype(e.type) + ")" + q);
+            if (e.eval_mode == EvalMode::Try) r.n = or_null(nn, err + " != 0");
+            else {
+                raise(err + " == 1", e.eval_mode == EvalMode::Ansi ? 3 : 4);
+                raise(err + " == 2", e.eval_mode == EvalMode::Ansi ? 1 : 0);
+                r.n = nn;
+            }
+            return r;
+        }
         std::string wide = fresh("w");
         const char* opc = e.kind == ExprKind::Add ? "+" : e.kind == ExprKind::Sub ? "-" : "*";
         if (bits < 64) {
@@ -667,7 +707,7 @@ void sig_expr(std::ostringstream& o, const Expr& e) {
     uint64_t fb;
     memcpy(&fb, &e.lit_f64, 8);
     o << (int)e.kind << '|' << e.type.str() << '|' << e.index << '|' << e.lit_null << '|' << e.lit_i64 << '|' << fb << '|' << (uint64_t)e.lit_dec << ','
-      << (uint64_t)(e.lit_dec >> 64) << '|' << e.lit_str << '|' << (int)e.eval_mode << '|' << e.fail_on_error << '|' << e.negated << '|' << e.wide_decimal << '|'
+      << (uint64_t)(e.lit_dec >> 64) << '|' << e.lit_str << '|' << (int)e.eval_mode << '|' << e.fail_on_error << '|' << e.negated << '|' << e.wide_decimal << '|' << e.integral_div << e.check_divide_overflow << '|'
       << e.return_type.str() << '(';
     for (auto& c : e.children) { sig_expr(o, *c); o << ','; }
     o << ')';

@@ -343,6 +343,123 @@ CB_HD bool i64_add_overflow(i64 a, i64 b, i64& r) { r = (i64)((u64)a + (u64)b); 
 CB_HD bool i64_sub_overflow(i64 a, i64 b, i64& r) { r = (i64)((u64)a - (u64)b); return ((a ^ b) & (a ^ r)) < 0; }
 CB_HD bool i64_mul_overflow(i64 a, i64 b, i64& r) { i128 p = mul_i64_i64(a, b); r = (i64)p.lo; return !i128_fits_i64(p); }
 
+
+// ------------------------------------------------------------------------------------------------
+// decimal division (spark-expr/src/math_funcs/div.rs:75-190 spark_decimal_div_internal)
+//   Decimal(p1,s1) / Decimal(p2,s2) -> Decimal(p3,s3):  q = trunc((l * 10^l_exp) / (r * 10^r_exp)) with
+//   l_exp = max(0, s2+s3+1-s1), r_exp = max(0, s1-(s2+s3+1)), i.e. one digit more than the result keeps, then
+//   HALF_UP on that digit: (q +- 5) / 10 (integral division keeps q).  The reference switches to BigInt when
+//   the scaled operands leave 38 digits; here ONE multi-limb routine covers both (numerator up to 384 bits).
+// ------------------------------------------------------------------------------------------------
+#define CB_DIV_NN 12 // 32-bit limbs of the numerator:  |l| < 2^127 times 10^77 < 2^256
+#define CB_DIV_ND 8  //                   the divisor:  |r| < 2^127 times 10^38 < 2^127
+CB_HD int limbs_len(const u32* a, int n) { while (n > 0 && a[n - 1] == 0) n--; return n; }
+CB_HD void limbs_mul_small(u32* a, int n, u32 m) {
+    u64 carry = 0;
+    for (int i = 0; i < n; i++) { u64 t = (u64)a[i] * m + carry; a[i] = (u32)t; carry = t >> 32; }
+}
+CB_HD void limbs_mul_pow10(u32* a, int n, int e) {
+    while (e >= 9) { limbs_mul_small(a, n, 1000000000u); e -= 9; }
+    if (e > 0) limbs_mul_small(a, n, (u32)pow10_u64(e));
+}
+CB_HD u32 limbs_div_small(u32* a, int n, u32 d) { // in place, returns the remainder
+    u64 rem = 0;
+    for (int i = n - 1; i >= 0; i--) { u64 cur = (rem << 32) | a[i]; a[i] = (u32)(cur / d); rem = cur % d; }
+    return (u32)rem;
+}
+CB_HD int clz32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+// q = n / d (truncating), Knuth TAOCP vol. 2 algorithm D in base 2^32.  n: CB_DIV_NN limbs, d: CB_DIV_ND limbs, d != 0.
+CB_HD void limbs_div(const u32* n, const u32* d, u32* q) {
+    for (int i = 0; i < CB_DIV_NN; i++) q[i] = 0;
+    const int m = limbs_len(d, CB_DIV_ND), ln = limbs_len(n, CB_DIV_NN);
+    if (ln < m) return;
+    if (m == 1) {
+        for (int i = 0; i < CB_DIV_NN; i++) q[i] = n[i];
+        limbs_div_small(q, CB_DIV_NN, d[0]);
+        return;
+    }
+    const int s = clz32(d[m - 1]);
+    u32 dn[CB_DIV_ND], un[CB_DIV_NN + 1];
+    for (int i = m - 1; i > 0; i--) dn[i] = s ? (d[i] << s) | (d[i - 1] >> (32 - s)) : d[i];
+    dn[0] = d[0] << s;
+    un[ln] = s ? n[ln - 1] >> (32 - s) : 0;
+    for (int i = ln - 1; i > 0; i--) un[i] = s ? (n[i] << s) | (n[i - 1] >> (32 - s)) : n[i];
+    un[0] = n[0] << s;
+    for (int j = ln - m; j >= 0; j--) {
+        const u64 num = ((u64)un[j + m] << 32) | un[j + m - 1];
+        u64 qhat = num / dn[m - 1], rhat = num % dn[m - 1];
+        while (qhat >= (1ull << 32) || qhat * dn[m - 2] > ((rhat << 32) | un[j + m - 2])) {
+            qhat--;
+            rhat += dn[m - 1];
+            if (rhat >= (1ull << 32)) break;
+        }
+        i64 borrow = 0;
+        u64 carry = 0;
+        for (int i = 0; i < m; i++) { // un[j..j+m] -= qhat * dn
+            const u64 p = qhat * dn[i] + carry;
+            carry = p >> 32;
+            const i64 t = (i64)un[i + j] - borrow - (i64)(p & 0xffffffffull);
+            un[i + j] = (u32)t;
+            borrow = t < 0 ? 1 : 0;
+        }
+        const i64 t = (i64)un[j + m] - borrow - (i64)carry;
+        un[j + m] = (u32)t;
+        if (t < 0) { // qhat was one too large: add the divisor back
+            qhat--;
+            u64 c = 0;
+            for (int i = 0; i < m; i++) { const u64 sum = (u64)un[i + j] + dn[i] + c; un[i + j] = (u32)sum; c = sum >> 32; }
+            un[j + m] += (u32)c;
+        }
+        q[j] = (u32)qhat;
+    }
+}
+// returns false when r == 0 (`out` = 0: the reference's unreachable fallback; ANSI callers raise DIVIDE_BY_ZERO).
+// fits_i64: the result fits a LONG (MathExpr.check_divide_overflow of integral division).
+CB_HD bool dec_div(i128 l, i128 r, int l_exp, int r_exp, bool integral, i128& out, bool& fits_i64) {
+    out = mk128(0, 0);
+    fits_i64 = true;
+    if (r.lo == 0 && r.hi == 0) return false;
+    const bool neg = (l.hi < 0) != (r.hi < 0);
+    const u128 la = i128_abs_u(l), ra = i128_abs_u(r);
+    u32 n[CB_DIV_NN], d[CB_DIV_ND], q[CB_DIV_NN];
+    for (int i = 0; i < CB_DIV_NN; i++) n[i] = 0;
+    for (int i = 0; i < CB_DIV_ND; i++) d[i] = 0;
+    n[0] = (u32)la.lo; n[1] = (u32)(la.lo >> 32); n[2] = (u32)la.hi; n[3] = (u32)(la.hi >> 32);
+    d[0] = (u32)ra.lo; d[1] = (u32)(ra.lo >> 32); d[2] = (u32)ra.hi; d[3] = (u32)(ra.hi >> 32);
+    limbs_mul_pow10(n, CB_DIV_NN, l_exp);
+    limbs_mul_pow10(d, CB_DIV_ND, r_exp);
+    limbs_div(n, d, q);
+    if (!integral) { // (div + 5) / 10 on the magnitude == (div -+ 5) / 10 truncating toward zero
+        u64 c = 5;
+        for (int i = 0; i < CB_DIV_NN && c; i++) { const u64 t = (u64)q[i] + c; q[i] = (u32)t; c = t >> 32; }
+        limbs_div_small(q, CB_DIV_NN, 10u);
+    }
+    // BigInt::to_i128().unwrap_or(i128::MAX): magnitudes past 2^127 - 1 (2^127 when negative) become the positive sentinel
+    bool big = false;
+    for (int i = 4; i < CB_DIV_NN; i++) big = big || q[i] != 0;
+    const u64 qlo = ((u64)q[1] << 32) | q[0], qhi = ((u64)q[3] << 32) | q[2];
+    if (!big && (qhi >> 63) != 0) big = !(neg && qhi == 0x8000000000000000ull && qlo == 0);
+    if (big) { out = mk128(~0ull, 0x7fffffffffffffffll); fits_i64 = false; return true; }
+    out = mk128(qlo, (i64)qhi);
+    if (neg) out = i128_neg(out);
+    fits_i64 = i128_fits_i64(out);
+    return true;
+}
+// integer division, truncating (Rust `/`): err = 1 divide by zero, 2 overflow (MIN / -1)
+CB_HD i64 i64_div_checked(i64 a, i64 b, int bits, int& err) {
+    err = 0;
+    if (b == 0) { err = 1; return 0; }
+    const i64 mn = bits == 64 ? (i64)0x8000000000000000ll : -((i64)1 << (bits - 1));
+    if (a == mn && b == -1) { err = 2; return mn; }
+    return a / b;
+}
+
 // ---- overflow certificate for decimal sums ------------------------------------------------------
 // The reference adds row by row and nulls the sum as soon as a running prefix leaves the precision
 // (agg_funcs/sum_decimal.rs:418-439).  A parallel sum reproduces that exactly whenever no ordering

@@ -18,7 +18,7 @@
 namespace cb200 {
 
 // error bits raised by kernels (device/cb_kernels.cuh set_err)
-enum { ERR_I128_OVERFLOW = 0, ERR_ANSI_OVERFLOW = 1, ERR_ORDER_DEPENDENT = 2 };
+enum { ERR_I128_OVERFLOW = 0, ERR_ANSI_OVERFLOW = 1, ERR_ORDER_DEPENDENT = 2, ERR_DIVIDE_BY_ZERO = 3, ERR_ARROW_DIVIDE_BY_ZERO = 4 };
 
 bool trace_on() {
     static int on = -1;
@@ -69,6 +69,10 @@ void ExecContext::check_device_errors() {
     cudaMemsetAsync(d_err, 0, sizeof(int), stream);
     if (e & (1 << ERR_ANSI_OVERFLOW))
         throw ExecError(10, "ARITHMETIC_OVERFLOW", "[ARITHMETIC_OVERFLOW] overflow in ANSI mode");
+    if (e & (1 << ERR_DIVIDE_BY_ZERO)) // SparkError::DivideByZero (spark-expr/src/error.rs)
+        throw ExecError(10, "DIVIDE_BY_ZERO", "[DIVIDE_BY_ZERO] Division by zero. Use `try_divide` to tolerate divisor being 0 and return NULL instead. "
+                                              "If necessary set \"spark.sql.ansi.enabled\" to \"false\" to bypass this error.");
+    if (e & (1 << ERR_ARROW_DIVIDE_BY_ZERO)) throw ExecError(11, "", "Arrow error: Divide by zero error"); // arrow-arith checked division in Legacy mode
     if (e & (1 << ERR_I128_OVERFLOW))
         throw ExecError(11, "", "Arrow error: Arithmetic overflow: Overflow happened on decimal arithmetic"); // arrow-arith checked ops
     if (e & (1 << ERR_ORDER_DEPENDENT))

@@ -50,6 +50,14 @@ void hm_avg(int64_t n, const i128* sum, const int64_t* count, int scaler_exp, in
         outv[i] = ok;
     }
 }
+// decimal_div: returns 0 ok, 1 divide by zero; fits = result fits i64
+void hm_dec_div(int64_t n, const i128* l, const i128* r, int l_exp, int r_exp, int integral, i128* out, uint8_t* zero, uint8_t* fits) {
+    for (int64_t i = 0; i < n; i++) {
+        bool f = true;
+        zero[i] = dec_div(l[i], r[i], l_exp, r_exp, integral != 0, out[i], f) ? 0 : 1;
+        fits[i] = f;
+    }
+}
 void hm_mm3_i32(int64_t n, const int32_t* v, uint32_t* h) { for (int64_t i = 0; i < n; i++) h[i] = mm3_i32(v[i], h[i]); }
 void hm_mm3_i64(int64_t n, const int64_t* v, uint32_t* h) { for (int64_t i = 0; i < n; i++) h[i] = mm3_i64(v[i], h[i]); }
 void hm_mm3_i128(int64_t n, const i128* v, uint32_t* h) { for (int64_t i = 0; i < n; i++) h[i] = mm3_i128(v[i], h[i]); }

@@ -24,6 +24,7 @@ CompiledModule::~CompiledModule() {
 }
 
 cudaKernel_t CompiledModule::kernel(const std::string& name) {
+    std::lock_guard<std::mutex> lk(mu);
     auto it = kernels.find(name);
     if (it != kernels.end()) return it->second;
     cudaKernel_t k = nullptr;

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@ struct CompiledModule {
     std::vector<char> cubin;
     cudaLibrary_t lib = nullptr;
     std::map<std::string, cudaKernel_t> kernels;
+    std::mutex mu; // modules are shared by every plan (and task thread) that uses the same pipeline
     bool loaded = false;
     ~CompiledModule();
     cudaKernel_t kernel(const std::string& name);

@@ -120,6 +120,7 @@ static ExprP decode_binary(ExprKind k, PbReader r, bool math) {
         else if (r.field == 2) rr = decode_expr(r.sub());
         else if (math && r.field == 4) e->return_type = decode_dtype(r.sub());
         else if (math && r.field == 5) e->eval_mode = (EvalMode)r.i64();
+        else if (math && r.field == 6) e->check_divide_overflow = r.i64() != 0;
         else r.skip();
     }
     if (!l || !rr) throw PlanError("binary expression is missing an operand");
@@ -170,6 +171,7 @@ static ExprP decode_expr(PbReader r) {
         case 5: out = decode_binary(ExprKind::Sub, r.sub(), true); break;
         case 6: out = decode_binary(ExprKind::Mul, r.sub(), true); break;
         case 7: out = decode_binary(ExprKind::Div, r.sub(), true); break;
+        case 59: out = decode_binary(ExprKind::Div, r.sub(), true); out->integral_div = true; break; // IntegralDivide
         case 8: { // Cast expr.proto:337
             out = mk(ExprKind::Cast);
             PbReader c = r.sub();
@@ -317,8 +319,14 @@ static void resolve(Expr& e, const std::vector<DType>& in) {
     }
     case ExprKind::Div: {
         const DType &l = ct(0), &r = ct(1);
-        if (l.is_float() && l == r) e.type = l;
-        else throw Unsupported("division on " + l.str() + " (decimal_div / integer division) is outside the GPU hot path");
+        if (l.is_decimal() && r.is_decimal()) { // decimal_div / decimal_integral_div UDFs (planner.rs:1028-1058): result type = the proto's
+            if (!e.return_type.is_decimal()) throw PlanError("decimal division without a Decimal128 return type");
+            e.type = e.return_type;
+        } else if ((l.is_float() || l.is_integer()) && l == r) {
+            if (e.integral_div && l.is_float()) throw Unsupported("integral division of floats");
+            e.type = e.return_type.id == TypeId::Null ? l : e.return_type;
+            if (e.type != l) throw Unsupported("division with implicit result cast " + l.str() + " -> " + e.type.str());
+        } else throw Unsupported("division on " + l.str() + " and " + r.str());
         break;
     }
     case ExprKind::Eq: case ExprKind::Neq: case ExprKind::Gt: case ExprKind::GtEq: case ExprKind::Lt: case ExprKind::LtEq: {

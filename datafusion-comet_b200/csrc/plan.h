@@ -73,6 +73,8 @@ struct Expr {
     EvalMode eval_mode = EvalMode::Legacy;
     bool fail_on_error = false;
     bool negated = false;  // In
+    bool integral_div = false;          // Div: IntegralDivide (expr.proto:81): the quotient without the HALF_UP digit
+    bool check_divide_overflow = false; // MathExpr.check_divide_overflow (expr.proto:335-340)
     // decimal arithmetic lowering chosen by the reference's rule (planner.rs:998-1027)
     bool wide_decimal = false;
 };

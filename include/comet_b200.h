@@ -117,6 +117,40 @@ int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_
  * the same segments as per-partition IPC blocks).  Returns the number of entries. */
 int32_t cb200_plan_partition_starts(cb200_plan* plan, int64_t* starts, int32_t cap);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch --------------------------------------------------------------
+ * The path shards by partition with no collective except ONE exchange step: the hash-repartition of partial aggregate state between
+ * Partial and Final (the reference's shuffle, native/shuffle/src/partitioners/multi_partition.rs:265-330, followed by
+ * Spark's block fetch).  A caller with N GPUs on one box creates one communicator per process: rank 0 draws the id and hands the
+ * 128 bytes to the others over whatever control channel it has (the JVM driver, torch.distributed, a file). */
+#define CB200_UNIQUE_ID_BYTES 128
+typedef struct cb200_comm cb200_comm;
+int cb200_comm_unique_id(uint8_t* id_out /* CB200_UNIQUE_ID_BYTES */, cb200_error* err);
+cb200_comm* cb200_comm_create(const uint8_t* id, int32_t rank, int32_t world, int32_t device_ordinal, cb200_error* err);
+void cb200_comm_destroy(cb200_comm* comm);
+int32_t cb200_comm_rank(cb200_comm* comm);
+int32_t cb200_comm_world(cb200_comm* comm);
+const char* cb200_nccl_info(void); /* which NCCL the library resolved, for logs */
+
+typedef struct cb200_exchange_stats {
+    int64_t rows_sent, rows_received;
+    int64_t bytes_sent, bytes_received; /* payload bytes incl. the segment this rank keeps */
+    double payload_ms;                  /* CUDA-event duration of the grouped send/recv on the communicator's stream */
+} cb200_exchange_stats;
+/* The exchange itself.  `map_plan` is a ShuffleWriter(HashPartitioning(keys, world)) plan whose last cb200_execute_device batch is
+ * still alive: its rows are ordered by partition id = pmod(murmur3(keys, 42), world).  Every rank calls this collectively; rank r gets
+ * back a device table (owned by the library, release with cb200_table_release) holding partition r of every rank, sources in rank
+ * order, rows in their map-side order -- ready to be bound as the input of the Final plan with cb200_plan_bind_table.
+ * Fixed-width columns only (aggregate state: keys, sums, counts, flags).  Returns NULL on error. */
+cb200_table* cb200_exchange(cb200_comm* comm, cb200_plan* map_plan, int64_t* n_rows_out, cb200_exchange_stats* stats, cb200_error* err);
+/* receive layout of that exchange from the gathered N x N count matrix (counts[s * world + p] = rows rank s holds for rank p):
+ * fills recv_counts / recv_offsets (either may be NULL), returns the rows rank `me` receives.  Pure host arithmetic. */
+int64_t cb200_exchange_layout(const int64_t* counts, int32_t world, int32_t me, int64_t* recv_counts, int64_t* recv_offsets);
+/* All-gather of one small host payload per rank (the serialized state batch of a dense / ungrouped Partial aggregate: a handful of
+ * rows; merged by the Final plan with merge_batch semantics, not by an all-reduce).  `out` has world slots of slot_bytes (a multiple
+ * of 16, >= n_bytes + 8); sizes_out[r] = payload length of rank r.  One NCCL collective, one synchronisation. */
+int cb200_comm_allgather_small(cb200_comm* comm, const void* payload, int64_t n_bytes, int64_t slot_bytes, void* out, int64_t* sizes_out,
+                               cb200_error* err);
+
 /* kernels launched so far by this plan (bench.py reports it as gpu_launches) */
 int64_t cb200_plan_kernel_launches(cb200_plan* plan);
 

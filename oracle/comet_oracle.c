@@ -899,3 +899,140 @@ void co_parallel_copy(void *dst, const void *src, int64_t n, int elem_bytes, int
         memcpy((char *)dst + lo * elem_bytes, (const char *)src + lo * elem_bytes, (size_t)(hi - lo) * (size_t)elem_bytes);
     }
 }
+
+/* =========================================================================================
+ * High-cardinality GROUP BY key SUM(value) (BASELINE configs[3]): Partial hash aggregate per partition
+ * (= OpenMP thread, contiguous rows) with the SumDecimal rules, hash partitioning of the state rows by
+ * pmod(murmur3(key, 42), T) exactly as the reference's shuffle assigns them (multi_partition.rs:298-310),
+ * Final merge per partition.  Open addressing over (key, state); 3P AggregateExec's own table layout is
+ * not restated -- only what it computes.
+ * out_keys / out_sum / out_valid: one row per group, partition by partition (capacity n).  Returns the
+ * number of groups, < 0 on error.
+ * ========================================================================================= */
+typedef struct { i128 sum; int64_t key; uint8_t used, valid, empty; } gb_slot;
+typedef struct { gb_slot *tab; uint64_t mask; int64_t n; } gb_table;
+static inline uint64_t gb_mix(uint64_t h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33; return h; }
+static inline gb_slot *gb_probe(gb_slot *tab, uint64_t mask, int64_t key) {
+    uint64_t s = gb_mix((uint64_t)key) & mask;
+    while (tab[s].used && tab[s].key != key) s = (s + 1) & mask;
+    return &tab[s];
+}
+static int gb_init(gb_table *t, uint64_t cap) { t->tab = (gb_slot *)calloc(cap, sizeof(gb_slot)); t->mask = cap - 1; t->n = 0; return t->tab != NULL; }
+static int gb_grow(gb_table *t) { /* double at load 1/2 */
+    gb_table b;
+    if (!gb_init(&b, (t->mask + 1) * 2)) return 0;
+    for (uint64_t k = 0; k <= t->mask; k++) if (t->tab[k].used) *gb_probe(b.tab, b.mask, t->tab[k].key) = t->tab[k];
+    b.n = t->n;
+    free(t->tab);
+    *t = b;
+    return 1;
+}
+static inline gb_slot *gb_upsert(gb_table *t, int64_t key) {
+    gb_slot *s = gb_probe(t->tab, t->mask, key);
+    if (s->used) return s;
+    if ((uint64_t)(t->n + 1) * 2 > t->mask + 1) { if (!gb_grow(t)) return NULL; s = gb_probe(t->tab, t->mask, key); }
+    s->used = 1; s->key = key; s->sum = 0; s->valid = 1; s->empty = 1; t->n++;
+    return s;
+}
+typedef struct { int64_t key; i128 sum; uint8_t valid, empty; } gb_row; /* one state row of the shuffle */
+int64_t co_groupby_sum_dec(int64_t n, const int64_t *keys, const i128 *vals, int precision, int n_threads,
+                           int64_t *out_keys, i128 *out_sum, uint8_t *out_valid) {
+    int T = nthreads_or_default(n_threads);
+    gb_row **rows = (gb_row **)calloc((size_t)T, sizeof(gb_row *));         /* map output of task t, ordered by destination */
+    int64_t *starts = (int64_t *)calloc((size_t)T * (size_t)(T + 1), sizeof(int64_t));
+    gb_table *ftabs = (gb_table *)calloc((size_t)T, sizeof(gb_table));
+    int64_t *gcount = (int64_t *)calloc((size_t)T + 1, sizeof(int64_t));
+    int failed = 0;
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        int t = omp_get_thread_num();
+#else
+        int t = 0;
+#endif
+        /* ---- Partial over this partition's rows ---- */
+        int64_t lo = n * t / T, hi = n * (t + 1) / T;
+        gb_table tb;
+        int ok = gb_init(&tb, 1 << 16);
+        for (int64_t i = lo; ok && i < hi; i++) {
+            gb_slot *s = gb_upsert(&tb, keys[i]);
+            if (!s) { ok = 0; break; }
+            sum_decimal_update_single(vals[i], &s->sum, &s->valid, &s->empty, precision, CO_LEGACY);
+        }
+        /* ---- ShuffleWriter: state rows bucketed by pmod(murmur3(key, 42), T), stable ---- */
+        int64_t *st = starts + (size_t)t * (size_t)(T + 1);
+        if (ok) {
+            uint32_t *pid = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(tb.mask + 1));
+            rows[t] = (gb_row *)malloc(sizeof(gb_row) * (size_t)(tb.n > 0 ? tb.n : 1));
+            ok = pid && rows[t];
+            if (ok) {
+                for (uint64_t k = 0; k <= tb.mask; k++) if (tb.tab[k].used) {
+                    uint32_t h = 42; co_murmur3_column(4, 1, &tb.tab[k].key, NULL, &h);
+                    pid[k] = co_pmod(h, (uint32_t)T); st[pid[k] + 1]++;
+                }
+                for (int p = 0; p < T; p++) st[p + 1] += st[p];
+                int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)T);
+                for (int p = 0; p < T; p++) cur[p] = st[p];
+                for (uint64_t k = 0; k <= tb.mask; k++) if (tb.tab[k].used) {
+                    gb_row *r = &rows[t][cur[pid[k]]++];
+                    r->key = tb.tab[k].key; r->sum = tb.tab[k].sum; r->valid = tb.tab[k].valid; r->empty = tb.tab[k].empty;
+                }
+                free(cur);
+            }
+            free(pid);
+        }
+        free(tb.tab);
+        if (!ok) {
+#pragma omp atomic write
+            failed = 1;
+        }
+#pragma omp barrier
+        /* ---- Final: partition t merges the rows every map task holds for it, in map-task order ---- */
+        if (!failed) {
+            int64_t incoming = 0;
+            for (int m = 0; m < T; m++) incoming += starts[(size_t)m * (size_t)(T + 1) + t + 1] - starts[(size_t)m * (size_t)(T + 1) + t];
+            uint64_t cap = 1 << 10;
+            while (cap < (uint64_t)incoming * 2 + 2) cap <<= 1;
+            if (gb_init(&ftabs[t], cap)) {
+                for (int m = 0; m < T; m++) {
+                    const int64_t *ms = starts + (size_t)m * (size_t)(T + 1);
+                    for (int64_t k = ms[t]; k < ms[t + 1]; k++) {
+                        const gb_row *r = &rows[m][k];
+                        gb_slot *s = gb_upsert(&ftabs[t], r->key);
+                        int64_t z = 0;
+                        co_sum_decimal_merge(1, &r->sum, &r->valid, &r->empty, &z, &s->sum, &s->valid, &s->empty, precision, CO_LEGACY);
+                    }
+                }
+                gcount[t + 1] = ftabs[t].n;
+            } else {
+#pragma omp atomic write
+                failed = 1;
+            }
+        }
+    }
+    int64_t total = -1;
+    if (!failed) {
+        for (int p = 0; p < T; p++) gcount[p + 1] += gcount[p];
+        total = gcount[T];
+        if (out_keys) {
+#pragma omp parallel num_threads(T)
+            {
+#ifdef _OPENMP
+                int p = omp_get_thread_num();
+#else
+                int p = 0;
+#endif
+                int64_t o = gcount[p];
+                const gb_table *ft = &ftabs[p];
+                for (uint64_t k = 0; k <= ft->mask; k++) if (ft->tab[k].used) {
+                    i128 r = 0; uint8_t rv = 0;
+                    co_sum_decimal_evaluate(1, &ft->tab[k].sum, &ft->tab[k].valid, &ft->tab[k].empty, precision, &r, &rv);
+                    out_keys[o] = ft->tab[k].key; out_sum[o] = r; out_valid[o] = rv; o++;
+                }
+            }
+        }
+    }
+    for (int t = 0; t < T; t++) { free(rows[t]); free(ftabs[t].tab); }
+    free(rows); free(starts); free(ftabs); free(gcount);
+    return total;
+}

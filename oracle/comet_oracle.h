@@ -191,4 +191,8 @@ int64_t co_filter_project_f64(int64_t n, const double *qty, const double *price,
 /* first-touch placement of baseline inputs (see comet_oracle.c) */
 void co_parallel_copy(void *dst, const void *src, int64_t n, int elem_bytes, int n_threads);
 
+/* GROUP BY key SUM(value), d(p,s): Partial per thread-partition, murmur3/pmod repartition, Final merge (BASELINE configs[3]) */
+int64_t co_groupby_sum_dec(int64_t n, const int64_t *keys, const co_i128 *vals, int precision, int n_threads,
+                           int64_t *out_keys, co_i128 *out_sum, uint8_t *out_valid);
+
 #endif

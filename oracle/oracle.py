@@ -144,6 +144,41 @@ def decimal_rescale_check(a, av, s_in, p_out, s_out, fail_on_error=False):
     return out, outv
 
 
+def decimal_div(l, lv, s1, r, rv, s2, s3, integral=False, eval_mode=LEGACY, check_divide_overflow=False):
+    """spark-expr/src/math_funcs/div.rs:75-190 (spark_decimal_div_internal), restated with Python integers -- the reference
+    itself falls back to BigInt for wide operands.  Rows where either side is NULL are not evaluated (try_binary).  Returns
+    ((n,2) uint64, valid); raises OracleError(2) for a zero divisor in ANSI mode, OracleError(1) for the integral overflow."""
+    ls, rs = dec_to_ints(l), dec_to_ints(r)
+    n = len(ls)
+    lv = np.ones(n, dtype=bool) if lv is None else np.asarray(lv, dtype=bool)
+    rv = np.ones(n, dtype=bool) if rv is None else np.asarray(rv, dtype=bool)
+    l_exp, r_exp = max(0, s2 + s3 + 1 - s1), max(0, s1 - (s2 + s3 + 1))
+    out, valid = [0] * n, lv & rv
+    for i in range(n):
+        if not valid[i]:
+            continue
+        a, b = ls[i] * 10 ** l_exp, rs[i] * 10 ** r_exp
+        if b == 0:
+            if eval_mode == ANSI:
+                raise OracleError(2)
+            div = 0
+        else:
+            div = abs(a) // abs(b)          # BigInt `/` truncates toward zero
+            if (a < 0) != (b < 0):
+                div = -div
+        if integral:
+            res = div
+        else:
+            t = div - 5 if div < 0 else div + 5
+            res = -((-t) // 10) if t < 0 else t // 10
+        if not (-(1 << 127) <= res < (1 << 127)):
+            res = (1 << 127) - 1            # to_i128().unwrap_or(i128::MAX)
+        if check_divide_overflow and eval_mode == ANSI and not (-(1 << 63) <= res < (1 << 63)):
+            raise OracleError(1)
+        out[i] = res
+    return dec_from_ints(out), valid.astype(np.uint8)
+
+
 def int_arith(op, width, l, lv, r, rv, eval_mode=LEGACY):
     l = np.ascontiguousarray(l, dtype=np.int64)
     r = np.ascontiguousarray(r, dtype=np.int64)
@@ -473,6 +508,24 @@ def filter_project_f64(qty, price, shipdate, cutoff, n_threads=0):
     m = lib().co_filter_project_f64(C.c_int64(n), _p(qty), _p(price), _p(shipdate), C.c_int32(cutoff),
                                     C.c_int(n_threads), _p(out))
     return out[:m]
+
+
+def groupby_sum_dec(keys, vals, n_threads=0, precision=22, want_rows=False):
+    """GROUP BY key SUM(value): number of groups (and, with want_rows, (keys, sums as python ints or None))."""
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    n = keys.shape[0]
+    f = lib().co_groupby_sum_dec
+    f.restype = C.c_int64
+    if not want_rows:
+        r = f(C.c_int64(n), _p(keys), _p(vals), C.c_int(precision), C.c_int(n_threads), None, None, None)
+        if r < 0:
+            raise MemoryError("co_groupby_sum_dec")
+        return int(r)
+    ok, os_, ov = np.zeros(n, dtype=np.int64), np.zeros((n, 2), dtype=np.uint64), np.zeros(n, dtype=np.uint8)
+    r = f(C.c_int64(n), _p(keys), _p(vals), C.c_int(precision), C.c_int(n_threads), _p(ok), _p(os_), _p(ov))
+    if r < 0:
+        raise MemoryError("co_groupby_sum_dec")
+    return ok[:r], dec_to_ints(os_[:r], ov[:r])
 
 
 def numa_spread(a, n_threads=0):

@@ -55,13 +55,20 @@ def _int_width(dt):
     return {"INT8": 8, "INT16": 16, "INT32": 32, "INT64": 64}[dt.name]
 
 
+class ArrowError(Exception):
+    """arrow-arith failed the query (Legacy-mode checked division)"""
+
+
 class Arith(Node):
-    """Add / Subtract / Multiply with the planner's lowering rules (planner.rs:976-1131)."""
+    """Add / Subtract / Multiply / Divide with the planner's lowering rules (planner.rs:976-1131)."""
 
     def __init__(self, op, l, r, ret, mode=LEGACY):
         self.op, self.l, self.r, self.ret, self.mode = op, l, r, ret, mode
         lt, rt = l.dt, r.dt
-        if lt.name == "DECIMAL":
+        if op == "divide":
+            self.wide = False
+            self.dt = ret
+        elif lt.name == "DECIMAL":
             if op == "multiply":
                 self.wide = lt.precision + rt.precision >= 38
             else:
@@ -79,8 +86,43 @@ class Arith(Node):
     def proto(self):
         return getattr(P, self.op)(self.l.proto(), self.r.proto(), self.ret, self.mode)
 
+    def eval_divide(self, a, av, b, bv):
+        lt, rt = self.l.dt, self.r.dt
+        av, bv = np.asarray(av, dtype=bool), np.asarray(bv, dtype=bool)
+        if lt.name == "DECIMAL":                       # decimal_div UDF, div.rs:75-190
+            try:
+                out, ov = O.decimal_div(a, av, lt.scale, b, bv, rt.scale, self.dt.scale, False, self.mode)
+            except O.OracleError:
+                raise AnsiError()
+            return out, ov.astype(bool)
+        valid = av & bv
+        if lt.name in ("DOUBLE", "FLOAT"):             # Legacy: IEEE; TRY / ANSI: checked_div (zero divisor -> NULL / DIVIDE_BY_ZERO)
+            with np.errstate(all="ignore"):
+                out = a / b
+            if self.mode != LEGACY:
+                z = valid & (b == 0)
+                if self.mode == ANSI and z.any():
+                    raise AnsiError()
+                out = np.where(z, 0, out).astype(a.dtype)
+                valid = valid & ~z
+            return out, valid
+        w = _int_width(lt)                             # integers: truncating division, zero divisor / MIN / -1 are errors
+        mn = -(1 << (w - 1))
+        bad = valid & ((b == 0) | ((a == mn) & (b == -1)))
+        if bad.any():
+            if self.mode == ANSI:
+                raise AnsiError()
+            if self.mode == LEGACY:
+                raise ArrowError()
+        safe_b = np.where(bad | (b == 0), 1, b)
+        q = np.abs(a.astype(object)) // np.abs(safe_b.astype(object))
+        q = np.where((a < 0) != (safe_b < 0), -q, q).astype(np.int64)
+        return np.where(bad, 0, q), valid & ~bad
+
     def eval(self, cols):
         (a, av), (b, bv) = self.l.eval(cols), self.r.eval(cols)
+        if self.op == "divide":
+            return self.eval_divide(a, av, b, bv)
         code = {"add": 0, "subtract": 1, "multiply": 2}[self.op]
         lt, rt = self.l.dt, self.r.dt
         if lt.name == "DECIMAL":

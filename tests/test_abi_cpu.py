@@ -69,9 +69,12 @@ def test_unsupported_plans_are_rejected_not_miscomputed(cb):
     assert ok, why
     ok, why = cb.native.supports(P.projection(sc, [P.if_(P.is_null(P.bound(1, P.INT64)), P.bound(0, P.STRING), P.literal("x", P.STRING))]))
     assert not ok and "string" in why
-    # decimal division (decimal_div UDF) -> outside the hot path
-    sc2 = P.scan([P.DECIMAL(12, 2), P.DECIMAL(12, 2)])
+    # decimal division (decimal_div UDF) is on the path; a division that mixes types is not
+    sc2 = P.scan([P.DECIMAL(12, 2), P.DECIMAL(12, 2), P.INT32])
     ok, why = cb.native.supports(P.projection(sc2, [P.divide(P.bound(0, P.DECIMAL(12, 2)), P.bound(1, P.DECIMAL(12, 2)), P.DECIMAL(27, 15))]))
+    assert ok, why
+    assert "cb::dec_div(" in cb.native.kernel_source(P.projection(sc2, [P.divide(P.bound(0, P.DECIMAL(12, 2)), P.bound(1, P.DECIMAL(12, 2)), P.DECIMAL(27, 15))]))
+    ok, why = cb.native.supports(P.projection(sc2, [P.divide(P.bound(0, P.DECIMAL(12, 2)), P.bound(2, P.INT32), P.DECIMAL(27, 15))]))
     assert not ok
     # garbage bytes -> plan error, not a crash
     ok, why = cb.native.supports(b"\xff\xff\xff\x07garbage")

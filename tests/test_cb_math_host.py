@@ -214,3 +214,27 @@ def test_snappy_decoder_vs_pyarrow(hm):
     bad[2] = 0x01 | (7 << 2)   # a copy with offset beyond the start of the output
     bad[3] = 0xff
     assert hm.hm_snappy(_p(bad), C.c_longlong(len(bad)), _p(out), C.c_longlong(4000)) == -1
+
+
+def test_decimal_div_matches_the_oracle(hm, oracle):
+    """cb::dec_div (multi-limb Knuth division on the device) vs the oracle's restatement of spark_decimal_div_internal
+    (div.rs:75-190) with Python integers: every scale combination incl. the BigInt-sized ones, zero divisors, the i128::MAX
+    sentinel, integral division."""
+    rng = np.random.default_rng(12)
+    n = 96
+    for trial in range(120):
+        p1, p2 = int(rng.integers(1, 39)), int(rng.integers(1, 39))
+        s1, s2, s3 = int(rng.integers(0, p1 + 1)), int(rng.integers(0, p2 + 1)), int(rng.integers(0, 39))
+        integral = bool(rng.integers(0, 4) == 0)
+        ls = [v % 10**p1 * (1 if v >= 0 else -1) for v in rand_dec(rng, n, 38)]
+        rs = [v % 10**p2 * (1 if v >= 0 else -1) for v in rand_dec(rng, n, 38)]
+        ls[:3], rs[:4] = [10**p1 - 1, -(10**p1 - 1), 0], [1, -1, 0, 3]
+        la, ra = oracle.dec_from_ints(ls), oracle.dec_from_ints(rs)
+        out, zero, fits = np.zeros((n, 2), dtype=np.uint64), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        l_exp, r_exp = max(0, s2 + s3 + 1 - s1), max(0, s1 - (s2 + s3 + 1))
+        hm.hm_dec_div(C.c_int64(n), _p(la), _p(ra), l_exp, r_exp, int(integral), _p(out), _p(zero), _p(fits))
+        exp, _ = oracle.decimal_div(la, None, s1, ra, None, s2, s3, integral)
+        assert (zero.astype(bool) == np.array([r == 0 for r in rs])).all()
+        assert oracle.dec_to_ints(out) == oracle.dec_to_ints(exp), (p1, s1, p2, s2, s3, integral)
+        got = oracle.dec_to_ints(out)
+        assert [bool(f) for f in fits] == [-(1 << 63) <= g < (1 << 63) for g in got]

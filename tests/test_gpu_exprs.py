@@ -215,3 +215,65 @@ def test_ansi_error_only_on_rows_that_take_the_branch(cb, E):
     assert res.num_rows == N
     with pytest.raises(cb.native.CometB200Error):
         gpu_eval(cb, dts, tbl, None, [E.If(E.Not(safe), E.Arith("add", i, i, P.INT32, E.ANSI), E.Lit(0, P.INT32))])
+
+
+# ---- division (round 2): decimal_div, checked float / integer division --------------------------------------------------------
+def test_decimal_division(cb, E):
+    """decimal_div (spark-expr/src/math_funcs/div.rs:75-190): HALF_UP on one extra digit, narrow and BigInt-sized operands.  The
+    JVM wraps the divisor in nullIf(= 0) outside ANSI mode; the tests do the same with IF."""
+    P = cb.proto
+    a, b, w, x = C(E, 3), C(E, 4), C(E, 5), C(E, 6)
+    nz = lambda e, dt: E.If(E.Cmp("eq", e, E.Lit(0, dt)), E.Lit(None, dt), e)
+    outs = [
+        E.CheckOverflow(E.Arith("divide", a, nz(b, P.DECIMAL(12, 2)), P.DECIMAL(27, 15)), P.DECIMAL(27, 15)),   # d(12,2) / d(12,2): Spark's result type
+        E.CheckOverflow(E.Arith("divide", w, nz(a, P.DECIMAL(12, 2)), P.DECIMAL(38, 15)), P.DECIMAL(38, 15)),   # d(26,4) / d(12,2)
+        E.CheckOverflow(E.Arith("divide", x, nz(w, P.DECIMAL(26, 4)), P.DECIMAL(38, 6)), P.DECIMAL(38, 6)),     # wide: scaled numerator beyond 38 digits
+        E.CheckOverflow(E.Arith("divide", a, nz(x, P.DECIMAL(38, 10)), P.DECIMAL(38, 20)), P.DECIMAL(38, 20)),  # l_exp = 29: BigInt path of the reference
+        E.Arith("divide", x, nz(a, P.DECIMAL(12, 2)), P.DECIMAL(38, 18)),                                       # quotients past i128 -> i128::MAX sentinel
+    ]
+    check(cb, E, None, outs[:4])
+    check(cb, E, E.Cmp("gt", b, E.Lit(0, P.DECIMAL(12, 2))), outs[:2], seed=4)
+    # the sentinel row values are what the reference stores before CheckOverflow turns them into NULL: compare through CheckOverflow
+    check(cb, E, None, [E.CheckOverflow(outs[4], P.DECIMAL(38, 18))], seed=2)
+
+
+def test_decimal_division_by_zero_in_ansi_mode_raises(cb, E):
+    P = cb.proto
+    tbl, cols, dts = table(0)
+    e = E.Arith("divide", C(E, 3), C(E, 4), P.DECIMAL(27, 15), E.ANSI)     # column 4 holds zeros
+    with pytest.raises(cb.native.CometB200Error) as ei:
+        gpu_eval(cb, dts, tbl, None, [e])
+    assert ei.value.error_class == "DIVIDE_BY_ZERO"
+    with pytest.raises(E.AnsiError):
+        e.eval(cols)
+    # rows that do not reach the division (filtered / NULL divisor) do not raise
+    check(cb, E, E.Cmp("gt", C(E, 4), E.Lit(0, P.DECIMAL(12, 2))), [e], seed=1)
+
+
+def test_float_division_modes(cb, E):
+    """Legacy: IEEE (x / 0 = +-Inf / NaN); TRY: NULL for a zero divisor; ANSI: DIVIDE_BY_ZERO (checked_arithmetic.rs:53-128, routed
+    there by planner.rs:1094-1125)."""
+    P = cb.proto
+    f = C(E, 2)
+    g = E.Arith("subtract", f, f, P.DOUBLE)                                # zeros, NaNs
+    check(cb, E, None, [E.Arith("divide", f, g, P.DOUBLE), E.Arith("divide", f, E.Lit(3.0, P.DOUBLE), P.DOUBLE), E.Arith("divide", f, g, P.DOUBLE, E.TRY),
+                       E.Arith("divide", g, f, P.DOUBLE, E.TRY)])
+    tbl, cols, dts = table(0)
+    with pytest.raises(cb.native.CometB200Error) as ei:
+        gpu_eval(cb, dts, tbl, None, [E.Arith("divide", f, g, P.DOUBLE, E.ANSI)])
+    assert ei.value.error_class == "DIVIDE_BY_ZERO"
+    check(cb, E, None, [E.Arith("divide", g, E.Lit(2.0, P.DOUBLE), P.DOUBLE, E.ANSI)])
+
+
+def test_integer_division_modes(cb, E):
+    P = cb.proto
+    a, b, c8 = C(E, 0), C(E, 1), C(E, 7)
+    nz32 = E.If(E.Cmp("eq", a, E.Lit(0, P.INT32)), E.Lit(7, P.INT32), a)
+    check(cb, E, None, [E.Arith("divide", a, E.Lit(7, P.INT32), P.INT32), E.Arith("divide", b, E.Lit(-3, P.INT64), P.INT64), E.Arith("divide", a, nz32, P.INT32),
+                       E.Arith("divide", c8, c8, P.INT8, E.TRY), E.Arith("divide", b, E.Lit(-1, P.INT64), P.INT64, E.TRY), E.Arith("divide", a, a, P.INT32, E.TRY)])
+    tbl, cols, dts = table(0)
+    with pytest.raises(cb.native.CometB200Error) as ei:
+        gpu_eval(cb, dts, tbl, None, [E.Arith("divide", c8, c8, P.INT8, E.ANSI)])          # column 7 holds zeros
+    assert ei.value.error_class == "DIVIDE_BY_ZERO"
+    with pytest.raises(cb.native.CometB200Error):
+        gpu_eval(cb, dts, tbl, None, [E.Arith("divide", c8, c8, P.INT8)])                  # Legacy: arrow-arith fails the query
