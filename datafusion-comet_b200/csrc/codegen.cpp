@@ -28,8 +28,9 @@ int phys_bytes(Phys p) {
 size_t GeneratedKernel::dyn_smem(int n_groups) const {
     size_t s = (entry == "cb_pipeline_agg" ? 128 : 256) + (size_t)stages * stage_bytes; // barrier area: CB_BAR_BYTES of the select kernels
     if (hash) return s;
-    if (!word_kinds.empty() && n_groups > 1) s += (size_t)n_groups * n_words * threads * 8;
-    else if (!word_kinds.empty() && n_groups == 1 && n_words > 0) s += 0;
+    // grouped dense pipelines keep thread-private accumulators in shared memory even when the key has ONE value (a dictionary of
+    // cardinality 1); only ungrouped pipelines (CB_G1) hold them in registers
+    if (!word_kinds.empty() && !ungrouped) s += (size_t)std::max(n_groups, 1) * n_words * threads * 8;
     return s;
 }
 
@@ -1276,6 +1277,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         }
 
         std::ostringstream defs;
+        g.ungrouped = spec.ungrouped;
         defs << "#define CB_KERNEL_AGG 1\n#define CB_WORDS " << g.n_words << "\n#define CB_G1 " << (spec.ungrouped ? 1 : 0) << "\n#define CB_W_ROWS " << w_rows
              << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n#define CB_KEY_WORDS " << (spec.hash ? g.key_words : 1) << "\n";
         tu << header(spec, defs.str());

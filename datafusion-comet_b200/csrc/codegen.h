@@ -66,6 +66,7 @@ struct GeneratedKernel {
     std::vector<int> out_bytes;       // element bytes of each output column (1 for bool-as-byte)
     int threads = 256, tile = 512, stages = 3;
     bool hash = false;
+    bool ungrouped = false;           // aggregate without keys: accumulators in registers (CB_G1)
     int n_key_cols = 0;               // hash: leading out_cols are the group keys
     int key_words = 1;                // hash: 64-bit words of the packed group key (1: the word is the table key; >1: tag + stored key)
     size_t dyn_smem(int n_groups) const;

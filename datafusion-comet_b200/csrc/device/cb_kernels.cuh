@@ -280,7 +280,10 @@ struct Acc {
         keep = keep_;
         bool same_prev = lane != 0;
 #pragma unroll
-        for (int i = 0; i < CB_KEY_WORDS; i++) same_prev = same_prev && (__shfl_up_sync(0xffffffffu, kw[i], 1) == kw[i]);
+        for (int i = 0; i < CB_KEY_WORDS; i++) {
+            const u64 up = __shfl_up_sync(0xffffffffu, kw[i], 1); // every lane shuffles: `a && shfl()` would let lane 0 skip the collective
+            same_prev = same_prev & (up == kw[i]);
+        }
         const bool prev_keep = __shfl_up_sync(0xffffffffu, (int)keep_, 1) != 0;
         const bool prev_null = __shfl_up_sync(0xffffffffu, (int)null_group, 1) != 0;
         head = keep_ && !(same_prev && prev_keep && prev_null == null_group);

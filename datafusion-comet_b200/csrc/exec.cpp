@@ -757,7 +757,7 @@ struct AggNode : FusedBase {
         }
         // first pass to learn the accumulator footprint, then size the ring to the remaining smem
         GeneratedKernel probe = generate_pipeline(s);
-        size_t acc = (n_groups > 1 && !hash_mode) ? (size_t)n_groups * probe.n_words * s.threads * 8 : 0;
+        size_t acc = (!ungrouped && !hash_mode) ? (size_t)std::max(n_groups, 1) * probe.n_words * s.threads * 8 : 0;
         while (acc + 2 * (size_t)probe.stage_bytes + 1024 > SMEM_BUDGET && s.threads > 32) {
             s.threads /= 2; // shrink the thread-private accumulator file (wide Final-mode merges are tiny inputs)
             acc /= 2;

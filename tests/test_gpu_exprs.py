@@ -82,9 +82,10 @@ def check(cb, E, pred, outs, seed=0):
     assert (res.num_rows if res is not None else 0) == n_keep
     if n_keep == 0:
         return
+    kept_cols = [(np.asarray(v)[keep], np.asarray(ok)[keep]) for v, ok in cols]   # ProjectionExec sees FilterExec's output only
     for j, o in enumerate(outs):
-        v, valid = o.eval(cols)
-        v, valid = v[keep], np.asarray(valid)[keep]
+        v, valid = o.eval(kept_cols)
+        valid = np.asarray(valid)
         col = res.column(j).combine_chunks()
         if pa.types.is_date32(col.type):
             col = col.cast(pa.int32())

@@ -283,7 +283,7 @@ def test_later_chunk_violates_the_sampled_range(cb, oracle):
             continue
         seen += 1
         g = got[(t.RETURNFLAGS[k // 2], t.LINESTATUS[k % 2])]
-        assert unscaled(g["col_2"], 2) == e["sum_qty"] and unscaled(g["col_3"], 2) == e["sum_base_price"]
+        assert unscaled(g["col_2"], 2) == e["sum_qty"] and unscaled(g["col_3"], 2) == e["sum_base"]
         assert unscaled(g["col_4"], 4) == e["sum_disc_price"] and unscaled(g["col_5"], 6) == e["sum_charge"]
         assert unscaled(g["col_6"], 6) == e["avg_qty"] and unscaled(g["col_7"], 6) == e["avg_price"] and unscaled(g["col_8"], 6) == e["avg_disc"]
         assert g["col_9"] == e["count"]
