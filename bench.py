@@ -345,9 +345,14 @@ def timed_region(env, sampler, step_fn, warmup, steps):
     if sampler:
         sampler.mark_begin()
     t0 = time.perf_counter()
-    outs = [step_fn() for _ in range(steps)]
+    outs, marks = [], [t0]
+    for _ in range(steps):
+        outs.append(step_fn())
+        marks.append(time.perf_counter())     # host time when the step's call returned (its result is on the host / synchronised by then)
     env["barrier"]()
     elapsed = time.perf_counter() - t0
+    per = sorted(1e3 * (b - a) for a, b in zip(marks, marks[1:]))
+    env["step_ms"] = {"min": per[0], "median": per[len(per) // 2], "max": per[-1]}
     if sampler:
         sampler.mark_end()
     gc.enable()
@@ -629,7 +634,7 @@ def workload_q1(args, env):
                          "kernel": "cb_pipeline_agg (fused scan+filter+project+partial aggregate)", "ms_per_launch": ms_per_launch,
                          "spec_peak": 8000.0, "frac_of_spec_peak": achieved / 8000.0,
                          "algorithmic_bytes_per_row": BYTES_PER_ROW[variant], "peak_source": peak_src},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "step_ms": env["step_ms"],
         }
         if e2e:
             line["e2e"] = e2e
@@ -678,6 +683,8 @@ def workload_groupby(args, env):
     state_types = [P.INT64, sdt, P.BOOL] if dec else [P.INT64, sdt]
     final_plan = P.hash_agg(P.scan(state_types, source="shuffle"), [P.bound(0, P.INT64)], [P.agg_sum(P.unbound("c", m), sdt)], P.FINAL)
     cfg = {"spark.comet.b200.chunkRows": str(args.groupby_chunk_rows)}
+    if os.environ.get("CB200_HASH_THREADS"):
+        cfg["spark.comet.b200.hashThreads"] = os.environ["CB200_HASH_THREADS"]
     table = native.DeviceTable(n)
     table.add(P.INT64, keys.data_ptr(), 8, keep=keys)
     table.add(m, val.data_ptr(), w, keep=val)
@@ -805,7 +812,7 @@ def workload_groupby(args, env):
             "phases_ms": {"partial_kernels": part_ms, "final_kernels": last["st2"]["pipeline_ms"], "exchange_payload": xs["payload_ms"]},
             "exchange": {"bytes_sent_per_gpu": xs["bytes_sent"], "bytes_received_per_gpu": xs["bytes_received"], "payload_ms": xs["payload_ms"],
                          "GBps_per_gpu": xs["bytes_sent"] / max(xs["payload_ms"], 1e-6) / 1e6, "nvlink_peak_GBps_per_direction": 900.0},
-            "gpu_launches": sum(o["st"]["kernel_launches"] + o["st2"]["kernel_launches"] for o in outs), "clocks": clocks,
+            "gpu_launches": sum(o["st"]["kernel_launches"] + o["st2"]["kernel_launches"] for o in outs), "clocks": clocks, "step_ms": env["step_ms"],
         }
         if e2e:
             line["e2e"] = e2e
@@ -877,7 +884,7 @@ def workload_select_or_q6(args, env):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel": kernel,
                              "ms_pipeline_kernels_per_step": pipe_ms, "spec_peak": 8000.0, "frac_of_spec_peak": achieved / 8000.0, "algorithmic_bytes_per_row": bytes_row,
                              "peak_source": peak_src},
-                "gpu_launches": sum(o[1]["kernel_launches"] for o in outs), "clocks": clocks}
+                "gpu_launches": sum(o[1]["kernel_launches"] for o in outs), "clocks": clocks, "step_ms": env["step_ms"]}
         print(json.dumps(line))
 
 
@@ -893,7 +900,7 @@ def main():
     ap.add_argument("--rows", type=int, default=int(os.environ.get("CB200_BENCH_ROWS", SF100_ROWS)))
     ap.add_argument("--ref-rows", type=int, default=60_000_000)
     ap.add_argument("--chunk-rows", type=int, default=1 << 30)
-    ap.add_argument("--groupby-chunk-rows", type=int, default=1 << 27)
+    ap.add_argument("--groupby-chunk-rows", type=int, default=1 << 28)
     ap.add_argument("--groupby-e2e-rows", type=int, default=1 << 28)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 22)

@@ -39,6 +39,8 @@ void parse_config(const uint8_t* cfg, size_t len, ExecContext& ctx) { // config.
         }
         if (k == "spark.comet.b200.chunkRows") ctx.chunk_rows = std::max<int64_t>(1024, atoll(v.c_str()));
         else if (k == "spark.comet.batchSize") ctx.batch_size = atoi(v.c_str()); // CometConf.scala:539
+        else if (k == "spark.comet.b200.streamAgg.minRows") ctx.stream_agg_min_rows = atoll(v.c_str());
+        else if (k == "spark.comet.b200.streamAgg.maxRatio") ctx.stream_agg_max_ratio = atof(v.c_str());
         else if (k == "spark.comet.b200.hashThreads") { int t = atoi(v.c_str()); if (t == 256 || t == 512 || t == 768 || t == 960) ctx.hash_threads = t; } // + the producer warp <= 1024 threads per CTA
     }
 }

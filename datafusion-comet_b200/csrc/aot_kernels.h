@@ -40,8 +40,9 @@ struct HashKeyCols {
     int n;
     HashKeyCol col[8];
 };
+long long partition_chunks(long long n); // entries per partition of launch_partition's chunk_tmp scratch
 void launch_partition(const HashKeyCols& kc, long long n, unsigned n_parts, unsigned* hashes, unsigned* pids, int* block_hist, long long* block_base,
-                      long long* starts, long long* row_idx, cudaStream_t st);
+                      long long* chunk_tmp, long long* starts, long long* row_idx, cudaStream_t st);
 void launch_gather(const void* in, int width, const long long* row_idx, long long n, void* out, cudaStream_t st);
 void launch_gather_bits(const void* in_bits, const long long* row_idx, long long n, void* out_bytes, cudaStream_t st);
 

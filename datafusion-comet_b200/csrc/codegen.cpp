@@ -639,6 +639,18 @@ std::string header(const PipelineSpec& s, const std::string& defs) {
     std::ostringstream o;
     o << "// generated by comet_b200 codegen -- do not edit\n";
     o << defs;
+    if (const char* x = getenv("CB200_JIT_DEFS")) { // tuning experiments: "CB_X_FOO=1;CB_X_BAR=2" -> #define lines (part of the source, hence of the cache key)
+        std::string d = x;
+        size_t i = 0;
+        while (i < d.size()) {
+            size_t j = d.find(';', i);
+            if (j == std::string::npos) j = d.size();
+            std::string one = d.substr(i, j - i);
+            size_t eq = one.find('=');
+            if (!one.empty()) o << "#define " << (eq == std::string::npos ? one : one.substr(0, eq) + " " + one.substr(eq + 1)) << "\n";
+            i = j + 1;
+        }
+    }
     o << "#define CB_NCOLS " << s.cols.size() << "\n#define CB_TILE " << s.tile << "\n#define CB_STAGES " << s.stages
       << "\n#define CB_THREADS " << s.threads << "\n";
     o << "#include \"cb_math.h\"\n";
@@ -715,7 +727,7 @@ void sig_expr(std::ostringstream& o, const Expr& e) {
 }
 std::string spec_signature(const PipelineSpec& s) {
     std::ostringstream o;
-    o << (int)s.sink << ';' << (int)s.mode << ';' << s.ungrouped << ';' << s.hash << ';' << s.tile << ';' << s.stages << ';' << s.threads << ';' << s.ltile << ";C";
+    o << (int)s.sink << ';' << (int)s.mode << ';' << s.ungrouped << ';' << s.hash << (s.stream ? "s" : "") << ';' << s.tile << ';' << s.stages << ';' << s.threads << ';' << s.ltile << ";C";
     for (auto& c : s.cols) o << c.src_index << ':' << c.type.str() << ':' << (int)c.phys << ':' << c.has_validity << ':' << c.assume_bits << ',';
     o << ";P";
     for (auto& e : s.predicates) { sig_expr(o, *e); o << ';'; }
@@ -1279,7 +1291,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         std::ostringstream defs;
         g.ungrouped = spec.ungrouped;
         defs << "#define CB_KERNEL_AGG 1\n#define CB_WORDS " << g.n_words << "\n#define CB_G1 " << (spec.ungrouped ? 1 : 0) << "\n#define CB_W_ROWS " << w_rows
-             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n#define CB_KEY_WORDS " << (spec.hash ? g.key_words : 1) << "\n";
+             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n#define CB_KEY_WORDS " << (spec.hash ? g.key_words : 1) << "\n#define CB_STREAM " << (spec.hash && spec.stream ? 1 : 0) << "\n";
         tu << header(spec, defs.str());
         tu << "constexpr __host__ __device__ int cb_word_kind(int w) { return ";
         for (size_t i = 0; i < slots.kinds.size(); i++) tu << "w == " << i << " ? " << slots.kinds[i] << " : ";

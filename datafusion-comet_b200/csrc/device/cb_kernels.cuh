@@ -167,6 +167,9 @@ CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& a
 #define CB_HASH 0
 #endif
 #define CB_EMPTY_KEY 0xffffffffffffffffull
+#ifndef CB_STREAM
+#define CB_STREAM 0
+#endif
 
 #if CB_HASH
 // ---- hash aggregation: accumulators live in a global open-addressing table, updated with atomics -------------
@@ -175,10 +178,20 @@ CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& a
 // once and issues one atomic per accumulator word with the run's combined value (segmented shuffle reduction); the other lanes
 // never touch the table.  Round 1 probed and issued 2-3 returning atomics per ROW and ran at < 5 % of the HBM roofline: the kernel
 // was bound by L2 atomic throughput, not by the 24 bytes per row it streams.
+//
+// CB_STREAM (Partial aggregates over inputs whose equal keys sit next to each other -- the host samples that): no key table at
+// all.  Every run becomes a NEW state row: its head draws a fresh id and STORES the run's combined words (the arrays need no
+// zero-fill).  A key whose rows are split over several runs appears in several state rows; that is a valid Partial result (the
+// Final stage merges state rows by key, as it does for the reference's own early-emitting partial aggregates), and it turns the
+// partial stage from ~8 dependent random HBM round trips per group into a stream.
 struct Acc {
     const PipeParams* p;
     u64 vm[2 * CB_NCOLS];
     // state of the current row iteration (begin() sets it)
+#ifdef CB_X_GIDBLOCK
+    int xg_next = 0, xg_end = 0;
+#endif
+    bool shared_g;  // CB_STREAM: g is the reserved NULL-key group, which other runs update too (atomics instead of stores)
     int g;          // group id (valid on head lanes)
     int run_end;    // last lane of this lane's run
     bool head, keep;
@@ -220,6 +233,31 @@ struct Acc {
     CB_D void resolve(const u64* kw, bool want, bool null_group) {
         const u32 lane = threadIdx.x & 31u, mask = p->hmask;
         g = 0;
+        shared_g = false;
+#if CB_STREAM
+        {
+            (void)mask;
+            bool fresh = want;
+            if (want && null_group) { g = p->max_groups + 1; shared_g = true; fresh = false; }
+            const u32 cm = __ballot_sync(0xffffffffu, fresh);
+            if (cm) {
+                const int leader = __ffs(cm) - 1;
+                int base = 0;
+                if ((int)lane == leader) base = atomicAdd(&p->hflags[4], __popc(cm));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (fresh) {
+                    int gn = base + __popc(cm & ((1u << lane) - 1u));
+                    if (gn >= p->max_groups) { atomicOr(p->hflags, 2); gn = p->max_groups; shared_g = true; } // out of state rows: the host grows the arrays and repeats the launch
+                    else {
+#pragma unroll
+                        for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)gn * CB_KEY_WORDS + i] = kw[i];
+                    }
+                    g = gn;
+                }
+            }
+            return;
+        }
+#endif
         bool unresolved = want;
         if (want && null_group) { g = p->max_groups + 1; unresolved = false; }           // reserved group of the NULL key
         if (CB_KEY_WORDS == 1 && unresolved && kw[0] == CB_EMPTY_KEY) { atomicOr(p->hflags, 1); g = p->max_groups; unresolved = false; } // the key equal to the empty pattern
@@ -250,8 +288,16 @@ struct Acc {
             if (cm) {
                 const int leader = __ffs(cm) - 1;
                 int base = 0;
+#ifdef CB_X_GIDBLOCK
+                {   // timing experiment: one global atomic per CB_X_GIDBLOCK ids (leaves holes; results are not usable)
+                    const int need = __popc(cm);
+                    if (xg_next + need > xg_end) { if (lane == 0) xg_next = atomicAdd(&p->hflags[4], CB_X_GIDBLOCK); xg_next = __shfl_sync(0xffffffffu, xg_next, 0); xg_end = xg_next + CB_X_GIDBLOCK; }
+                    base = xg_next; xg_next += need;
+                }
+#else
                 if ((int)lane == leader) base = atomicAdd(&p->hflags[4], __popc(cm));
                 base = __shfl_sync(0xffffffffu, base, leader);
+#endif
                 if (claimed) {
                     int gn = base + __popc(cm & ((1u << lane) - 1u));
                     if (gn >= p->max_groups) { atomicOr(p->hflags, 2); gn = p->max_groups; } // cannot happen: host sizes max_groups >= rows
@@ -259,7 +305,7 @@ struct Acc {
 #pragma unroll
                         for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)gn * CB_KEY_WORDS + i] = kw[i];
                     }
-                    __threadfence();
+                    if (CB_KEY_WORDS > 1) __threadfence(); // readers of a wide key compare the stored words once they see the id; a one-word key IS the slot key
                     *((volatile i32*)&p->hkeys[2 * (size_t)s + 1]) = gn;
                     g = gn;
                     unresolved = false;
@@ -267,7 +313,7 @@ struct Acc {
             }
             if (pending) {
                 const int gs = wait_gid(s);
-                __threadfence(); // the claimer's key words are visible once its id is
+                if (CB_KEY_WORDS > 1) __threadfence(); // the claimer's key words are visible once its id is
                 if (CB_KEY_WORDS == 1 || gs >= p->max_groups || same_key(gs, kw)) { g = gs; unresolved = false; }
                 else s = (s + 1u) & mask; // tag collision: keep probing
             }
@@ -294,6 +340,7 @@ struct Acc {
     }
 
     CB_D u64* W(int w) const { return p->htotals + ((size_t)g * CB_WORDS + w) * 2; }
+    CB_D void store2(int w, u64 a, u64 b) const { *reinterpret_cast<ulonglong2*>(W(w)) = make_ulonglong2(a, b); } // CB_STREAM: the run's word, written once
     CB_D bool in_run(int off) const { return (int)(threadIdx.x & 31u) + off <= run_end; }
     // count of rows of the run with `c`: no shuffles needed, the ballot has it
     CB_D void h_count(bool c, int w) {
@@ -302,6 +349,7 @@ struct Acc {
         if (head) {
             const u32 run = (run_end == 31 ? 0xffffffffu : ((2u << run_end) - 1u)) & ~((1u << lane) - 1u);
             const int n = __popc(m & run);
+            if (CB_STREAM && !shared_g) { store2(w, (u64)n, 0ull); return; }
             if (n) atomicAdd((unsigned long long*)W(w), (unsigned long long)n);
         }
     }
@@ -309,6 +357,7 @@ struct Acc {
         u64 x = (keep && c) ? (u64)v : 0ull;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const u64 o = __shfl_down_sync(0xffffffffu, x, off); if (in_run(off)) x += o; }
+        if (CB_STREAM && head && !shared_g) { store2(w, x, 0ull); return; }
         if (head && x) atomicAdd((unsigned long long*)W(w), (unsigned long long)x);
     }
     CB_D void h_add_i128(bool c, int w, i128 v) { // exact 128-bit sum: (lo, hi) words with carry
@@ -320,6 +369,10 @@ struct Acc {
             const i64 ohi = __shfl_down_sync(0xffffffffu, hi, off);
             if (in_run(off)) { const u64 n = lo + olo; hi += ohi + (n < lo ? 1 : 0); lo = n; }
         }
+        if (CB_STREAM && head && !shared_g) { store2(w, lo, (u64)hi); return; }
+#ifdef CB_X_NOCARRY
+        if (head && (lo | (u64)hi)) { u64* s = W(w); if (lo) atomicAdd((unsigned long long*)&s[0], (unsigned long long)lo); if (hi) atomicAdd((unsigned long long*)&s[1], (unsigned long long)hi); return; } // timing experiment
+#endif
         if (head && (lo | (u64)hi)) {
             u64* s = W(w);
             u64 carry = 0;
@@ -342,6 +395,7 @@ struct Acc {
             const bool oany = __shfl_down_sync(0xffffffffu, (int)any, off) != 0;
             if (in_run(off) && oany) { if (any) dd_add_dd(a, o); else a = o; any = true; }
         }
+        if (CB_STREAM && head && !shared_g) { store2(w, (u64)__double_as_longlong(any ? a.hi : 0.0), (u64)__double_as_longlong(any ? a.lo : 0.0)); return; }
         if (!(head && any)) return;
         u64* s = W(w);
         u64 o0 = __ldcg(&s[0]), o1 = __ldcg(&s[1]);
@@ -370,12 +424,14 @@ struct Acc {
         i64 x = (keep && c) ? key : (i64)0x7fffffffffffffffll;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const i64 o = __shfl_down_sync(0xffffffffu, x, off); if (in_run(off) && o < x) x = o; }
+        if (CB_STREAM && head && !shared_g) { store2(w, (u64)x, 0ull); return; }
         if (head && x != (i64)0x7fffffffffffffffll) atomicMin((long long*)W(w), (long long)x);
     }
     CB_D void h_max(bool c, int w, i64 key) {
         i64 x = (keep && c) ? key : (i64)0x8000000000000000ll;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const i64 o = __shfl_down_sync(0xffffffffu, x, off); if (in_run(off) && o > x) x = o; }
+        if (CB_STREAM && head && !shared_g) { store2(w, (u64)x, 0ull); return; }
         if (head && x != (i64)0x8000000000000000ll) atomicMax((long long*)W(w), (long long)x);
     }
 };

@@ -475,11 +475,15 @@ CB_HD i128 i128_abs_of_i64(i64 v) { i128 m = i128_from_i64(v); return m.hi < 0 ?
 CB_HD int cert_level(i64 n, u64 blo, u64 bhi, int p) {
     if (n <= 0) return 0;
     if (bhi == ~0ull) return 2;
+    const bool twos = (bhi >> 63) != 0;   // flag set by the host when B comes straight from a column's value mask (see below)
+    bhi &= ~(1ull << 63);
     const u64 m = (u64)n;
     const u64 p0 = blo * m, c0 = umulhi64(blo, m);
     const u64 q = bhi * m, p1 = q + c0;
     const u64 p2 = umulhi64(bhi, m) + (p1 < q ? 1ull : 0ull);
-    if (p2 != 0 || (p1 >> 63) != 0) return 2;                     // n * B >= 2^127: the 128-bit total may have wrapped
+    // n * B >= 2^127: the 128-bit total may have wrapped.  When B = 2^bits is the two's-complement bound of a column's value mask,
+    // every addend lies in [-B, B - 1], the total in [-n*B, n*B - n], and n * B == 2^127 exactly is still exact.
+    if (p2 != 0 || ((p1 >> 63) != 0 && !(twos && p1 == (1ull << 63) && p0 == 0))) return 2;
     const u128 mx = pow10_u128(p);
     return (p1 < mx.hi || (p1 == mx.hi && p0 < mx.lo)) ? 0 : 1;   // n * B <= 10^p - 1 ?
 }

@@ -32,7 +32,7 @@ double now_ms() {
 }
 TraceSpan::TraceSpan(const char* n) : name(n), t0(trace_on() ? now_ms() : 0) {}
 TraceSpan::~TraceSpan() {
-    if (trace_on()) fprintf(stderr, "[cb200 trace] %-28s %8.3f ms\n", name, now_ms() - t0);
+    if (trace_on()) { static const double tz = now_ms(); const double t1 = now_ms(); fprintf(stderr, "[cb200 trace] %-28s %8.3f ms   (ends at +%.3f ms)\n", name, t1 - t0, t1 - tz); }
 }
 
 void cuda_check(cudaError_t e, const char* what) {
@@ -698,6 +698,9 @@ struct AggNode : FusedBase {
 
     // ---- hash aggregation state ---------------------------------------------------------------------------
     bool hash_mode = false, strategy_decided = false;
+    // Partial + hash over clustered keys: one state row per run of equal adjacent keys, no key table (device/cb_kernels.cuh CB_STREAM)
+    bool stream_mode = false, stream_decided = false;
+    double stream_ratio = 1.0;         // state rows per input row seen so far in stream mode
     DeviceBufP hkeys, hkey_of_gid, htotals, hflags;
     int64_t hcap = 0, max_groups = 0;
     int key_words = 1;                 // 64-bit words per packed group key (hkey_of_gid stride)
@@ -754,6 +757,7 @@ struct AggNode : FusedBase {
             const int ht = ctx ? ctx->hash_threads : hash_threads;
             s.threads = ht;
             s.tile = 2 * ht;
+            s.stream = stream_mode;
         }
         // first pass to learn the accumulator footprint, then size the ring to the remaining smem
         GeneratedKernel probe = generate_pipeline(s);
@@ -988,6 +992,11 @@ struct AggNode : FusedBase {
             // When the source knows how many rows are still to come, size for them at the distinct ratio seen so far (+30 %) in ONE
             // step: growing means copying the totals and re-inserting every key.
             const int64_t remaining = child->rows_hint();
+            if (remaining > 0 && rows_scanned == 0 && mode != AggMode::Partial) {
+                // merging state rows (Final / PartialMerge): most keys are new -- size for everything that is still to come at once
+                nm = std::max(nm, need + remaining);
+                if (nm + 2 >= INT32_MAX) nm = INT32_MAX - 3;
+            }
             if (remaining > 0 && rows_scanned > 0 && cur > 0) {
                 const double ratio = std::min(1.0, 1.3 * (double)cur / (double)rows_scanned);
                 const int64_t est = cur + incoming + (int64_t)(ratio * (double)remaining);
@@ -1026,9 +1035,142 @@ struct AggNode : FusedBase {
         }
     }
 
+    // ---- stream mode: state-row arrays only (no key table).  ids max_groups / max_groups + 1 stay reserved (the NULL-key group is
+    //      shared by all its runs and updated with atomics: zero / identity filled) -----------------------------------------------
+    int64_t stream_groups = 0;         // state rows handed out so far (host copy of hflags[4])
+    DeviceBufP reserved_snap;          // totals of the two reserved groups before a launch (restored when the launch is repeated)
+    void ensure_stream_rows(const std::shared_ptr<CompiledModule>& mod, int64_t cur, int64_t want_groups) {
+        cudaStream_t st = ctx->stream;
+        if (!hflags) {
+            hflags = std::make_shared<DeviceBuf>(64);
+            cuda_check(cudaMemsetAsync(hflags->ptr, 0, 64, st), "memset hash flags");
+        }
+        if (want_groups + 2 >= INT32_MAX) throw ExecError(16, "", "more than 2^31 state rows in one partition; lower spark.comet.b200.chunkRows");
+        if (htotals && want_groups <= max_groups) return;
+        const int64_t nm = std::max<int64_t>(want_groups, max_groups + max_groups / 2);
+        auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
+        auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 * key_words + 16);
+        cb::u64* tp = (cb::u64*)ntot->ptr;
+        if (cur > 0) {
+            cuda_check(cudaMemcpyAsync(tp, htotals->ptr, (size_t)cur * n_words * 16, cudaMemcpyDeviceToDevice, st), "copy state rows");
+            cuda_check(cudaMemcpyAsync(nkog->ptr, hkey_of_gid->ptr, (size_t)cur * 8 * key_words, cudaMemcpyDeviceToDevice, st), "copy group keys");
+        }
+        if (htotals)
+            cuda_check(cudaMemcpyAsync(tp + (size_t)nm * n_words * 2, (cb::u64*)htotals->ptr + (size_t)max_groups * n_words * 2, (size_t)2 * n_words * 16,
+                                       cudaMemcpyDeviceToDevice, st), "copy reserved groups");
+        else init_totals(mod, tp, nm, 2);
+        cuda_check(cudaStreamSynchronize(st), "state rows growth"); // old buffers die below
+        htotals = ntot; hkey_of_gid = nkog; max_groups = nm;
+    }
+    // one CB_STREAM launch over rows [r0, r1) of b; returns the flags after it (flags[4] = state rows handed out so far)
+    void stream_launch(Batch& b, int64_t r0, int64_t r1, const PipelineSpec& spec, const GeneratedKernel& g, const std::shared_ptr<CompiledModule>& mod,
+                       int flags[8]) {
+        if (!vmask) vmask = std::make_shared<DeviceBuf>(CB_MAX_COLS * 16);
+        cuda_check(cudaMemsetAsync(vmask->ptr, 0, CB_MAX_COLS * 16, ctx->stream), "memset vmask");
+        cb::PipeParams p;
+        fill_inputs(p, b, g.tile, r0, r1);
+        p.hkeys = nullptr;
+        p.hkey_of_gid = (cb::u64*)hkey_of_gid->ptr;
+        p.htotals = (cb::u64*)htotals->ptr;
+        p.hmask = 0;
+        p.max_groups = (cb::i32)max_groups;
+        p.hflags = (cb::i32*)hflags->ptr;
+        p.vmask = (cb::u64*)vmask->ptr;
+        p.n_groups = 2;
+        int grid = std::max(1, std::min(ctx->num_sms, p.n_tiles));
+        launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(0), &p);
+        uint64_t masks[CB_MAX_COLS * 2];
+        cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, ctx->stream), "read value masks"); ctx->d2h_bytes += (int64_t)(sizeof(masks));
+        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags"); ctx->d2h_bytes += (int64_t)(8 * sizeof(int));
+        ctx->check_device_errors();
+        if (flags[0] & 4) throw Unsupported("decimal(p > 18) group key whose value does not fit 64 bits");
+        if (!(flags[0] & 2))
+            for (size_t i = 0; i < spec.cols.size(); i++) {
+                if (!spec.cols[i].type.is_decimal()) continue;
+                uint64_t lo = masks[2 * i], hi = masks[2 * i + 1];
+                int bl = hi ? 64 + r_bitlen(hi) : r_bitlen(lo);
+                observed_bits[(size_t)used_cols[i]] = std::max(observed_bits[(size_t)used_cols[i]], bl);
+            }
+    }
+    void stream_set_flags(int flags[8]) { // host -> device (after a discarded launch)
+        cuda_check(cudaMemcpyAsync(hflags->ptr, flags, 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "write hash flags");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "flags sync");
+    }
+    void snapshot_reserved(bool restore) {
+        const size_t bytes = (size_t)2 * n_words * 16;
+        if (!reserved_snap || reserved_snap->bytes < bytes) reserved_snap = std::make_shared<DeviceBuf>(bytes);
+        cb::u64* tail = (cb::u64*)htotals->ptr + (size_t)max_groups * n_words * 2;
+        if (restore) cuda_check(cudaMemcpyAsync(tail, reserved_snap->ptr, bytes, cudaMemcpyDeviceToDevice, ctx->stream), "restore reserved groups");
+        else cuda_check(cudaMemcpyAsync(reserved_snap->ptr, tail, bytes, cudaMemcpyDeviceToDevice, ctx->stream), "snapshot reserved groups");
+    }
+    // Are equal keys adjacent?  Run the stream kernel over the first rows of the first batch and look at state rows per input row.
+    void decide_stream(Batch& b) {
+        stream_decided = true;
+        stream_mode = false;
+        if (mode != AggMode::Partial || !ctx || ctx->stream_agg_min_rows < 0) return;
+        const int64_t hint = child->rows_hint();
+        if (b.n_rows + std::max<int64_t>(hint, 0) < ctx->stream_agg_min_rows || b.n_rows == 0) return;
+        stream_mode = true;
+        PipelineSpec spec = make_spec(&b, 2, SAFE);
+        GeneratedKernel g = generate_pipeline(spec);
+        auto mod = jit_get(g, true);
+        n_words = g.n_words; word_kinds = g.word_kinds; key_words = g.key_words;
+        const int64_t sample = std::min<int64_t>(b.n_rows, 1 << 20);
+        ensure_stream_rows(mod, 0, sample + 1024);
+        int flags[8];
+        stream_launch(b, 0, sample, spec, g, mod, flags);
+        stream_ratio = (double)flags[4] / (double)sample;
+        // the sample's rows are scanned again with the rest: forget its state rows (and whatever it added to the shared NULL-key group)
+        int zero[8] = {0};
+        stream_set_flags(zero);
+        init_totals(mod, (cb::u64*)htotals->ptr, max_groups, 2);
+        if (stream_ratio > ctx->stream_agg_max_ratio) {
+            stream_mode = false;
+            htotals.reset(); hkey_of_gid.reset(); hflags.reset(); max_groups = 0; n_words = 0; word_kinds.clear();
+        }
+    }
+    void consume_stream(Batch& b) {
+        PipelineSpec spec = make_spec(&b, 2, SAFE);
+        GeneratedKernel g = generate_pipeline(spec);
+        auto mod = jit_get(g, true);
+        ctx->last_kernel_key = g.key;
+        if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds || g.key_words != key_words))
+            throw ExecError(15, "", "internal: accumulator layout changed between launches");
+        n_words = g.n_words; word_kinds = g.word_kinds; key_words = g.key_words;
+        const int64_t cur = stream_groups;
+        // state rows this batch (and, when the source says how much is still to come, the rest) will need at the ratio seen so far
+        const int64_t remaining = std::max<int64_t>(child->rows_hint(), 0);
+        int64_t want = cur + std::min<int64_t>(b.n_rows, (int64_t)(1.25 * stream_ratio * (double)b.n_rows) + 65536);
+        if (!htotals || want > max_groups) want += std::min<int64_t>(remaining, (int64_t)(1.25 * stream_ratio * (double)remaining));
+        int flags[8];
+        while (true) {
+            {
+                TraceSpan ts("stream.ensure_rows");
+                ensure_stream_rows(mod, cur, want);
+            }
+            snapshot_reserved(false);
+            stream_launch(b, 0, b.n_rows, spec, g, mod, flags);
+            if (!(flags[0] & 2)) break;
+            // more runs than state rows: nothing of this launch is kept (its rows only touched ids >= cur and the shared group)
+            snapshot_reserved(true);
+            flags[0] &= ~2; flags[4] = (int)cur;
+            stream_set_flags(flags);
+            want = cur + b.n_rows; // every row its own run
+        }
+        ctx->pipeline_rows += b.n_rows;
+        stream_groups = flags[4];
+        if (b.n_rows > 0) stream_ratio = std::max(stream_ratio, (double)(stream_groups - cur) / (double)b.n_rows);
+        rows_scanned += b.n_rows;
+        have_totals = true;
+        last_gen = g;
+        last_mod = mod;
+    }
+
     void consume_hash(Batch& b) {
         if (keys.size() > CB_MAX_KEYS) throw Unsupported("more than 4 group keys");
         if (observed_bits.empty()) observed_bits.assign(child->schema.size(), -1);
+        if (!stream_decided) decide_stream(b);
+        if (stream_mode) { consume_stream(b); return; }
         // updates go straight into the table, so a launch cannot be discarded: no speculative assumptions here
         PipelineSpec spec = make_spec(&b, 2, SAFE);
         GeneratedKernel g = generate_pipeline(spec);
@@ -1245,6 +1387,9 @@ struct AggNode : FusedBase {
             const u128r b = certificate(ai);
             fp.cert_b[ai][0] = b >= RSAT ? ~0ull : (uint64_t)b;
             fp.cert_b[ai][1] = b >= RSAT ? ~0ull : (uint64_t)(b >> 64);
+            // bit 63 of the high word (free: B < 2^127): B is the bound 2^bits of a value mask, i.e. addends lie in [-B, B - 1]
+            const bool direct = mode != AggMode::Partial || aggs[ai].children[0]->kind == ExprKind::Bound;
+            if (b < RSAT && b != 0 && direct) fp.cert_b[ai][1] |= 1ull << 63;
         }
     }
 
@@ -1452,9 +1597,10 @@ struct PartitionNode : ExecNode {
         auto starts = std::make_shared<DeviceBuf>((size_t)(n_parts + 1) * 8);
         auto row_idx = std::make_shared<DeviceBuf>((size_t)n * 8 + 16);
         cuda_check(cudaMemsetAsync(starts->ptr, 0, (size_t)(n_parts + 1) * 8, st), "memset starts");
-        launch_partition(kc, n, (unsigned)n_parts, nullptr, (unsigned*)pids->ptr, (int*)hist->ptr, (long long*)base->ptr, (long long*)starts->ptr,
-                         (long long*)row_idx->ptr, st);
-        ctx->kernel_launches += 4;
+        auto chunk_tmp = std::make_shared<DeviceBuf>((size_t)(partition_chunks(n) + 1) * n_parts * 8);
+        launch_partition(kc, n, (unsigned)n_parts, nullptr, (unsigned*)pids->ptr, (int*)hist->ptr, (long long*)base->ptr, (long long*)chunk_tmp->ptr,
+                         (long long*)starts->ptr, (long long*)row_idx->ptr, st);
+        ctx->kernel_launches += 6;
         out.n_rows = n;
         out.cols.clear();
         for (auto& c : in.cols) {

@@ -84,6 +84,10 @@ struct ExecContext {
     int num_sms = 148;
     int64_t chunk_rows = 1ll << 26;
     int hash_threads = 512;   // consumer threads per CTA of the hash-aggregate kernel (tuning knob)
+    // Partial hash aggregates over inputs of at least this many rows sample whether equal keys are adjacent and, if so, emit one state
+    // row per run instead of building a key table (spark.comet.b200.streamAgg.minRows; -1 disables, 0 = always sample)
+    int64_t stream_agg_min_rows = 4 << 20;
+    double stream_agg_max_ratio = 0.5; // state rows per input row above which the key table is used (spark.comet.b200.streamAgg.maxRatio)
     int batch_size = 8192;
     int* d_err = nullptr;   // device error flags
     int* h_err = nullptr;   // pinned host mirror

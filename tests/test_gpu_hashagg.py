@@ -191,3 +191,122 @@ def test_dense_to_hash_migration_mid_stream(cb):
     assert state.num_rows > len(exp)                                       # the early groups appear twice: once per path
     res = run(cb, final, [state])
     assert {r["col_0"]: [r["col_1"], r["col_2"]] for r in res.to_pylist()} == exp
+
+
+# ---- stream mode (CB_STREAM): Partial aggregates over clustered keys emit one state row per run, no key table --------------------
+def run_cfg(cb, plan, inputs, cfg):
+    with cb.native.Plan(plan, inputs, config={k: str(v) for k, v in cfg.items()}) as p:
+        return p.collect()
+
+
+STREAM = {"spark.comet.b200.streamAgg.minRows": 0}
+
+
+def merge_states(rows, ncols):
+    """Final-stage semantics for (sum, count, min, max) state rows keyed by col_0: what merging the partial rows must give."""
+    out = {}
+    for r in rows:
+        e = out.get(r["col_0"])
+        if e is None:
+            out[r["col_0"]] = [r[f"col_{j}"] for j in range(1, ncols)]
+        else:
+            for j, f in enumerate(("sum", "sum", "min", "max")[: ncols - 1]):
+                a, b = e[j], r[f"col_{j + 1}"]
+                if a is None or b is None:
+                    e[j] = a if b is None else b
+                else:
+                    e[j] = a + b if f == "sum" else (min(a, b) if f == "min" else max(a, b))
+    return out
+
+
+@pytest.mark.parametrize("chunk", [None, 150_000])
+def test_stream_partial_over_clustered_keys(cb, chunk):
+    """Clustered keys (every key ~5 times in a row, some NULL keys and NULL values): runs of equal adjacent keys become state rows.
+    A key may appear in more than one state row (runs split at warp / chunk borders); merged by key they are the exact groups."""
+    P = cb.proto
+    rng = np.random.default_rng(12)
+    n = 600_000
+    k = np.repeat(np.arange(n // 5 + 1, dtype=np.int64) * 3 - 1000, rng.integers(1, 10, n // 5 + 1))[:n]
+    v = rng.integers(-10**6, 10**6, n)
+    km, vm = np.zeros(n, dtype=bool), rng.random(n) < 0.1
+    km[1000:1040] = True
+    km[300_000:300_003] = True
+    tbl = pa.table({"k": pa.array(k, mask=km), "v": pa.array(v, mask=vm)})
+    plan = P.hash_agg(P.scan([P.INT64, P.INT64]), [P.bound(0, P.INT64)],
+                      [P.agg_sum(P.bound(1, P.INT64), P.INT64), P.agg_count([P.bound(1, P.INT64)]), P.agg_min(P.bound(1, P.INT64), P.INT64),
+                       P.agg_max(P.bound(1, P.INT64), P.INT64)], P.PARTIAL)
+    cfg = dict(STREAM)
+    if chunk:
+        cfg["spark.comet.b200.chunkRows"] = chunk
+    out = run_cfg(cb, plan, [tbl.to_batches(max_chunksize=8192)], cfg)
+    exp = {}
+    for kk, vv, a, b in zip(k.tolist(), v.tolist(), km.tolist(), vm.tolist()):
+        key = None if a else kk
+        e = exp.setdefault(key, [None, 0, None, None])
+        if not b:
+            e[0] = vv if e[0] is None else e[0] + vv
+            e[1] += 1
+            e[2] = vv if e[2] is None else min(e[2], vv)
+            e[3] = vv if e[3] is None else max(e[3], vv)
+    assert len(exp) <= out.num_rows < 0.5 * n                       # streamed (no table): at most a few split runs more than groups
+    assert merge_states(out.to_pylist(), 5) == exp
+
+
+def test_stream_partial_feeds_final_decimal_and_f64(cb):
+    """The Config 4 shape end to end: streamed Partial state -> Final, decimal sums bit-exact, f64 sums within 1 ULP of the exact sum."""
+    t = cb.tpch
+    n = 500_000
+    cols = t.gen_lineitem(n, seed=11)
+    for variant in ("dec", "f64"):
+        partial, final = plans(cb, variant)
+        price = cols["l_extendedprice"]
+        vcol = t._dec_array(price) if variant == "dec" else pa.array(price.astype(np.float64) / 100.0)
+        tbl = pa.table({"k": pa.array(cols["l_orderkey"]), "v": vcol})
+        state = run_cfg(cb, partial, [tbl.to_batches(max_chunksize=8192)], STREAM)
+        uk, inv = np.unique(cols["l_orderkey"], return_inverse=True)
+        assert len(uk) <= state.num_rows <= len(uk) + n // 32 + 1024
+        res = run(cb, final, [state])
+        keys = np.array(res.column(0).to_pylist())
+        order = np.argsort(keys)
+        assert (keys[order] == uk).all()
+        if variant == "dec":
+            exp = np.zeros(len(uk), dtype=np.int64)
+            np.add.at(exp, inv, price)
+            got = np.array([unscaled(x) for x in res.column(1).to_pylist()], dtype=np.int64)[order]
+            assert (got == exp).all()
+        else:
+            vals = np.array(res.column(1).to_pylist())[order]
+            pf = price.astype(np.float64) / 100.0
+            for i in range(0, len(uk), 4999):
+                exact = math.fsum(pf[inv == i])
+                assert abs(vals[i] - exact) <= math.ulp(exact)
+
+
+def test_stream_sample_sees_scattered_keys_and_keeps_the_table(cb):
+    """Keys in random order: the sample finds (almost) one run per row, so the key table is used and every group is one state row."""
+    P = cb.proto
+    n = 300_000
+    rng = np.random.default_rng(5)
+    k = rng.integers(0, 5000, n)
+    v = np.ones(n, dtype=np.int64)
+    plan = P.hash_agg(P.scan([P.INT64, P.INT64]), [P.bound(0, P.INT64)], [P.agg_sum(P.bound(1, P.INT64), P.INT64)], P.PARTIAL)
+    out = run_cfg(cb, plan, [pa.table({"k": k, "v": v}).to_batches(max_chunksize=8192)], STREAM)
+    assert out.num_rows == len(np.unique(k)) and sum(out.column(1).to_pylist()) == n
+
+
+def test_stream_runs_outgrow_the_estimate(cb):
+    """The sampled prefix is clustered (8 rows per key), the tail is not (every row its own key): the launch runs out of state rows,
+    is discarded, the arrays grow and it is repeated -- nothing may be lost or counted twice (incl. the shared NULL-key group)."""
+    P = cb.proto
+    n_head, n_tail = 1_200_000, 900_000
+    k = np.concatenate([np.repeat(np.arange(n_head // 8, dtype=np.int64), 8), 10**9 + np.arange(n_tail, dtype=np.int64)])
+    km = np.zeros(len(k), dtype=bool)
+    km[5:9] = True
+    km[n_head + 10:n_head + 12] = True
+    v = np.arange(len(k), dtype=np.int64) % 1000
+    plan = P.hash_agg(P.scan([P.INT64, P.INT64]), [P.bound(0, P.INT64)], [P.agg_sum(P.bound(1, P.INT64), P.INT64), P.agg_count([P.bound(1, P.INT64)])], P.PARTIAL)
+    out = run_cfg(cb, plan, [pa.table({"k": pa.array(k, mask=km), "v": v}).to_batches(max_chunksize=65536)], STREAM)
+    got = merge_states(out.to_pylist(), 3)
+    assert got[None] == [int(v[km].sum()), int(km.sum())]
+    assert len(got) == n_head // 8 + n_tail + 1 - 2          # keys 0 and 1 lose rows to NULL but survive; two tail keys are NULL
+    assert sum(e[1] for e in got.values()) == len(k) and sum(e[0] for e in got.values()) == int(v.sum())
