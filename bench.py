@@ -692,14 +692,22 @@ def workload_groupby(args, env):
     def view(ptr, nbytes):
         return torch.as_tensor(_DevPtr(ptr, nbytes), device=device) if nbytes else torch.empty(0, dtype=torch.uint8, device=device)
 
+    py_trace = bool(os.environ.get("CB200_TRACE"))
+
     def step(keep_result=False):
+        tm = [time.perf_counter()]
         p = native.Plan(map_plan, [table], config=cfg, device=DEVICE)
+        tm.append(time.perf_counter())
         rows_state, _ = p.execute_device()
+        tm.append(time.perf_counter())
         st = p.stats()
         recv, xs = comm.exchange(p)
+        tm.append(time.perf_counter())
         p.release()
+        tm.append(time.perf_counter())
         p2 = native.Plan(final_plan, [recv], config=cfg, device=DEVICE)
         out = p2.execute_device()
+        tm.append(time.perf_counter())
         n_out = out[0] if out else 0
         st2 = p2.stats()
         result = None
@@ -709,15 +717,22 @@ def workload_groupby(args, env):
             vv = (vv.view(torch.int64).view(-1, 2)[:, 0] if dec else vv.view(torch.float64)).clone()
             result = (kk, vv)
         torch.cuda.synchronize()
+        tm.append(time.perf_counter())
         p2.release()
+        tm.append(time.perf_counter())
         recv.release()
+        tm.append(time.perf_counter())
+        if py_trace:
+            names = ["create", "map.execute", "exchange", "map.release", "final.create+execute", "sync", "final.release", "recv.release"]
+            print("[py trace] " + "  ".join(f"{k} {1e3 * (b - a):.2f}" for k, a, b in zip(names, tm, tm[1:])), file=sys.stderr)
         return dict(rows_state=rows_state, n_out=n_out, st=st, st2=st2, xs=xs, result=result)
 
     sampler = ClockSampler(env["local_rank"])
-    if rank == 0:
+    use_sampler = rank == 0 and not os.environ.get("CB200_BENCH_NO_SAMPLER")
+    if use_sampler:
         sampler.start()
-    elapsed, outs = timed_region(env, sampler if rank == 0 else None, step, args.warmup, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    elapsed, outs = timed_region(env, sampler if use_sampler else None, step, args.warmup, args.steps)
+    clocks = sampler.stop() if use_sampler else None
     last = outs[-1]
 
     # ---- checks: exact totals per key (N = 1), ownership + global checksums (any N) -------------------------------------------------

@@ -309,6 +309,13 @@ int32_t cb200_plan_partition_starts(cb200_plan* plan, int64_t* starts, int32_t c
 
 int64_t cb200_plan_kernel_launches(cb200_plan* plan) { return plan ? plan->ctx.kernel_launches : -1; }
 
+int64_t cb200_release_cached_memory(int32_t device_ordinal) {
+    try {
+        if (cudaSetDevice(device_ordinal) != cudaSuccess) return 0;
+        return (int64_t)release_cached_device_memory();
+    } catch (...) { return 0; }
+}
+
 int cb200_plan_stats(cb200_plan* plan, cb200_stats* out) {
     if (!plan || !out) return -1;
     const ExecContext& c = plan->ctx;

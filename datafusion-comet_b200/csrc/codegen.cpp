@@ -1291,7 +1291,8 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         std::ostringstream defs;
         g.ungrouped = spec.ungrouped;
         defs << "#define CB_KERNEL_AGG 1\n#define CB_WORDS " << g.n_words << "\n#define CB_G1 " << (spec.ungrouped ? 1 : 0) << "\n#define CB_W_ROWS " << w_rows
-             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n#define CB_KEY_WORDS " << (spec.hash ? g.key_words : 1) << "\n#define CB_STREAM " << (spec.hash && spec.stream ? 1 : 0) << "\n";
+             << "\n#define CB_HASH " << (spec.hash ? 1 : 0) << "\n#define CB_KEY_WORDS " << (spec.hash ? g.key_words : 1) << "\n#define CB_STREAM " << (spec.hash && spec.stream ? 1 : 0)
+             << "\n#define CB_CAS_FIRST " << (spec.hash && spec.mode != AggMode::Partial ? 1 : 0) << "\n";
         tu << header(spec, defs.str());
         tu << "constexpr __host__ __device__ int cb_word_kind(int w) { return ";
         for (size_t i = 0; i < slots.kinds.size(); i++) tu << "w == " << i << " ? " << slots.kinds[i] << " : ";

@@ -170,6 +170,9 @@ CB_D void cb_row_agg(const Tile& t, int r, i64 grow, const PipeParams& p, Acc& a
 #ifndef CB_STREAM
 #define CB_STREAM 0
 #endif
+#ifndef CB_CAS_FIRST
+#define CB_CAS_FIRST 0
+#endif
 
 #if CB_HASH
 // ---- hash aggregation: accumulators live in a global open-addressing table, updated with atomics -------------
@@ -188,9 +191,6 @@ struct Acc {
     const PipeParams* p;
     u64 vm[2 * CB_NCOLS];
     // state of the current row iteration (begin() sets it)
-#ifdef CB_X_GIDBLOCK
-    int xg_next = 0, xg_end = 0;
-#endif
     bool shared_g;  // CB_STREAM: g is the reserved NULL-key group, which other runs update too (atomics instead of stores)
     int g;          // group id (valid on head lanes)
     int run_end;    // last lane of this lane's run
@@ -222,6 +222,29 @@ struct Acc {
         return eq;
     }
 
+    // Fresh group ids for the lanes with `need` (warp-collective: every lane calls it).  One atomic per warp on the counter of the
+    // warp's home id range; a full range sends the lanes that did not fit to the next one.  -1: every range is full.
+    CB_D int alloc_gids(bool need) {
+        const u32 lane = threadIdx.x & 31u;
+        const int R = p->max_groups / CB_GID_RANGES;
+        u32 r = (blockIdx.x * (CB_THREADS / 32) + (threadIdx.x >> 5)) % CB_GID_RANGES;
+        int gn = -1;
+        for (int tries = 0; tries < CB_GID_RANGES; tries++) {
+            const u32 cm = __ballot_sync(0xffffffffu, need);
+            if (!cm) break;
+            const int leader = __ffs(cm) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(&p->hflags[CB_HFLAG_CTR + r], __popc(cm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                const int local = base + __popc(cm & ((1u << lane) - 1u));
+                if (base >= 0 && local < R) { gn = (int)r * R + local; need = false; } // (a counter that ran past R stays there: the host clamps)
+            }
+            r = (r + 1u) % CB_GID_RANGES;
+        }
+        return gn;
+    }
+
     // Group ids of the head lanes' keys, inserting new keys.  Called by the whole warp (convergent).
     //   probe   : linear probing from the key's home slot; a hit on a published slot resolves the lane, an empty slot is claimed
     //             with a CAS, a slot whose id is not published yet leaves the lane PENDING (no spinning here: the publisher may be
@@ -239,15 +262,11 @@ struct Acc {
             (void)mask;
             bool fresh = want;
             if (want && null_group) { g = p->max_groups + 1; shared_g = true; fresh = false; }
-            const u32 cm = __ballot_sync(0xffffffffu, fresh);
-            if (cm) {
-                const int leader = __ffs(cm) - 1;
-                int base = 0;
-                if ((int)lane == leader) base = atomicAdd(&p->hflags[4], __popc(cm));
-                base = __shfl_sync(0xffffffffu, base, leader);
+            (void)lane;
+            if (__any_sync(0xffffffffu, fresh)) {
+                int gn = alloc_gids(fresh);
                 if (fresh) {
-                    int gn = base + __popc(cm & ((1u << lane) - 1u));
-                    if (gn >= p->max_groups) { atomicOr(p->hflags, 2); gn = p->max_groups; shared_g = true; } // out of state rows: the host grows the arrays and repeats the launch
+                    if (gn < 0) { atomicOr(p->hflags, 2); gn = p->max_groups; shared_g = true; } // out of state rows: the host grows the arrays and repeats the launch
                     else {
 #pragma unroll
                         for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)gn * CB_KEY_WORDS + i] = kw[i];
@@ -269,6 +288,13 @@ struct Acc {
             if (unresolved) {
                 while (true) {
                     if (probes++ > mask) { atomicOr(p->hflags, 2); g = p->max_groups; unresolved = false; break; } // table full: cannot happen (host sizes it)
+#if CB_CAS_FIRST
+                    // merging state rows: most keys are new, so claim first and look second -- one L2 / HBM round trip instead of two
+                    ulonglong2 slot;
+                    slot.x = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)tag);
+                    if (slot.x == CB_EMPTY_KEY) { claimed = true; break; }
+                    slot.y = slot.x == tag ? __ldcg(&p->hkeys[2 * (size_t)s + 1]) : 0ull;
+#else
                     ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2*>(p->hkeys) + s);
                     if (slot.x == CB_EMPTY_KEY) {
                         const u64 prev = atomicCAS((unsigned long long*)&p->hkeys[2 * (size_t)s], (unsigned long long)CB_EMPTY_KEY, (unsigned long long)tag);
@@ -276,6 +302,7 @@ struct Acc {
                         slot.x = prev;
                         slot.y = ~0ull; // somebody else just took it: its id may not be out yet
                     }
+#endif
                     if (slot.x == tag) {
                         const int gs = (i32)(u32)slot.y;
                         if (gs < 0) { pending = true; break; }
@@ -284,23 +311,11 @@ struct Acc {
                     s = (s + 1u) & mask;
                 }
             }
-            const u32 cm = __ballot_sync(0xffffffffu, claimed);
-            if (cm) {
-                const int leader = __ffs(cm) - 1;
-                int base = 0;
-#ifdef CB_X_GIDBLOCK
-                {   // timing experiment: one global atomic per CB_X_GIDBLOCK ids (leaves holes; results are not usable)
-                    const int need = __popc(cm);
-                    if (xg_next + need > xg_end) { if (lane == 0) xg_next = atomicAdd(&p->hflags[4], CB_X_GIDBLOCK); xg_next = __shfl_sync(0xffffffffu, xg_next, 0); xg_end = xg_next + CB_X_GIDBLOCK; }
-                    base = xg_next; xg_next += need;
-                }
-#else
-                if ((int)lane == leader) base = atomicAdd(&p->hflags[4], __popc(cm));
-                base = __shfl_sync(0xffffffffu, base, leader);
-#endif
+            (void)lane;
+            if (__any_sync(0xffffffffu, claimed)) {
+                int gn = alloc_gids(claimed);
                 if (claimed) {
-                    int gn = base + __popc(cm & ((1u << lane) - 1u));
-                    if (gn >= p->max_groups) { atomicOr(p->hflags, 2); gn = p->max_groups; } // cannot happen: host sizes max_groups >= rows
+                    if (gn < 0) { atomicOr(p->hflags, 2); gn = p->max_groups; } // cannot happen: host sizes max_groups >= rows
                     else {
 #pragma unroll
                         for (int i = 0; i < CB_KEY_WORDS; i++) p->hkey_of_gid[(size_t)gn * CB_KEY_WORDS + i] = kw[i];
@@ -696,10 +711,13 @@ extern "C" __global__ void cb_hash_init(u64* totals, long long first, long long 
 #pragma unroll
     for (int w = 0; w < CB_WORDS; w++) { totals[(i * CB_WORDS + w) * 2] = acc_identity(cb_word_kind(w)); totals[(i * CB_WORDS + w) * 2 + 1] = 0; }
 }
-// re-insert every group's key into a bigger key table, keeping its id (keys are unique: a claim always succeeds)
-extern "C" __global__ void cb_hash_rehash(const u64* key_of_gid, int n_groups, u64* hkeys, u32 mask) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
+// re-insert every group's key into a fresh key table under its (possibly relocated) id; ids: see CB_GID_RANGES
+extern "C" __global__ void cb_hash_rehash(const u64* key_of_gid, int range_rows, const i32* counters, u64* hkeys, u32 mask) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)range_rows * CB_GID_RANGES) return;
+    const int r = (int)(idx / range_rows), l = (int)(idx % range_rows);
+    if (l >= counters[r]) return;
+    const int g = (int)idx;
 #if CB_KEY_WORDS > 1
     u64 kw[CB_KEY_WORDS];
 #pragma unroll
@@ -761,6 +779,11 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
     // output row g: groups 0..n_hash_groups-1 in id order, then the reserved groups that were used
     int gid = g;
     bool is_sentinel = false, is_null_group = false;
+    if (g < fp.n_hash_groups) { // the g-th id in (range, local) order
+        int lo = 0, hi = CB_GID_RANGES - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (fp.gid_prefix[mid] <= g) lo = mid; else hi = mid - 1; }
+        gid = lo * fp.gid_range + (g - fp.gid_prefix[lo]);
+    }
     if (g >= fp.n_hash_groups) {
         int extra = g - fp.n_hash_groups;
         if (fp.sentinel_used && extra == 0) is_sentinel = true;

@@ -44,13 +44,93 @@ void cuda_check(cudaError_t e, const char* what) {
 static thread_local cudaStream_t tl_alloc_stream = nullptr;
 void set_alloc_stream(cudaStream_t s) { tl_alloc_stream = s; }
 
+// Large blocks are recycled by the library itself.  A query step allocates and frees the same multi-GB buffers over and over
+// (state rows, partition outputs, exchange buffers); the driver's stream-ordered pool serves them from its free list most of the
+// time, but when its best-fit search fails it maps fresh memory from the OS, and single cudaMallocAsync calls were measured at
+// 400-530 ms (a 90 ms step became 650 ms).  Blocks >= 1 MiB are rounded up to a size class (1/8 octave, <= 12.5 % slack) and kept
+// on a per-device free list keyed by class; a block freed on one stream and taken by another is ordered by an event.
+namespace {
+struct CachedBlock { void* ptr; cudaStream_t stream; cudaEvent_t ev; };
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, CachedBlock> free_blocks;
+    size_t cached_bytes = 0;
+};
+BlockCache g_block_cache[64];
+const size_t BLOCK_CACHE_MIN = 1 << 20;
+size_t block_cache_limit() {
+    static size_t lim = 0;
+    if (!lim) { const char* e = getenv("CB200_BLOCK_CACHE_BYTES"); lim = e && *e ? (size_t)atoll(e) : (size_t)96 << 30; if (!lim) lim = 1; }
+    return lim;
+}
+size_t size_class(size_t n) {
+    size_t p2 = (size_t)1 << 20;
+    while ((p2 << 1) <= n) p2 <<= 1;
+    const size_t step = p2 >> 3;
+    return (n + step - 1) / step * step;
+}
+int current_device() { int d = 0; cudaGetDevice(&d); return d >= 0 && d < 64 ? d : 0; }
+// drop every cached block of a device (called when an allocation fails, and by cb200_release_cached_memory)
+size_t block_cache_flush(int dev) {
+    BlockCache& c = g_block_cache[dev];
+    std::multimap<size_t, CachedBlock> take;
+    size_t freed = 0;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        take.swap(c.free_blocks);
+        freed = c.cached_bytes;
+        c.cached_bytes = 0;
+    }
+    for (auto& kv : take) { cudaEventSynchronize(kv.second.ev); cudaFreeAsync(kv.second.ptr, nullptr); cudaEventDestroy(kv.second.ev); } // the owner stream may be gone by now
+    return freed;
+}
+} // namespace
+size_t release_cached_device_memory() { return block_cache_flush(current_device()); }
+
 DeviceBuf::DeviceBuf(size_t n) {
     bytes = (n + 255) / 256 * 256 + 256; // padded: TMA bulk copies round sizes up to 16 B
     stream = tl_alloc_stream;
-    cuda_check(cudaMallocAsync(&ptr, bytes, stream), "cudaMallocAsync");
+    if (bytes >= BLOCK_CACHE_MIN) {
+        bytes = size_class(bytes);
+        BlockCache& c = g_block_cache[current_device()];
+        CachedBlock blk{nullptr, nullptr, nullptr};
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            auto it = c.free_blocks.find(bytes);
+            if (it != c.free_blocks.end()) { blk = it->second; c.free_blocks.erase(it); c.cached_bytes -= bytes; }
+        }
+        if (blk.ptr) {
+            if (blk.stream != stream) cudaStreamWaitEvent(stream, blk.ev, 0); // the previous owner's work on this block is done before ours starts
+            cudaEventDestroy(blk.ev);
+            ptr = blk.ptr;
+            return;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(&ptr, bytes, stream);
+    if (e == cudaErrorMemoryAllocation) { // give the cached blocks back and try once more
+        cudaGetLastError();
+        block_cache_flush(current_device());
+        cudaStreamSynchronize(stream);
+        e = cudaMallocAsync(&ptr, bytes, stream);
+    }
+    cuda_check(e, "cudaMallocAsync");
 }
 DeviceBuf::~DeviceBuf() {
-    if (owned && ptr) cudaFreeAsync(ptr, stream);
+    if (!(owned && ptr)) return;
+    if (bytes >= BLOCK_CACHE_MIN && bytes == size_class(bytes)) {
+        BlockCache& c = g_block_cache[current_device()];
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess && cudaEventRecord(ev, stream) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(c.mu);
+            if (c.cached_bytes + bytes <= block_cache_limit()) {
+                c.free_blocks.insert({bytes, CachedBlock{ptr, stream, ev}});
+                c.cached_bytes += bytes;
+                return;
+            }
+        }
+        if (ev) cudaEventDestroy(ev);
+    }
+    cudaFreeAsync(ptr, stream);
 }
 
 void ExecContext::collect_timing() {
@@ -973,20 +1053,77 @@ struct AggNode : FusedBase {
             launch_named(mod, "cb_hash_init", dim3((unsigned)((n + 255) / 256)), dim3(256), a1);
         }
     }
+    // ---- group ids: CB_GID_RANGES counters (device/cb_params.h); the host sees per-range counts ------------------------------------
+    static constexpr int GK = CB_GID_RANGES;
+    struct HashFlags { int w[CB_HFLAG_WORDS]; };
+    void ensure_flags() {
+        if (hflags) return;
+        hflags = std::make_shared<DeviceBuf>(sizeof(HashFlags));
+        cuda_check(cudaMemsetAsync(hflags->ptr, 0, sizeof(HashFlags), ctx->stream), "memset hash flags");
+    }
+    // device -> host (synchronises); cnt[r] = ids handed out in range r (a counter that ran past its range is clamped); returns their sum
+    int64_t read_flags(HashFlags& hf, int64_t cnt[GK]) {
+        memset(&hf, 0, sizeof(hf));
+        if (hflags) {
+            cuda_check(cudaMemcpyAsync(&hf, hflags->ptr, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags"); ctx->d2h_bytes += (int64_t)sizeof(hf);
+            cuda_check(cudaStreamSynchronize(ctx->stream), "hash flags sync");
+        }
+        const int64_t R = max_groups / GK;
+        int64_t total = 0;
+        bool overshoot = false;
+        for (int r = 0; r < GK; r++) {
+            if (hf.w[CB_HFLAG_CTR + r] > R || hf.w[CB_HFLAG_CTR + r] < 0) overshoot = true;
+            cnt[r] = std::min<int64_t>(std::max(hf.w[CB_HFLAG_CTR + r], 0), R);
+            if (hf.w[CB_HFLAG_CTR + r] < 0) cnt[r] = R; // wrapped: it was full long ago
+            total += cnt[r];
+        }
+        if (overshoot && hflags) { // warps that found a range full still bumped its counter: put it back to "full" so it can never wrap
+            for (int r = 0; r < GK; r++) hf.w[CB_HFLAG_CTR + r] = (int)cnt[r];
+            write_flags(hf);
+        }
+        return total;
+    }
+    void write_flags(const HashFlags& hf) {
+        cuda_check(cudaMemcpyAsync(hflags->ptr, &hf, sizeof(hf), cudaMemcpyHostToDevice, ctx->stream), "write hash flags");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "flags sync");
+    }
+    // new accumulator / key arrays for nm ids (a multiple of GK): range r's rows move from r * R_old to r * R_new, the two reserved
+    // groups to the new tail.  zero_fill: every other word gets its identity (the key table path updates with atomics).
+    void grow_rows(const std::shared_ptr<CompiledModule>& mod, const int64_t cnt[GK], int64_t nm, bool zero_fill) {
+        cudaStream_t st = ctx->stream;
+        if (nm + 2 >= INT32_MAX) throw ExecError(16, "", "more than 2^31 groups in one partition; lower spark.comet.b200.chunkRows");
+        const int64_t Ro = max_groups / GK, Rn = nm / GK;
+        auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
+        auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 * key_words + 16);
+        cb::u64* tp = (cb::u64*)ntot->ptr;
+        if (zero_fill) init_totals(mod, tp, 0, nm + 2);
+        else if (!htotals) init_totals(mod, tp, nm, 2);
+        if (htotals) {
+            for (int r = 0; r < GK; r++) {
+                if (cnt[r] <= 0) continue;
+                cuda_check(cudaMemcpyAsync(tp + (size_t)r * Rn * n_words * 2, (cb::u64*)htotals->ptr + (size_t)r * Ro * n_words * 2, (size_t)cnt[r] * n_words * 16,
+                                           cudaMemcpyDeviceToDevice, st), "copy totals");
+                cuda_check(cudaMemcpyAsync((cb::u64*)nkog->ptr + (size_t)r * Rn * key_words, (cb::u64*)hkey_of_gid->ptr + (size_t)r * Ro * key_words,
+                                           (size_t)cnt[r] * 8 * key_words, cudaMemcpyDeviceToDevice, st), "copy group keys");
+            }
+            cuda_check(cudaMemcpyAsync(tp + (size_t)nm * n_words * 2, (cb::u64*)htotals->ptr + (size_t)max_groups * n_words * 2, (size_t)2 * n_words * 16,
+                                       cudaMemcpyDeviceToDevice, st), "copy reserved groups");
+        }
+        cuda_check(cudaStreamSynchronize(st), "table growth"); // old buffers die below
+        htotals = ntot; hkey_of_gid = nkog; max_groups = nm;
+    }
+    static int64_t round_ids(int64_t n) { return (n + GK - 1) / GK * GK; }
+
     // make sure `incoming` more rows (each possibly a new group) fit: dense accumulators by group id, key table at load <= 0.5
     void ensure_table(const std::shared_ptr<CompiledModule>& mod, int64_t incoming) {
         cudaStream_t st = ctx->stream;
-        int flags[8] = {0};
-        if (hflags) {
-            cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "hash flags"); ctx->d2h_bytes += (int64_t)(sizeof(flags));
-            cuda_check(cudaStreamSynchronize(st), "hash flags sync");
-        } else {
-            hflags = std::make_shared<DeviceBuf>(64);
-            cuda_check(cudaMemsetAsync(hflags->ptr, 0, 64, st), "memset hash flags");
-        }
-        const int64_t cur = flags[4];
+        ensure_flags();
+        HashFlags hf;
+        int64_t cnt[GK];
+        const int64_t cur = read_flags(hf, cnt);
         const int64_t need = cur + incoming;
         if (need + 2 >= INT32_MAX) throw ExecError(16, "", "more than 2^31 groups in one partition; lower spark.comet.b200.chunkRows");
+        bool relocated = false;
         if (need > max_groups) {
             int64_t nm = std::max<int64_t>(need, max_groups + max_groups / 4);
             // When the source knows how many rows are still to come, size for them at the distinct ratio seen so far (+30 %) in ONE
@@ -995,40 +1132,29 @@ struct AggNode : FusedBase {
             if (remaining > 0 && rows_scanned == 0 && mode != AggMode::Partial) {
                 // merging state rows (Final / PartialMerge): most keys are new -- size for everything that is still to come at once
                 nm = std::max(nm, need + remaining);
-                if (nm + 2 >= INT32_MAX) nm = INT32_MAX - 3;
             }
             if (remaining > 0 && rows_scanned > 0 && cur > 0) {
                 const double ratio = std::min(1.0, 1.3 * (double)cur / (double)rows_scanned);
                 const int64_t est = cur + incoming + (int64_t)(ratio * (double)remaining);
                 nm = std::max(nm, std::min<int64_t>(est, cur + incoming + remaining));
-                if (nm + 2 >= INT32_MAX) nm = INT32_MAX - 3;
             }
-            auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
-            auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 * key_words + 16);
-            cb::u64* tp = (cb::u64*)ntot->ptr;
-            if (cur > 0) {
-                cuda_check(cudaMemcpyAsync(tp, htotals->ptr, (size_t)cur * n_words * 16, cudaMemcpyDeviceToDevice, st), "copy totals");
-                cuda_check(cudaMemcpyAsync(nkog->ptr, hkey_of_gid->ptr, (size_t)cur * 8 * key_words, cudaMemcpyDeviceToDevice, st), "copy group keys");
-            }
-            init_totals(mod, tp, cur, nm + 2 - cur);
-            if (htotals) // reserved groups move to the new tail
-                cuda_check(cudaMemcpyAsync(tp + (size_t)nm * n_words * 2, (cb::u64*)htotals->ptr + (size_t)max_groups * n_words * 2, (size_t)2 * n_words * 16,
-                                           cudaMemcpyDeviceToDevice, st), "copy reserved groups");
-            cuda_check(cudaStreamSynchronize(st), "table growth"); // old buffers die below
-            htotals = ntot; hkey_of_gid = nkog; max_groups = nm;
+            if (nm + 2 + GK >= INT32_MAX) nm = INT32_MAX - 3 - GK;
+            relocated = cur > 0;
+            grow_rows(mod, cnt, round_ids(nm), true);
         }
         int64_t cap = std::max<int64_t>(hcap, 1 << 16);
         while (cap < 2 * std::max(need, max_groups)) cap <<= 1; // load <= 0.5 even when every reserved group id gets used
-        if (cap != hcap) {
-            auto nkeys = std::make_shared<DeviceBuf>((size_t)cap * 16);
+        if (cap != hcap || relocated) { // a relocation changes the ids: the slots must be rebuilt even at the same capacity
+            auto nkeys = cap != hcap ? std::make_shared<DeviceBuf>((size_t)cap * 16) : hkeys;
             cuda_check(cudaMemsetAsync(nkeys->ptr, 0xff, (size_t)cap * 16, st), "memset key slots");
             if (cur > 0) {
                 const cb::u64* kog = (const cb::u64*)hkey_of_gid->ptr;
-                int ng = (int)cur;
+                int rr = (int)(max_groups / GK);
+                const int* ctr = (const int*)hflags->ptr + CB_HFLAG_CTR;
                 cb::u64* kp = (cb::u64*)nkeys->ptr;
                 cb::u32 mask = (cb::u32)(cap - 1);
-                void* a2[] = {&kog, &ng, &kp, &mask};
-                launch_named(mod, "cb_hash_rehash", dim3((unsigned)((cur + 255) / 256)), dim3(256), a2);
+                void* a2[] = {&kog, &rr, &ctr, &kp, &mask};
+                launch_named(mod, "cb_hash_rehash", dim3((unsigned)((max_groups + 255) / 256)), dim3(256), a2);
                 cuda_check(cudaStreamSynchronize(st), "rehash");
             }
             hkeys = nkeys; hcap = cap;
@@ -1037,34 +1163,16 @@ struct AggNode : FusedBase {
 
     // ---- stream mode: state-row arrays only (no key table).  ids max_groups / max_groups + 1 stay reserved (the NULL-key group is
     //      shared by all its runs and updated with atomics: zero / identity filled) -----------------------------------------------
-    int64_t stream_groups = 0;         // state rows handed out so far (host copy of hflags[4])
+    int64_t stream_groups = 0;         // state rows handed out so far
     DeviceBufP reserved_snap;          // totals of the two reserved groups before a launch (restored when the launch is repeated)
-    void ensure_stream_rows(const std::shared_ptr<CompiledModule>& mod, int64_t cur, int64_t want_groups) {
-        cudaStream_t st = ctx->stream;
-        if (!hflags) {
-            hflags = std::make_shared<DeviceBuf>(64);
-            cuda_check(cudaMemsetAsync(hflags->ptr, 0, 64, st), "memset hash flags");
-        }
-        if (want_groups + 2 >= INT32_MAX) throw ExecError(16, "", "more than 2^31 state rows in one partition; lower spark.comet.b200.chunkRows");
+    void ensure_stream_rows(const std::shared_ptr<CompiledModule>& mod, const int64_t cnt[GK], int64_t want_groups) {
+        ensure_flags();
         if (htotals && want_groups <= max_groups) return;
-        const int64_t nm = std::max<int64_t>(want_groups, max_groups + max_groups / 2);
-        auto ntot = std::make_shared<DeviceBuf>((size_t)(nm + 2) * n_words * 16);
-        auto nkog = std::make_shared<DeviceBuf>((size_t)nm * 8 * key_words + 16);
-        cb::u64* tp = (cb::u64*)ntot->ptr;
-        if (cur > 0) {
-            cuda_check(cudaMemcpyAsync(tp, htotals->ptr, (size_t)cur * n_words * 16, cudaMemcpyDeviceToDevice, st), "copy state rows");
-            cuda_check(cudaMemcpyAsync(nkog->ptr, hkey_of_gid->ptr, (size_t)cur * 8 * key_words, cudaMemcpyDeviceToDevice, st), "copy group keys");
-        }
-        if (htotals)
-            cuda_check(cudaMemcpyAsync(tp + (size_t)nm * n_words * 2, (cb::u64*)htotals->ptr + (size_t)max_groups * n_words * 2, (size_t)2 * n_words * 16,
-                                       cudaMemcpyDeviceToDevice, st), "copy reserved groups");
-        else init_totals(mod, tp, nm, 2);
-        cuda_check(cudaStreamSynchronize(st), "state rows growth"); // old buffers die below
-        htotals = ntot; hkey_of_gid = nkog; max_groups = nm;
+        grow_rows(mod, cnt, round_ids(std::max<int64_t>(want_groups, max_groups + max_groups / 2)), false);
     }
-    // one CB_STREAM launch over rows [r0, r1) of b; returns the flags after it (flags[4] = state rows handed out so far)
-    void stream_launch(Batch& b, int64_t r0, int64_t r1, const PipelineSpec& spec, const GeneratedKernel& g, const std::shared_ptr<CompiledModule>& mod,
-                       int flags[8]) {
+    // one CB_STREAM launch over rows [r0, r1) of b; returns the state rows handed out so far (and the flags / per-range counts after it)
+    int64_t stream_launch(Batch& b, int64_t r0, int64_t r1, const PipelineSpec& spec, const GeneratedKernel& g, const std::shared_ptr<CompiledModule>& mod,
+                          HashFlags& hf, int64_t cnt[GK]) {
         if (!vmask) vmask = std::make_shared<DeviceBuf>(CB_MAX_COLS * 16);
         cuda_check(cudaMemsetAsync(vmask->ptr, 0, CB_MAX_COLS * 16, ctx->stream), "memset vmask");
         cb::PipeParams p;
@@ -1081,20 +1189,17 @@ struct AggNode : FusedBase {
         launch(mod->kernel(g.entry), dim3(grid), dim3(g.threads + 32), g.dyn_smem(0), &p);
         uint64_t masks[CB_MAX_COLS * 2];
         cuda_check(cudaMemcpyAsync(masks, vmask->ptr, sizeof(masks), cudaMemcpyDeviceToHost, ctx->stream), "read value masks"); ctx->d2h_bytes += (int64_t)(sizeof(masks));
-        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "read hash flags"); ctx->d2h_bytes += (int64_t)(8 * sizeof(int));
         ctx->check_device_errors();
-        if (flags[0] & 4) throw Unsupported("decimal(p > 18) group key whose value does not fit 64 bits");
-        if (!(flags[0] & 2))
+        const int64_t total = read_flags(hf, cnt);
+        if (hf.w[0] & 4) throw Unsupported("decimal(p > 18) group key whose value does not fit 64 bits");
+        if (!(hf.w[0] & 2))
             for (size_t i = 0; i < spec.cols.size(); i++) {
                 if (!spec.cols[i].type.is_decimal()) continue;
                 uint64_t lo = masks[2 * i], hi = masks[2 * i + 1];
                 int bl = hi ? 64 + r_bitlen(hi) : r_bitlen(lo);
                 observed_bits[(size_t)used_cols[i]] = std::max(observed_bits[(size_t)used_cols[i]], bl);
             }
-    }
-    void stream_set_flags(int flags[8]) { // host -> device (after a discarded launch)
-        cuda_check(cudaMemcpyAsync(hflags->ptr, flags, 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "write hash flags");
-        cuda_check(cudaStreamSynchronize(ctx->stream), "flags sync");
+        return total;
     }
     void snapshot_reserved(bool restore) {
         const size_t bytes = (size_t)2 * n_words * 16;
@@ -1116,13 +1221,14 @@ struct AggNode : FusedBase {
         auto mod = jit_get(g, true);
         n_words = g.n_words; word_kinds = g.word_kinds; key_words = g.key_words;
         const int64_t sample = std::min<int64_t>(b.n_rows, 1 << 20);
-        ensure_stream_rows(mod, 0, sample + 1024);
-        int flags[8];
-        stream_launch(b, 0, sample, spec, g, mod, flags);
-        stream_ratio = (double)flags[4] / (double)sample;
+        HashFlags hf;
+        int64_t cnt[GK] = {0};
+        ensure_stream_rows(mod, cnt, 2 * sample + 4096); // room for every row being its own run, in whichever ranges the warps draw from
+        const int64_t runs = stream_launch(b, 0, sample, spec, g, mod, hf, cnt);
+        stream_ratio = (hf.w[0] & 2) ? 1.0 : (double)runs / (double)sample;
         // the sample's rows are scanned again with the rest: forget its state rows (and whatever it added to the shared NULL-key group)
-        int zero[8] = {0};
-        stream_set_flags(zero);
+        memset(&hf, 0, sizeof(hf));
+        write_flags(hf);
         init_totals(mod, (cb::u64*)htotals->ptr, max_groups, 2);
         if (stream_ratio > ctx->stream_agg_max_ratio) {
             stream_mode = false;
@@ -1137,28 +1243,28 @@ struct AggNode : FusedBase {
         if (have_totals && (g.n_words != n_words || g.word_kinds != word_kinds || g.key_words != key_words))
             throw ExecError(15, "", "internal: accumulator layout changed between launches");
         n_words = g.n_words; word_kinds = g.word_kinds; key_words = g.key_words;
-        const int64_t cur = stream_groups;
+        HashFlags before, hf;
+        int64_t cnt0[GK], cnt[GK];
+        const int64_t cur = read_flags(before, cnt0);
         // state rows this batch (and, when the source says how much is still to come, the rest) will need at the ratio seen so far
         const int64_t remaining = std::max<int64_t>(child->rows_hint(), 0);
         int64_t want = cur + std::min<int64_t>(b.n_rows, (int64_t)(1.25 * stream_ratio * (double)b.n_rows) + 65536);
         if (!htotals || want > max_groups) want += std::min<int64_t>(remaining, (int64_t)(1.25 * stream_ratio * (double)remaining));
-        int flags[8];
         while (true) {
             {
                 TraceSpan ts("stream.ensure_rows");
-                ensure_stream_rows(mod, cur, want);
+                ensure_stream_rows(mod, cnt0, want);
             }
             snapshot_reserved(false);
-            stream_launch(b, 0, b.n_rows, spec, g, mod, flags);
-            if (!(flags[0] & 2)) break;
-            // more runs than state rows: nothing of this launch is kept (its rows only touched ids >= cur and the shared group)
+            stream_groups = stream_launch(b, 0, b.n_rows, spec, g, mod, hf, cnt);
+            if (!(hf.w[0] & 2)) break;
+            // more runs than state rows: nothing of this launch is kept (its rows only touched ids past the old counts and the shared group)
             snapshot_reserved(true);
-            flags[0] &= ~2; flags[4] = (int)cur;
-            stream_set_flags(flags);
-            want = cur + b.n_rows; // every row its own run
+            for (int r = 0; r < GK; r++) before.w[CB_HFLAG_CTR + r] = (int)cnt0[r];
+            write_flags(before);
+            want = cur + b.n_rows + GK; // every row its own run
         }
         ctx->pipeline_rows += b.n_rows;
-        stream_groups = flags[4];
         if (b.n_rows > 0) stream_ratio = std::max(stream_ratio, (double)(stream_groups - cur) / (double)b.n_rows);
         rows_scanned += b.n_rows;
         have_totals = true;
@@ -1219,10 +1325,10 @@ struct AggNode : FusedBase {
         TraceSpan ts("agg.finalize_hash");
         const GeneratedKernel& g = last_gen;
         cudaStream_t st = ctx->stream;
-        int flags[8];
-        cuda_check(cudaMemcpyAsync(flags, hflags->ptr, sizeof(flags), cudaMemcpyDeviceToHost, st), "read hash flags"); ctx->d2h_bytes += (int64_t)(sizeof(flags));
-        cuda_check(cudaStreamSynchronize(st), "flags sync");
-        const int64_t ng = flags[4];
+        HashFlags hfl;
+        int64_t cnt[GK];
+        const int64_t ng = read_flags(hfl, cnt);
+        const int* flags = hfl.w;
         const int64_t n_out = ng + ((flags[0] & 1) ? 1 : 0) + ((flags[0] & 8) ? 1 : 0);
         cb::FinParams fp;
         memset(&fp, 0, sizeof(fp));
@@ -1232,6 +1338,12 @@ struct AggNode : FusedBase {
         fp.null_group_used = (flags[0] & 8) ? 1 : 0;
         fp.n_hash_groups = (int)ng;
         fp.max_groups = (int)max_groups;
+        fp.gid_range = (int)(max_groups / GK);
+        {
+            int64_t run = 0;
+            for (int r = 0; r < GK; r++) { fp.gid_prefix[r] = (int)run; run += cnt[r]; }
+            fp.gid_prefix[GK] = (int)run;
+        }
         fp.n_groups = (int)n_out;
         fp.err = ctx->d_err;
         fill_certificates(fp);

@@ -35,6 +35,7 @@ struct TraceSpan {
 bool trace_on();
 double now_ms();
 void set_alloc_stream(cudaStream_t s); // stream used by DeviceBuf allocations made on this thread
+size_t release_cached_device_memory();  // frees the library's recycled large blocks on the current device; returns the bytes released
 
 struct DeviceBuf {
     void* ptr = nullptr;

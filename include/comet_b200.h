@@ -176,6 +176,12 @@ typedef struct cb200_stats {
 } cb200_stats;
 int cb200_plan_stats(cb200_plan* plan, cb200_stats* out);
 
+/* The library recycles device blocks >= 1 MiB on a per-device free list instead of returning them to the driver (a query step
+ * allocates the same multi-GB buffers again and again; see csrc/exec.cpp DeviceBuf).  This gives them back, e.g. before another
+ * framework in the same process needs the memory.  Returns the bytes released.  No reference equivalent (the reference's memory
+ * pools are host-side, native/core/src/execution/memory_pools/). */
+int64_t cb200_release_cached_memory(int32_t device_ordinal);
+
 /* Build-time: generate and NVRTC-compile (sm_100a; needs no GPU) every pipeline kernel the plan would
  * use for null-free inputs; cubins land in the JIT cache that ships with the library.  Writes the
  * comma-separated kernel keys to `keys_out`.  Returns the number of kernels, <0 on error. */

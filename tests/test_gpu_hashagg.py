@@ -226,7 +226,7 @@ def test_stream_partial_over_clustered_keys(cb, chunk):
     P = cb.proto
     rng = np.random.default_rng(12)
     n = 600_000
-    k = np.repeat(np.arange(n // 5 + 1, dtype=np.int64) * 3 - 1000, rng.integers(1, 10, n // 5 + 1))[:n]
+    k = np.repeat(np.arange(n // 3, dtype=np.int64) * 3 - 1000, rng.integers(1, 10, n // 3))[:n]      # ~5 adjacent rows per key
     v = rng.integers(-10**6, 10**6, n)
     km, vm = np.zeros(n, dtype=bool), rng.random(n) < 0.1
     km[1000:1040] = True
