@@ -727,7 +727,7 @@ void sig_expr(std::ostringstream& o, const Expr& e) {
 }
 std::string spec_signature(const PipelineSpec& s) {
     std::ostringstream o;
-    o << (int)s.sink << ';' << (int)s.mode << ';' << s.ungrouped << ';' << s.hash << (s.stream ? "s" : "") << ';' << s.tile << ';' << s.stages << ';' << s.threads << ';' << s.ltile << ";C";
+    o << (int)s.sink << ';' << (int)s.mode << ';' << s.ungrouped << ';' << s.hash << (s.stream ? "s" : "") << (s.masked ? "m" : "") << ';' << s.tile << ';' << s.stages << ';' << s.threads << ';' << s.ltile << ";C";
     for (auto& c : s.cols) o << c.src_index << ':' << c.type.str() << ':' << (int)c.phys << ':' << c.has_validity << ':' << c.assume_bits << ',';
     o << ";P";
     for (auto& e : s.predicates) { sig_expr(o, *e); o << ';'; }
@@ -800,7 +800,7 @@ GeneratedKernel generate_pipeline_uncached(const PipelineSpec& spec) {
         if (spec.outputs.size() > 16) throw Unsupported("more than 16 output columns");
         em.body << "    if (!(" << keep << ")) return false;\n";
         std::ostringstream defs;
-        defs << "#define CB_KERNEL_SELECT 1\n#define CB_NOUT " << spec.outputs.size() << "\n";
+        defs << "#define CB_KERNEL_SELECT 1\n#define CB_NOUT " << spec.outputs.size() << "\n#define CB_SEL_MASKED " << (spec.masked ? 1 : 0) << "\n";
         std::vector<Val> outs;
         for (size_t i = 0; i < spec.outputs.size(); i++) {
             Val v = em.emit(*spec.outputs[i]);

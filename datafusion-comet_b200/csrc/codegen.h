@@ -49,6 +49,7 @@ struct PipelineSpec {
     AggMode mode = AggMode::Partial;
     bool ungrouped = false;
     bool hash = false;                    // high-cardinality: global open-addressing table keyed by the packed key columns
+    bool masked = false;                  // Select sink: the keep decision comes from pass 1's bit mask (PipeParams::sel_mask), not from `predicates`
     bool stream = false;                  // hash + Partial over clustered keys: one state row per run of equal adjacent keys, no key table (CB_STREAM)
     // tuning
     int tile = 512, stages = 3, threads = 256;

@@ -824,6 +824,9 @@ extern "C" __global__ void cb_finalize(const __grid_constant__ FinParams fp) {
 #ifdef CB_KERNEL_SELECT
 namespace cb {
 
+#ifndef CB_SEL_MASKED
+#define CB_SEL_MASKED 0
+#endif
 #define CB_BAR_BYTES 256                     // up to 16 stages: narrow pipelines (pass 1 reads 4 bytes per row) need depth to keep enough bytes in flight
 // Pass 1 stages CB_TILE rows at a time but counts per LOGICAL tile of CB_LTILE rows (= pass 2's CB_TILE): its rows are
 // 4 bytes wide, and a 1024-row stage would leave each warp ~170 cycles per tile at HBM speed -- less than one
@@ -883,12 +886,17 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_select_count
 #pragma unroll
         for (int sub = 0; sub < SEL_SUB; sub++) {
             cnt[sub] = 0;
+            u32 mine = 0; // lane q keeps the keep-mask of round q: the SEL_ROUNDS words of (logical tile, warp) leave as one coalesced store
 #pragma unroll
             for (int q = 0; q < SEL_ROUNDS; q++) {
                 const int r = sub * CB_LTILE + wid * SEL_RPW + q * 32 + lane;
                 const bool keep = r < rows ? cb_row_keep(t, r, row0 + r, p) : false;
-                cnt[sub] += __popc(__ballot_sync(0xffffffffu, keep));
+                const u32 bal = __ballot_sync(0xffffffffu, keep);
+                cnt[sub] += __popc(bal);
+                if (lane == q) mine = bal;
             }
+            if (p.sel_mask && lane < SEL_ROUNDS && sub * CB_LTILE + wid * SEL_RPW + lane * 32 < rows)
+                p.sel_mask[((row0 + sub * CB_LTILE + wid * SEL_RPW) >> 5) + lane] = mine;
         }
         __syncwarp();
         if (lane == 0) {
@@ -927,16 +935,31 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_sel
     // issued one tile ahead so their latency (longer than a tile's share of HBM time) overlaps the previous tile.
     // (the two halves stay separate registers until the tile is processed: adding them at load time would wait for them)
     u32 nx_chunk = 0, nx_off = 0;
+#if CB_SEL_MASKED
+    u32 nx_mask[SEL_ROUNDS];
+#pragma unroll
+    for (int q = 0; q < SEL_ROUNDS; q++) nx_mask[q] = 0;
+#endif
     auto load_base = [&](int tile) {
         const size_t e = (size_t)tile * SEL_NW + wid;
         nx_chunk = p.sel_chunk[e / CB_SCAN_CHUNK];
         nx_off = p.sel_off[e];
+#if CB_SEL_MASKED
+        const u32* mw = p.sel_mask + ((((i64)tile * CB_TILE) + wid * SEL_RPW) >> 5); // the warp's rows of this tile: SEL_ROUNDS consecutive words
+#pragma unroll
+        for (int q = 0; q < SEL_ROUNDS; q++) nx_mask[q] = __ldg(mw + q);
+#endif
     };
     const bool filtered = p.sel_off != nullptr;
     if (filtered && my_tiles > 0) load_base(first);
     for (int k = 0; k < my_tiles; k++) {
         const int s = k % CB_STAGES;
         const u32 cur_chunk = nx_chunk, cur_off = nx_off;
+#if CB_SEL_MASKED
+        u32 cur_mask[SEL_ROUNDS];
+#pragma unroll
+        for (int q = 0; q < SEL_ROUNDS; q++) cur_mask[q] = nx_mask[q];
+#endif
         if (filtered && k + 1 < my_tiles) load_base(first + (k + 1) * step);
         mbar_wait(&full[s], (u32)((k / CB_STAGES) & 1));
         Tile t;
@@ -954,8 +977,15 @@ extern "C" __global__ void __launch_bounds__(CB_THREADS + 32, 1) cb_pipeline_sel
         for (int q = 0; q < SEL_ROUNDS; q++) {
             const int r = wid * SEL_RPW + q * 32 + lane;
             SelOut o;
+#if CB_SEL_MASKED
+            // pass 1 already decided: its keep bits are this round's ballot, and only kept rows run the projections
+            const u32 bal = (wid * SEL_RPW + q * 32 < rows) ? cur_mask[q] : 0u; // words past the last row were never written
+            const bool keep = r < rows && ((bal >> lane) & 1u) != 0;
+            if (keep) (void)cb_row_select(t, r, row0 + r, p, o);
+#else
             const bool keep = r < rows ? cb_row_select(t, r, row0 + r, p, o) : false;
             const u32 bal = __ballot_sync(0xffffffffu, keep);
+#endif
             const int rank = __popc(bal & ((1u << lane) - 1u));
             if (keep) {
 #pragma unroll

@@ -26,6 +26,8 @@ struct PipeParams {
     // of the chunk); pass 2 writes the kept rows at sel_chunk[e / CB_SCAN_CHUNK] + sel_off[e].  nullptr = keep all.
     u32* sel_off;
     u32* sel_chunk;
+    u32* sel_mask;                   // select: keep bit of every row (bit r & 31 of word r >> 5), written by pass 1, read by pass 2 when it is
+                                     //         compiled CB_SEL_MASKED (then pass 2 neither stages nor re-evaluates the predicate columns)
     i64* out_count;                  // select: total rows kept
     u8* partials;                    // agg: per-CTA partial slots [grid][n_groups][CB_WORDS] x 16 B
     u64* spill;                      // agg: exact 128-bit escape accumulators [n_groups][CB_WORDS][2]

@@ -624,12 +624,21 @@ struct SelectNode : FusedBase {
     DeviceBufP sel_off, sel_chunk, counters; // reused across batches
     std::vector<int> pred_cols;              // child columns the predicates read (pass 1 stages only these)
     std::map<int, int> pred_slot_of;
+    std::vector<int> out_cols_used;          // child columns the projections read (all a masked pass 2 stages)
+    std::map<int, int> out_slot_of;
+    DeviceBufP sel_mask;                     // keep bit per row, pass 1 -> pass 2
 
     void assign_pred_slots() {
         std::set<int> seen;
         for (auto& e : predicates) collect_bound(e, pred_cols, seen);
         for (size_t i = 0; i < pred_cols.size(); i++) pred_slot_of[pred_cols[i]] = (int)i;
+        std::set<int> seen2;
+        for (auto& e : outputs) collect_bound(e, out_cols_used, seen2);
+        for (size_t i = 0; i < out_cols_used.size(); i++) out_slot_of[out_cols_used[i]] = (int)i;
     }
+    // With predicates, pass 2 takes pass 1's keep bits instead of staging and evaluating the predicate columns a second time
+    // (Config 1: 4 of 27.7 bytes per row).  Needs at least one projected column to stage.
+    bool masked() const { return !predicates.empty() && !out_cols_used.empty(); }
     static int stage_bytes_for(const PipelineSpec& s) {
         int sb = 0;
         for (auto& c : s.cols) {
@@ -645,9 +654,15 @@ struct SelectNode : FusedBase {
     }
     PipelineSpec make_spec(const Batch* b) const {
         PipelineSpec s;
-        s.cols = stage_cols(b);
-        s.predicates = to_slots(predicates, slot_of);
-        s.outputs = to_slots(outputs, slot_of);
+        if (masked()) {
+            s.cols = stage_cols_of(b, out_cols_used);
+            s.outputs = to_slots(outputs, out_slot_of);
+            s.masked = true;
+        } else {
+            s.cols = stage_cols(b);
+            s.predicates = to_slots(predicates, slot_of);
+            s.outputs = to_slots(outputs, slot_of);
+        }
         s.sink = SinkKind::Select;
         s.threads = 256;
         s.tile = 1024;
@@ -687,7 +702,8 @@ struct SelectNode : FusedBase {
         auto mod = jit_get(g, true);
         ctx->last_kernel_key = g.key;
         cb::PipeParams p;
-        fill_inputs(p, in, g.tile);
+        if (masked()) fill_inputs_of(p, in, out_cols_used, g.tile);
+        else fill_inputs(p, in, g.tile);
         out.cols.clear();
         out.cols.resize(g.out_cols.size());
         cudaStream_t st = ctx->stream;
@@ -726,6 +742,12 @@ struct SelectNode : FusedBase {
             if (!sel_chunk || sel_chunk->bytes < (n_chunks + 1) * 4) sel_chunk = std::make_shared<DeviceBuf>((n_chunks + 1) * 4 + n_chunks * 2);
             if (!counters) counters = std::make_shared<DeviceBuf>(64);
             cp.sel_off = (cb::u32*)sel_off->ptr;
+            if (masked()) {
+                const size_t words = (size_t)p.n_tiles * (size_t)g.tile / 32 + 64;
+                if (!sel_mask || sel_mask->bytes < words * 4) sel_mask = std::make_shared<DeviceBuf>(words * 4 + words);
+                cp.sel_mask = (cb::u32*)sel_mask->ptr;
+                p.sel_mask = cp.sel_mask;
+            }
             launch(cmod->kernel(cg.entry), dim3(std::min(ctx->num_sms, cp.n_tiles)), dim3(cg.threads + 32), cg.dyn_smem(0), &cp);
             launch_scan_u32((unsigned*)sel_off->ptr, (long long)m, CB_SCAN_CHUNK, (unsigned*)sel_chunk->ptr, (long long*)counters->ptr, st);
             ctx->kernel_launches += 2;

@@ -127,13 +127,14 @@ def test_case_when_decodes_to_guarded_branches(cb):
 
 
 def test_filter_project_is_two_streaming_passes(cb):
-    """pass 1 stages only the predicate columns and counts per (tile, warp); pass 2 writes at scanned offsets; no look-back."""
+    """pass 1 stages only the predicate columns, counts per (tile, warp) and leaves a keep bit per row; pass 2 writes at scanned offsets; no look-back."""
     plan = cb.tpch.config1_plan("f64")
     keys = cb.native.compile_plan(plan)
     assert len(keys) == 2
     sel, cnt = cb.native.kernel_source(plan, 0), cb.native.kernel_source(plan, 1)
     assert "#define CB_SELECT_COUNT 1" in cnt and "#define CB_NCOLS 1\n" in cnt and "#define CB_LTILE 1024" in cnt   # only l_shipdate is staged
-    assert "#define CB_NCOLS 3\n" in sel and "CB_SELECT_COUNT" not in sel
+    # pass 2 takes pass 1's keep bits: it stages the two projected columns only, never l_shipdate again
+    assert "#define CB_NCOLS 2\n" in sel and "#define CB_SEL_MASKED 1" in sel and "CB_SELECT_COUNT" not in sel
     hdr = open(os.path.join(ROOT, "datafusion-comet_b200", "csrc", "device", "cb_kernels.cuh")).read()
     assert "sel_chunk" in hdr and "tile_state" not in hdr
 

@@ -70,6 +70,6 @@ def test_varint_and_literal_encoding_roundtrip_through_the_decoder():
     sc = P.scan([P.DECIMAL(12, 2), P.INT32])
     pred = P.and_(P.gt(P.bound(0, P.DECIMAL(12, 2)), P.literal(-12345, P.DECIMAL(12, 2))), P.gt(P.bound(1, P.INT32), P.literal(-7, P.INT32)))
     plan = P.projection(P.filter_(sc, pred), [P.bound(1, P.INT32)])
-    src = native.kernel_source(plan)
+    src = native.kernel_source(plan, 1)      # the predicates live in the count pass (kernel 1); pass 2 takes its keep bits
     assert "((cb::i32)-7)" in src
     assert str((-12345) & ((1 << 64) - 1)) + "ull" in src  # sign-extended low limb of the decimal literal
