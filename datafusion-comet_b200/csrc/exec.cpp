@@ -664,7 +664,7 @@ struct SelectNode : FusedBase {
             s.outputs = to_slots(outputs, slot_of);
         }
         s.sink = SinkKind::Select;
-        s.threads = 256;
+        s.threads = 512; // 16 consumer warps: with 8 both passes were issue / latency bound (ncu: 14 % achieved occupancy, pass 1 at 3.5 TB/s)
         s.tile = 1024;
         s.stages = stages_for(s);
         return s;
@@ -675,7 +675,7 @@ struct SelectNode : FusedBase {
         s.cols = stage_cols_of(b, pred_cols);
         s.predicates = to_slots(predicates, pred_slot_of);
         s.sink = SinkKind::Count;
-        s.threads = 256;
+        s.threads = 512;
         s.ltile = 1024;
         for (int tile : {4096, 2048, 1024}) { // the widest stage that still leaves a 3-deep ring (wide predicate columns: decimals)
             s.tile = tile;
