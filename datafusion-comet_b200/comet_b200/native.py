@@ -265,6 +265,19 @@ class Comm:
             pass
 
 
+def snappy_decompress(comp, uncompressed_len, device=0):
+    """One raw Snappy buffer through the scan's device decompressor.  Returns (bytes, path): path 0 = segmented, 1 = serial fallback."""
+    f = lib().cb200_snappy_decompress
+    f.restype = C.c_int64
+    f.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_Error)]
+    out = C.create_string_buffer(max(uncompressed_len, 1))
+    path, err = C.c_int32(-1), _Error()
+    n = f(bytes(comp), len(comp), out, uncompressed_len, device, C.byref(path), C.byref(err))
+    if n < 0:
+        _raise(err)
+    return out.raw[:uncompressed_len], path.value
+
+
 def nccl_info():
     f = lib().cb200_nccl_info
     f.restype = C.c_char_p

@@ -2,6 +2,7 @@
 #include "../../include/comet_b200.h"
 
 #include "abi_internal.h"
+#include "parquet_kernels.h"
 #include "exec.h"
 #include "jit.h"
 #include "plan.h"
@@ -360,6 +361,40 @@ int cb200_register_memory_file(const char* name, const void* data, size_t len) {
     if (!name) return -1;
     register_memory_file(name, (const uint8_t*)data, len);
     return 0;
+}
+
+int64_t cb200_snappy_decompress(const uint8_t* comp, size_t comp_len, uint8_t* out, size_t uncompressed_len, int32_t device_ordinal, int32_t* path_taken,
+                                cb200_error* err) {
+    return cb200_guarded(err, [&]() -> int64_t {
+        if (!comp || (!out && uncompressed_len) || comp_len >= ((size_t)1 << 31) || uncompressed_len >= ((size_t)1 << 31)) throw PlanError("cb200_snappy_decompress: bad arguments");
+        cuda_check(cudaSetDevice(device_ordinal), "cudaSetDevice");
+        cudaStream_t st = nullptr; // legacy default stream: a diagnostic entry point, not a hot path
+        set_alloc_stream(st);
+        DeviceBuf dcomp(comp_len + 64), dout(uncompressed_len + 64), dpage(sizeof(PqPage)), derr(64);
+        const int n_segs = (int)((uncompressed_len + PQ_SNAPPY_SEG - 1) / PQ_SNAPPY_SEG);
+        DeviceBuf dck((size_t)(n_segs + 1) * 4);
+        PqPage pg;
+        memset(&pg, 0, sizeof(pg));
+        pg.body = (unsigned char*)dout.ptr;
+        pg.body_bytes = (int)uncompressed_len;
+        pg.comp = (const unsigned char*)dcomp.ptr;
+        pg.comp_bytes = (int)comp_len;
+        pg.seg_base = 0;
+        pg.n_segs = n_segs;
+        cuda_check(cudaMemsetAsync(dcomp.ptr, 0, comp_len + 64, st), "memset");
+        cuda_check(cudaMemcpyAsync(dcomp.ptr, comp, comp_len, cudaMemcpyHostToDevice, st), "copy in");
+        cuda_check(cudaMemcpyAsync(dpage.ptr, &pg, sizeof(pg), cudaMemcpyHostToDevice, st), "copy page");
+        cuda_check(cudaMemsetAsync(derr.ptr, 0, 64, st), "memset err");
+        launch_pq_snappy_segmented((PqPage*)dpage.ptr, 1, (unsigned*)dck.ptr, n_segs, (int*)derr.ptr, st);
+        int e = 0;
+        cuda_check(cudaMemcpyAsync(&e, derr.ptr, 4, cudaMemcpyDeviceToHost, st), "read err");
+        cuda_check(cudaMemcpyAsync(&pg, dpage.ptr, sizeof(pg), cudaMemcpyDeviceToHost, st), "read page");
+        if (uncompressed_len) cuda_check(cudaMemcpyAsync(out, dout.ptr, uncompressed_len, cudaMemcpyDeviceToHost, st), "copy out");
+        cuda_check(cudaStreamSynchronize(st), "sync");
+        if (path_taken) *path_taken = (pg.flags & PQ_PAGE_SN_SERIAL) ? 1 : 0;
+        if (e) throw ExecError(14, "", "malformed Snappy stream (device error flags " + std::to_string(e) + ")");
+        return (int64_t)uncompressed_len;
+    }, (int64_t)-1);
 }
 
 int cb200_parquet_describe(const char* path, char* out, size_t cap, cb200_error* err) {

@@ -57,13 +57,14 @@ constexpr int SN_RING = 16384, SN_WIN = 512, SN_WARPS = 4;
 // A lone warp issues one dependent instruction every ~4.5 cycles, so the cost of a page is (elements x instructions
 // per element): positions are 32-bit offsets (a page is < 2 GiB), the common shapes -- a literal or a copy of at
 // most 32 bytes -- take one predicated step without a loop, and validation is a handful of compares.
-__global__ void __launch_bounds__(SN_WARPS * 32) k_pq_snappy(PqPage* pages, int n_pages, int* err) {
+__global__ void __launch_bounds__(SN_WARPS * 32) k_pq_snappy(PqPage* pages, int n_pages, int* err, int only_flagged) {
     extern __shared__ __align__(16) u8 sn_smem[];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = blockIdx.x * SN_WARPS + wib;
     if (warp >= n_pages) return; // warps are independent: no block-wide barrier below
     const PqPage pg = pages[warp];
     if (!pg.comp) return;
+    if (only_flagged && (pg.flags & (PQ_PAGE_SN_SERIAL | PQ_PAGE_SN_BAD)) != PQ_PAGE_SN_SERIAL) return; // the segmented decoder did (or rejected) this page
     u8* ring = sn_smem + wib * (SN_RING + SN_WIN);
     u8* win = ring + SN_RING;
     const u8* in = pg.comp;
@@ -159,11 +160,217 @@ __global__ void __launch_bounds__(SN_WARPS * 32) k_pq_snappy(PqPage* pages, int 
     }
     if ((bad || o != ulen) && lane == 0) atomicOr(err, 8);
 }
+// ---- Snappy, segmented ------------------------------------------------------------------------------------------------------------
+// One warp per page leaves most of the GPU idle (a batch has a few hundred pages) and a page of small elements -- PLAIN INT64
+// decimals compress to a literal + copy pair per value -- took ~80 ms.  The stock compressor works on independent 64 KB fragments
+// of the input: no element straddles, and no back-reference crosses, a 64 KB boundary of the OUTPUT.  So:
+//   k_pq_snappy_index  (warp per page)     walks the element chain WITHOUT moving bytes -- every lane parses the element that would
+//                      start at its byte of a 32-byte window, the chain is followed through the lanes' answers with one shuffle pair
+//                      per element -- and records the input position of every 64 KB output boundary (checkpoint table);
+//   k_pq_snappy_seg    (warp per segment)  decodes [checkpoint s, checkpoint s + 1) exactly like the serial kernel: 16 x more warps
+//                      per 1 MB page;
+//   k_pq_snappy        (only_flagged)      pages that do not have that shape (an element across a boundary, a reference into an
+//                      earlier segment: legal Snappy, never produced by the stock compressor) are redone serially.
+constexpr int SX_WARPS = 8, SX_WIN = 1024, SX_RING = 8192;
+
+// element starting at w[0] (w points into a window with >= 5 readable bytes): bytes to the next element / bytes produced; adv == 0: malformed
+__device__ __forceinline__ void sn_elem_len(const u8* w, u32& adv, u32& out) {
+    const u32 tag = w[0], t = tag & 3u;
+    if (t == 0) {
+        u32 len = tag >> 2, hdr = 1;
+        if (len >= 60) {
+            const u32 extra = len - 59;
+            const u32 raw = (u32)w[1] | ((u32)w[2] << 8) | ((u32)w[3] << 16) | ((u32)w[4] << 24);
+            len = extra == 4 ? raw : raw & ((1u << (8 * extra)) - 1u);
+            hdr += extra;
+        }
+        if (len >= (1u << 30)) { adv = 0; out = 0; return; }
+        out = len + 1;
+        adv = hdr + out;
+    } else if (t == 1) { adv = 2; out = ((tag >> 2) & 7u) + 4; }
+    else { adv = t == 2 ? 3 : 5; out = (tag >> 2) + 1; }
+}
+
+__global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_index(PqPage* pages, int n_pages, u32* ckpt, int* err) {
+    __shared__ __align__(16) u8 sx_win[SX_WARPS][SX_WIN + 16];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * SX_WARPS + wib;
+    if (warp >= n_pages) return;
+    const PqPage pg = pages[warp];
+    if (!pg.comp) return;
+    u8* win = sx_win[wib];
+    const u8* in = pg.comp;
+    const u32 n = (u32)pg.comp_bytes;
+    u64 ulen64 = 0;
+    long long pre = 0;
+    if (lane == 0) pre = snappy_preamble(in, n, ulen64);
+    pre = __shfl_sync(0xffffffffu, pre, 0);
+    ulen64 = __shfl_sync(0xffffffffu, ulen64, 0);
+    if (pre < 0 || ulen64 != (u64)pg.body_bytes) { if (lane == 0) { atomicOr(err, 8); atomicOr(&pages[warp].flags, PQ_PAGE_SN_BAD); } return; }
+    u32* ck = ckpt + pg.seg_base;
+    const u32 misalign = (u32)((size_t)in & 15);
+    u32 pos = (u32)pre, o = 0, bnd = 0;
+    int k = 0;           // next checkpoint to record (output offset bnd = k * PQ_SNAPPY_SEG)
+    int wbase = -SX_WIN - 16;
+    int status = 0;      // 1: irregular (serial decoder), 2: malformed
+    while (pos < n && status == 0) {
+        // the window must hold the 32 candidate tags at pos .. pos + 31 and 4 bytes after each
+        if (pos - (u32)wbase + 36 > (u32)SX_WIN || (int)pos < wbase) {
+            wbase = (int)((pos + misalign) & ~15u) - (int)misalign;
+            __syncwarp();
+            for (int j = lane; j < SX_WIN / 16; j += 32) {
+                const int lo = wbase + j * 16;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (lo < (int)n) v = *(const uint4*)(in + lo); // < 16 bytes outside the page: inside the padded chunk buffer
+                ((uint4*)win)[j] = v;
+            }
+            __syncwarp();
+        }
+        u32 adv, out;
+        sn_elem_len(win + (pos - (u32)wbase) + lane, adv, out);
+        if (pos + lane >= n) { adv = 0; out = 0; }
+        u32 cur = 0;
+        while (cur < 32u && pos + cur < n) {
+            const u32 a = __shfl_sync(0xffffffffu, adv, cur), ou = __shfl_sync(0xffffffffu, out, cur);
+            if (o == bnd) { if (lane == 0 && k < pg.n_segs) ck[k] = pos + cur; k++; bnd += (u32)PQ_SNAPPY_SEG; }
+            else if (o > bnd) { status = 1; break; }             // an element straddles a 64 KB output boundary
+            if (a == 0 || a > n - (pos + cur) || ou > (u32)pg.body_bytes - o) { status = 2; break; }
+            o += ou;
+            cur += a;
+        }
+        pos += cur;
+    }
+    if (status == 0 && (o != (u32)pg.body_bytes || k != pg.n_segs)) status = (o == (u32)pg.body_bytes && k < pg.n_segs) ? 1 : 2;
+    if (lane == 0) {
+        if (status == 2) { atomicOr(err, 8); atomicOr(&pages[warp].flags, PQ_PAGE_SN_BAD); }
+        else if (status == 1) atomicOr(&pages[warp].flags, PQ_PAGE_SN_SERIAL);
+    }
+}
+
+__global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, int n_pages, const u32* ckpt, int n_segs_total, int* err) {
+    extern __shared__ __align__(16) u8 sn_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg_global = blockIdx.x * SX_WARPS + wib;
+    if (seg_global >= n_segs_total) return;
+    // which page: the last one whose seg_base <= seg_global (pages without segments repeat their successor's base)
+    int lo = 0, hi = n_pages - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pages[mid].seg_base <= seg_global) lo = mid; else hi = mid - 1; }
+    const PqPage pg = pages[lo];
+    const int sidx = seg_global - pg.seg_base;
+    if (!pg.comp || sidx >= pg.n_segs || (pg.flags & (PQ_PAGE_SN_SERIAL | PQ_PAGE_SN_BAD))) return;
+    u8* ring = sn_smem + wib * (SX_RING + SN_WIN);
+    u8* win = ring + SX_RING;
+    const u8* in = pg.comp;
+    const u32 n = sidx + 1 < pg.n_segs ? ckpt[pg.seg_base + sidx + 1] : (u32)pg.comp_bytes; // end of this segment's input
+    const u32 o0 = (u32)sidx * (u32)PQ_SNAPPY_SEG;
+    const u32 oend = min((u32)pg.body_bytes, o0 + (u32)PQ_SNAPPY_SEG);
+    u8* out = pg.body;
+    const u32 misalign = (u32)((size_t)in & 15);
+    u32 pos = ckpt[pg.seg_base + sidx], o = o0;
+    int wbase = -SN_WIN - 16;
+    int status = 0;
+    while (pos < n) {
+        u32 wp = pos - (u32)wbase;
+        if (wp + 5 > (u32)SN_WIN) {
+            wbase = (int)((pos + misalign) & ~15u) - (int)misalign;
+            const int l0 = wbase + lane * 16;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (l0 < (int)pg.comp_bytes) v = *(const uint4*)(in + l0);
+            __syncwarp();
+            ((uint4*)win)[lane] = v;
+            __syncwarp();
+            wp = pos - (u32)wbase;
+        }
+        u32 w0 = 0xffffffffu, w1 = 0;
+        if (lane == 0) {
+            const u8* p = win + wp;
+            const u32 tag = p[0], t = tag & 3u;
+            u32 len, src = 0, hdr;
+            if (t == 0) {
+                hdr = 1; len = tag >> 2;
+                if (len >= 60) {
+                    const u32 extra = len - 59;
+                    const u32 raw = (u32)p[1] | ((u32)p[2] << 8) | ((u32)p[3] << 16) | ((u32)p[4] << 24);
+                    len = extra == 4 ? raw : raw & ((1u << (8 * extra)) - 1u);
+                    hdr += extra;
+                }
+                len += 1;
+                if (len < (1u << 27) && len <= oend - o && hdr + len <= n - pos) w0 = len | (hdr << 27);
+            } else {
+                if (t == 1) { hdr = 2; len = ((tag >> 2) & 7u) + 4; src = ((tag >> 5) << 8) | p[1]; }
+                else if (t == 2) { hdr = 3; len = (tag >> 2) + 1; src = (u32)p[1] | ((u32)p[2] << 8); }
+                else { hdr = 5; len = (tag >> 2) + 1; src = (u32)p[1] | ((u32)p[2] << 8) | ((u32)p[3] << 16) | ((u32)p[4] << 24); }
+                if (src - 1u < o - o0 && len <= oend - o && hdr <= n - pos) { w0 = len | (hdr << 27) | (1u << 30); w1 = src; }
+                else if (src - 1u < o && len <= oend - o && hdr <= n - pos) w0 = 0xfffffffeu; // reaches into an earlier segment: legal, but not ours to race on
+            }
+        }
+        w0 = __shfl_sync(0xffffffffu, w0, 0);
+        if (w0 >= 0xfffffffeu) { status = w0 == 0xfffffffeu ? 1 : 2; break; }
+        const u32 len = w0 & ((1u << 27) - 1), hdr = (w0 >> 27) & 7u;
+        if (!(w0 & (1u << 30))) {
+            if (wp + hdr + len <= (u32)SN_WIN) {
+                for (u32 i = lane; i < len; i += 32) {
+                    const u8 b = win[wp + hdr + i];
+                    out[o + i] = b;
+                    ring[(o + i) & (SX_RING - 1)] = b;
+                }
+            } else {
+                const u8* s = in + pos + hdr;
+                for (u32 i = lane; i < len; i += 32) {
+                    const u8 b = s[i];
+                    out[o + i] = b;
+                    ring[(o + i) & (SX_RING - 1)] = b;
+                }
+            }
+            pos += hdr + len;
+        } else {
+            const u32 d = __shfl_sync(0xffffffffu, w1, 0);
+            const bool near = d + 64 <= (u32)SX_RING;
+            if (d >= len) {
+                for (u32 i = lane; i < len; i += 32) {
+                    const u32 sp = o - d + i;
+                    const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
+                    out[o + i] = b;
+                    ring[(o + i) & (SX_RING - 1)] = b;
+                }
+            } else {
+                for (u32 i = lane; i < len; i += 32) {
+                    const u32 sp = o - d + i % d;
+                    const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
+                    out[o + i] = b;
+                    ring[(o + i) & (SX_RING - 1)] = b;
+                }
+            }
+            pos += hdr;
+        }
+        __syncwarp();
+        o += len;
+    }
+    if (status == 0 && o != oend) status = 2;
+    if (lane == 0) {
+        if (status == 2) { atomicOr(err, 8); atomicOr(&pages[lo].flags, PQ_PAGE_SN_BAD); }
+        else if (status == 1) atomicOr(&pages[lo].flags, PQ_PAGE_SN_SERIAL);
+    }
+}
+
+void launch_pq_snappy_segmented(PqPage* pages, int n_pages, unsigned* ckpt, int n_segs_total, int* err, cudaStream_t st) {
+    if (n_pages <= 0) return;
+    k_pq_snappy_index<<<(n_pages + SX_WARPS - 1) / SX_WARPS, SX_WARPS * 32, 0, st>>>(pages, n_pages, ckpt, err);
+    if (n_segs_total > 0) {
+        const int smem = SX_WARPS * (SX_RING + SN_WIN);
+        cudaFuncSetAttribute(k_pq_snappy_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_pq_snappy_seg<<<(n_segs_total + SX_WARPS - 1) / SX_WARPS, SX_WARPS * 32, smem, st>>>(pages, n_pages, ckpt, n_segs_total, err);
+    }
+    const int smem1 = SN_WARPS * (SN_RING + SN_WIN);
+    cudaFuncSetAttribute(k_pq_snappy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    k_pq_snappy<<<(n_pages + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem1, st>>>(pages, n_pages, err, 1); // irregular pages only
+}
+
 void launch_pq_snappy(PqPage* pages, int n_pages, int* err, cudaStream_t st) {
     if (n_pages <= 0) return;
     const int smem = SN_WARPS * (SN_RING + SN_WIN);
     cudaFuncSetAttribute(k_pq_snappy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); // per device, idempotent
-    k_pq_snappy<<<(n_pages + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem, st>>>(pages, n_pages, err);
+    k_pq_snappy<<<(n_pages + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem, st>>>(pages, n_pages, err, 0);
 }
 
 // ---- locate levels / values inside the page body ------------------------------------------------------------------------

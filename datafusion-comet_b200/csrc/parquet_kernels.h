@@ -6,7 +6,7 @@
 
 namespace cb200 {
 
-enum { PQ_PAGE_V1_LEVELS = 1 }; // body starts with [u32 byte length][RLE definition levels] (DataPage v1 of an optional column)
+enum { PQ_PAGE_V1_LEVELS = 1, PQ_PAGE_SN_SERIAL = 2, PQ_PAGE_SN_BAD = 4 }; // SN_*: set by the Snappy index / segment kernels (page needs the serial decoder / is malformed); // body starts with [u32 byte length][RLE definition levels] (DataPage v1 of an optional column)
 
 // One page of a column chunk resident on the device.  The host fills what the page HEADER tells it; everything
 // that lives inside the (possibly compressed) page body is resolved on the device by k_pq_resolve.
@@ -30,6 +30,8 @@ struct PqPage {
     int def_max_runs;
     long long dict_off;           // element offset of this page's dictionary inside the column's combined dictionary buffer
     int dict_size;
+    int seg_base;                 // Snappy pages: first entry of this page in the column's checkpoint table (one entry per 64 KB of output)
+    int n_segs;
 };
 
 struct PqRun {              // one run of the RLE / bit-packed hybrid
@@ -49,6 +51,9 @@ enum PqConv { PQ_COPY32, PQ_COPY64, PQ_I32_TO_I64, PQ_FLBA_TO_I64, PQ_FLBA_TO_I1
 void launch_pq_copy(void* dst, const void* src, size_t bytes, cudaStream_t st);
 // Snappy: one warp per compressed page (pages with comp == nullptr are skipped)
 void launch_pq_snappy(PqPage* pages_dev, int n_pages, int* err, cudaStream_t st);
+// segmented decoder: `ckpt` has room for n_segs_total entries (sum of PqPage::n_segs, n_segs = ceil(body_bytes / PQ_SNAPPY_SEG))
+constexpr int PQ_SNAPPY_SEG = 65536;
+void launch_pq_snappy_segmented(PqPage* pages_dev, int n_pages, unsigned* ckpt_dev, int n_segs_total, int* err, cudaStream_t st);
 // locate levels / values inside every page body; nonnull = num_values
 void launch_pq_resolve(PqPage* pages_dev, int n_pages, cudaStream_t st);
 // PLAIN fixed-width pages -> out[dst_row + k] for the page's k-th encoded value (element width given by the conversion)

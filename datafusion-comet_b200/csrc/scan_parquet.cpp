@@ -313,10 +313,11 @@ struct NativeScanSource : ExecNode {
         std::vector<int32_t> remap;  // string columns: combined code remap tables
         int64_t run_base = 0, def_run_base = 0, dict_elems = 0;
         size_t unc_bytes = 0;
+        int64_t n_segs_total = 0;    // Snappy: 64 KB output segments over all compressed pages (checkpoint table entries)
         bool optional = false, null_aware = false, any_compressed = false;
         // device buffers (offsets into the slot's work block while planning, pointers after bind)
         uint8_t *out = nullptr, *dunc = nullptr, *dpd = nullptr, *ddict = nullptr, *dense = nullptr, *dvalid = nullptr, *didx = nullptr, *druns = nullptr,
-                *dcounts = nullptr, *validity = nullptr, *runs = nullptr, *counts = nullptr;
+                *dcounts = nullptr, *validity = nullptr, *runs = nullptr, *counts = nullptr, *dckpt = nullptr;
         size_t out_bytes = 0, validity_bytes = 0;
     };
 
@@ -710,6 +711,7 @@ struct NativeScanSource : ExecNode {
                 d.comp_bytes = comp_bytes;
                 d.body = (unsigned char*)(uintptr_t)cp.unc_bytes; // offset for now
                 d.body_bytes = unc;
+                d.n_segs = (unc + PQ_SNAPPY_SEG - 1) / PQ_SNAPPY_SEG; // checkpoint entries of the segmented Snappy decoder
                 cp.unc_bytes += ((size_t)unc + 31) / 16 * 16;     // 16-byte aligned, >= 8 spare bytes for the unaligned-word loads
                 cp.any_compressed = true;
             } else {
@@ -717,6 +719,7 @@ struct NativeScanSource : ExecNode {
                 d.comp_bytes = 0;
                 d.body = (unsigned char*)src;
                 d.body_bytes = comp_bytes;
+                d.n_segs = 0;
             }
         };
         for (size_t u = 0; u < units.size(); u++) {
@@ -832,7 +835,12 @@ struct NativeScanSource : ExecNode {
         cp.out_bytes = n * (size_t)cp.out_w;
         reqs.push_back({&cp.out, cp.out_bytes});
         if (cp.pages.empty()) return;
-        if (cp.any_compressed) reqs.push_back({&cp.dunc, cp.unc_bytes + 64});
+        if (cp.any_compressed) {
+            reqs.push_back({&cp.dunc, cp.unc_bytes + 64});
+            cp.n_segs_total = 0;
+            for (auto& d : cp.pages) { d.seg_base = (int)cp.n_segs_total; cp.n_segs_total += d.comp ? d.n_segs : 0; if (!d.comp) d.n_segs = 0; }
+            reqs.push_back({&cp.dckpt, (size_t)(cp.n_segs_total + 1) * 4});
+        }
         if (cp.dict_elems > 0 && cp.remap.empty()) reqs.push_back({&cp.ddict, (size_t)cp.dict_elems * (size_t)cp.out_w + 16}); // string dictionaries: the remap table in the mirror IS the dictionary
         if (cp.null_aware) {
             reqs.push_back({&cp.dense, n * (size_t)cp.out_w});
@@ -880,7 +888,7 @@ struct NativeScanSource : ExecNode {
         PqPage* data_pages = all_pages;
         const PqPage* dict_pages_dev = data_pages + n_data;
         uint8_t* dense = cp.null_aware ? cp.dense : cp.out;
-        if (cp.any_compressed) { launch_pq_snappy(all_pages, n_all, derr, ds); ctx->kernel_launches++; }
+        if (cp.any_compressed) { launch_pq_snappy_segmented(all_pages, n_all, (unsigned*)cp.dckpt, (int)cp.n_segs_total, derr, ds); ctx->kernel_launches += 3; }
         launch_pq_resolve(all_pages, n_all, ds);
         ctx->kernel_launches++;
         if (cp.n_dict_pages) { launch_pq_plain(dict_pages_dev, (int)cp.n_dict_pages, cp.conv, cp.type_length, cp.ddict, derr, ds); ctx->kernel_launches++; }

@@ -160,6 +160,13 @@ int64_t cb200_plan_kernel_launches(cb200_plan* plan);
  * executor has after fetching an object-store range.  Encoded pages are copied H2D as they are and decoded on
  * the device.  `data` = NULL unregisters. */
 int cb200_register_memory_file(const char* name, const void* data, size_t len);
+/* One raw Snappy buffer through the scan's device decompressor (index pass + 64 KB segments + serial fallback, csrc/parquet_kernels.cu),
+ * host in / host out.  Returns the bytes produced (= `uncompressed_len`) or -1.  `path_taken` (may be NULL): 0 segmented, 1 the page
+ * went to the serial kernel.  For tests and diagnostics: lets hand-made streams (elements across a 64 KB boundary, references into an
+ * earlier segment, malformed input) reach kernels that Parquet writers never exercise.  Reference: the `snap` crate behind the
+ * third-party parquet reader (native/core/Cargo.toml:40). */
+int64_t cb200_snappy_decompress(const uint8_t* comp, size_t comp_len, uint8_t* out, size_t uncompressed_len, int32_t device_ordinal, int32_t* path_taken,
+                                cb200_error* err);
 /* JSON description of a Parquet file's footer as this library parsed it (tests compare it with pyarrow). */
 int cb200_parquet_describe(const char* path, char* out, size_t cap, cb200_error* err);
 
