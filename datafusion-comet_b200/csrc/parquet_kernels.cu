@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(SN_WARPS * 32) k_pq_snappy(PqPage* pages, int 
 //                      per 1 MB page;
 //   k_pq_snappy        (only_flagged)      pages that do not have that shape (an element across a boundary, a reference into an
 //                      earlier segment: legal Snappy, never produced by the stock compressor) are redone serially.
-constexpr int SX_WARPS = 8, SX_WIN = 1024, SX_RING = 8192;
+constexpr int SX_WARPS = 8, SX_RING = 8192;
 
 // element starting at w[0] (w points into a window with >= 5 readable bytes): bytes to the next element / bytes produced; adv == 0: malformed
 __device__ __forceinline__ void sn_elem_len(const u8* w, u32& adv, u32& out) {
@@ -191,14 +191,26 @@ __device__ __forceinline__ void sn_elem_len(const u8* w, u32& adv, u32& out) {
     else { adv = t == 2 ? 3 : 5; out = (tag >> 2) + 1; }
 }
 
-__global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_index(PqPage* pages, int n_pages, u32* ckpt, int* err) {
-    __shared__ __align__(16) u8 sx_win[SX_WARPS][SX_WIN + 16];
+// Index pass.  A warp looks at SXI_W input bytes at a time.  Every byte position is treated as if an element started there
+// (lane l owns positions l, l + 32, ...): nxt = where the following element would start, sum = output bytes it produces.  Pointer
+// jumping (each round: sum += sum[nxt], nxt = nxt[nxt], all positions at once through shared memory) then gives, for EVERY
+// position, where its chain leaves the window and how many bytes it produced on the way -- only position 0's answer is the true one,
+// but computing them all is what makes it parallel: ~10 rounds per window instead of one dependent shuffle pair per element (a
+// page of 4-byte elements took 25 ms that way).  Only a window that contains a 64 KB output boundary is walked element by element.
+constexpr int SXI_WARPS = 4, SXI_W = 1024, SXI_PER_LANE = SXI_W / 32;
+constexpr u32 SXI_INVALID = 0xffffffffu;
+
+__global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* pages, int n_pages, u32* ckpt, int* err) {
+    extern __shared__ __align__(16) u8 sxi_smem[];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * SX_WARPS + wib;
+    const int warp = blockIdx.x * SXI_WARPS + wib;
     if (warp >= n_pages) return;
     const PqPage pg = pages[warp];
     if (!pg.comp) return;
-    u8* win = sx_win[wib];
+    u8* base = sxi_smem + (size_t)wib * (SXI_W + 32 + SXI_W * 8);
+    u8* win = base;                                              // SXI_W + 32 input bytes
+    u32* s_nxt = reinterpret_cast<u32*>(base + SXI_W + 32);      // [SXI_W]
+    u32* s_sum = s_nxt + SXI_W;                                  // [SXI_W]
     const u8* in = pg.comp;
     const u32 n = (u32)pg.comp_bytes;
     u64 ulen64 = 0;
@@ -209,38 +221,73 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_index(PqPage* pages
     if (pre < 0 || ulen64 != (u64)pg.body_bytes) { if (lane == 0) { atomicOr(err, 8); atomicOr(&pages[warp].flags, PQ_PAGE_SN_BAD); } return; }
     u32* ck = ckpt + pg.seg_base;
     const u32 misalign = (u32)((size_t)in & 15);
+    const u32 body = (u32)pg.body_bytes;
     u32 pos = (u32)pre, o = 0, bnd = 0;
     int k = 0;           // next checkpoint to record (output offset bnd = k * PQ_SNAPPY_SEG)
-    int wbase = -SX_WIN - 16;
     int status = 0;      // 1: irregular (serial decoder), 2: malformed
     while (pos < n && status == 0) {
-        // the window must hold the 32 candidate tags at pos .. pos + 31 and 4 bytes after each
-        if (pos - (u32)wbase + 36 > (u32)SX_WIN || (int)pos < wbase) {
-            wbase = (int)((pos + misalign) & ~15u) - (int)misalign;
+        if (o == bnd) { if (lane == 0 && k < pg.n_segs) ck[k] = pos; k++; bnd += (u32)PQ_SNAPPY_SEG; }
+        else if (o > bnd) { status = 1; break; }                 // an element straddles a 64 KB output boundary
+        // ---- window: input bytes [pos, pos + SXI_W + 4), 16-byte aligned loads ----
+        const int wbase = (int)((pos + misalign) & ~15u) - (int)misalign; // <= pos, pos - wbase < 16
+        __syncwarp();
+        for (int j = lane; j < (SXI_W + 32) / 16; j += 32) {
+            const int lo = wbase + j * 16;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (lo < (int)n) v = *(const uint4*)(in + lo);       // < 16 bytes outside the page: inside the padded chunk buffer
+            ((uint4*)win)[j] = v;
+        }
+        __syncwarp();
+        const u32 woff = pos - (u32)wbase;                       // window byte of position 0
+        const u32 L = min((u32)SXI_W - 16u, n - pos);            // positions examined (the loads above cover L + 4 bytes from any woff < 16)
+        // ---- every position's own element ----
+        u32 nx[SXI_PER_LANE], sm[SXI_PER_LANE];
+#pragma unroll
+        for (int j = 0; j < SXI_PER_LANE; j++) {
+            const u32 i = (u32)j * 32u + (u32)lane;
+            u32 adv = 0, out = 0;
+            if (i < L) sn_elem_len(win + woff + i, adv, out);
+            const bool ok = i < L && adv != 0 && adv <= n - (pos + i);
+            nx[j] = ok ? i + adv : SXI_INVALID;
+            sm[j] = ok ? out : 0u;
+        }
+        // ---- pointer jumping ----
+        for (int round = 0; round < 11; round++) {
+#pragma unroll
+            for (int j = 0; j < SXI_PER_LANE; j++) { s_nxt[j * 32 + lane] = nx[j]; s_sum[j * 32 + lane] = sm[j]; }
             __syncwarp();
-            for (int j = lane; j < SX_WIN / 16; j += 32) {
-                const int lo = wbase + j * 16;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (lo < (int)n) v = *(const uint4*)(in + lo); // < 16 bytes outside the page: inside the padded chunk buffer
-                ((uint4*)win)[j] = v;
+            bool changed = false;
+#pragma unroll
+            for (int j = 0; j < SXI_PER_LANE; j++) {
+                const u32 t = nx[j];
+                if (t < L) { sm[j] += s_sum[t]; nx[j] = s_nxt[t]; changed = true; }
             }
+            const bool any = __any_sync(0xffffffffu, changed);
             __syncwarp();
+            if (!any) break;
         }
-        u32 adv, out;
-        sn_elem_len(win + (pos - (u32)wbase) + lane, adv, out);
-        if (pos + lane >= n) { adv = 0; out = 0; }
-        u32 cur = 0;
-        while (cur < 32u && pos + cur < n) {
-            const u32 a = __shfl_sync(0xffffffffu, adv, cur), ou = __shfl_sync(0xffffffffu, out, cur);
-            if (o == bnd) { if (lane == 0 && k < pg.n_segs) ck[k] = pos + cur; k++; bnd += (u32)PQ_SNAPPY_SEG; }
-            else if (o > bnd) { status = 1; break; }             // an element straddles a 64 KB output boundary
-            if (a == 0 || a > n - (pos + cur) || ou > (u32)pg.body_bytes - o) { status = 2; break; }
-            o += ou;
-            cur += a;
+        // position 0 is owned by lane 0, register slot 0
+        const u32 E = __shfl_sync(0xffffffffu, nx[0], 0), S = __shfl_sync(0xffffffffu, sm[0], 0);
+        if (E == SXI_INVALID || E < L || S > body - o) { status = 2; break; } // (E < L after 11 rounds cannot happen: every hop advances >= 1 byte... 2^11 > SXI_W)
+        if (o + S <= bnd) { o += S; pos += E; continue; }         // no boundary strictly inside this window's chain (landing on it: recorded above, next trip)
+        // ---- a 64 KB boundary lies inside: walk element by element (32 candidate positions at a time) until it is reached ----
+        while (pos < n && o < bnd && status == 0) {
+            u32 adv, out;
+            const u32 wp = pos - (u32)wbase;
+            if (wp + 36 > (u32)SXI_W + 32u) break;               // left the window: reload (outer loop)
+            sn_elem_len(win + wp + lane, adv, out);
+            if (pos + lane >= n) { adv = 0; out = 0; }
+            u32 cur = 0;
+            while (cur < 32u && pos + cur < n && o < bnd) {
+                const u32 a = __shfl_sync(0xffffffffu, adv, cur), ou = __shfl_sync(0xffffffffu, out, cur);
+                if (a == 0 || a > n - (pos + cur) || ou > body - o) { status = 2; break; }
+                o += ou;
+                cur += a;
+            }
+            pos += cur;
         }
-        pos += cur;
     }
-    if (status == 0 && (o != (u32)pg.body_bytes || k != pg.n_segs)) status = (o == (u32)pg.body_bytes && k < pg.n_segs) ? 1 : 2;
+    if (status == 0 && (o != body || k != pg.n_segs)) status = (o == body && pos == n && k < pg.n_segs) ? 1 : 2;
     if (lane == 0) {
         if (status == 2) { atomicOr(err, 8); atomicOr(&pages[warp].flags, PQ_PAGE_SN_BAD); }
         else if (status == 1) atomicOr(&pages[warp].flags, PQ_PAGE_SN_SERIAL);
@@ -355,7 +402,9 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
 
 void launch_pq_snappy_segmented(PqPage* pages, int n_pages, unsigned* ckpt, int n_segs_total, int* err, cudaStream_t st) {
     if (n_pages <= 0) return;
-    k_pq_snappy_index<<<(n_pages + SX_WARPS - 1) / SX_WARPS, SX_WARPS * 32, 0, st>>>(pages, n_pages, ckpt, err);
+    const int smem_i = SXI_WARPS * (SXI_W + 32 + SXI_W * 8);
+    cudaFuncSetAttribute(k_pq_snappy_index, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    k_pq_snappy_index<<<(n_pages + SXI_WARPS - 1) / SXI_WARPS, SXI_WARPS * 32, smem_i, st>>>(pages, n_pages, ckpt, err);
     if (n_segs_total > 0) {
         const int smem = SX_WARPS * (SX_RING + SN_WIN);
         cudaFuncSetAttribute(k_pq_snappy_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

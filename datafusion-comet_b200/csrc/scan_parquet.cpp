@@ -146,6 +146,11 @@ struct ScanRes {
     cudaStream_t copy_stream = nullptr, decode_stream = nullptr;
     cudaEvent_t decoded[2] = {nullptr, nullptr}, uploaded[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, consumer = nullptr;
     int* h_flags = nullptr;
+    // Snappy: the columns of a batch are decompressed side by side (a column's index pass has one warp per page -- a few hundred
+    // warps -- and would leave most SMs idle if the columns queued behind each other on the decode stream)
+    static constexpr int N_SIDE = 4;
+    cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t side_begin = nullptr, side_done[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
 };
 std::mutex g_res_mu;
 std::map<int, std::vector<ScanRes>> g_res_pool;
@@ -165,6 +170,11 @@ ScanRes acquire_res(int device) {
         cuda_check(cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming), "event");
     }
     cuda_check(cudaEventCreateWithFlags(&r.consumer, cudaEventDisableTiming), "event");
+    cuda_check(cudaEventCreateWithFlags(&r.side_begin, cudaEventDisableTiming), "event");
+    for (int i = 0; i < ScanRes::N_SIDE; i++) {
+        cuda_check(cudaStreamCreateWithFlags(&r.side[i], cudaStreamNonBlocking), "side stream");
+        cuda_check(cudaEventCreateWithFlags(&r.side_done[i], cudaEventDisableTiming), "event");
+    }
     cuda_check(cudaMallocHost((void**)&r.h_flags, 64), "cudaMallocHost flags");
     return r;
 }
@@ -608,6 +618,27 @@ struct NativeScanSource : ExecNode {
         launch_pq_copy(meta_dev, meta_host_dev, align_up(sl.meta_used, 16), res.decode_stream);
         ctx->kernel_launches++;
         cuda_check(cudaStreamWaitEvent(res.decode_stream, res.uploaded[si], 0), "stream wait"); // decode kernels start when the batch has landed
+        {   // compressed columns first, spread over the side streams; the decode stream carries on when all of them are done
+            bool used[ScanRes::N_SIDE] = {false, false, false, false};
+            int n_comp = 0;
+            for (auto& cp : plans) if (cp.any_compressed && !cp.pages.empty()) n_comp++;
+            if (n_comp > 0) {
+                cuda_check(cudaEventRecord(res.side_begin, res.decode_stream), "event record");
+                int k = 0;
+                for (auto& cp : plans) {
+                    if (!cp.any_compressed || cp.pages.empty()) continue;
+                    const int sid = k++ % ScanRes::N_SIDE;
+                    if (!used[sid]) { cuda_check(cudaStreamWaitEvent(res.side[sid], res.side_begin, 0), "stream wait"); used[sid] = true; }
+                    launch_pq_snappy_segmented((PqPage*)cp.dpd, (int)cp.pages.size(), (unsigned*)cp.dckpt, (int)cp.n_segs_total, derr, res.side[sid]);
+                    ctx->kernel_launches += 3;
+                }
+                for (int i = 0; i < ScanRes::N_SIDE; i++) {
+                    if (!used[i]) continue;
+                    cuda_check(cudaEventRecord(res.side_done[i], res.side[i]), "event record");
+                    cuda_check(cudaStreamWaitEvent(res.decode_stream, res.side_done[i], 0), "stream wait");
+                }
+            }
+        }
         for (size_t c = 0; c < fields.size(); c++) bind_and_launch(c, plans[c], total, out.cols[c], derr, sl);
         t_launch += now_ms() - tt;
         if (trace_on()) fprintf(stderr, "[cb200 trace]   issue breakdown: h2d enqueue (%zu ranges) %.3f  page tables %.3f  launches %.3f ms; work %.1f MB\n", ranges.size(), t_h2d, t_pages, t_launch, sl.work_used / 1e6);
@@ -888,7 +919,6 @@ struct NativeScanSource : ExecNode {
         PqPage* data_pages = all_pages;
         const PqPage* dict_pages_dev = data_pages + n_data;
         uint8_t* dense = cp.null_aware ? cp.dense : cp.out;
-        if (cp.any_compressed) { launch_pq_snappy_segmented(all_pages, n_all, (unsigned*)cp.dckpt, (int)cp.n_segs_total, derr, ds); ctx->kernel_launches += 3; }
         launch_pq_resolve(all_pages, n_all, ds);
         ctx->kernel_launches++;
         if (cp.n_dict_pages) { launch_pq_plain(dict_pages_dev, (int)cp.n_dict_pages, cp.conv, cp.type_length, cp.ddict, derr, ds); ctx->kernel_launches++; }

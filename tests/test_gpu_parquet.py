@@ -153,6 +153,27 @@ def test_nulls_and_snappy_roundtrip(cb, tmp_path, compression, version, dictiona
             assert got.cast(want.type).equals(want), name
 
 
+def test_snappy_pages_of_a_megabyte_are_decoded_by_segments(cb, tmp_path):
+    """1 MB data pages (pyarrow's default size) of Snappy: 16 segments of 64 KB per page, every kind of stream the Q1 columns produce
+    (PLAIN INT64 decimals = a literal + copy pair per value, random doubles = 64 KB literals, bit-packed dictionary indices)."""
+    import pyarrow.parquet as pq
+    n = 1_500_000
+    tbl = _nullable_table(n, seed=21, null_frac=0.02)
+    path = str(tmp_path / "big_pages.parquet")
+    pq.write_table(tbl, path, row_group_size=700_000, compression="SNAPPY", use_dictionary=["word", "low"], data_page_version="1.0", store_decimal_as_integer=True)
+    res, st = run(cb, _scan_all(cb, tbl, [path]), chunk_rows=1_000_000)
+    assert res.num_rows == n
+    for j, name in enumerate(tbl.column_names):
+        got, want = res.column(j).combine_chunks(), tbl.column(name).combine_chunks()
+        assert got.null_count == want.null_count, name
+        if name == "f64":
+            gv, wv = got.to_numpy(zero_copy_only=False), want.to_numpy(zero_copy_only=False)
+            ok = ~np.isnan(wv)
+            assert (np.isnan(gv) == np.isnan(wv)).all() and (gv[ok].view(np.uint64) == wv[ok].view(np.uint64)).all(), name
+        else:
+            assert got.cast(want.type).equals(want), name
+
+
 def test_aggregate_over_nullable_parquet_columns(cb, tmp_path):
     import pyarrow.compute as pc
     import pyarrow.parquet as pq
