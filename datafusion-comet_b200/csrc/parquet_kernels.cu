@@ -191,13 +191,14 @@ __device__ __forceinline__ void sn_elem_len(const u8* w, u32& adv, u32& out) {
     else { adv = t == 2 ? 3 : 5; out = (tag >> 2) + 1; }
 }
 
-// Index pass.  A warp looks at SXI_W input bytes at a time.  Every byte position is treated as if an element started there
-// (lane l owns positions l, l + 32, ...): nxt = where the following element would start, sum = output bytes it produces.  Pointer
-// jumping (each round: sum += sum[nxt], nxt = nxt[nxt], all positions at once through shared memory) then gives, for EVERY
-// position, where its chain leaves the window and how many bytes it produced on the way -- only position 0's answer is the true one,
-// but computing them all is what makes it parallel: ~10 rounds per window instead of one dependent shuffle pair per element (a
-// page of 4-byte elements took 25 ms that way).  Only a window that contains a 64 KB output boundary is walked element by element.
-constexpr int SXI_WARPS = 4, SXI_W = 1024, SXI_PER_LANE = SXI_W / 32;
+// Index pass.  A warp looks at SXI_W input bytes at a time.  Every byte position is treated as if an element started there: nxt =
+// where the following element would start, sum = output bytes it produces.  Lane l owns the 32 positions of block l and collapses
+// the chains inside it with one backward sweep (the entry of a later position is final when an earlier one needs it), so every
+// position knows where its chain leaves its block; the TRUE chain -- the one from position 0 -- then hops from block to block in
+// at most 32 dependent shared-memory lookups.  All candidate chains are computed although one is real: that is what makes the
+// sweep parallel.  (Following the chain element by element with a shuffle pair each took 25 ms for a page of 4-byte elements,
+// pointer jumping over all 1024 positions 10 ms.)  Only a window that contains a 64 KB output boundary is walked element by element.
+constexpr int SXI_WARPS = 4, SXI_W = 1024;
 constexpr u32 SXI_INVALID = 0xffffffffu;
 
 __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* pages, int n_pages, u32* ckpt, int* err) {
@@ -207,10 +208,10 @@ __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* page
     if (warp >= n_pages) return;
     const PqPage pg = pages[warp];
     if (!pg.comp) return;
-    u8* base = sxi_smem + (size_t)wib * (SXI_W + 32 + SXI_W * 8);
+    u8* base = sxi_smem + (size_t)wib * (SXI_W + 32 + (SXI_W + 32) * 8);
     u8* win = base;                                              // SXI_W + 32 input bytes
-    u32* s_nxt = reinterpret_cast<u32*>(base + SXI_W + 32);      // [SXI_W]
-    u32* s_sum = s_nxt + SXI_W;                                  // [SXI_W]
+    u32* s_nxt = reinterpret_cast<u32*>(base + SXI_W + 32);      // [SXI_W + 32] (skewed)
+    u32* s_sum = s_nxt + SXI_W + 32;                             // [SXI_W + 32]
     const u8* in = pg.comp;
     const u32 n = (u32)pg.comp_bytes;
     u64 ulen64 = 0;
@@ -240,35 +241,40 @@ __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* page
         __syncwarp();
         const u32 woff = pos - (u32)wbase;                       // window byte of position 0
         const u32 L = min((u32)SXI_W - 16u, n - pos);            // positions examined (the loads above cover L + 4 bytes from any woff < 16)
-        // ---- every position's own element ----
-        u32 nx[SXI_PER_LANE], sm[SXI_PER_LANE];
-#pragma unroll
-        for (int j = 0; j < SXI_PER_LANE; j++) {
-            const u32 i = (u32)j * 32u + (u32)lane;
-            u32 adv = 0, out = 0;
-            if (i < L) sn_elem_len(win + woff + i, adv, out);
-            const bool ok = i < L && adv != 0 && adv <= n - (pos + i);
-            nx[j] = ok ? i + adv : SXI_INVALID;
-            sm[j] = ok ? out : 0u;
-        }
-        // ---- pointer jumping ----
-        for (int round = 0; round < 11; round++) {
-#pragma unroll
-            for (int j = 0; j < SXI_PER_LANE; j++) { s_nxt[j * 32 + lane] = nx[j]; s_sum[j * 32 + lane] = sm[j]; }
-            __syncwarp();
-            bool changed = false;
-#pragma unroll
-            for (int j = 0; j < SXI_PER_LANE; j++) {
-                const u32 t = nx[j];
-                if (t < L) { sm[j] += s_sum[t]; nx[j] = s_nxt[t]; changed = true; }
+        // ---- lane l owns the 32 positions [32 l, 32 l + 32): one backward sweep collapses the chains inside its block, so that
+        //      s_nxt / s_sum of a position say where its chain LEAVES the block and what it produced until then (a later position's
+        //      entry is final when an earlier one needs it).  Entries are skewed by one word per block: a warp-wide access to the same
+        //      k of every block would otherwise hit one bank 32 times.
+        {
+            const u32 b0 = (u32)lane * 32u, bend = b0 + 32u;
+#pragma unroll 4
+            for (int kk = 31; kk >= 0; kk--) {
+                const u32 i = b0 + (u32)kk;
+                u32 adv = 0, out = 0;
+                if (i < L) sn_elem_len(win + woff + i, adv, out);
+                const bool ok = i < L && adv != 0 && adv <= n - (pos + i);
+                u32 nxt = SXI_INVALID, sum = 0;
+                if (ok) {
+                    const u32 t = i + adv;
+                    if (t < bend && t < L) { const u32 ti = t + (t >> 5); nxt = s_nxt[ti]; sum = out + s_sum[ti]; }
+                    else { nxt = t; sum = out; }
+                }
+                const u32 ii = i + (i >> 5);
+                s_nxt[ii] = nxt;
+                s_sum[ii] = sum;
             }
-            const bool any = __any_sync(0xffffffffu, changed);
-            __syncwarp();
-            if (!any) break;
         }
-        // position 0 is owned by lane 0, register slot 0
-        const u32 E = __shfl_sync(0xffffffffu, nx[0], 0), S = __shfl_sync(0xffffffffu, sm[0], 0);
-        if (E == SXI_INVALID || E < L || S > body - o) { status = 2; break; } // (E < L after 11 rounds cannot happen: every hop advances >= 1 byte... 2^11 > SXI_W)
+        __syncwarp();
+        // ---- the true chain starts at position 0 and hops from block to block: at most 32 dependent lookups ----
+        u32 E = 0, S = 0;
+        while (E < L) {
+            const u32 ei = E + (E >> 5);
+            const u32 nx = s_nxt[ei];
+            S += s_sum[ei];
+            if (nx == SXI_INVALID || S > body) { E = SXI_INVALID; break; }
+            E = nx;
+        }
+        if (E == SXI_INVALID || E < L || S > body - o) { status = 2; break; } // (E < L cannot happen: the walk only stops past L)
         if (o + S <= bnd) { o += S; pos += E; continue; }         // no boundary strictly inside this window's chain (landing on it: recorded above, next trip)
         // ---- a 64 KB boundary lies inside: walk element by element (32 candidate positions at a time) until it is reached ----
         while (pos < n && o < bnd && status == 0) {
@@ -316,9 +322,11 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
     u32 pos = ckpt[pg.seg_base + sidx], o = o0;
     int wbase = -SN_WIN - 16;
     int status = 0;
-    while (pos < n) {
+    // 32 candidate elements are parsed at once (lane l: the element that would start at input byte pos + l); the true chain is then
+    // followed through the lanes' answers -- two shuffles per element instead of ~60 dependent instructions of one lane parsing it
+    while (pos < n && status == 0) {
         u32 wp = pos - (u32)wbase;
-        if (wp + 5 > (u32)SN_WIN) {
+        if (wp + 36 > (u32)SN_WIN) { // the window must hold the 32 candidate tags and 4 bytes after each
             wbase = (int)((pos + misalign) & ~15u) - (int)misalign;
             const int l0 = wbase + lane * 16;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -328,11 +336,11 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
             __syncwarp();
             wp = pos - (u32)wbase;
         }
-        u32 w0 = 0xffffffffu, w1 = 0;
-        if (lane == 0) {
-            const u8* p = win + wp;
-            const u32 tag = p[0], t = tag & 3u;
-            u32 len, src = 0, hdr;
+        u32 w0 = 0xffffffffu, w1 = 0; // this lane's candidate: len | hdr << 27 | copy << 30, copy distance
+        if (pos + lane < n) {
+            const u8* p = win + wp + lane;
+            const u32 tag = p[0], t = tag & 3u, room = n - (pos + lane);
+            u32 len, hdr;
             if (t == 0) {
                 hdr = 1; len = tag >> 2;
                 if (len >= 60) {
@@ -342,56 +350,61 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
                     hdr += extra;
                 }
                 len += 1;
-                if (len < (1u << 27) && len <= oend - o && hdr + len <= n - pos) w0 = len | (hdr << 27);
+                if (len < (1u << 27) && hdr <= room && len <= room - hdr) w0 = len | (hdr << 27);
             } else {
-                if (t == 1) { hdr = 2; len = ((tag >> 2) & 7u) + 4; src = ((tag >> 5) << 8) | p[1]; }
-                else if (t == 2) { hdr = 3; len = (tag >> 2) + 1; src = (u32)p[1] | ((u32)p[2] << 8); }
-                else { hdr = 5; len = (tag >> 2) + 1; src = (u32)p[1] | ((u32)p[2] << 8) | ((u32)p[3] << 16) | ((u32)p[4] << 24); }
-                if (src - 1u < o - o0 && len <= oend - o && hdr <= n - pos) { w0 = len | (hdr << 27) | (1u << 30); w1 = src; }
-                else if (src - 1u < o && len <= oend - o && hdr <= n - pos) w0 = 0xfffffffeu; // reaches into an earlier segment: legal, but not ours to race on
+                if (t == 1) { hdr = 2; len = ((tag >> 2) & 7u) + 4; w1 = ((tag >> 5) << 8) | p[1]; }
+                else if (t == 2) { hdr = 3; len = (tag >> 2) + 1; w1 = (u32)p[1] | ((u32)p[2] << 8); }
+                else { hdr = 5; len = (tag >> 2) + 1; w1 = (u32)p[1] | ((u32)p[2] << 8) | ((u32)p[3] << 16) | ((u32)p[4] << 24); }
+                if (hdr <= room) w0 = len | (hdr << 27) | (1u << 30);
             }
         }
-        w0 = __shfl_sync(0xffffffffu, w0, 0);
-        if (w0 >= 0xfffffffeu) { status = w0 == 0xfffffffeu ? 1 : 2; break; }
-        const u32 len = w0 & ((1u << 27) - 1), hdr = (w0 >> 27) & 7u;
-        if (!(w0 & (1u << 30))) {
-            if (wp + hdr + len <= (u32)SN_WIN) {
-                for (u32 i = lane; i < len; i += 32) {
-                    const u8 b = win[wp + hdr + i];
-                    out[o + i] = b;
-                    ring[(o + i) & (SX_RING - 1)] = b;
+        u32 cur = 0;
+        while (cur < 32u && pos + cur < n) {
+            const u32 e0 = __shfl_sync(0xffffffffu, w0, cur), d = __shfl_sync(0xffffffffu, w1, cur);
+            if (e0 == 0xffffffffu) { status = 2; break; }
+            const u32 len = e0 & ((1u << 27) - 1), hdr = (e0 >> 27) & 7u;
+            if (len > oend - o) { status = 2; break; }
+            if (!(e0 & (1u << 30))) {
+                const u32 lp = wp + cur + hdr; // literal bytes: in the window when short, else straight from the page
+                if (lp + len <= (u32)SN_WIN) {
+                    for (u32 i = lane; i < len; i += 32) {
+                        const u8 b = win[lp + i];
+                        out[o + i] = b;
+                        ring[(o + i) & (SX_RING - 1)] = b;
+                    }
+                } else {
+                    const u8* s = in + pos + cur + hdr;
+                    for (u32 i = lane; i < len; i += 32) {
+                        const u8 b = s[i];
+                        out[o + i] = b;
+                        ring[(o + i) & (SX_RING - 1)] = b;
+                    }
                 }
+                cur += hdr + len;
             } else {
-                const u8* s = in + pos + hdr;
-                for (u32 i = lane; i < len; i += 32) {
-                    const u8 b = s[i];
-                    out[o + i] = b;
-                    ring[(o + i) & (SX_RING - 1)] = b;
+                if (d - 1u >= o - o0) { status = d - 1u < o ? 1 : 2; break; } // reaches into an earlier segment (legal, not ours to race on) / before the page
+                const bool near = d + 64 <= (u32)SX_RING;
+                if (d >= len) {
+                    for (u32 i = lane; i < len; i += 32) {
+                        const u32 sp = o - d + i;
+                        const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
+                        out[o + i] = b;
+                        ring[(o + i) & (SX_RING - 1)] = b;
+                    }
+                } else {
+                    for (u32 i = lane; i < len; i += 32) {
+                        const u32 sp = o - d + i % d;
+                        const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
+                        out[o + i] = b;
+                        ring[(o + i) & (SX_RING - 1)] = b;
+                    }
                 }
+                cur += hdr;
             }
-            pos += hdr + len;
-        } else {
-            const u32 d = __shfl_sync(0xffffffffu, w1, 0);
-            const bool near = d + 64 <= (u32)SX_RING;
-            if (d >= len) {
-                for (u32 i = lane; i < len; i += 32) {
-                    const u32 sp = o - d + i;
-                    const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
-                    out[o + i] = b;
-                    ring[(o + i) & (SX_RING - 1)] = b;
-                }
-            } else {
-                for (u32 i = lane; i < len; i += 32) {
-                    const u32 sp = o - d + i % d;
-                    const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
-                    out[o + i] = b;
-                    ring[(o + i) & (SX_RING - 1)] = b;
-                }
-            }
-            pos += hdr;
+            __syncwarp(); // the next element may read what this one wrote
+            o += len;
         }
-        __syncwarp();
-        o += len;
+        pos += cur;
     }
     if (status == 0 && o != oend) status = 2;
     if (lane == 0) {
@@ -402,7 +415,7 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
 
 void launch_pq_snappy_segmented(PqPage* pages, int n_pages, unsigned* ckpt, int n_segs_total, int* err, cudaStream_t st) {
     if (n_pages <= 0) return;
-    const int smem_i = SXI_WARPS * (SXI_W + 32 + SXI_W * 8);
+    const int smem_i = SXI_WARPS * (SXI_W + 32 + (SXI_W + 32) * 8);
     cudaFuncSetAttribute(k_pq_snappy_index, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
     k_pq_snappy_index<<<(n_pages + SXI_WARPS - 1) / SXI_WARPS, SXI_WARPS * 32, smem_i, st>>>(pages, n_pages, ckpt, err);
     if (n_segs_total > 0) {
