@@ -806,8 +806,9 @@ def workload_groupby(args, env):
         in_bytes = 8 + w
         part_ms, part_launches = last["st"]["pipeline_ms"], max(last["st"]["pipeline_launches"], 1)
         rows_per_launch = n / part_launches
-        # algorithmic bytes of the partial kernel: the input columns once + per GROUP one 16-byte slot, its key word and its 32 bytes of totals
-        gbytes = 16 + 8 + 32
+        # algorithmic bytes of the partial kernel (stream mode: clustered keys, one state row per run of equal adjacent keys, no key
+        # table): the input columns once + per state row its key word and its two 16-byte accumulator words, written once
+        gbytes = 8 + 32
         alg = in_bytes * n + gbytes * last["rows_state"]
         achieved = alg / (part_ms * 1e-3) / 1e9
         xs = last["xs"]
@@ -821,8 +822,8 @@ def workload_groupby(args, env):
                        "parallelism": f"hash-repartition x{world} (cb200_exchange: one ncclAllGather of counts + one grouped send/recv per state column; {native.nccl_info()})",
                        "l2": f"inputs ({in_bytes * n / 1e9:.1f} GB per GPU) and the hash table exceed L2; no flush needed", "checks": checks},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "cb_pipeline_agg [CB_HASH] (fused scan + hash aggregate, partial stage)", "ms_per_launch": part_ms / part_launches,
-                         "rows_per_launch": rows_per_launch, "algorithmic_bytes": f"{in_bytes} B/row input + {gbytes} B per group (slot + key + totals)",
+                         "kernel": "cb_pipeline_agg [CB_HASH, CB_STREAM] (fused scan + run-combining partial aggregate)", "ms_per_launch": part_ms / part_launches,
+                         "rows_per_launch": rows_per_launch, "algorithmic_bytes": f"{in_bytes} B/row input + {gbytes} B per state row (key + accumulator words)",
                          "peak_source": peak_src},
             "phases_ms": {"partial_kernels": part_ms, "final_kernels": last["st2"]["pipeline_ms"], "exchange_payload": xs["payload_ms"]},
             "exchange": {"bytes_sent_per_gpu": xs["bytes_sent"], "bytes_received_per_gpu": xs["bytes_received"], "payload_ms": xs["payload_ms"],

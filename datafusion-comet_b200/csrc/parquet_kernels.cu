@@ -198,7 +198,8 @@ __device__ __forceinline__ void sn_elem_len(const u8* w, u32& adv, u32& out) {
 // at most 32 dependent shared-memory lookups.  All candidate chains are computed although one is real: that is what makes the
 // sweep parallel.  (Following the chain element by element with a shuffle pair each took 25 ms for a page of 4-byte elements,
 // pointer jumping over all 1024 positions 10 ms.)  Only a window that contains a 64 KB output boundary is walked element by element.
-constexpr int SXI_WARPS = 4, SXI_W = 1024;
+constexpr int SXI_WARPS = 8, SXI_W = 512; // 4.9 KB of shared memory per warp: the sweep is a chain of dependent shared-memory accesses (ncu: 0.09 IPC per
+                                             // scheduler at 12 warps per SM with 1 KB windows), so what it needs is resident warps
 constexpr u32 SXI_INVALID = 0xffffffffu;
 
 __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* pages, int n_pages, u32* ckpt, int* err) {
@@ -246,9 +247,10 @@ __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* page
         //      entry is final when an earlier one needs it).  Entries are skewed by one word per block: a warp-wide access to the same
         //      k of every block would otherwise hit one bank 32 times.
         {
-            const u32 b0 = (u32)lane * 32u, bend = b0 + 32u;
+            constexpr u32 BLK = SXI_W / 32;
+            const u32 b0 = (u32)lane * BLK, bend = b0 + BLK;
 #pragma unroll 4
-            for (int kk = 31; kk >= 0; kk--) {
+            for (int kk = (int)BLK - 1; kk >= 0; kk--) {
                 const u32 i = b0 + (u32)kk;
                 u32 adv = 0, out = 0;
                 if (i < L) sn_elem_len(win + woff + i, adv, out);
@@ -256,10 +258,10 @@ __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* page
                 u32 nxt = SXI_INVALID, sum = 0;
                 if (ok) {
                     const u32 t = i + adv;
-                    if (t < bend && t < L) { const u32 ti = t + (t >> 5); nxt = s_nxt[ti]; sum = out + s_sum[ti]; }
+                    if (t < bend && t < L) { const u32 ti = t + t / BLK; nxt = s_nxt[ti]; sum = out + s_sum[ti]; }
                     else { nxt = t; sum = out; }
                 }
-                const u32 ii = i + (i >> 5);
+                const u32 ii = i + i / BLK;
                 s_nxt[ii] = nxt;
                 s_sum[ii] = sum;
             }
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(SXI_WARPS * 32) k_pq_snappy_index(PqPage* page
         // ---- the true chain starts at position 0 and hops from block to block: at most 32 dependent lookups ----
         u32 E = 0, S = 0;
         while (E < L) {
-            const u32 ei = E + (E >> 5);
+            const u32 ei = E + E / (SXI_W / 32);
             const u32 nx = s_nxt[ei];
             S += s_sum[ei];
             if (nx == SXI_INVALID || S > body) { E = SXI_INVALID; break; }
@@ -366,7 +368,13 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
             if (len > oend - o) { status = 2; break; }
             if (!(e0 & (1u << 30))) {
                 const u32 lp = wp + cur + hdr; // literal bytes: in the window when short, else straight from the page
-                if (lp + len <= (u32)SN_WIN) {
+                if (len <= 32u && lp + len <= (u32)SN_WIN) { // the common shape: one predicated step, no loop
+                    if (lane < len) {
+                        const u8 b = win[lp + lane];
+                        out[o + lane] = b;
+                        ring[(o + lane) & (SX_RING - 1)] = b;
+                    }
+                } else if (lp + len <= (u32)SN_WIN) {
                     for (u32 i = lane; i < len; i += 32) {
                         const u8 b = win[lp + i];
                         out[o + i] = b;
@@ -384,7 +392,13 @@ __global__ void __launch_bounds__(SX_WARPS * 32) k_pq_snappy_seg(PqPage* pages, 
             } else {
                 if (d - 1u >= o - o0) { status = d - 1u < o ? 1 : 2; break; } // reaches into an earlier segment (legal, not ours to race on) / before the page
                 const bool near = d + 64 <= (u32)SX_RING;
-                if (d >= len) {
+                if (len <= 32u && near) { // the common shape: a short copy out of the ring
+                    if (lane < len) {
+                        const u8 b = ring[(o - d + (d >= len ? lane : lane % d)) & (SX_RING - 1)];
+                        out[o + lane] = b;
+                        ring[(o + lane) & (SX_RING - 1)] = b;
+                    }
+                } else if (d >= len) {
                     for (u32 i = lane; i < len; i += 32) {
                         const u32 sp = o - d + i;
                         const u8 b = near ? ring[sp & (SX_RING - 1)] : __ldcg(out + sp);
