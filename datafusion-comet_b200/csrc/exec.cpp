@@ -1969,6 +1969,11 @@ std::vector<GeneratedKernel> plan_kernels_for_build(const OperatorP& op, const s
             a->key_has_null.assign(a->keys.size(), false);
             for (auto& k : a->keys) if (!k->type.is_string() && k->type.id != TypeId::Bool) a->hash_mode = true;
             out.push_back(generate_pipeline(a->make_spec(nullptr, a->ungrouped ? 1 : 6)));
+            if (a->hash_mode && a->mode == AggMode::Partial) { // the run-combining variant the sampled decision may pick at run time
+                a->stream_mode = true;
+                out.push_back(generate_pipeline(a->make_spec(nullptr, 6)));
+                a->stream_mode = false;
+            }
             walk(a->child);
         }
     };

@@ -40,11 +40,17 @@ def to_ms(v, u):
 
 print(f"# {rep}: ncu --set full --clock-control none (cold-cache, serialised; times are not bench values)")
 stall_cols = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
-seen = {}
+# per kernel name keep the `maxl` LONGEST launches (a scan launches the same kernel for every column; the tiny ones say nothing)
+by_name = {}
+for k, r in enumerate(rows[2:]):
+    by_name.setdefault(r[col["Kernel Name"]], []).append((to_ms(val(r, "gpu__time_duration.sum") or 0.0, unit("gpu__time_duration.sum")), k))
+keep = set()
+for name, lst in by_name.items():
+    keep.update(k for _, k in sorted(lst, reverse=True)[:maxl])
+    print(f"# {name[:100]}: {len(lst)} launches captured, {sum(t for t, _ in lst):.3f} ms in total, longest {max(t for t, _ in lst):.3f} ms")
 for k, r in enumerate(rows[2:]):
     name = r[col["Kernel Name"]]
-    seen[name] = seen.get(name, 0) + 1
-    if seen[name] > maxl:
+    if k not in keep:
         continue
     t = to_ms(val(r, "gpu__time_duration.sum"), unit("gpu__time_duration.sum"))
     rd = to_bytes(val(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum"))
@@ -77,6 +83,8 @@ for k, r in enumerate(rows[2:]):
             data.append((int(x[i_st]), x[i_src].strip()))
         except (ValueError, IndexError):
             pass
+    tot = sum(d[0] for d in data) or 1
+    data = data[: len(data) // 2] if len(data) % 2 == 0 and data[: len(data) // 2] == data[len(data) // 2:] else data   # the listing comes twice
     tot = sum(d[0] for d in data) or 1
     top = sorted(range(len(data)), key=lambda i: -data[i][0])[:6]
     print("   hottest SASS (share of stall samples): " + " | ".join(f"{100 * data[i][0] / tot:.1f}% {data[i][1][:44]}" for i in sorted(top)))

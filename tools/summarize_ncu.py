@@ -11,7 +11,10 @@ if mode == "launches":
     agg = collections.OrderedDict()
     total = 0.0
     seq = []
+    mi = hdr.index("Metric Name") if "Metric Name" in hdr else -1
     for r in rows[1:]:
+        if mi >= 0 and r[mi] != "gpu__time_duration.sum":
+            continue                                     # the csv may carry more metrics per launch (DRAM bytes): this table is about time
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v     # -> us
         k = r[ki]
