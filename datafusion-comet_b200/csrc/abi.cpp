@@ -158,11 +158,34 @@ static int64_t execute_common(cb200_plan* plan, cb200_error* err, const std::fun
     }, (int64_t)-2);
 }
 
+// A batch the plan produced is handed to the caller in slices of at most spark.comet.batchSize rows (CometConf.scala:539-544; the JVM side
+// sizes its vectors for that), each a zero-offset Arrow batch like prepare_output's (jni_api.rs:674-742).
 int64_t cb200_execute(cb200_plan* plan, struct ArrowArray* out_arrays, struct ArrowSchema* out_schemas, int32_t n_cols, cb200_error* err) {
-    return execute_common(plan, err, [&](Batch& b) { export_batch(b, &plan->ctx, out_arrays, out_schemas, n_cols); });
+    if (plan && plan->export_pending) {
+        TraceSpan ts("execute(slice)");
+        return cb200_guarded(err, [&]() -> int64_t {
+            cuda_check(cudaSetDevice(plan->ctx.device), "cudaSetDevice");
+            set_alloc_stream(plan->ctx.stream);
+            const int64_t n = std::min<int64_t>(std::max(plan->ctx.batch_size, 1), plan->last.n_rows - plan->export_pos);
+            export_batch(plan->last, &plan->ctx, out_arrays, out_schemas, n_cols, plan->export_pos, n);
+            plan->export_pos += n;
+            plan->export_pending = plan->export_pos < plan->last.n_rows;
+            return n;
+        }, (int64_t)-2);
+    }
+    int64_t first = 0;
+    const int64_t rc = execute_common(plan, err, [&](Batch& b) {
+        first = std::min<int64_t>(std::max(plan->ctx.batch_size, 1), b.n_rows);
+        export_batch(b, &plan->ctx, out_arrays, out_schemas, n_cols, 0, first);
+        plan->export_pos = first;
+        plan->export_pending = first < b.n_rows;
+    });
+    return rc < 0 ? rc : first;
 }
 
 int64_t cb200_execute_device(cb200_plan* plan, cb200_device_column* cols, int32_t n_cols, cb200_error* err) {
+    if (plan && plan->export_pending)
+        return cb200_guarded(err, [&]() -> int64_t { throw PlanError("cb200_execute_device: the current batch is still being handed out by cb200_execute"); }, (int64_t)-2);
     return execute_common(plan, err, [&](Batch& b) {
         if ((int)b.cols.size() != n_cols) throw PlanError("execute_device: plan produces " + std::to_string(b.cols.size()) + " columns");
         for (int i = 0; i < n_cols; i++) {

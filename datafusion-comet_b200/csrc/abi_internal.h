@@ -21,6 +21,8 @@ struct cb200_plan {
     cb200::ExecNodeP root;
     cb200::Batch last; // keeps device results alive for cb200_execute_device
     bool started = false, finished = false;
+    int64_t export_pos = 0;      // cb200_execute hands `last` out in slices of at most spark.comet.batchSize rows: next row to export
+    bool export_pending = false; // ... and whether rows of `last` are still waiting
     int partition = 0, partition_count = 1;
 };
 

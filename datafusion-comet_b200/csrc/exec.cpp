@@ -2025,10 +2025,27 @@ std::vector<uint8_t> pack_bits(const uint8_t* bytes, size_t n) {
 }
 } // namespace
 
-void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols) {
+// bits [row0, row0 + n) of a device bitmap as a host bitmap that starts at bit 0 (Arrow export is zero-offset only, jni_api.rs:716-732)
+static std::vector<uint8_t> fetch_bits(ExecContext* ctx, const void* dev_bitmap, int64_t row0, size_t n) {
+    const size_t first = (size_t)row0 >> 3, shift = (size_t)row0 & 7, nbytes = (shift + n + 7) / 8;
+    std::vector<uint8_t> raw(nbytes + 9, 0);
+    if (n) {
+        cuda_check(cudaMemcpyAsync(raw.data(), (const uint8_t*)dev_bitmap + first, nbytes, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
+        ctx->d2h_bytes += (int64_t)nbytes;
+    }
+    if (shift == 0) { raw.resize((n + 7) / 8 + 8); return raw; }
+    std::vector<uint8_t> out((n + 7) / 8 + 8, 0);
+    for (size_t i = 0; i < (n + 7) / 8; i++) out[i] = (uint8_t)((raw[i] >> shift) | (raw[i + 1] << (8 - shift)));
+    return out;
+}
+
+// rows [row0, row0 + n_rows) of batch b as Arrow C Data arrays (the caller's spark.comet.batchSize slices a large batch, CometConf.scala:539-544)
+void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols, int64_t row0, int64_t n_rows) {
     TraceSpan ts("export_batch");
     if ((int)b.cols.size() != n_cols) throw PlanError("executePlan: caller passed " + std::to_string(n_cols) + " output slots, plan produces " + std::to_string(b.cols.size()) + " columns");
-    size_t n = (size_t)b.n_rows;
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > b.n_rows) throw PlanError("export_batch: slice out of range");
+    const size_t n = (size_t)n_rows, r0 = (size_t)row0;
     for (int i = 0; i < n_cols; i++) {
         Column& c = b.cols[(size_t)i];
         auto* h = new ArrayHolder();
@@ -2036,24 +2053,29 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
         std::vector<uint8_t> validity, data, offs;
         if (c.on_host) {
             if (!c.h_valid.empty()) {
-                validity = pack_bits(c.h_valid.data(), n);
-                for (size_t r = 0; r < n; r++) null_count += c.h_valid[r] ? 0 : 1;
+                validity = pack_bits(c.h_valid.data() + r0, n);
+                for (size_t r = 0; r < n; r++) null_count += c.h_valid[r0 + r] ? 0 : 1;
             }
             if (c.type.is_string()) {
                 offs.resize((n + 1) * 4);
-                memcpy(offs.data(), c.h_offsets.data(), (n + 1) * 4);
-                data = c.h_data;
+                const int32_t* ho = (const int32_t*)c.h_offsets.data();
+                int32_t* o = (int32_t*)offs.data();
+                for (size_t r = 0; r <= n; r++) o[r] = ho[r0 + r] - ho[r0];
+                data.assign(c.h_data.begin() + ho[r0], c.h_data.begin() + ho[r0 + n]);
                 data.resize(data.size() + 8);
-            } else if (c.type.id == TypeId::Bool) data = pack_bits(c.h_data.data(), n);
-            else { data = c.h_data; data.resize(data.size() + 8); }
+            } else if (c.type.id == TypeId::Bool) data = pack_bits(c.h_data.data() + r0, n);
+            else {
+                const size_t w = (size_t)c.type.arrow_width();
+                data.assign(c.h_data.begin() + (ptrdiff_t)(r0 * w), c.h_data.begin() + (ptrdiff_t)((r0 + n) * w));
+                data.resize(data.size() + 8);
+            }
         } else if (c.is_dict) {
             // dictionary-coded string keys of a hash aggregate: fetch the codes, spell the strings out on the host
             std::vector<int32_t> codes(n + 1);
-            if (n) cuda_check(cudaMemcpyAsync(codes.data(), c.data->ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H key codes");
-            std::vector<uint8_t> vb((n + 7) / 8 + 8, 0xff);
-            if (c.validity && n) { cuda_check(cudaMemcpyAsync(vb.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity"); ctx->d2h_bytes += (int64_t)((n + 7) / 8); }
+            if (n) cuda_check(cudaMemcpyAsync(codes.data(), (const uint8_t*)c.data->ptr + r0 * 4, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H key codes");
             cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
             ctx->d2h_bytes += (int64_t)n * 4;
+            std::vector<uint8_t> vb = c.validity && n ? fetch_bits(ctx, c.validity->ptr, row0, n) : std::vector<uint8_t>((n + 7) / 8 + 8, 0xff);
             offs.resize((n + 1) * 4);
             int32_t* o = (int32_t*)offs.data();
             o[0] = 0;
@@ -2069,14 +2091,11 @@ void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchem
             if (c.type.is_string()) throw Unsupported("export of device string columns");
             int w = c.type.id == TypeId::Bool ? 1 : c.type.arrow_width();
             std::vector<uint8_t> raw(n * (size_t)w + 8);
-            if (n) cuda_check(cudaMemcpyAsync(raw.data(), c.data->ptr, n * (size_t)w, cudaMemcpyDeviceToHost, ctx->stream), "D2H output");
+            if (n) cuda_check(cudaMemcpyAsync(raw.data(), (const uint8_t*)c.data->ptr + r0 * (size_t)w, n * (size_t)w, cudaMemcpyDeviceToHost, ctx->stream), "D2H output");
             ctx->d2h_bytes += (int64_t)(n * (size_t)w);
-            if (c.validity) {
-                validity.resize((n + 7) / 8 + 8);
-                if (n) { cuda_check(cudaMemcpyAsync(validity.data(), c.validity->ptr, (n + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H validity"); ctx->d2h_bytes += (int64_t)((n + 7) / 8); }
-            }
             cuda_check(cudaStreamSynchronize(ctx->stream), "D2H sync");
             if (c.validity) {
+                validity = fetch_bits(ctx, c.validity->ptr, row0, n);
                 for (size_t r = 0; r < n; r++) null_count += ((validity[r >> 3] >> (r & 7)) & 1) ? 0 : 1;
                 if (null_count == 0) validity.clear();
             }

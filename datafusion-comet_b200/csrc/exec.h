@@ -137,7 +137,7 @@ ExecNodeP build_exec(const OperatorP& op, ExecContext* ctx, PlanInputs* inputs);
 ExecNodeP make_native_scan(const OperatorP& op, ExecContext* ctx);
 
 // Export helpers (host-visible Arrow C Data)
-void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols);
+void export_batch(Batch& b, ExecContext* ctx, ArrowArray* out_arrays, ArrowSchema* out_schemas, int n_cols, int64_t row0, int64_t n_rows);
 
 // Debug / build-time: generate (and NVRTC-compile, no device needed) the kernels a plan would use,
 // assuming inputs without nulls and dictionary-encoded string keys.

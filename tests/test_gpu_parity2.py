@@ -426,3 +426,35 @@ def test_two_plan_handles_from_two_threads(cb, oracle):
                 continue
             g = got[(t.RETURNFLAGS[k // 2], t.LINESTATUS[k % 2])]
             assert unscaled(g["col_5"], 6) == e["sum_charge"] and unscaled(g["col_8"], 6) == e["avg_disc"] and g["col_9"] == e["count"], seed
+
+
+# ---- (i) spark.comet.batchSize on export (CometConf.scala:539-544, prepare_output jni_api.rs:674-742) ---------------------------------
+@pytest.mark.parametrize("batch_size", [1000, 1001, 4096])
+def test_output_batches_respect_the_batch_size(cb, batch_size):
+    """A result larger than spark.comet.batchSize leaves cb200_execute in zero-offset slices of at most that many rows -- values, NULLs
+    (bitmap slices that do not start on a byte), booleans and dictionary strings all line up with the unsliced result."""
+    P = cb.proto
+    rng = np.random.default_rng(7)
+    n = 10_007
+    a = rng.integers(-1000, 1000, n)
+    mask = rng.random(n) < 0.2
+    tbl = pa.table({"a": pa.array(a, mask=mask), "w": pa.DictionaryArray.from_arrays(pa.array(rng.integers(0, 4, n).astype(np.int32)), pa.array(["x", "yy", "zzz", ""])),
+                    "d": dec_arr([int(v) * 7 for v in a], 12, 2, mask=np.roll(mask, 3))})
+    plan = P.projection(P.scan([P.INT64, P.STRING, P.DECIMAL(12, 2)]),
+                        [P.bound(0, P.INT64), P.gt(P.bound(0, P.INT64), P.literal(0, P.INT64)), P.bound(1, P.STRING), P.bound(2, P.DECIMAL(12, 2))])
+    sizes = []
+    with cb.native.Plan(plan, [tbl.to_batches(max_chunksize=3000)], batch_size=batch_size) as p:
+        batches = []
+        while True:
+            b = p.execute()
+            if b is None:
+                break
+            sizes.append(b.num_rows)
+            batches.append(b)
+    assert sum(sizes) == n and max(sizes) <= batch_size and all(s == batch_size for s in sizes[:-1])
+    got = pa.Table.from_batches(batches)
+    assert got.column(0).combine_chunks().equals(tbl.column("a").combine_chunks())
+    exp_gt = pa.array([None if m else bool(v > 0) for v, m in zip(a.tolist(), mask.tolist())])
+    assert got.column(1).combine_chunks().equals(exp_gt)
+    assert got.column(2).to_pylist() == tbl.column("w").to_pylist()
+    assert got.column(3).combine_chunks().equals(tbl.column("d").combine_chunks())
