@@ -6,7 +6,10 @@
 
 namespace cb200 {
 
-enum { PQ_PAGE_V1_LEVELS = 1, PQ_PAGE_SN_SERIAL = 2, PQ_PAGE_SN_BAD = 4 }; // SN_*: set by the Snappy index / segment kernels (page needs the serial decoder / is malformed); // body starts with [u32 byte length][RLE definition levels] (DataPage v1 of an optional column)
+// PqPage::flags.  V1_LEVELS: body starts with [u32 byte length][RLE definition levels] (DataPage v1 of an optional column).  SN_*: set by the
+// Snappy index / segment kernels (the page needs the serial decoder / is malformed).  HOSTDEC (host bookkeeping only): the body was produced
+// on the host -- decompressed (csrc/host_codecs.h) or PLAIN strings turned into dictionary codes -- and travels with the page tables.
+enum { PQ_PAGE_V1_LEVELS = 1, PQ_PAGE_SN_SERIAL = 2, PQ_PAGE_SN_BAD = 4, PQ_PAGE_HOSTDEC = 8 };
 
 // One page of a column chunk resident on the device.  The host fills what the page HEADER tells it; everything
 // that lives inside the (possibly compressed) page body is resolved on the device by k_pq_resolve.

@@ -20,12 +20,14 @@
 #include "device/cb_snappy.h"
 #include "parquet.h"
 #include "parquet_kernels.h"
+#include "host_codecs.h"
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 
 namespace cb200 {
 
@@ -303,6 +305,7 @@ struct NativeScanSource : ExecNode {
     size_t next_batch = 0;
     bool opened = false;
     std::vector<DictionaryP> dicts;
+    std::vector<std::unordered_map<std::string, int32_t>> dict_index; // value -> code of dicts[c] (PLAIN string pages: one lookup per row)
     int64_t pruned_row_groups = 0, pruned_rows = 0;
 
     struct Slot {
@@ -324,6 +327,7 @@ struct NativeScanSource : ExecNode {
         int64_t run_base = 0, def_run_base = 0, dict_elems = 0;
         size_t unc_bytes = 0;
         int64_t n_segs_total = 0;    // Snappy: 64 KB output segments over all compressed pages (checkpoint table entries)
+        std::vector<uint8_t> hostdec; // bodies of the pages decompressed on the host (ZSTD / LZ4 / GZIP), 16-byte aligned each; shipped with the page tables
         bool optional = false, null_aware = false, any_compressed = false;
         // device buffers (offsets into the slot's work block while planning, pointers after bind)
         uint8_t *out = nullptr, *dunc = nullptr, *dpd = nullptr, *ddict = nullptr, *dense = nullptr, *dvalid = nullptr, *didx = nullptr, *druns = nullptr,
@@ -584,7 +588,7 @@ struct NativeScanSource : ExecNode {
         for (size_t c = 0; c < fields.size(); c++) plan_column(c, units, total, loc[c], out.cols[c], plans[c]);
         // ---- work block: one bump allocation per buffer, sized now that every page is known ----------------------------------
         size_t need = 1024, meta_need = 4096;
-        for (auto& p : plans) meta_need += align_up(p.pages.size() * sizeof(PqPage), 64) + align_up(p.remap.size() * 4, 64) + 128;
+        for (auto& p : plans) meta_need += align_up(p.pages.size() * sizeof(PqPage), 64) + align_up(p.remap.size() * 4, 64) + align_up(p.hostdec.size(), 64) + 192;
         std::vector<std::pair<uint8_t**, size_t>> reqs;
         uint8_t *derr_p = nullptr, *meta_dev = nullptr; // meta_dev: device mirror of the slot's pinned page tables / remap tables
         reqs.push_back({&derr_p, 64});
@@ -736,7 +740,22 @@ struct NativeScanSource : ExecNode {
         bool nulls_possible = false;
         std::vector<uint8_t> host_scratch;
         // compressed page bodies are decompressed into `dunc`; its offsets are assigned here and turned into pointers in bind
-        auto place_body = [&](PqPage& d, const unsigned char* src, int comp_bytes, int unc, bool compressed) {
+        // codec: pq::UNCOMPRESSED (or an uncompressed v2 values section), pq::SNAPPY (device), or a host codec
+        auto place_body = [&](PqPage& d, const unsigned char* src, const uint8_t* host_src, int comp_bytes, int unc, int codec) {
+            const bool compressed = codec == pq::SNAPPY;
+            if (codec != pq::UNCOMPRESSED && codec != pq::SNAPPY) {
+                if (unc < 0 || comp_bytes < 0) throw PlanError("parquet: negative page size");
+                const size_t off = cp.hostdec.size();
+                cp.hostdec.resize(off + (((size_t)unc + 31) / 16) * 16, 0); // 16-byte aligned, >= 8 spare bytes for the unaligned-word loads
+                host_decompress(codec, host_src, (size_t)comp_bytes, cp.hostdec.data() + off, (size_t)unc);
+                d.comp = nullptr;
+                d.comp_bytes = 0;
+                d.body = (unsigned char*)(uintptr_t)off; // offset for now (stage_tables turns it into the device address)
+                d.body_bytes = unc;
+                d.n_segs = 0;
+                d.flags |= PQ_PAGE_HOSTDEC;
+                return;
+            }
             if (compressed) {
                 d.comp = src;
                 d.comp_bytes = comp_bytes;
@@ -753,6 +772,61 @@ struct NativeScanSource : ExecNode {
                 d.n_segs = 0;
             }
         };
+        // PLAIN-encoded string page (a writer's dictionary fallback).  Strings live on the device as codes of the plan-wide dictionary
+        // only, so the host -- which already parses every string dictionary page -- turns the page's values into codes: the page
+        // the device sees is [levels as written][int32 codes], PLAIN.  `vals` = the uncompressed value section on the host.
+        auto place_plain_strings = [&](PqPage& d, const uint8_t* prefix, size_t prefix_len, const uint8_t* vals, size_t vals_len) {
+            if (dict_index.size() < fields.size()) dict_index.resize(fields.size());
+            Dictionary& gd = *dicts[c];
+            auto& index = dict_index[c];
+            if (index.size() != gd.values.size()) { index.clear(); for (size_t k = 0; k < gd.values.size(); k++) index.emplace(gd.values[k], (int32_t)k); }
+            const size_t off = cp.hostdec.size();
+            cp.hostdec.resize(off + prefix_len, 0);
+            if (prefix_len) memcpy(cp.hostdec.data() + off, prefix, prefix_len);
+            size_t n_vals = 0;
+            const uint8_t *p = vals, *e = vals + vals_len;
+            while (p < e) {
+                if (p + 4 > e) throw PlanError("parquet: truncated PLAIN string page");
+                uint32_t len;
+                memcpy(&len, p, 4);
+                p += 4;
+                if (len > (size_t)(e - p)) throw PlanError("parquet: truncated PLAIN string page");
+                std::string v((const char*)p, len);
+                p += len;
+                auto it = index.find(v);
+                int32_t code;
+                if (it == index.end()) {
+                    if (gd.values.size() >= (size_t)INT32_MAX) throw Unsupported("parquet: more than 2^31 distinct strings in one column");
+                    code = (int32_t)gd.values.size();
+                    gd.values.push_back(v);
+                    index.emplace(std::move(v), code);
+                } else code = it->second;
+                const size_t at = cp.hostdec.size();
+                cp.hostdec.resize(at + 4);
+                memcpy(cp.hostdec.data() + at, &code, 4);
+                n_vals++;
+            }
+            const size_t body_bytes = cp.hostdec.size() - off;
+            cp.hostdec.resize(off + ((body_bytes + 31) / 16) * 16, 0);
+            d.comp = nullptr;
+            d.comp_bytes = 0;
+            d.body = (unsigned char*)(uintptr_t)off;
+            d.body_bytes = (int)body_bytes;
+            d.n_segs = 0;
+            d.flags |= PQ_PAGE_HOSTDEC;
+            d.encoding = 0;
+            cp.conv = PQ_COPY32; // k_pq_plain copies the codes of PLAIN pages; dictionary pages of the same column go through k_pq_rle_decode
+            (void)n_vals;
+        };
+        // uncompressed bytes of a page section on the host (any codec), valid until the next call
+        auto host_section = [&](const uint8_t* p, int comp, int unc, int codec_) -> const uint8_t* {
+            if (codec_ == pq::UNCOMPRESSED) return p;
+            host_scratch.assign((size_t)unc + 16, 0);
+            if (codec_ == pq::SNAPPY) {
+                if (cb::snappy_decode_serial(p, comp, host_scratch.data(), unc) != unc) throw PlanError("parquet: malformed Snappy page");
+            } else host_decompress(codec_, p, (size_t)comp, host_scratch.data(), (size_t)unc);
+            return host_scratch.data();
+        };
         for (size_t u = 0; u < units.size(); u++) {
             const OpenFile& of = open_files[units[u].file];
             const pq::SchemaElement& use = of.meta.leaf(of.leaf_of[c]);
@@ -762,9 +836,10 @@ struct NativeScanSource : ExecNode {
             cp.optional = cp.optional || opt_u;
             const pq::ColumnChunkMeta& cc = chunk_meta(units[u], c);
             if (opt_u && cc.null_count != 0) nulls_possible = true; // unknown (-1) counts as possible
-            if (cc.codec != pq::UNCOMPRESSED && cc.codec != pq::SNAPPY)
-                throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (device decompression covers UNCOMPRESSED and SNAPPY; ZSTD / LZ4 / GZIP are next-row work)");
+            if (cc.codec != pq::UNCOMPRESSED && cc.codec != pq::SNAPPY && !host_codec_supported(cc.codec))
+                throw Unsupported("parquet codec " + std::to_string(cc.codec) + " (UNCOMPRESSED and SNAPPY are decompressed on the device, ZSTD / LZ4 / LZ4_RAW / GZIP on the host; BROTLI / LZO are not read)");
             const bool snappy = cc.codec == pq::SNAPPY;
+            const int codec = cc.codec;
             if (cc.num_values != units[u].rows) throw Unsupported("parquet: repeated column (num_values != num_rows)");
             const size_t clen = (size_t)cc.total_compressed;
             const uint8_t* host = loc[u].host;
@@ -786,6 +861,11 @@ struct NativeScanSource : ExecNode {
                                 throw PlanError("parquet: malformed Snappy dictionary page");
                             p = host_scratch.data();
                             e = p + pg.uncompressed_size;
+                        } else if (codec != pq::UNCOMPRESSED) {
+                            host_scratch.assign((size_t)pg.uncompressed_size + 16, 0);
+                            host_decompress(codec, p, (size_t)pg.compressed_size, host_scratch.data(), (size_t)pg.uncompressed_size);
+                            p = host_scratch.data();
+                            e = p + pg.uncompressed_size;
                         }
                         Dictionary& gd = *dicts[c];
                         for (int k = 0; k < this_dict_size; k++) {
@@ -803,7 +883,7 @@ struct NativeScanSource : ExecNode {
                     } else {
                         PqPage dp;
                         memset(&dp, 0, sizeof(dp));
-                        place_body(dp, dc + pg.data_offset, pg.compressed_size, pg.uncompressed_size, snappy);
+                        place_body(dp, dc + pg.data_offset, host + pg.data_offset, pg.compressed_size, pg.uncompressed_size, codec);
                         dp.num_values = this_dict_size;
                         dp.dst_row = cp.dict_elems; // decoded into the combined dictionary at this element offset
                         dict_pages.push_back(dp);
@@ -817,20 +897,39 @@ struct NativeScanSource : ExecNode {
                 d.dst_row = row;
                 d.num_values = (int)pg.num_values;
                 const unsigned char* body = dc + pg.data_offset;
-                if (pg.type == pq::DATA_PAGE) {
+                const bool plain_str = se.type == pq::BYTE_ARRAY && pg.encoding == pq::PLAIN;
+                if (plain_str && pg.type == pq::DATA_PAGE) {
+                    if (opt_u) d.flags |= PQ_PAGE_V1_LEVELS;
+                    const uint8_t* b = host_section(host + pg.data_offset, pg.compressed_size, pg.uncompressed_size, codec);
+                    size_t pre = 0;
+                    if (opt_u) { // [u32 byte length][RLE definition levels] stay as they are
+                        if (pg.uncompressed_size < 4) throw PlanError("parquet: data page shorter than its level header");
+                        uint32_t ll;
+                        memcpy(&ll, b, 4);
+                        if ((size_t)ll + 4 > (size_t)pg.uncompressed_size) throw PlanError("parquet: definition levels exceed the page");
+                        pre = 4 + ll;
+                    }
+                    place_plain_strings(d, b, pre, b + pre, (size_t)pg.uncompressed_size - pre);
+                } else if (plain_str) {
+                    const int lv = pg.rep_levels_bytes + pg.def_levels_bytes;
+                    if (lv > pg.compressed_size || lv > pg.uncompressed_size) throw PlanError("parquet: data page v2 level sizes exceed the page");
+                    d.def_ptr = body + pg.rep_levels_bytes;
+                    d.def_bytes = pg.def_levels_bytes;
+                    const uint8_t* b = host_section(host + pg.data_offset + lv, pg.compressed_size - lv, pg.uncompressed_size - lv, pg.v2_compressed ? codec : (int)pq::UNCOMPRESSED);
+                    place_plain_strings(d, nullptr, 0, b, (size_t)(pg.uncompressed_size - lv));
+                } else if (pg.type == pq::DATA_PAGE) {
                     // v1: [u32 length + definition levels (optional columns)] [values], compressed as one block
                     if (opt_u) d.flags |= PQ_PAGE_V1_LEVELS;
-                    place_body(d, body, pg.compressed_size, pg.uncompressed_size, snappy);
+                    place_body(d, body, host + pg.data_offset, pg.compressed_size, pg.uncompressed_size, codec);
                 } else {
                     // v2: repetition + definition levels sit uncompressed in front of the (optionally compressed) values
                     const int lv = pg.rep_levels_bytes + pg.def_levels_bytes;
                     if (lv > pg.compressed_size || lv > pg.uncompressed_size) throw PlanError("parquet: data page v2 level sizes exceed the page");
                     d.def_ptr = body + pg.rep_levels_bytes;
                     d.def_bytes = pg.def_levels_bytes;
-                    place_body(d, body + lv, pg.compressed_size - lv, pg.uncompressed_size - lv, snappy && pg.v2_compressed);
+                    place_body(d, body + lv, host + pg.data_offset + lv, pg.compressed_size - lv, pg.uncompressed_size - lv, pg.v2_compressed ? codec : (int)pq::UNCOMPRESSED);
                 }
                 if (pg.encoding == pq::PLAIN) {
-                    if (se.type == pq::BYTE_ARRAY) throw Unsupported("parquet: PLAIN-encoded string page (dictionary fallback); only dictionary-encoded strings are decoded");
                     d.encoding = 0;
                 } else if (pg.encoding == pq::RLE_DICTIONARY || pg.encoding == pq::PLAIN_DICTIONARY) {
                     if (this_dict_off < 0) throw PlanError("parquet: dictionary-encoded page without a dictionary page");
@@ -899,6 +998,13 @@ struct NativeScanSource : ExecNode {
     void stage_tables(ColPlan& cp, Slot& sl, uint8_t* meta_dev) {
         if (cp.pages.empty()) return;
         if (cp.any_compressed) for (auto& d : cp.pages) if (d.comp) d.body = cp.dunc + (size_t)(uintptr_t)d.body;
+        if (!cp.hostdec.empty()) { // host-decompressed page bodies ride in the pinned block; the pages point at its device mirror
+            uint8_t* pin_body = meta_take(sl, cp.hostdec.size());
+            memcpy(pin_body, cp.hostdec.data(), cp.hostdec.size());
+            uint8_t* dev_body = meta_dev + (pin_body - sl.meta->ptr);
+            for (auto& d : cp.pages) if (d.flags & PQ_PAGE_HOSTDEC) d.body = dev_body + (size_t)(uintptr_t)d.body;
+            std::vector<uint8_t>().swap(cp.hostdec);
+        }
         uint8_t* pin_pages = meta_take(sl, cp.pages.size() * sizeof(PqPage));
         memcpy(pin_pages, cp.pages.data(), cp.pages.size() * sizeof(PqPage));
         cp.dpd = meta_dev + (pin_pages - sl.meta->ptr);

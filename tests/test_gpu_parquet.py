@@ -153,6 +153,63 @@ def test_nulls_and_snappy_roundtrip(cb, tmp_path, compression, version, dictiona
             assert got.cast(want.type).equals(want), name
 
 
+@pytest.mark.parametrize("compression,version", [("ZSTD", "1.0"), ("ZSTD", "2.0"), ("LZ4", "1.0"), ("GZIP", "2.0")])
+def test_host_decompressed_codecs_roundtrip(cb, tmp_path, compression, version):
+    """ZSTD (the codec of the reference's benchmark data, benchmarks/results/0.16.0/comet-tpch.json:8), LZ4 and GZIP pages: the bytes are
+    decompressed on the host (csrc/host_codecs.cpp), levels / dictionaries / values are decoded by the same device kernels."""
+    import pyarrow.parquet as pq
+    n = 70_000
+    tbl = _nullable_table(n, seed=8)
+    path = str(tmp_path / "codec.parquet")
+    pq.write_table(tbl, path, row_group_size=25_000, compression=compression, use_dictionary=["word", "low"], data_page_version=version, data_page_size=16384,
+                   store_decimal_as_integer=True)
+    res, st = run(cb, _scan_all(cb, tbl, [path]), chunk_rows=40_000)
+    assert res.num_rows == n
+    for j, name in enumerate(tbl.column_names):
+        got, want = res.column(j).combine_chunks(), tbl.column(name).combine_chunks()
+        assert got.null_count == want.null_count, name
+        if name == "f64":
+            gv, wv = got.to_numpy(zero_copy_only=False), want.to_numpy(zero_copy_only=False)
+            ok = ~np.isnan(wv)
+            assert (np.isnan(gv) == np.isnan(wv)).all() and (gv[ok].view(np.uint64) == wv[ok].view(np.uint64)).all(), name
+        else:
+            assert got.cast(want.type).equals(want), name
+
+
+@pytest.mark.parametrize("compression,version", [("NONE", "1.0"), ("SNAPPY", "2.0"), ("ZSTD", "1.0")])
+def test_plain_encoded_string_pages(cb, tmp_path, compression, version):
+    """A string column without (or after falling back from) dictionary encoding: PLAIN BYTE_ARRAY pages.  The host turns their values
+    into codes of the plan-wide dictionary, the device scatters the codes like any PLAIN INT32 page; mixed with dictionary pages of the
+    same column (second file) the codes agree."""
+    import pyarrow.parquet as pq
+    P = cb.proto
+    n = 50_000
+    rng = np.random.default_rng(4)
+    words = np.array([f"w{i:05d}" for i in range(3000)] + ["", "ünï", "a" * 300])[rng.integers(0, 3003, n)]
+    mask = rng.random(n) < 0.1
+    tbl = pa.table({"word": pa.array(words.tolist(), mask=mask).cast(pa.string()), "req": pa.array(np.arange(n, dtype=np.int64))})
+    p1, p2 = str(tmp_path / "plain.parquet"), str(tmp_path / "dict.parquet")
+    pq.write_table(tbl, p1, row_group_size=20_000, compression=compression, use_dictionary=False, data_page_version=version, data_page_size=8192)
+    pq.write_table(tbl, p2, row_group_size=20_000, compression=compression, use_dictionary=["word"], data_page_version=version)
+    fields = [("word", P.STRING, True), ("req", P.INT64, True)]
+    plan = P.projection(P.native_scan(fields, fields, [p1, p2]), [P.bound(0, P.STRING), P.bound(1, P.INT64)])
+    res, _ = run(cb, plan, chunk_rows=30_000)
+    assert res.num_rows == 2 * n
+    want = tbl.column("word").to_pylist()
+    assert res.column(0).to_pylist() == want + want
+    assert res.column(1).to_pylist() == list(range(n)) * 2
+    # and as a group key: COUNT(*) per word over the PLAIN file
+    agg = P.hash_agg(P.native_scan(fields, fields, [p1]), [P.bound(0, P.STRING)], [P.agg_count([P.literal(1, P.INT32)])], P.PARTIAL)
+    out, _ = run(cb, agg)
+    exp = {}
+    for w in want:
+        exp[w] = exp.get(w, 0) + 1
+    got = {}
+    for r in out.to_pylist():
+        got[r["col_0"]] = got.get(r["col_0"], 0) + r["col_1"]
+    assert got == exp
+
+
 def test_snappy_pages_of_a_megabyte_are_decoded_by_segments(cb, tmp_path):
     """1 MB data pages (pyarrow's default size) of Snappy: 16 segments of 64 KB per page, every kind of stream the Q1 columns produce
     (PLAIN INT64 decimals = a literal + copy pair per value, random doubles = 64 KB literals, bit-packed dictionary indices)."""

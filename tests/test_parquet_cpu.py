@@ -107,3 +107,29 @@ def test_parquet_oracle_matches_pyarrow(tmp_path, compression, version, dictiona
                 assert struct.pack("<d", g) == struct.pack("<d", w), name
             else:
                 assert g == w, name
+
+
+def test_host_codecs_decompress_what_pyarrow_compressed():
+    """ZSTD / LZ4_RAW / LZ4 (Hadoop framing) / GZIP pages are decompressed on the host (csrc/host_codecs.cpp: libzstd and liblz4 through
+    dlopen, zlib linked) before the device decodes them; checked here against pyarrow's compressors without a GPU."""
+    import ctypes as C
+    import os
+    import pyarrow as pa
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "datafusion-comet_b200", "libcomet_b200.so"))
+    f = getattr(lib, "_ZN5cb20015host_decompressEiPKhmPhm")       # cb200::host_decompress(int, const uint8_t*, size_t, uint8_t*, size_t)
+    f.restype = None
+    f.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    rng = np.random.default_rng(0)
+    raw = rng.integers(0, 1000, 300_000).astype(np.int64).tobytes() + bytes(50_000) + rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes()
+    for codec_id, name in ((6, "zstd"), (7, "lz4_raw"), (5, "lz4_hadoop"), (5, "lz4_raw"), (2, "gzip")):
+        if name == "lz4_hadoop":     # the deprecated LZ4 codec as Hadoop frames it: [u32 BE uncompressed][u32 BE compressed][raw block], here two blocks
+            half = len(raw) // 2
+            comp = b""
+            for part in (raw[:half], raw[half:]):
+                blk = pa.compress(part, codec="lz4_raw", asbytes=True)
+                comp += len(part).to_bytes(4, "big") + len(blk).to_bytes(4, "big") + blk
+        else:
+            comp = pa.compress(raw, codec=name, asbytes=True)
+        out = C.create_string_buffer(len(raw))
+        f(codec_id, comp, len(comp), out, len(raw))
+        assert out.raw == raw, name
