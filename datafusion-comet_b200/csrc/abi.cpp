@@ -175,7 +175,9 @@ int64_t cb200_execute(cb200_plan* plan, struct ArrowArray* out_arrays, struct Ar
     }
     int64_t first = 0;
     const int64_t rc = execute_common(plan, err, [&](Batch& b) {
-        first = std::min<int64_t>(std::max(plan->ctx.batch_size, 1), b.n_rows);
+        // a ShuffleWriter's batch is one unit: cb200_plan_partition_starts / cb200_exchange address its rows by partition offsets
+        const bool whole = plan->op->kind == OpKind::ShuffleWriter;
+        first = whole ? b.n_rows : std::min<int64_t>(std::max(plan->ctx.batch_size, 1), b.n_rows);
         export_batch(b, &plan->ctx, out_arrays, out_schemas, n_cols, 0, first);
         plan->export_pos = first;
         plan->export_pending = first < b.n_rows;

@@ -181,6 +181,7 @@ def test_plain_encoded_string_pages(cb, tmp_path, compression, version):
     """A string column without (or after falling back from) dictionary encoding: PLAIN BYTE_ARRAY pages.  The host turns their values
     into codes of the plan-wide dictionary, the device scatters the codes like any PLAIN INT32 page; mixed with dictionary pages of the
     same column (second file) the codes agree."""
+    import pyarrow as pa
     import pyarrow.parquet as pq
     P = cb.proto
     n = 50_000
