@@ -89,4 +89,7 @@ void hm_dd_sum_tree(int64_t n, const double* v, int lanes, double* out) { // lan
     *out = t.hi;
 }
 long long hm_snappy(const uint8_t* in, long long n, uint8_t* out, long long cap) { return snappy_decode_serial(in, n, out, cap); }
+// the per-group overflow certificate of decimal SUM / AVG (cb_finalize): 0 fits, 1 overflows in every row order, 2 order-dependent
+int hm_sum_cert(int64_t n, uint64_t blo, uint64_t bhi, int p, const i128* total) { return sum_cert(cert_level(n, blo, bhi, p), dec_fits_p(*total, p)); }
+int hm_cert_level(int64_t n, uint64_t blo, uint64_t bhi, int p) { return cert_level(n, blo, bhi, p); }
 }

@@ -238,3 +238,47 @@ def test_decimal_div_matches_the_oracle(hm, oracle):
         assert oracle.dec_to_ints(out) == oracle.dec_to_ints(exp), (p1, s1, p2, s2, s3, integral)
         got = oracle.dec_to_ints(out)
         assert [bool(f) for f in fits] == [-(1 << 63) <= g < (1 << 63) for g in got]
+
+
+def test_overflow_certificate_against_every_row_order(hm, oracle):
+    """cb::cert_level / cb::sum_cert decide from (n, bound B on |addend|, exact total) what the reference's row-by-row sum
+    (sum_decimal.rs:418-439: NULL as soon as a prefix leaves the precision) returns in EVERY row order.  Brute force over all
+    permutations of small groups: verdict 0 => no order overflows and the total fits; 1 => every order overflows; 2 => undecided
+    (the engine refuses those).  B is what the host derives from the value masks: the smallest 2^bits with -B <= v <= B - 1."""
+    import itertools
+    hm.hm_sum_cert.restype = C.c_int
+    p = 3                                            # decimal(3, 0): |sum| <= 999
+    lim = 10**p - 1
+    rng = np.random.default_rng(0)
+    seen = set()
+    for _ in range(4000):
+        n = int(rng.integers(1, 6))
+        vals = [int(v) for v in rng.integers(-lim, lim + 1, n)]
+        bits = max(((v ^ (v >> 63)).bit_length()) for v in vals)          # value-mask bit length, as the kernels record it
+        B = 1 << bits
+        total = sum(vals)
+        t = oracle.dec_from_ints([total])
+        verdict = hm.hm_sum_cert(C.c_int64(n), C.c_uint64(B & (2**64 - 1)), C.c_uint64((B >> 64) | (1 << 63)), C.c_int(p), _p(t))
+        outcomes = set()
+        for perm in set(itertools.permutations(vals)):
+            s, ovf = 0, False
+            for v in perm:
+                s += v
+                if abs(s) > lim:
+                    ovf = True
+                    break
+            outcomes.add(ovf)
+        seen.add(verdict)
+        if verdict == 0:
+            assert outcomes == {False} and abs(total) <= lim, (vals, verdict)
+        elif verdict == 1:
+            assert outcomes == {True}, (vals, verdict)
+        else:
+            assert verdict == 2
+    assert seen == {0, 1, 2}
+    # the edge the Final merge of two 8e37 partial sums hits (decimal(38, 0)): n * B == 2^127 exactly is still an exact total
+    hm.hm_cert_level.restype = C.c_int
+    B = 1 << 126
+    assert hm.hm_cert_level(C.c_int64(2), C.c_uint64(0), C.c_uint64((B >> 64) | (1 << 63)), C.c_int(38)) == 1     # two's-complement bound: exact
+    assert hm.hm_cert_level(C.c_int64(2), C.c_uint64(0), C.c_uint64(B >> 64), C.c_int(38)) == 2                    # magnitude bound: may have wrapped
+    assert hm.hm_cert_level(C.c_int64(3), C.c_uint64(0), C.c_uint64((B >> 64) | (1 << 63)), C.c_int(38)) == 2
