@@ -1,4 +1,7 @@
-"""Model of the NEXT Snappy page decoder (not product code; runs on the CPU, no GPU needed).
+"""Round-1 design study of the segmented Snappy page decoder (not product code; runs on the CPU, no GPU needed).
+The decoder was built in round 2 (csrc/parquet_kernels.cu: k_pq_snappy_index / k_pq_snappy_seg); the algorithm as shipped is modelled and
+checked in tests/test_snappy_index_model.py.  Kept for the stream statistics it prints (elements per window, cross-segment references).
+
 
 Today's kernel (parquet_kernels.cu k_pq_snappy) lets lane 0 parse one element per loop trip: ~115 dependent instructions per
 element at ~4.5 cycles each.  The plan for the next round is a two-pass decode per page:
