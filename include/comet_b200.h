@@ -66,7 +66,10 @@ int32_t cb200_plan_num_columns(cb200_plan* plan);
 
 /* Replaces Native.executePlan (Native.scala:98-103, jni_api.rs:767-775): produce the next output
  * batch into caller-allocated ArrowArray/ArrowSchema structs (moved, release callbacks set).  Returns
- * the row count, -1 at end of stream (jni_api.rs:891,933), -2 on error. */
+ * the row count, -1 at end of stream (jni_api.rs:891,933), -2 on error.  A batch never has more than
+ * spark.comet.batchSize rows (CometConf.scala:539-544; `batch_size` of cb200_create_plan when > 0): larger
+ * results leave in consecutive zero-offset slices (jni_api.rs:716-732), except the batch of a ShuffleWriter
+ * plan, which cb200_plan_partition_starts / cb200_exchange address as a whole. */
 int64_t cb200_execute(cb200_plan* plan, struct ArrowArray* out_arrays, struct ArrowSchema* out_schemas,
                       int32_t n_cols, cb200_error* err);
 
