@@ -425,3 +425,34 @@ def test_q1_dec_threads_agree(oracle):
     keep = c["l_shipdate"] <= tpch.Q1_CUTOFF
     k0 = keep & (c["l_returnflag"] == 0) & (c["l_linestatus"] == 0)
     assert a[0]["sum_qty"] == int(c["l_quantity"][k0].sum()) and a[0]["count"] == int(k0.sum())
+
+
+# ---- more of checked_arithmetic.rs's own tests (:266-340) --------------------------------------------------------------------------
+def test_checked_add_propagates_nulls(oracle):  # :266-273
+    out, outv = oracle.int_arith(0, 32, [1, 0, 3, 0], [1, 0, 1, 0], [10, 20, 0, 0], [1, 1, 0, 0], ANSI)
+    assert list(outv) == [1, 0, 0, 0] and out[0] == 11
+
+
+def test_checked_sub_and_mul_overflow_try(oracle):  # :289-297
+    out, outv = oracle.int_arith(1, 32, [-(2**31), 5], None, [1, 3], None, TRY)
+    assert list(outv) == [0, 1] and out[1] == 2
+    out, outv = oracle.int_arith(2, 32, [2**31 - 1, 5], None, [2, 3], None, TRY)
+    assert list(outv) == [0, 1] and out[1] == 15
+
+
+def test_null_row_with_garbage_value_does_not_error_in_ansi_mode(oracle):  # :322-340
+    out, outv = oracle.int_arith(0, 32, [2**31 - 1, 1], [0, 1], [1, 1], None, ANSI)     # slot 0 is NULL and holds i32::MAX
+    assert list(outv) == [0, 1] and out[1] == 2 and out[0] == 0
+
+
+def test_checked_div_by_zero_through_the_expression_interpreter():  # :300-319; tests/exprs.py is what the GPU expression tests compare with
+    import exprs as E
+    from comet_b200 import proto as P
+    cols = [(np.array([1.0, 8.0]), np.array([True, True])), (np.array([0.0, 2.0]), np.array([True, True]))]
+    a, b = E.Col(0, P.DOUBLE), E.Col(1, P.DOUBLE)
+    v, valid = E.Arith("divide", a, b, P.DOUBLE, E.TRY).eval(cols)
+    assert list(valid) == [False, True] and v[1] == 4.0
+    with pytest.raises(E.AnsiError):
+        E.Arith("divide", a, b, P.DOUBLE, E.ANSI).eval(cols)
+    v, valid = E.Arith("divide", a, b, P.DOUBLE).eval(cols)                               # Legacy: IEEE
+    assert list(valid) == [True, True] and np.isinf(v[0]) and v[1] == 4.0
