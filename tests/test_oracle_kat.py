@@ -456,3 +456,24 @@ def test_checked_div_by_zero_through_the_expression_interpreter():  # :300-319; 
         E.Arith("divide", a, b, P.DOUBLE, E.ANSI).eval(cols)
     v, valid = E.Arith("divide", a, b, P.DOUBLE).eval(cols)                               # Legacy: IEEE
     assert list(valid) == [True, True] and np.isinf(v[0]) and v[1] == 4.0
+
+
+# ---- CheckOverflow array vectors: math_funcs/internal/checkoverflow.rs:417-512 --------------------------------------------------------
+def _co(oracle, vals, precision, ansi=False):
+    a = oracle.dec_from_ints([0 if v is None else v for v in vals])
+    av = np.array([v is not None for v in vals], dtype=np.uint8)
+    out, outv = oracle.check_overflow(a, av, precision, ansi)
+    return oracle.dec_to_ints(out, outv)
+
+
+def test_check_overflow_array_vectors(oracle):
+    assert _co(oracle, [999, 12, None, 5], 3) == [999, 12, None, 5]                  # :417-427 nothing overflows, NULLs kept
+    assert _co(oracle, [999, 1000, None, 5], 3) == [999, None, None, 5]              # :430-439
+    assert _co(oracle, [999, None, 5], 3, ansi=True) == [999, None, 5]               # :442-449
+    assert _co(oracle, [-1000, 5], 3) == [None, 5]                                   # :459-465 the lower bound is its own branch
+    assert _co(oracle, [None, None, None], 3) == [None, None, None]                  # :480-487
+    assert _co(oracle, [1000, 5000, -2000], 3) == [None, None, None]                 # :490-495
+    assert _co(oracle, [999, 9999], 3) == [999, None]                                # :505-511 off-by-one on the bound
+    for bad in ([999, 1000], [5, -1000], [1000, 5000]):                              # :452-456, :468-477, :498-502 ANSI raises on either side
+        with pytest.raises(oracle.OracleError):
+            _co(oracle, bad, 3, ansi=True)
