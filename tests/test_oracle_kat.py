@@ -477,3 +477,22 @@ def test_check_overflow_array_vectors(oracle):
     for bad in ([999, 1000], [5, -1000], [1000, 5000]):                              # :452-456, :468-477, :498-502 ANSI raises on either side
         with pytest.raises(oracle.OracleError):
             _co(oracle, bad, 3, ansi=True)
+
+
+# ---- the rest of sum_int.rs's own tests (:933-947, :977-1015) ---------------------------------------------------------------------
+def test_sum_int_filter_null_is_exclude_and_no_filter(oracle):
+    acc = oracle.SumIntGroups(1)                       # :933-947: a NULL filter entry excludes the row (filter passed as "true AND valid")
+    acc.update([10, 20, 30], None, [0, 0, 0], filt=[1, 0, 1])
+    assert acc.sums[0] == 40 and acc.sums_valid[0] == 1
+    acc = oracle.SumIntGroups(1)                       # :977-988
+    acc.update([1, 2, 3], None, [0, 0, 0])
+    assert acc.sums[0] == 6
+
+
+def test_sum_int_merge_consumes_every_state_row(oracle):  # :995-1015: merging partial sums = summing the non-NULL state rows, all of them
+    acc = oracle.SumIntGroups(1)
+    acc.update([1, 2, 0, 3], [1, 1, 0, 1], [0, 0, 0, 0])
+    assert acc.sums[0] == 6
+    acc = oracle.SumIntGroups(1, ANSI)
+    acc.update([10, 20, 0, 30], [1, 1, 0, 1], [0, 0, 0, 0])
+    assert acc.sums[0] == 60
